@@ -1,0 +1,207 @@
+"""ctypes binding of libequss_b200.so (C-ABI declared in include/equss_b200.h).
+
+PyTorch is used only for device memory and streams: every wrapper below takes CUDA tensors, passes
+their raw ``data_ptr()`` and the current stream to the C entry point, and raises on any error code.
+There is no CPU or eager-PyTorch fallback: if the library is missing, cannot be loaded, or no sm_100
+device is visible, calls fail loudly with :class:`EqussNativeError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+__all__ = [
+    "EqussNativeError", "lib", "lib_path", "load", "NORM_MODES", "ZDesc", "zdesc_for",
+    "ASSIGN_AUTO", "ASSIGN_SIMT", "ASSIGN_TCGEN05", "EXPORTS",
+]
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libequss_b200.so"
+
+NORM_MODES = {"none": 0, None: 0, "l2": 1, "z_norm": 2, "z_trainable": 3, "affine": 3}
+ASSIGN_AUTO, ASSIGN_SIMT, ASSIGN_TCGEN05 = 0, 1, 2
+LAYOUT_FLAT, LAYOUT_NCHW = 0, 1
+
+# every symbol include/equss_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "equss_last_error_string", "equss_version", "equss_device_check", "equss_launch_count",
+    "equss_pq_assign_workspace_bytes", "equss_pq_assign", "equss_pq_cnorm2", "equss_pq_gather_loss",
+    "equss_pq_gather_loss_bwd", "equss_pq_accumulate", "equss_ema_update", "equss_pq_distance_prob",
+    "equss_probe_cpad", "equss_probe_logits", "equss_probe_argmax_confusion", "equss_confusion_update",
+    "equss_knn_workspace_bytes", "equss_knn_topk",
+]
+
+
+class EqussNativeError(RuntimeError):
+    pass
+
+
+class ZDesc(C.Structure):
+    _fields_ = [("n_pixels", C.c_int64), ("hw", C.c_int64), ("stride_b", C.c_int64),
+                ("stride_s", C.c_int64), ("stride_c", C.c_int64), ("dim", C.c_int32), ("layout", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return os.path.join(_PKG_DIR, _LIB_NAME)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is the job of ``__graft_entry__.build()`` / ``build.py``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EqussNativeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). equss_b200 has no CPU or PyTorch fallback.")
+    try:
+        L = C.CDLL(path)
+    except OSError as e:  # pragma: no cover
+        raise EqussNativeError(f"cannot load {path}: {e}") from e
+    _declare(L)
+    _lib = L
+    return L
+
+
+def lib() -> C.CDLL:
+    return load()
+
+
+def _declare(L: C.CDLL) -> None:
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    zp = C.POINTER(ZDesc)
+    L.equss_last_error_string.restype = C.c_char_p
+    L.equss_last_error_string.argtypes = []
+    L.equss_version.restype = i32
+    L.equss_device_check.restype = i32
+    L.equss_device_check.argtypes = [i32]
+    L.equss_launch_count.restype = i64
+    L.equss_pq_assign_workspace_bytes.restype = i64
+    L.equss_pq_assign_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
+    L.equss_pq_assign.restype = i32
+    L.equss_pq_assign.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, i32, vp]
+    L.equss_pq_cnorm2.restype = i32
+    L.equss_pq_cnorm2.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.equss_pq_gather_loss.restype = i32
+    L.equss_pq_gather_loss.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.equss_pq_gather_loss_bwd.restype = i32
+    L.equss_pq_gather_loss_bwd.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.equss_pq_accumulate.restype = i32
+    L.equss_pq_accumulate.argtypes = [vp, zp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.equss_ema_update.restype = i32
+    L.equss_ema_update.argtypes = [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, vp]
+    L.equss_pq_distance_prob.restype = i32
+    L.equss_pq_distance_prob.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, f32, vp, vp]
+    L.equss_probe_cpad.restype = i32
+    L.equss_probe_cpad.argtypes = [i32]
+    L.equss_probe_logits.restype = i32
+    L.equss_probe_logits.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.equss_probe_argmax_confusion.restype = i32
+    L.equss_probe_argmax_confusion.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32,
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                               C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int32), vp]
+    L.equss_confusion_update.restype = i32
+    L.equss_confusion_update.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    L.equss_knn_workspace_bytes.restype = i64
+    L.equss_knn_workspace_bytes.argtypes = [i64, i64, i32, i32]
+    L.equss_knn_topk.restype = i32
+    L.equss_knn_topk.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, vp, i64, vp]
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().equss_last_error_string().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise EqussNativeError(f"{what} failed with code {rc}: {msg}")
+
+
+def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise EqussNativeError(
+                "equss_b200 kernels need CUDA tensors on a B200 (sm_100a); got a "
+                f"{t.device} tensor. There is no CPU fallback.")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise EqussNativeError(f"tensors on different devices: {t.device} vs {dev}")
+    if dev is None:
+        raise EqussNativeError("no tensor given")
+    return dev
+
+
+_checked_devices = set()
+
+
+def ensure_device(dev: torch.device) -> None:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx in _checked_devices:
+        return
+    check(lib().equss_device_check(idx), "equss_device_check")
+    _checked_devices.add(idx)
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view/copy (host plumbing)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def zdesc_for(z: torch.Tensor, M: int) -> "tuple[ZDesc, int, str]":
+    """Describe an activation tensor without copying it.
+
+    2-D (n, D) contiguous          -> flat layout            (model/quantizer.py:396)
+    4-D (B, D, h, w) contiguous    -> NCHW layout            (model/quantizer.py:112 consumes this after a permute)
+    Returns (descriptor, d, layout_name).
+    """
+    if z.dim() == 2:
+        n, D = z.shape
+        if D % M != 0:
+            raise ValueError(f"Embed dim {D} should be divisible by #PQ {M}.")
+        zd = ZDesc(n, max(n, 1), max(n, 1) * D, D, 1, D, LAYOUT_FLAT)
+        return zd, D // M, "flat"
+    if z.dim() == 4:
+        B, D, h, w = z.shape
+        if D % M != 0:
+            raise ValueError(f"Embed dim {D} should be divisible by #PQ {M}.")
+        hw = h * w
+        zd = ZDesc(B * hw, max(hw, 1), D * hw, 1, hw, D, LAYOUT_NCHW)
+        return zd, D // M, "nchw"
+    raise ValueError(f"expected a (n, D) or (B, D, h, w) tensor, got shape {tuple(z.shape)}")
+
+
+def as_voidp_array(ptrs: Sequence[Optional[int]]):
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def as_i32_array(vals: Sequence[int]):
+    arr = (C.c_int32 * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr

@@ -1,0 +1,322 @@
+// eval_probe.cu -- cluster / linear probe prediction at label resolution (K8) and the confusion
+// histogram (K9).  Reference: model/evaluator.py:46-82,85-111 and model/metric.py:44-58.
+//
+// The reference bilinearly upsamples the (B, D, h, w) feature map to label resolution (13.4 GB at the
+// cocostuff27 eval shape) and only then takes the 27 inner products per pixel.  Both steps are linear,
+// and the per-pixel L2 normalisation is a positive scalar, so
+//     argmax_j <normalize(interp(x)), c_j>  ==  argmax_j interp(<x, c_j>)
+// (and the linear probe commutes with the interpolation exactly because the four weights sum to one).
+// K8 therefore runs in two HBM-friendly steps: token-resolution logits (reads x once), then one pass
+// over the label pixels that interpolates 27 logits from an L2-resident table, takes the argmax and
+// feeds warp-privatised shared-memory confusion bins.
+#include <cstring>
+#include "equss_common.cuh"
+
+namespace equss {
+
+constexpr int kProbeMaxHeads = 4;
+
+// ------------------------------------------------------------------------------------------------
+// step 1: logits[b*hw + s][j] = sum_c feat[b][c][s] * w[j][c] + bias[j]
+//   block = 128 threads, PT pixels per thread (consecutive threads = consecutive pixels: every
+//   channel read is a coalesced 512-byte row), CT output channels per block kept in registers,
+//   weights staged transposed in shared memory ([DC][CT]) so each feature value meets CT/4 broadcast
+//   LDS.128.
+// ------------------------------------------------------------------------------------------------
+template <int CT, int PT>
+__global__ void __launch_bounds__(128)
+probe_logits_kernel(const float* __restrict__ feat, int D, int hw, const float* __restrict__ wmat,
+                    const float* __restrict__ bias, int c_total, int c_pad, float* __restrict__ logits) {
+  constexpr int DC = 128;                       // feature channels per shared-memory chunk
+  __shared__ __align__(16) float s_w[DC * CT];  // [c][j]
+  const int b = blockIdx.y;
+  const int j0 = blockIdx.z * CT;               // first output channel of this block
+  const int s0 = blockIdx.x * (128 * PT);
+  const float* fb = feat + (long long)b * D * hw;
+  float acc[PT][CT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[p][j] = 0.f;
+  int s[PT];
+  bool live[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) { s[p] = s0 + threadIdx.x + p * 128; live[p] = s[p] < hw; }
+  for (int c0 = 0; c0 < D; c0 += DC) {
+    const int dc = min(DC, D - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < dc * CT; i += 128) {
+      int c = i / CT, j = i - c * CT;
+      s_w[i] = (j0 + j < c_total) ? __ldg(wmat + (long long)(j0 + j) * D + c0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < dc; ++c) {
+      float x[PT];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) x[p] = live[p] ? __ldcs(fb + (long long)(c0 + c) * hw + s[p]) : 0.f;
+      const float4* w4 = reinterpret_cast<const float4*>(s_w + c * CT);
+#pragma unroll
+      for (int j4 = 0; j4 < CT / 4; ++j4) {
+        float4 w = w4[j4];
+#pragma unroll
+        for (int p = 0; p < PT; ++p) {
+          acc[p][4 * j4 + 0] = fmaf(x[p], w.x, acc[p][4 * j4 + 0]);
+          acc[p][4 * j4 + 1] = fmaf(x[p], w.y, acc[p][4 * j4 + 1]);
+          acc[p][4 * j4 + 2] = fmaf(x[p], w.z, acc[p][4 * j4 + 2]);
+          acc[p][4 * j4 + 3] = fmaf(x[p], w.w, acc[p][4 * j4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    if (!live[p]) continue;
+    float* o = logits + ((long long)b * hw + s[p]) * c_pad + j0;
+#pragma unroll
+    for (int j4 = 0; j4 < CT / 4; ++j4) {
+      if (j0 + 4 * j4 >= c_pad) break;
+      float4 v;
+      v.x = acc[p][4 * j4 + 0] + ((bias && j0 + 4 * j4 + 0 < c_total) ? __ldg(bias + j0 + 4 * j4 + 0) : 0.f);
+      v.y = acc[p][4 * j4 + 1] + ((bias && j0 + 4 * j4 + 1 < c_total) ? __ldg(bias + j0 + 4 * j4 + 1) : 0.f);
+      v.z = acc[p][4 * j4 + 2] + ((bias && j0 + 4 * j4 + 2 < c_total) ? __ldg(bias + j0 + 4 * j4 + 2) : 0.f);
+      v.w = acc[p][4 * j4 + 3] + ((bias && j0 + 4 * j4 + 3 < c_total) ? __ldg(bias + j0 + 4 * j4 + 3) : 0.f);
+      *reinterpret_cast<float4*>(o + 4 * j4) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-privatised histogram helpers
+// ------------------------------------------------------------------------------------------------
+// Adds one count for `bin` (or nothing if bin < 0) for every lane; equal neighbouring bins inside the
+// warp are merged into a single shared-memory atomic (labels are spatially coherent).
+__device__ __forceinline__ void warp_hist_add(int* hist, int bin) {
+  const unsigned lane = threadIdx.x & 31;
+  int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+  bool start = (lane == 0) || (prev != bin);
+  unsigned starts = __ballot_sync(0xffffffffu, start);
+  if (start && bin >= 0) {
+    unsigned higher = (lane == 31) ? 0u : (starts >> (lane + 1));
+    int run = higher ? (__ffs(higher)) : (32 - (int)lane);
+    atomicAdd(hist + bin, run);
+  }
+}
+
+struct ProbeHeads {
+  int n_heads;
+  int off[kProbeMaxHeads];
+  int cnt[kProbeMaxHeads];
+  int rows[kProbeMaxHeads];
+  long long* preds[kProbeMaxHeads];
+  unsigned long long* conf[kProbeMaxHeads];
+  int hist_off[kProbeMaxHeads];   // offset (ints) of this head's bins inside one warp's private area
+  int hist_per_warp;              // ints per warp
+};
+
+// step 2: thread per label pixel.
+__global__ void __launch_bounds__(256)
+probe_argmax_confusion_kernel(const float* __restrict__ logits, int B, int h, int w, int c_pad,
+                              const long long* __restrict__ label, int H, int W, int C,
+                              ProbeHeads heads, float scale_h, float scale_w) {
+  extern __shared__ int s_hist[];   // [warps][hist_per_warp]
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < nwarps * heads.hist_per_warp; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  int* myhist = s_hist + warp * heads.hist_per_warp;
+  const long long P = (long long)B * H * W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // all lanes of a warp iterate together (P rounded up to a multiple of 32 inside the loop bound)
+  const long long P32 = (P + 31) & ~31LL;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P32; p += stride) {
+    const bool live = p < P;
+    int bins[kProbeMaxHeads];
+#pragma unroll
+    for (int hd = 0; hd < kProbeMaxHeads; ++hd) bins[hd] = -1;
+    if (live) {
+      int X = (int)(p % W);
+      long long t = p / W;
+      int Y = (int)(t % H);
+      int b = (int)(t / H);
+      // PyTorch upsample_bilinear2d, align_corners=False (area_pixel_compute_source_index)
+      float sy = scale_h * ((float)Y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+      float sx = scale_w * ((float)X + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+      int y0 = (int)sy, x0 = (int)sx;
+      int y1 = y0 + ((y0 < h - 1) ? 1 : 0), x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+      float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+      float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      const float* base = logits + (long long)b * h * w * c_pad;
+      const float* p00 = base + ((long long)y0 * w + x0) * c_pad;
+      const float* p01 = base + ((long long)y0 * w + x1) * c_pad;
+      const float* p10 = base + ((long long)y1 * w + x0) * c_pad;
+      const float* p11 = base + ((long long)y1 * w + x1) * c_pad;
+      long long lab = __ldcs(label + p);
+#pragma unroll
+      for (int hd = 0; hd < kProbeMaxHeads; ++hd) {
+        if (hd >= heads.n_heads) break;
+        float best = -INFINITY;
+        int bj = 0;
+        const int off = heads.off[hd], cnt = heads.cnt[hd];
+        for (int j = 0; j < cnt; ++j) {
+          float v00 = __ldg(p00 + off + j), v01 = __ldg(p01 + off + j);
+          float v10 = __ldg(p10 + off + j), v11 = __ldg(p11 + off + j);
+          float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+          if (v > best) { best = v; bj = j; }     // first maximal index wins (torch.argmax)
+        }
+        if (heads.preds[hd]) __stcs(heads.preds[hd] + p, (long long)bj);
+        if (heads.conf[hd] && lab >= 0 && lab < C && bj < C) bins[hd] = bj * C + (int)lab;
+      }
+    }
+#pragma unroll
+    for (int hd = 0; hd < kProbeMaxHeads; ++hd) {
+      if (hd >= heads.n_heads) break;
+      if (heads.conf[hd]) warp_hist_add(myhist + heads.hist_off[hd], bins[hd]);
+    }
+  }
+  __syncthreads();
+  for (int hd = 0; hd < heads.n_heads; ++hd) {
+    if (!heads.conf[hd]) continue;
+    const int nb = heads.rows[hd] * C;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      int t = 0;
+      for (int wv = 0; wv < nwarps; ++wv) t += s_hist[wv * heads.hist_per_warp + heads.hist_off[hd] + i];
+      if (t) atomicAdd(heads.conf[hd] + i, (unsigned long long)t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 standalone confusion histogram (UnSegMetrics.update)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+confusion_kernel(const long long* __restrict__ preds, const long long* __restrict__ label, long long n,
+                 int C, int rows, unsigned long long* __restrict__ conf, int use_smem) {
+  extern __shared__ int s_hist[];   // [warps][rows*C] when use_smem
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nb = rows * C;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < nwarps * nb; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+  }
+  int* myhist = s_hist + warp * nb;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n32 = (n + 31) & ~31LL;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n32; p += stride) {
+    int bin = -1;
+    if (p < n) {
+      long long pr = __ldcs(preds + p), lb = __ldcs(label + p);
+      // mask of model/metric.py:49 -- predictions >= num_classes are dropped even with extra classes
+      if (lb >= 0 && lb < C && pr >= 0 && pr < C) bin = (int)pr * C + (int)lb;
+    }
+    if (use_smem) {
+      warp_hist_add(myhist, bin);
+    } else if (bin >= 0) {
+      atomicAdd(conf + bin, 1ULL);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      int t = 0;
+      for (int wv = 0; wv < nwarps; ++wv) t += s_hist[wv * nb + i];
+      if (t) atomicAdd(conf + i, (unsigned long long)t);
+    }
+  }
+}
+
+}  // namespace equss
+
+using namespace equss;
+
+extern "C" int equss_probe_cpad(int c_total) { return (c_total + 3) & ~3; }
+
+extern "C" int equss_probe_logits(const float* feat, int B, int D, int h, int w, const float* wmat,
+                                  const float* bias, int c_total, float* logits, void* stream) {
+  EQUSS_REQUIRE(feat && wmat && logits, EQUSS_ERR_INVALID_ARG, "equss_probe_logits: null pointer");
+  EQUSS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && c_total > 0, EQUSS_ERR_INVALID_ARG,
+                "equss_probe_logits: bad shape B=%d D=%d h=%d w=%d C=%d", B, D, h, w, c_total);
+  EQUSS_REQUIRE(!((uintptr_t)logits & 15), EQUSS_ERR_INVALID_ARG, "equss_probe_logits: logits must be 16-byte aligned");
+  const int hw = h * w;
+  const int c_pad = equss_probe_cpad(c_total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c_pad <= 32) {
+    dim3 grid((hw + 255) / 256, B, 1);
+    probe_logits_kernel<32, 2><<<grid, 128, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+  } else {
+    dim3 grid((hw + 127) / 128, B, (c_pad + 63) / 64);
+    probe_logits_kernel<64, 1><<<grid, 128, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+  }
+  EQUSS_LAUNCH_OK("probe_logits_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
+                                            const int64_t* label, int H, int W, int num_classes, int n_heads,
+                                            const int32_t* head_off_host, const int32_t* head_cnt_host,
+                                            int64_t* const* preds_out_host, int64_t* const* confusion_host,
+                                            const int32_t* conf_rows_host, void* stream) {
+  EQUSS_REQUIRE(logits && label && head_off_host && head_cnt_host, EQUSS_ERR_INVALID_ARG,
+                "equss_probe_argmax_confusion: null pointer");
+  EQUSS_REQUIRE(B > 0 && h > 0 && w > 0 && H > 0 && W > 0 && c_total > 0 && num_classes > 0, EQUSS_ERR_INVALID_ARG,
+                "equss_probe_argmax_confusion: bad shape");
+  EQUSS_REQUIRE(n_heads >= 1 && n_heads <= kProbeMaxHeads, EQUSS_ERR_UNSUPPORTED, "n_heads=%d outside [1,%d]", n_heads,
+                kProbeMaxHeads);
+  ProbeHeads hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.n_heads = n_heads;
+  int per_warp = 0;
+  for (int i = 0; i < n_heads; ++i) {
+    hd.off[i] = head_off_host[i];
+    hd.cnt[i] = head_cnt_host[i];
+    EQUSS_REQUIRE(hd.off[i] >= 0 && hd.cnt[i] > 0 && hd.off[i] + hd.cnt[i] <= c_total, EQUSS_ERR_INVALID_ARG,
+                  "head %d covers channels [%d,%d) outside [0,%d)", i, hd.off[i], hd.off[i] + hd.cnt[i], c_total);
+    hd.preds[i] = preds_out_host ? (long long*)preds_out_host[i] : nullptr;
+    hd.conf[i] = confusion_host ? (unsigned long long*)confusion_host[i] : nullptr;
+    hd.rows[i] = (conf_rows_host && hd.conf[i]) ? conf_rows_host[i] : 0;
+    if (hd.conf[i]) {
+      EQUSS_REQUIRE(hd.rows[i] >= num_classes, EQUSS_ERR_INVALID_ARG, "confusion rows %d < num_classes %d", hd.rows[i],
+                    num_classes);
+      hd.hist_off[i] = per_warp;
+      per_warp += hd.rows[i] * num_classes;
+    }
+  }
+  hd.hist_per_warp = per_warp;
+  const int threads = 256;
+  size_t smem = (size_t)(threads / 32) * per_warp * sizeof(int);
+  EQUSS_REQUIRE(smem <= 200 * 1024, EQUSS_ERR_UNSUPPORTED, "confusion bins (%d per warp) do not fit shared memory", per_warp);
+  if (smem > 48 * 1024)
+    EQUSS_CUDA_OK(cudaFuncSetAttribute(probe_argmax_confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long P = (long long)B * H * W;
+  long long blocks = (P + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  const float scale_h = (float)h / (float)H, scale_w = (float)w / (float)W;
+  probe_argmax_confusion_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
+      logits, B, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w);
+  EQUSS_LAUNCH_OK("probe_argmax_confusion_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_confusion_update(const int64_t* preds, const int64_t* label, int64_t n, int num_classes,
+                                      int rows, int64_t* confusion, void* stream) {
+  EQUSS_REQUIRE(preds && label && confusion, EQUSS_ERR_INVALID_ARG, "equss_confusion_update: null pointer");
+  EQUSS_REQUIRE(n >= 0 && num_classes > 0 && rows >= num_classes, EQUSS_ERR_INVALID_ARG,
+                "equss_confusion_update: bad shape n=%lld C=%d rows=%d", (long long)n, num_classes, rows);
+  if (n == 0) return EQUSS_OK;
+  const int threads = 256;
+  size_t smem = (size_t)(threads / 32) * rows * num_classes * sizeof(int);
+  int use_smem = smem <= 96 * 1024;
+  if (!use_smem) smem = 0;
+  if (smem > 48 * 1024)
+    EQUSS_CUDA_OK(cudaFuncSetAttribute(confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long blocks = (n + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  confusion_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
+      (const long long*)preds, (const long long*)label, (long long)n, num_classes, rows,
+      (unsigned long long*)confusion, use_smem);
+  EQUSS_LAUNCH_OK("confusion_kernel");
+  return EQUSS_OK;
+}

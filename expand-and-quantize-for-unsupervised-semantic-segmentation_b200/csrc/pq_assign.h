@@ -1,0 +1,14 @@
+// pq_assign.h -- internal interface between the assign dispatcher (pq_assign_simt.cu) and the
+// tcgen05 kernel (pq_assign_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/equss_b200.h"
+
+namespace equss {
+bool assign_tc_supported(const equss_zdesc* zd, int M, int K, int d, int norm_mode, bool want_margin);
+int64_t assign_tc_workspace_bytes(int64_t n_pixels, int M, int K, int d);
+int assign_tc_launch(const float* z, const equss_zdesc* zd, const float* codebook_norm, const float* cnorm2,
+                     int M, int K, int d, int norm_mode, const float* norm_a, const float* norm_b,
+                     int32_t* idx_out, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+}  // namespace equss

@@ -1,0 +1,560 @@
+// pq_rows.cu -- HBM-bound per-row passes of the PQ head:
+//   K3  gather + commitment/codebook squared error + straight-through value  (model/quantizer.py:474,514,534-536)
+//   K3' backward of K3 w.r.t. z and the gathered codebook rows
+//   K4  per-code counts and sums (segmented scatter-add in shared memory)    (model/quantizer.py:485-488)
+//   K6  EMA codebook update                                                   (model/quantizer.py:233-254)
+//
+// Two mappings per pass:
+//   * "flat vector" path: activations are (n, D) row-major, d/4 is a power of two <= 32.  LPS = d/4
+//     consecutive lanes own one (pixel, subspace) row, one float4 each: every global access is a fully
+//     coalesced 16-byte-per-lane stream; row statistics are an xor-shuffle butterfly over LPS lanes.
+//   * "strided scalar" path: any strides (NCHW: consecutive threads = consecutive pixels, so each
+//     channel read is coalesced) and any d <= 256; one thread owns a row.
+// Both produce bit-identical z_norm (canonical association order, equss_common.cuh).
+#include "equss_common.cuh"
+
+namespace equss {
+
+// ------------------------------------------------------------------------------------------------
+// Row holder for the scalar path: DT > 0 -> row cached in registers, DT == 0 -> re-read from global.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+struct ScalarRow {
+  float x[DT > 0 ? DT : 1];
+  const float* p;
+  long long sc;
+  int d;
+  __device__ __forceinline__ void load(const float* base, long long stride_c, int d_) {
+    p = base; sc = stride_c; d = d_;
+    if (DT > 0) {
+#pragma unroll
+      for (int j = 0; j < (DT > 0 ? DT : 1); ++j) x[j] = __ldg(base + j * stride_c);
+    }
+  }
+  __device__ __forceinline__ float raw(int j) const {
+    if (DT > 0) return x[j];
+    return __ldg(p + j * sc);
+  }
+  __device__ __forceinline__ RowNorm norm(int mode) const {
+    if (DT >= 4) {
+      RowNorm r; r.shift = 0.f; r.denom = 1.f;
+      constexpr int G = (DT >= 4 ? DT / 4 : 1);
+      if (mode == EQUSS_NORM_L2) {
+        float g[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) g[i] = group_sumsq(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        r = l2_from_sumsq(butterfly_array<G>(g));
+      } else if (mode == EQUSS_NORM_ZNORM) {
+        float g[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) g[i] = group_sum(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        float mean = butterfly_array<G>(g) / (float)DT;
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+          g[i] = group_sumsq(x[4 * i] - mean, x[4 * i + 1] - mean, x[4 * i + 2] - mean, x[4 * i + 3] - mean);
+        float stdv = sqrtf(butterfly_array<G>(g) / (float)(DT - 1));
+        r.shift = mean; r.denom = stdv + kStdEps;
+      }
+      return r;
+    } else {
+      return row_norm_generic(mode, d, [&](int j) { return raw(j); });
+    }
+  }
+};
+
+__device__ __forceinline__ float norm_elem(float x, const RowNorm& r, int mode, const float* na,
+                                           const float* nb, int ch) {
+  if (mode == EQUSS_NORM_AFFINE) return (x - __ldg(na + ch)) / __ldg(nb + ch);
+  return apply_norm(x, r, mode);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 flat vector path
+// ------------------------------------------------------------------------------------------------
+template <int LPS>
+__global__ void __launch_bounds__(256)
+gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4, int M, int K,
+                        const float4* __restrict__ src, const int32_t* __restrict__ idx, int mode,
+                        const float* __restrict__ na, const float* __restrict__ nb,
+                        float4* __restrict__ out, float4* __restrict__ znorm_out,
+                        double* __restrict__ sqerr) {
+  extern __shared__ float s_sq[];  // [M]
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s_sq[i] = 0.f;
+  __syncthreads();
+  const long long total = n_pixels * D4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += stride) {
+    long long n = f / D4;
+    int c4 = (int)(f - n * D4);
+    int m = c4 / LPS;
+    int l = c4 - m * LPS;
+    float4 v = __ldcs(z + f);
+    RowNorm r; r.shift = 0.f; r.denom = 1.f;
+    if (mode == EQUSS_NORM_L2) {
+      r = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v.x, v.y, v.z, v.w)));
+    } else if (mode == EQUSS_NORM_ZNORM) {
+      constexpr int d = LPS * 4;
+      float mean = butterfly_lanes<LPS>(group_sum(v.x, v.y, v.z, v.w)) / (float)d;
+      float ssd = butterfly_lanes<LPS>(group_sumsq(v.x - mean, v.y - mean, v.z - mean, v.w - mean));
+      r.shift = mean; r.denom = sqrtf(ssd / (float)(d - 1)) + kStdEps;
+    }
+    int ch = c4 * 4;
+    float4 zn;
+    zn.x = norm_elem(v.x, r, mode, na, nb, ch);
+    zn.y = norm_elem(v.y, r, mode, na, nb, ch + 1);
+    zn.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
+    zn.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
+    int code = __ldg(idx + (long long)m * n_pixels + n);
+    float4 q = __ldg(src + ((long long)m * K + code) * LPS + l);
+    float4 dq, o;
+    dq.x = q.x - zn.x; dq.y = q.y - zn.y; dq.z = q.z - zn.z; dq.w = q.w - zn.w;
+    o.x = zn.x + dq.x; o.y = zn.y + dq.y; o.z = zn.z + dq.z; o.w = zn.w + dq.w;   // STE value (:536)
+    __stcs(out + f, o);
+    if (znorm_out) __stcs(znorm_out + f, zn);
+    float e = group_sumsq(dq.x, dq.y, dq.z, dq.w);
+    e = butterfly_lanes<LPS>(e);
+    if (l == 0) atomicAdd(&s_sq[m], e);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float v = s_sq[i];
+    if (v != 0.f) atomicAdd(sqerr + i, (double)v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 strided scalar path: grid = (pixel chunks, M); thread = one pixel of subspace blockIdx.y
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(128)
+gather_loss_scalar_kernel(const float* __restrict__ z, ZView zv, int M, int K, int d,
+                          const float* __restrict__ src, const int32_t* __restrict__ idx, int mode,
+                          const float* __restrict__ na, const float* __restrict__ nb,
+                          float* __restrict__ out, float* __restrict__ znorm_out,
+                          double* __restrict__ sqerr) {
+  const int m = blockIdx.y;
+  float local = 0.f;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < zv.n_pixels;
+       n += (long long)gridDim.x * blockDim.x) {
+    long long base = pixel_base(zv, n) + (long long)m * d * zv.stride_c;
+    ScalarRow<DT> row;
+    row.load(z + base, zv.stride_c, d);
+    RowNorm r = row.norm(mode);
+    int code = __ldg(idx + (long long)m * zv.n_pixels + n);
+    const float* q = src + ((long long)m * K + code) * d;
+    float e = 0.f;
+    const int dd = DT > 0 ? DT : d;
+    // error accumulated in the canonical group order so both paths agree
+    float g = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < dd; ++j) {
+      float zn = norm_elem(row.raw(j), r, mode, na, nb, m * d + j);
+      float dq = __ldg(q + j) - zn;
+      out[base + j * zv.stride_c] = zn + dq;
+      if (znorm_out) znorm_out[base + j * zv.stride_c] = zn;
+      g = ((j & 3) == 0) ? dq * dq : fmaf(dq, dq, g);
+      if ((j & 3) == 3 || j == dd - 1) { e += g; g = 0.f; }
+    }
+    local += e;
+  }
+  local = warp_sum(local);
+  __shared__ float s_part[4];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_part[i];
+    if (t != 0.f) atomicAdd(sqerr + m, (double)t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3' backward, scalar mapping for every layout (the row is needed twice; registers hold it).
+//   g = grad_out + coef[m]*(z_norm - q);   grad_z = J^T g
+//   NONE  : grad_z = g
+//   L2    : grad_z = (g - z_norm * <z_norm, g>) / denom           (denom = max(||z||, eps); the
+//            clamp branch has zero measure and is treated like the unclamped one, as autograd does
+//            for ||z|| > eps)
+//   ZNORM : y = (x-mean)/(std+eps);  grad_x = (g - mean(g) - y * sum(g*y) * std/((d-1)*(std+eps)) ... )
+//            derived below; AFFINE: grad_z = g / denom[c]
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(128)
+gather_loss_bwd_kernel(const float* __restrict__ z, ZView zv, int M, int K, int d,
+                       const float* __restrict__ src, const int32_t* __restrict__ idx, int mode,
+                       const float* __restrict__ na, const float* __restrict__ nb,
+                       const float* __restrict__ grad_out, const float* __restrict__ coef,
+                       float* __restrict__ grad_z, const float* __restrict__ cb_coef,
+                       float* __restrict__ grad_codebook) {
+  const int m = blockIdx.y;
+  const float cf = coef ? __ldg(coef + m) : 0.f;
+  const float cbf = (cb_coef && grad_codebook) ? __ldg(cb_coef + m) : 0.f;
+  const int dd = DT > 0 ? DT : d;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < zv.n_pixels;
+       n += (long long)gridDim.x * blockDim.x) {
+    long long base = pixel_base(zv, n) + (long long)m * d * zv.stride_c;
+    ScalarRow<DT> row;
+    row.load(z + base, zv.stride_c, d);
+    RowNorm r = row.norm(mode);
+    int code = __ldg(idx + (long long)m * zv.n_pixels + n);
+    const float* q = src + ((long long)m * K + code) * d;
+    float* gc = grad_codebook ? grad_codebook + ((long long)m * K + code) * d : nullptr;
+    // pass 1: reductions needed by the Jacobian
+    float s_gy = 0.f, s_g = 0.f;
+    for (int j = 0; j < dd; ++j) {
+      float zn = norm_elem(row.raw(j), r, mode, na, nb, m * d + j);
+      float dq = zn - __ldg(q + j);
+      float g = (grad_out ? grad_out[base + j * zv.stride_c] : 0.f) + cf * dq;
+      s_gy = fmaf(g, zn, s_gy);
+      s_g += g;
+      if (gc && cbf != 0.f) atomicAdd(gc + j, -cbf * dq);   // d/dq of cb_coef/2 * (q - z_norm)^2 summed
+    }
+    if (!grad_z) continue;
+    float inv = 1.f / r.denom;
+    float stdv = r.denom - kStdEps;
+    for (int j = 0; j < dd; ++j) {
+      float zn = norm_elem(row.raw(j), r, mode, na, nb, m * d + j);
+      float dq = zn - __ldg(q + j);
+      float g = (grad_out ? grad_out[base + j * zv.stride_c] : 0.f) + cf * dq;
+      float gz;
+      if (mode == EQUSS_NORM_NONE) {
+        gz = g;
+      } else if (mode == EQUSS_NORM_L2) {
+        gz = (g - zn * s_gy) * inv;
+      } else if (mode == EQUSS_NORM_ZNORM) {
+        // y_j = (x_j - mu)/(s+e);  dy_j/dx_i = (delta_ij - 1/d)/(s+e) - (x_j-mu)(x_i-mu)/((d-1) s (s+e)^2)
+        // grad_x_i = (g_i - mean(g))/(s+e) - y_i * (s+e) * sum_j(g_j y_j) / ((d-1) s (s+e)) ... simplified:
+        float yi = zn;
+        float term = (stdv > 0.f) ? yi * s_gy * r.denom / ((float)(dd - 1) * stdv) : 0.f;
+        gz = (g - s_g / (float)dd - term) * inv;
+      } else {  // AFFINE
+        gz = g / __ldg(nb + m * d + j);
+      }
+      grad_z[base + j * zv.stride_c] = gz;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 segmented scatter-add.  grid = (pixel chunks, M).  Shared accumulators [K][d+1] for subspace
+// blockIdx.y (column d = count), flushed with one global atomic per touched entry.
+// ------------------------------------------------------------------------------------------------
+template <int LPS>
+__global__ void __launch_bounds__(256)
+accumulate_flat_kernel(const float* __restrict__ z, long long n_pixels, int D, int K,
+                       const int32_t* __restrict__ idx, int use_norm, int mode,
+                       const float* __restrict__ na, const float* __restrict__ nb,
+                       float* __restrict__ packed, long long rows_per_block) {
+  constexpr int d = LPS * 4;
+  extern __shared__ float s_acc[];  // [K][d+1]
+  const int m = blockIdx.y;
+  const int ld = d + 1;
+  for (int i = threadIdx.x; i < K * ld; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const long long n0 = (long long)blockIdx.x * rows_per_block;
+  long long n1 = n0 + rows_per_block;
+  if (n1 > n_pixels) n1 = n_pixels;
+  const int rows_per_iter = blockDim.x / LPS;
+  const int rl = threadIdx.x / LPS, l = threadIdx.x % LPS;
+  const int32_t* idxm = idx + (long long)m * n_pixels;
+  for (long long n = n0 + rl; n < n1; n += rows_per_iter) {
+    float4 v = __ldcs(reinterpret_cast<const float4*>(z + n * D + (long long)m * d) + l);
+    if (use_norm && mode != EQUSS_NORM_NONE) {
+      RowNorm r; r.shift = 0.f; r.denom = 1.f;
+      if (mode == EQUSS_NORM_L2) {
+        r = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v.x, v.y, v.z, v.w)));
+      } else if (mode == EQUSS_NORM_ZNORM) {
+        float mean = butterfly_lanes<LPS>(group_sum(v.x, v.y, v.z, v.w)) / (float)d;
+        float ssd = butterfly_lanes<LPS>(group_sumsq(v.x - mean, v.y - mean, v.z - mean, v.w - mean));
+        r.shift = mean; r.denom = sqrtf(ssd / (float)(d - 1)) + kStdEps;
+      }
+      int ch = m * d + l * 4;
+      v.x = norm_elem(v.x, r, mode, na, nb, ch);
+      v.y = norm_elem(v.y, r, mode, na, nb, ch + 1);
+      v.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
+      v.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
+    }
+    int code = __ldg(idxm + n);
+    float* a = s_acc + code * ld + l * 4;
+    atomicAdd(a + 0, v.x);
+    atomicAdd(a + 1, v.y);
+    atomicAdd(a + 2, v.z);
+    atomicAdd(a + 3, v.w);
+    if (l == 0) atomicAdd(s_acc + code * ld + d, 1.f);
+  }
+  __syncthreads();
+  float* pm = packed + (long long)m * K * ld;
+  for (int i = threadIdx.x; i < K * ld; i += blockDim.x) {
+    float v = s_acc[i];
+    if (v != 0.f) atomicAdd(pm + i, v);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(128)
+accumulate_scalar_kernel(const float* __restrict__ z, ZView zv, int K, int d,
+                         const int32_t* __restrict__ idx, int use_norm, int mode,
+                         const float* __restrict__ na, const float* __restrict__ nb,
+                         float* __restrict__ packed, long long rows_per_block, int use_smem) {
+  extern __shared__ float s_acc[];  // [K][d+1] when use_smem
+  const int m = blockIdx.y;
+  const int ld = d + 1;
+  float* pm = packed + (long long)m * K * ld;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < K * ld; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
+  }
+  float* acc = use_smem ? s_acc : pm;
+  const long long n0 = (long long)blockIdx.x * rows_per_block;
+  long long n1 = n0 + rows_per_block;
+  if (n1 > zv.n_pixels) n1 = zv.n_pixels;
+  const int dd = DT > 0 ? DT : d;
+  for (long long n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+    long long base = pixel_base(zv, n) + (long long)m * d * zv.stride_c;
+    ScalarRow<DT> row;
+    row.load(z + base, zv.stride_c, d);
+    RowNorm r; r.shift = 0.f; r.denom = 1.f;
+    const int nm = use_norm ? mode : EQUSS_NORM_NONE;
+    if (nm != EQUSS_NORM_NONE) r = row.norm(nm);
+    int code = __ldg(idx + (long long)m * zv.n_pixels + n);
+    float* a = acc + (long long)code * ld;
+#pragma unroll 4
+    for (int j = 0; j < dd; ++j) atomicAdd(a + j, norm_elem(row.raw(j), r, nm, na, nb, m * d + j));
+    atomicAdd(a + d, 1.f);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * ld; i += blockDim.x) {
+      float v = s_acc[i];
+      if (v != 0.f) atomicAdd(pm + i, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 EMA update: one block per subspace.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ema_update_kernel(const float* __restrict__ packed, int K, int d, float decay, float alpha, float eps,
+                  float k_eps, float* __restrict__ vq_count, float* __restrict__ weight_avg,
+                  float* __restrict__ weight, float* __restrict__ exact_count,
+                  int32_t* __restrict__ unused_out) {
+  const int m = blockIdx.x;
+  const int ld = d + 1;
+  const float* pm = packed + (long long)m * K * ld;
+  float* cnt = vq_count + (long long)m * K;
+  __shared__ float s_red[8];
+  __shared__ int s_unused[8];
+  __shared__ float s_n;
+  // vq_count.mul_(decay).add_(count, alpha=1-decay)   (model/quantizer.py:242)
+  float part = 0.f;
+  int unused = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float c = pm[(long long)k * ld + d];
+    float v = cnt[k] * decay;
+    v = v + alpha * c;
+    cnt[k] = v;
+    part += v;
+    if (exact_count) exact_count[(long long)m * K + k] += c;
+    unused += (c == 0.f);
+  }
+  part = warp_sum(part);
+  for (int o = 16; o > 0; o >>= 1) unused += __shfl_xor_sync(0xffffffffu, unused, o);
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = part; s_unused[threadIdx.x >> 5] = unused; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f; int u = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t += s_red[i]; u += s_unused[i]; }
+    s_n = t;
+    if (unused_out) unused_out[m] = u;
+  }
+  __syncthreads();
+  const float n = s_n;
+  const float denom_n = n + k_eps;   // n + num_codebook * eps, the product formed in double (:250)
+  // weight_avg.mul_(decay).add_(sum, alpha=1-decay); weight = weight_avg / smoothed   (:245-254)
+  for (int i = threadIdx.x; i < K * d; i += blockDim.x) {
+    int k = i / d, j = i - k * d;
+    long long o = (long long)m * K * d + i;
+    float a = weight_avg[o] * decay;
+    a = a + alpha * pm[(long long)k * ld + j];
+    weight_avg[o] = a;
+    float smoothed = (cnt[k] + eps) / denom_n * n;
+    weight[o] = a / smoothed;
+  }
+}
+
+// cnorm2[m][k] = sum_j c^2 (canonical order)
+__global__ void cnorm2_kernel(const float* __restrict__ cb, long long rows, int d, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* c = cb + i * d;
+  out[i] = canonical_sumsq(d, [&](int j) { return __ldg(c + j); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// host dispatch
+// ------------------------------------------------------------------------------------------------
+static inline bool flat_vector_ok(const equss_zdesc* zd, int d, const void* p0, const void* p1) {
+  if (zd->stride_c != 1 || zd->stride_s != zd->dim || zd->stride_b != zd->hw * (int64_t)zd->dim) return false;
+  if (d % 4 != 0) return false;
+  int lps = d / 4;
+  if (lps > 32 || (lps & (lps - 1)) != 0) return false;
+  if (((uintptr_t)p0 & 15) || ((uintptr_t)p1 & 15)) return false;
+  return true;
+}
+
+#define EQUSS_DISPATCH_LPS(lps, ...)       \
+  switch (lps) {                            \
+    case 1: { constexpr int LPS = 1; __VA_ARGS__; break; }   \
+    case 2: { constexpr int LPS = 2; __VA_ARGS__; break; }   \
+    case 4: { constexpr int LPS = 4; __VA_ARGS__; break; }   \
+    case 8: { constexpr int LPS = 8; __VA_ARGS__; break; }   \
+    case 16: { constexpr int LPS = 16; __VA_ARGS__; break; } \
+    default: { constexpr int LPS = 32; __VA_ARGS__; break; } \
+  }
+#define EQUSS_DISPATCH_DT(d, ...)          \
+  switch (d) {                              \
+    case 4: { constexpr int DT = 4; __VA_ARGS__; break; }    \
+    case 8: { constexpr int DT = 8; __VA_ARGS__; break; }    \
+    case 16: { constexpr int DT = 16; __VA_ARGS__; break; }  \
+    case 32: { constexpr int DT = 32; __VA_ARGS__; break; }  \
+    case 64: { constexpr int DT = 64; __VA_ARGS__; break; }  \
+    default: { constexpr int DT = 0; __VA_ARGS__; break; }   \
+  }
+
+static int check_norm_args(int mode, const float* na, const float* nb) {
+  EQUSS_REQUIRE(mode >= EQUSS_NORM_NONE && mode <= EQUSS_NORM_AFFINE, EQUSS_ERR_INVALID_ARG,
+                "Unsupported normalize type %d", mode);
+  EQUSS_REQUIRE(mode != EQUSS_NORM_AFFINE || (na && nb), EQUSS_ERR_INVALID_ARG,
+                "EQUSS_NORM_AFFINE needs norm_a and norm_b");
+  return EQUSS_OK;
+}
+
+}  // namespace equss
+
+using namespace equss;
+
+extern "C" int equss_pq_cnorm2(const float* codebook_norm, int M, int K, int d, float* cnorm2, void* stream) {
+  EQUSS_REQUIRE(codebook_norm && cnorm2 && M > 0 && K > 0 && d > 0 && d <= kMaxD, EQUSS_ERR_INVALID_ARG,
+                "equss_pq_cnorm2: bad arguments (M=%d K=%d d=%d)", M, K, d);
+  long long rows = (long long)M * K;
+  cnorm2_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(codebook_norm, rows, d, cnorm2);
+  EQUSS_LAUNCH_OK("cnorm2_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_gather_loss(const float* z, const equss_zdesc* zd, const float* gather_src,
+                                    const int32_t* idx, int M, int K, int d, int norm_mode,
+                                    const float* norm_a, const float* norm_b, float* out,
+                                    float* znorm_out, double* sqerr, void* stream) {
+  EQUSS_REQUIRE(z && zd && gather_src && idx && out && sqerr, EQUSS_ERR_INVALID_ARG,
+                "equss_pq_gather_loss: null pointer");
+  int rc = validate_zdesc(zd, M, d); if (rc) return rc;
+  rc = check_norm_args(norm_mode, norm_a, norm_b); if (rc) return rc;
+  EQUSS_REQUIRE(K > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_gather_loss: K=%d", K);
+  if (zd->n_pixels == 0) return EQUSS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = flat_vector_ok(zd, d, z, out) && !((uintptr_t)gather_src & 15) &&
+                   (!znorm_out || !((uintptr_t)znorm_out & 15));
+  if (vec) {
+    int lps = d / 4;
+    long long total = zd->n_pixels * (zd->dim / 4);
+    int blocks = (int)((total + 255) / 256);
+    int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    EQUSS_DISPATCH_LPS(lps, (gather_loss_flat_kernel<LPS><<<blocks, 256, M * sizeof(float), st>>>(
+        reinterpret_cast<const float4*>(z), zd->n_pixels, zd->dim / 4, M, K,
+        reinterpret_cast<const float4*>(gather_src), idx, norm_mode, norm_a, norm_b,
+        reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(znorm_out), sqerr)));
+    EQUSS_LAUNCH_OK("gather_loss_flat_kernel");
+  } else {
+    ZView zv = make_view(zd);
+    long long bx = (zd->n_pixels + 127) / 128;
+    long long cap = (long long)num_sms() * 16 / M + 1;
+    if (bx > cap) bx = cap;
+    dim3 grid((unsigned)bx, (unsigned)M);
+    EQUSS_DISPATCH_DT(d, (gather_loss_scalar_kernel<DT><<<grid, 128, 0, st>>>(
+        z, zv, M, K, d, gather_src, idx, norm_mode, norm_a, norm_b, out, znorm_out, sqerr)));
+    EQUSS_LAUNCH_OK("gather_loss_scalar_kernel");
+  }
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_gather_loss_bwd(const float* z, const equss_zdesc* zd, const float* gather_src,
+                                        const int32_t* idx, int M, int K, int d, int norm_mode,
+                                        const float* norm_a, const float* norm_b,
+                                        const float* grad_out, const float* coef, float* grad_z,
+                                        const float* cb_coef, float* grad_codebook, void* stream) {
+  EQUSS_REQUIRE(z && zd && gather_src && idx, EQUSS_ERR_INVALID_ARG, "equss_pq_gather_loss_bwd: null pointer");
+  EQUSS_REQUIRE(grad_z || grad_codebook, EQUSS_ERR_INVALID_ARG, "equss_pq_gather_loss_bwd: nothing to compute");
+  int rc = validate_zdesc(zd, M, d); if (rc) return rc;
+  rc = check_norm_args(norm_mode, norm_a, norm_b); if (rc) return rc;
+  if (zd->n_pixels == 0) return EQUSS_OK;
+  ZView zv = make_view(zd);
+  long long bx = (zd->n_pixels + 127) / 128;
+  long long cap = (long long)num_sms() * 16 / M + 1;
+  if (bx > cap) bx = cap;
+  dim3 grid((unsigned)bx, (unsigned)M);
+  cudaStream_t st = (cudaStream_t)stream;
+  EQUSS_DISPATCH_DT(d, (gather_loss_bwd_kernel<DT><<<grid, 128, 0, st>>>(
+      z, zv, M, K, d, gather_src, idx, norm_mode, norm_a, norm_b, grad_out, coef, grad_z, cb_coef,
+      grad_codebook)));
+  EQUSS_LAUNCH_OK("gather_loss_bwd_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_accumulate(const float* z, const equss_zdesc* zd, const int32_t* idx, int M, int K,
+                                   int d, int use_norm, int norm_mode, const float* norm_a,
+                                   const float* norm_b, float* packed, void* stream) {
+  EQUSS_REQUIRE(z && zd && idx && packed, EQUSS_ERR_INVALID_ARG, "equss_pq_accumulate: null pointer");
+  int rc = validate_zdesc(zd, M, d); if (rc) return rc;
+  rc = check_norm_args(norm_mode, norm_a, norm_b); if (rc) return rc;
+  EQUSS_REQUIRE(K > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_accumulate: K=%d", K);
+  if (zd->n_pixels == 0) return EQUSS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)K * (d + 1) * sizeof(float);
+  const bool smem_ok = smem <= 200 * 1024;
+  // chunking: about 4 blocks per SM in total
+  long long chunks = ((long long)num_sms() * 4 + M - 1) / M;
+  if (smem > 96 * 1024) chunks = ((long long)num_sms() + M - 1) / M;
+  if (chunks < 1) chunks = 1;
+  long long rows_per_block = (zd->n_pixels + chunks - 1) / chunks;
+  if (rows_per_block < 256) rows_per_block = 256;
+  chunks = (zd->n_pixels + rows_per_block - 1) / rows_per_block;
+  dim3 grid((unsigned)chunks, (unsigned)M);
+  if (flat_vector_ok(zd, d, z, z) && smem_ok) {
+    int lps = d / 4;
+    EQUSS_DISPATCH_LPS(lps, {
+      if (smem > 48 * 1024)
+        EQUSS_CUDA_OK(cudaFuncSetAttribute(accumulate_flat_kernel<LPS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      accumulate_flat_kernel<LPS><<<grid, 256, smem, st>>>(z, zd->n_pixels, zd->dim, K, idx, use_norm,
+                                                           norm_mode, norm_a, norm_b, packed, rows_per_block);
+    });
+    EQUSS_LAUNCH_OK("accumulate_flat_kernel");
+  } else {
+    ZView zv = make_view(zd);
+    EQUSS_DISPATCH_DT(d, {
+      if (smem_ok && smem > 48 * 1024)
+        EQUSS_CUDA_OK(cudaFuncSetAttribute(accumulate_scalar_kernel<DT>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      accumulate_scalar_kernel<DT><<<grid, 128, smem_ok ? smem : 0, st>>>(
+          z, zv, K, d, idx, use_norm, norm_mode, norm_a, norm_b, packed, rows_per_block, smem_ok ? 1 : 0);
+    });
+    EQUSS_LAUNCH_OK("accumulate_scalar_kernel");
+  }
+  return EQUSS_OK;
+}
+
+extern "C" int equss_ema_update(const float* packed, int M, int K, int d, double decay, double eps,
+                                float* vq_count, float* weight_avg, float* weight, float* exact_count,
+                                int32_t* unused_out, void* stream) {
+  EQUSS_REQUIRE(packed && vq_count && weight_avg && weight, EQUSS_ERR_INVALID_ARG, "equss_ema_update: null pointer");
+  EQUSS_REQUIRE(M > 0 && K > 0 && d > 0, EQUSS_ERR_INVALID_ARG, "equss_ema_update: bad shape M=%d K=%d d=%d", M, K, d);
+  // Python scalars are doubles: `1 - decay` and `K * eps` are formed in double, then cast to fp32 by torch.
+  ema_update_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(packed, K, d, (float)decay, (float)(1.0 - decay),
+                                                          (float)eps, (float)((double)K * eps), vq_count,
+                                                          weight_avg, weight, exact_count, unused_out);
+  EQUSS_LAUNCH_OK("ema_update_kernel");
+  return EQUSS_OK;
+}

@@ -1,0 +1,277 @@
+"""Functional host API: one thin function per C entry point (include/equss_b200.h).
+
+Tensors in, tensors out; allocation and stream selection are PyTorch's, the arithmetic is the
+sm_100a kernels'.  These functions do not record autograd history; the nn.Module mirrors in
+``quantizer.py`` wrap them in ``torch.autograd.Function`` where the reference needs gradients.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+__all__ = [
+    "pq_cnorm2", "pq_assign", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
+    "pq_distance_prob", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "launch_count",
+]
+
+
+def launch_count() -> int:
+    """Kernels launched by the library since load (bench.py's ``gpu_launches``)."""
+    return int(N.lib().equss_launch_count())
+
+
+def _norm_args(normalize, norm_a, norm_b, D, dev):
+    if normalize not in N.NORM_MODES:
+        raise ValueError(f"Unsupported normalize type {normalize}")
+    mode = N.NORM_MODES[normalize]
+    if mode == 3:
+        if norm_a is None or norm_b is None:
+            raise ValueError("z_trainable normalisation needs per-channel mean and denominator vectors")
+        norm_a = N.f32c(norm_a.detach()).reshape(-1)
+        norm_b = N.f32c(norm_b.detach()).reshape(-1)
+        if norm_a.numel() != D or norm_b.numel() != D:
+            raise ValueError(f"normalisation vectors must have {D} elements")
+    else:
+        norm_a = norm_b = None
+    return mode, norm_a, norm_b
+
+
+def _prep_z(z: torch.Tensor, M: int):
+    dev = N.require_cuda(z)
+    N.ensure_device(dev)
+    z = N.f32c(z.detach())
+    zd, d, layout = N.zdesc_for(z, M)
+    return z, zd, d, dev
+
+
+def pq_cnorm2(codebook_norm: torch.Tensor) -> torch.Tensor:
+    """sum(c**2, dim=-1) for a stacked codebook [M, K, d]  (model/quantizer.py:459)."""
+    dev = N.require_cuda(codebook_norm)
+    N.ensure_device(dev)
+    cb = N.f32c(codebook_norm.detach())
+    M, K, d = cb.shape
+    out = torch.empty((M, K), dtype=torch.float32, device=dev)
+    N.check(N.lib().equss_pq_cnorm2(cb.data_ptr(), M, K, d, out.data_ptr(), N.stream_ptr(dev)), "equss_pq_cnorm2")
+    return out
+
+
+def pq_assign(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optional[torch.Tensor] = None,
+              normalize: Optional[str] = "l2", norm_a=None, norm_b=None, algo: int = N.ASSIGN_AUTO,
+              return_margin: bool = False):
+    """Nearest-codeword indices for every (pixel, subspace): int32 [M, N]  (model/quantizer.py:457-467)."""
+    cb = N.f32c(codebook_norm.detach())
+    M, K, d = cb.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    N.require_cuda(z, cb)
+    if dz != d:
+        raise ValueError(f"codebook sub-dim {d} does not match activation sub-dim {dz}")
+    if cnorm2 is None:
+        cnorm2 = pq_cnorm2(cb)
+    cnorm2 = N.f32c(cnorm2)
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    n = zd.n_pixels
+    idx = torch.empty((M, n), dtype=torch.int32, device=dev)
+    margin = torch.empty((M, n), dtype=torch.float32, device=dev) if return_margin else None
+    L = N.lib()
+    wsb = int(L.equss_pq_assign_workspace_bytes(n, M, K, d, algo))
+    ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev) if wsb > 0 else None
+    rc = L.equss_pq_assign(z.data_ptr(), zd, cb.data_ptr(), cnorm2.data_ptr(), M, K, d, mode, N.ptr(na), N.ptr(nb),
+                           idx.data_ptr(), N.ptr(margin), N.ptr(ws), wsb, algo, N.stream_ptr(dev))
+    N.check(rc, "equss_pq_assign")
+    return (idx, margin) if return_margin else idx
+
+
+def pq_gather_loss(z: torch.Tensor, gather_src: torch.Tensor, idx: torch.Tensor, normalize: Optional[str] = "l2",
+                   norm_a=None, norm_b=None, want_znorm: bool = False
+                   ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """Gather + squared error + straight-through value (model/quantizer.py:474,514,534-536).
+
+    Returns (out, sqerr, z_norm):  out has z's shape/layout, sqerr is float64 [M] with
+    sum((z_norm - q)**2) per subspace, z_norm is returned only when ``want_znorm``."""
+    src = N.f32c(gather_src.detach())
+    M, K, d = src.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    if dz != d:
+        raise ValueError(f"gather source sub-dim {d} does not match activation sub-dim {dz}")
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    idx = idx.contiguous()
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (M, zd.n_pixels)
+    out = torch.empty_like(z)
+    zn = torch.empty_like(z) if want_znorm else None
+    sqerr = torch.zeros((M,), dtype=torch.float64, device=dev)
+    rc = N.lib().equss_pq_gather_loss(z.data_ptr(), zd, src.data_ptr(), idx.data_ptr(), M, K, d, mode, N.ptr(na),
+                                      N.ptr(nb), out.data_ptr(), N.ptr(zn), sqerr.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_gather_loss")
+    return out, sqerr, zn
+
+
+def pq_gather_loss_bwd(z: torch.Tensor, gather_src: torch.Tensor, idx: torch.Tensor, normalize: Optional[str],
+                       grad_out: Optional[torch.Tensor], coef: Optional[torch.Tensor],
+                       norm_a=None, norm_b=None, want_grad_z: bool = True,
+                       cb_coef: Optional[torch.Tensor] = None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Backward of :func:`pq_gather_loss`: returns (grad_z, grad_gather_src)."""
+    src = N.f32c(gather_src.detach())
+    M, K, d = src.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    go = N.f32c(grad_out.detach()) if grad_out is not None else None
+    if go is not None:
+        assert go.shape == z.shape
+    cf = N.f32c(coef.detach()).reshape(-1) if coef is not None else None
+    cbf = N.f32c(cb_coef.detach()).reshape(-1) if cb_coef is not None else None
+    gz = torch.empty_like(z) if want_grad_z else None
+    gcb = torch.zeros_like(src) if cbf is not None else None
+    rc = N.lib().equss_pq_gather_loss_bwd(z.data_ptr(), zd, src.data_ptr(), idx.contiguous().data_ptr(), M, K, d, mode,
+                                          N.ptr(na), N.ptr(nb), N.ptr(go), N.ptr(cf), N.ptr(gz), N.ptr(cbf),
+                                          N.ptr(gcb), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_gather_loss_bwd")
+    return gz, gcb
+
+
+def pq_accumulate(z: torch.Tensor, idx: torch.Tensor, num_codebook: int, use_norm: bool = False,
+                  normalize: Optional[str] = "l2", norm_a=None, norm_b=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-code sums and counts packed as [M, K, d+1] (column d = count)  (model/quantizer.py:485-488)."""
+    M = idx.shape[0]
+    z, zd, d, dev = _prep_z(z, M)
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    K = int(num_codebook)
+    if out is None:
+        out = torch.zeros((M, K, d + 1), dtype=torch.float32, device=dev)
+    else:
+        assert out.is_contiguous() and tuple(out.shape) == (M, K, d + 1) and out.dtype == torch.float32
+    rc = N.lib().equss_pq_accumulate(z.data_ptr(), zd, idx.contiguous().data_ptr(), M, K, d, int(bool(use_norm)), mode,
+                                     N.ptr(na), N.ptr(nb), out.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_accumulate")
+    return out
+
+
+def ema_update(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.Tensor, weight_avg: torch.Tensor,
+               weight: torch.Tensor, exact_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place EMA codebook update on stacked state [M,K](,d)  (model/quantizer.py:233-254).
+    Returns int32 [M]: number of codes that received no pixel this step (:509)."""
+    dev = N.require_cuda(packed, vq_count, weight_avg, weight, exact_count)
+    M, K, d1 = packed.shape
+    d = d1 - 1
+    for t, shp in ((vq_count, (M, K)), (weight_avg, (M, K, d)), (weight, (M, K, d))):
+        assert t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == shp, (t.shape, shp)
+    if exact_count is not None:
+        assert exact_count.is_contiguous() and tuple(exact_count.shape) == (M, K)
+    unused = torch.empty((M,), dtype=torch.int32, device=dev)
+    rc = N.lib().equss_ema_update(packed.contiguous().data_ptr(), M, K, d, float(decay), float(eps), vq_count.data_ptr(),
+                                  weight_avg.data_ptr(), weight.data_ptr(), N.ptr(exact_count), unused.data_ptr(),
+                                  N.stream_ptr(dev))
+    N.check(rc, "equss_ema_update")
+    return unused
+
+
+def pq_distance_prob(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optional[torch.Tensor] = None,
+                     normalize: Optional[str] = "l2", norm_a=None, norm_b=None,
+                     temperature: float = 1.0) -> torch.Tensor:
+    """softmax(-distance / temperature) for all subspaces, [N, M*K]  (model/quantizer.py:468,609)."""
+    cb = N.f32c(codebook_norm.detach())
+    M, K, d = cb.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    if cnorm2 is None:
+        cnorm2 = pq_cnorm2(cb)
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    prob = torch.empty((zd.n_pixels, M * K), dtype=torch.float32, device=dev)
+    rc = N.lib().equss_pq_distance_prob(z.data_ptr(), zd, cb.data_ptr(), N.f32c(cnorm2).data_ptr(), M, K, d, mode,
+                                        N.ptr(na), N.ptr(nb), float(temperature), prob.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_distance_prob")
+    return prob
+
+
+def probe_logits(feat: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-resolution probe logits [B*h*w, C_pad] from NCHW features (model/evaluator.py:67,98-100)."""
+    dev = N.require_cuda(feat, wmat, bias)
+    N.ensure_device(dev)
+    feat = N.f32c(feat.detach())
+    wmat = N.f32c(wmat.detach())
+    B, D, h, w = feat.shape
+    Ct, D2 = wmat.shape
+    if D2 != D:
+        raise ValueError(f"probe weight has {D2} input channels, features have {D}")
+    b = N.f32c(bias.detach()).reshape(-1) if bias is not None else None
+    cpad = int(N.lib().equss_probe_cpad(Ct))
+    logits = torch.empty((B * h * w, cpad), dtype=torch.float32, device=dev)
+    rc = N.lib().equss_probe_logits(feat.data_ptr(), B, D, h, w, wmat.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
+                                    N.stream_ptr(dev))
+    N.check(rc, "equss_probe_logits")
+    return logits
+
+
+def probe_argmax_confusion(logits: torch.Tensor, B: int, h: int, w: int, c_total: int, label: torch.Tensor,
+                           num_classes: int, heads: Sequence[Tuple[int, int]],
+                           want_preds: bool = True,
+                           confusions: Optional[Sequence[Optional[torch.Tensor]]] = None
+                           ) -> List[Optional[torch.Tensor]]:
+    """Bilinear interpolation of token logits + per-head argmax at label resolution, fused with the
+    confusion histogram (model/evaluator.py:53-54,68-70 + model/metric.py:44-58).
+
+    heads: [(first_channel, n_channels), ...];  confusions[i]: int64 [rows_i, num_classes] or None
+    (accumulated in place).  Returns the per-head int64 (B, H, W) predictions (None if not wanted)."""
+    dev = N.require_cuda(logits, label)
+    label = label.contiguous()
+    assert label.dtype == torch.int64 and label.dim() == 3 and label.shape[0] == B
+    H, W = int(label.shape[1]), int(label.shape[2])
+    nh = len(heads)
+    preds = [torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_preds else None for _ in range(nh)]
+    confs = list(confusions) if confusions is not None else [None] * nh
+    rows = []
+    for c in confs:
+        if c is not None:
+            assert c.is_cuda and c.dtype == torch.int64 and c.is_contiguous() and c.shape[1] == num_classes
+            rows.append(int(c.shape[0]))
+        else:
+            rows.append(0)
+    rc = N.lib().equss_probe_argmax_confusion(
+        logits.data_ptr(), B, h, w, c_total, label.data_ptr(), H, W, num_classes, nh,
+        N.as_i32_array([o for o, _ in heads]), N.as_i32_array([c for _, c in heads]),
+        N.as_voidp_array([N.ptr(p) for p in preds]), N.as_voidp_array([N.ptr(c) for c in confs]),
+        N.as_i32_array(rows), N.stream_ptr(dev))
+    N.check(rc, "equss_probe_argmax_confusion")
+    return preds
+
+
+def confusion_update(preds: torch.Tensor, label: torch.Tensor, num_classes: int, confusion: torch.Tensor) -> None:
+    """confusion[pred, label] += 1 with the reference's mask (model/metric.py:44-58); in place."""
+    dev = N.require_cuda(preds, label, confusion)
+    N.ensure_device(dev)
+    p = preds.reshape(-1).contiguous()
+    l = label.reshape(-1).contiguous()
+    if p.dtype != torch.int64:
+        p = p.long()
+    if l.dtype != torch.int64:
+        l = l.long()
+    assert p.numel() == l.numel()
+    assert confusion.dtype == torch.int64 and confusion.is_contiguous() and confusion.shape[1] == num_classes
+    rc = N.lib().equss_confusion_update(p.data_ptr(), l.data_ptr(), p.numel(), num_classes, int(confusion.shape[0]),
+                                        confusion.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_confusion_update")
+
+
+def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int, return_sims: bool = False):
+    """Indices of the k most similar database rows for each query, int64 [nq, k], best first
+    (data/precompute_knns.py:313-315)."""
+    dev = N.require_cuda(queries, db)
+    N.ensure_device(dev)
+    q = N.f32c(queries.detach())
+    d = N.f32c(db.detach())
+    nq, F = q.shape
+    n, F2 = d.shape
+    if F != F2:
+        raise ValueError(f"feature dims differ: {F} vs {F2}")
+    idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sims = torch.empty((nq, k), dtype=torch.float32, device=dev) if return_sims else None
+    L = N.lib()
+    wsb = int(L.equss_knn_workspace_bytes(nq, n, F, k))
+    ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+    rc = L.equss_knn_topk(q.data_ptr(), nq, d.data_ptr(), n, F, k, idx.data_ptr(), N.ptr(sims), ws.data_ptr(), wsb,
+                          N.stream_ptr(dev))
+    N.check(rc, "equss_knn_topk")
+    return (idx, sims) if return_sims else idx

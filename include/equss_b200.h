@@ -1,0 +1,206 @@
+/*
+ * equss_b200.h -- C-ABI of the B200-native EQUSS product-quantization hot path.
+ *
+ * The reference (pitlover/Expand-and-Quantize-for-Unsupervised-Semantic-Segmentation) is pure
+ * Python/PyTorch and has no FFI layer; its boundary for this path is a set of nn.Module methods.
+ * Each entry point below replaces the PyTorch op sequence cited next to it (paths relative to the
+ * reference root).  The Python host side (package `equss_b200`) binds these with ctypes and keeps
+ * the reference's module names / signatures; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all tensors are dense fp32 unless stated; indices are int32 [M][N] (subspace-major);
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream;
+ *   - return value: 0 = ok, negative = error (see EQUSS_ERR_*); the message is available from
+ *     equss_last_error_string().  No entry point throws, allocates device memory, retains pointers
+ *     or falls back to the CPU: an unsupported shape is an explicit error.
+ *
+ * Activation layout (`equss_zdesc`): element (pixel n, channel c) of the expanded feature map with
+ * n = b*HW + s lives at  z[b*stride_b + s*stride_s + c*stride_c]:
+ *   flat  (n, D) row-major  (model/quantizer.py:396 "z_flat = z")  : stride_b=HW*D, stride_s=D, stride_c=1
+ *   NCHW  (B, D, h, w)      (model/quantizer.py:112 permute path)  : stride_b=D*HW, stride_s=1, stride_c=HW
+ */
+#ifndef EQUSS_B200_H_
+#define EQUSS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQUSS_OK                 0
+#define EQUSS_ERR_INVALID_ARG   -1   /* null pointer, non-positive size, bad enum          */
+#define EQUSS_ERR_UNSUPPORTED   -2   /* shape outside what the sm_100a kernels implement   */
+#define EQUSS_ERR_CUDA          -3   /* a CUDA runtime / driver call failed                */
+#define EQUSS_ERR_NO_DEVICE     -4   /* no sm_100 device visible: there is no CPU fallback */
+
+/* z-side normalisation applied per (pixel, subspace) row before the distance
+ * (model/quantizer.py:419-455; the codebook side is normalised by the caller, it is M*K*d elements). */
+#define EQUSS_NORM_NONE    0   /* "none"                                                        */
+#define EQUSS_NORM_L2      1   /* "l2":     z / max(||z||_2, 1e-12)         (F.normalize)        */
+#define EQUSS_NORM_ZNORM   2   /* "z_norm": (z - mean) / (std_unbiased + 1e-5) over the d dims  */
+#define EQUSS_NORM_AFFINE  3   /* "z_trainable": (z - mean[c]) / denom[c], vectors of length D   */
+
+#define EQUSS_LAYOUT_FLAT  0
+#define EQUSS_LAYOUT_NCHW  1
+
+/* Which assign kernel to run (equss_pq_assign `algo`). AUTO picks the tcgen05 kernel whenever the
+ * shape is supported and the exact SIMT kernel otherwise; both are CUDA, neither is a fallback to CPU. */
+#define EQUSS_ASSIGN_AUTO     0
+#define EQUSS_ASSIGN_SIMT     1   /* exact fp32 CUDA-core scan (validator + odd shapes)          */
+#define EQUSS_ASSIGN_TCGEN05  2   /* split-tf32 tcgen05/TMEM GEMM + fused argmin + fp32 re-score */
+
+typedef struct equss_zdesc {
+  int64_t n_pixels;   /* N = B*HW                                  */
+  int64_t hw;         /* pixels per image (N for a flat (n,D) view) */
+  int64_t stride_b;   /* element strides, see header comment        */
+  int64_t stride_s;
+  int64_t stride_c;
+  int32_t dim;        /* D = M*d                                    */
+  int32_t layout;     /* EQUSS_LAYOUT_* (a hint; strides are authoritative) */
+} equss_zdesc;
+
+/* ---------------------------------------------------------------------------------------------
+ * library / device
+ * ------------------------------------------------------------------------------------------- */
+const char* equss_last_error_string(void);            /* thread-local, never NULL                */
+int  equss_version(void);                              /* 10000*major + 100*minor + patch         */
+int  equss_device_check(int device);                   /* 0 if `device` is sm_100; else NO_DEVICE  */
+/* number of kernels this library launched since load (bench.py's `gpu_launches`) */
+int64_t equss_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  distance + argmin            replaces model/quantizer.py:457-467 (twins quantizer_v2.py:262-270,
+ *                                  dino_pqgo.py:646-654, dino_new_vq.py:391-397) executed M times.
+ *   idx[m][n] = argmin_k ( (sum z_norm^2 + cnorm2[m][k]) - 2 * <z_norm[n, m*d:(m+1)*d], codebook_norm[m][k]> )
+ *   first minimal index wins (torch.argmin).  codebook_norm: [M][K][d].  cnorm2: [M][K] = sum(c^2).
+ *   norm_a / norm_b: per-channel vectors [D] for EQUSS_NORM_AFFINE (mean, denominator), else NULL.
+ *   margin_out (optional, may be NULL): [M][N] fp32 relative gap between best and second-best fp32
+ *   distance, used by the near-tie audit.
+ *   workspace: device scratch of equss_pq_assign_workspace_bytes() bytes (may be NULL if that is 0).
+ * ------------------------------------------------------------------------------------------- */
+int64_t equss_pq_assign_workspace_bytes(int64_t n_pixels, int M, int K, int d, int algo);
+int equss_pq_assign(const float* z, const equss_zdesc* zd,
+                    const float* codebook_norm, const float* cnorm2, int M, int K, int d,
+                    int norm_mode, const float* norm_a, const float* norm_b,
+                    int32_t* idx_out, float* margin_out,
+                    void* workspace, int64_t workspace_bytes, int algo, void* stream);
+
+/* cnorm2[m][k] = sum_j codebook_norm[m][k][j]^2   (model/quantizer.py:459) */
+int equss_pq_cnorm2(const float* codebook_norm, int M, int K, int d, float* cnorm2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  gather + losses + straight-through value     replaces model/quantizer.py:474,514,534-536
+ *                                                  (param variant :153,175-184).
+ *   q = gather_src[m][idx[m][n]]            gather_src: [M][K][d] (codebook_norm, or raw weight for
+ *                                           dino_new_vq.py:403 / dino_pqgo.py:665)
+ *   out(n, m*d+j)  = z_norm + (q - z_norm)  evaluated in fp32 exactly like the reference's STE line
+ *   sqerr[m]      += sum_{n,j} (z_norm - q)^2     (double accumulators, caller zeroes them;
+ *                                                  mse = sqerr[m] / (N*d))
+ *   out uses the same strides as z.  znorm_out (optional) receives z_norm in the same layout.
+ * ------------------------------------------------------------------------------------------- */
+int equss_pq_gather_loss(const float* z, const equss_zdesc* zd,
+                         const float* gather_src, const int32_t* idx, int M, int K, int d,
+                         int norm_mode, const float* norm_a, const float* norm_b,
+                         float* out, float* znorm_out, double* sqerr, void* stream);
+
+/* backward of K3 w.r.t. z for the straight-through output and the commitment/codebook MSE terms
+ * (SURVEY 8b "Autograd"):  g_znorm = grad_out + coef[m] * (z_norm - q),   grad_z = J_norm(z)^T g_znorm
+ *   coef[m] = 2*beta*grad_loss_m/(N*d) is supplied by the caller ([M] fp32 on device).
+ *   Supported norm modes: NONE, L2, ZNORM, AFFINE.
+ *   grad_codebook (optional, [M][K][d], caller-zeroed): += cb_coef[m] * (q - z_norm) scattered by idx
+ *   (gradient of the codebook loss w.r.t. the gathered rows, model/quantizer.py:175). */
+int equss_pq_gather_loss_bwd(const float* z, const equss_zdesc* zd,
+                             const float* gather_src, const int32_t* idx, int M, int K, int d,
+                             int norm_mode, const float* norm_a, const float* norm_b,
+                             const float* grad_out, const float* coef,
+                             float* grad_z,
+                             const float* cb_coef, float* grad_codebook, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  per-code counts and sums     replaces model/quantizer.py:485-488 (one_hot + one_hot^T @ z_flat)
+ *   counts[m][k] += #{n : idx[m][n]==k}          (fp32, like the reference's float one-hot sum)
+ *   sums[m][k][:] += sum_{n: idx==k} src(n)      src = raw z rows (use_norm=0, quantizer.py:488,
+ *                                                dino_new_vq.py:411) or z_norm rows (use_norm=1,
+ *                                                quantizer_v2.py:266,281)
+ *   `packed` is ONE buffer [M][K][d+1]: column 0..d-1 = sums, column d = count, so that the
+ *   data-parallel exchange (K5, quantizer.py:490-491) is a single all-reduce.  Caller zeroes it.
+ * ------------------------------------------------------------------------------------------- */
+int equss_pq_accumulate(const float* z, const equss_zdesc* zd, const int32_t* idx,
+                        int M, int K, int d, int use_norm,
+                        int norm_mode, const float* norm_a, const float* norm_b,
+                        float* packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  EMA codebook update          replaces EmbeddingEMA.update, model/quantizer.py:233-254
+ *   vq_count  <- decay*vq_count  + (1-decay)*count
+ *   weight_avg<- decay*weight_avg+ (1-decay)*sum
+ *   n = sum_k vq_count;  weight = weight_avg / ((vq_count+eps)/(n+K*eps)*n)
+ *   packed: [M][K][d+1] as produced by K4 (after the all-reduce). All state tensors are [M][K](x[d]).
+ *   exact_count (optional, [M][K]): += count  (the non-persistent `vq_count` of EMAVectorQuantizer,
+ *   quantizer.py:493).  unused_out (optional, [M] int32): number of codes with count==0 (:509).
+ * ------------------------------------------------------------------------------------------- */
+int equss_ema_update(const float* packed, int M, int K, int d, double decay, double eps,
+                     float* vq_count, float* weight_avg, float* weight,
+                     float* exact_count, int32_t* unused_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  soft assignment              replaces model/quantizer.py:468 + :609 (softmax(-distance), concatenated
+ *                                  over subspaces on the last dim; dino_pqgo.py:655 divides by jsd_ts)
+ *   prob[n][m*K + k] = softmax_k( -distance[n][m][k] / temperature )     prob: [N][M*K] fp32
+ * ------------------------------------------------------------------------------------------- */
+int equss_pq_distance_prob(const float* z, const equss_zdesc* zd,
+                           const float* codebook_norm, const float* cnorm2, int M, int K, int d,
+                           int norm_mode, const float* norm_a, const float* norm_b,
+                           float temperature, float* prob, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8  cluster / linear probe at label resolution   replaces model/evaluator.py:53-54,67-70,95-106
+ *   step 1 (token resolution):  logits[b][s][j] = <feat[b,:,s], w[j,:]> + bias[j]
+ *           feat: NCHW (B, D, h, w);  w: [C_total][D] (rows 0..C'-1 = L2-normalised cluster centres,
+ *           optional rows C'.. = linear-probe weights); bias: [C_total] or NULL;
+ *           logits: [B*h*w][C_pad] with C_pad = equss_probe_cpad(C_total).
+ *   step 2 (label resolution):  bilinear (align_corners=False) interpolation of the token logits,
+ *           argmax over each head's channel range, int64 predictions, fused confusion histogram.
+ *           Because bilinear interpolation is linear and the per-pixel L2 norm is a positive scalar,
+ *           argmax_j <normalize(interp(x)), c_j> == argmax_j interp(<x, c_j>)  (SURVEY 7.4).
+ *   head h covers channels [head_off[h], head_off[h]+head_cnt[h]) of the logits.
+ *   preds_out[h]: (B,H,W) int64 or NULL.  confusion[h]: [rows_h][C] int64 accumulated in place
+ *   (rows = prediction, cols = label, model/metric.py:53-57) or NULL; rows_h = conf_rows[h].
+ *   Masking as UnSegMetrics.update: 0<=label<C and 0<=pred<C (metric.py:49).
+ * ------------------------------------------------------------------------------------------- */
+int equss_probe_cpad(int c_total);
+int equss_probe_logits(const float* feat, int B, int D, int h, int w,
+                       const float* wmat, const float* bias, int c_total,
+                       float* logits, void* stream);
+int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
+                                 const int64_t* label, int H, int W, int num_classes,
+                                 int n_heads, const int32_t* head_off_host, const int32_t* head_cnt_host,
+                                 int64_t* const* preds_out_host, int64_t* const* confusion_host,
+                                 const int32_t* conf_rows_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9  confusion histogram          replaces UnSegMetrics.update, model/metric.py:44-58
+ *   confusion[pred][label] += 1 for every position with 0<=label<C and 0<=pred<C.
+ *   confusion: [rows][C] int64 with rows = C + extra_classes.
+ * ------------------------------------------------------------------------------------------- */
+int equss_confusion_update(const int64_t* preds, const int64_t* label, int64_t n,
+                           int num_classes, int rows, int64_t* confusion, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K11 global-feature kNN           replaces data/precompute_knns.py:313-315 (einsum + topk)
+ *   For each query row, the k database rows with the largest inner product, sorted by decreasing
+ *   similarity (ties: lower index first).  queries: [nq][F], db: [n][F] fp32 (caller normalises,
+ *   precompute_knns.py:169).  idx_out: [nq][k] int64 (the `nns` array), sim_out: [nq][k] fp32 or NULL.
+ *   1 <= k <= 32.
+ * ------------------------------------------------------------------------------------------- */
+int64_t equss_knn_workspace_bytes(int64_t nq, int64_t n, int F, int k);
+int equss_knn_topk(const float* queries, int64_t nq, const float* db, int64_t n, int F, int k,
+                   int64_t* idx_out, float* sim_out,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* EQUSS_B200_H_ */

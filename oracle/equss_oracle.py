@@ -1,0 +1,269 @@
+"""CPU oracle for the EQUSS product-quantization hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain PyTorch-on-CPU restatement of the reference's algorithm for the path in SURVEY.md section 8
+(the reference is pure Python/PyTorch, so the restatement uses the same ATen CPU primitives the
+reference calls: matmul, argmin, softmax, embedding, one_hot, interpolate, einsum, bincount, topk --
+torch 2.11.0 in this image; the reference pins no versions).  Every function cites the reference lines
+it follows (paths relative to the reference root).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg
+may import this module, and only as the checker or the timed CPU baseline -- never as a product path.
+
+Parity pinning: the reference ships no tests, golden vectors or fixtures for this path, so
+this oracle is pinned against outputs of the reference ITSELF: ``oracle/make_golden.py`` imports the
+reference modules from /root/reference (with stubs for the off-path torchmetrics / pydensecrf imports),
+runs them on seeded inputs, asserts this oracle reproduces them bit for bit, and writes the vectors to
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` re-checks the oracle against those files.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------
+# normalisation  (model/quantizer.py:419-455)
+# --------------------------------------------------------------------------------------------------
+
+
+def normalize_pair(z_flat: torch.Tensor, codebook: torch.Tensor, mode: Optional[str],
+                   z_mean: Optional[torch.Tensor] = None, z_log_var: Optional[torch.Tensor] = None,
+                   ema_style: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (z_norm, codebook_norm).  ``ema_style`` selects the z_trainable flavour of
+    EMAVectorQuantizer (:428-450, codebook standardised over dim 0) versus VectorQuantizer (:129-133)."""
+    if mode == "l2":
+        return F.normalize(z_flat, dim=1), F.normalize(codebook, dim=1)          # :420-421
+    if mode == "z_norm":
+        zs, zm = torch.std_mean(z_flat, dim=1, keepdim=True)                      # :423
+        cs, cm = torch.std_mean(codebook, dim=1, keepdim=True)                    # :426
+        return (z_flat - zm) / (zs + 1e-5), (codebook - cm) / (cs + 1e-5)
+    if mode == "z_trainable":
+        std = z_log_var.exp().sqrt()                                              # :430
+        zn = (z_flat - z_mean) / (std + 1e-5)                                     # :446
+        if ema_style:
+            cs, cm = torch.std_mean(codebook, dim=0)                              # :449
+            return zn, (codebook - cm) / (cs + 1e-5)
+        return zn, (codebook - z_mean) / (std + 1e-5)                             # :133
+    if mode == "none":
+        return z_flat, codebook
+    raise ValueError(f"Unsupported normalize type {mode}")                        # :455
+
+
+def sq_distance(z_norm: torch.Tensor, codebook_norm: torch.Tensor) -> torch.Tensor:
+    """(n, K) squared L2 distance in the reference's association order (model/quantizer.py:457-461)."""
+    return (torch.sum(z_norm ** 2, dim=1, keepdim=True)
+            + torch.sum(codebook_norm ** 2, dim=1)
+            - 2 * torch.matmul(z_norm, codebook_norm.t()))
+
+
+def histogram_percentiles(count: torch.Tensor, prefix: str) -> Dict[str, Optional[float]]:
+    """Usage percentiles p10/p50/p90 (model/quantizer.py:15-30): first rank whose cumulative sorted
+    probability reaches the level, divided by K; None if never reached."""
+    prob = count.float() / (count.sum() + 1)
+    K = prob.numel()
+    csum = torch.cumsum(torch.sort(prob, dim=0, descending=True)[0], dim=0)
+    out: Dict[str, Optional[float]] = {}
+    for tag, level in (("p10", 0.1), ("p50", 0.5), ("p90", 0.9)):
+        hit = torch.nonzero(csum >= level)
+        out[f"{prefix}-{tag}"] = (int(hit[0, 0]) / K) if hit.numel() else None
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# EMA state  (model/quantizer.py:203-254)
+# --------------------------------------------------------------------------------------------------
+
+
+class EmaState:
+    """weight / weight_avg / vq_count of one EmbeddingEMA (model/quantizer.py:215-221)."""
+
+    def __init__(self, weight: torch.Tensor, weight_avg: Optional[torch.Tensor] = None,
+                 vq_count: Optional[torch.Tensor] = None, decay: float = 0.99, eps: float = 1e-5):
+        self.weight = weight.clone()
+        self.weight_avg = weight.clone() if weight_avg is None else weight_avg.clone()
+        self.vq_count = torch.zeros(weight.shape[0]) if vq_count is None else vq_count.clone()
+        self.decay, self.eps = decay, eps
+
+    def update(self, count: torch.Tensor, total: torch.Tensor) -> None:
+        K = self.weight.shape[0]
+        self.vq_count.mul_(self.decay).add_(count, alpha=1 - self.decay)          # :242
+        self.weight_avg.mul_(self.decay).add_(total, alpha=1 - self.decay)        # :245
+        n = self.vq_count.sum()                                                   # :248
+        smoothed = (self.vq_count + self.eps) / (n + K * self.eps) * n            # :249-251
+        self.weight.copy_(self.weight_avg / smoothed.unsqueeze(1))                # :253-254
+
+
+def ema_vq_forward(z_flat: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: Optional[str],
+                   beta: float = 0.25, training: bool = True, update_norm: bool = True,
+                   allreduce=None) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """One subspace of EMAVectorQuantizer.forward (model/quantizer.py:383-542; l2/z_norm/none modes,
+    top-1 assignment, no restart/split/gumbel).  ``allreduce`` stands for all_reduce_tensor(:490-491).
+    Returns (z_q_ste, outputs, distance_prob, indices)."""
+    z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize)
+    dist = sq_distance(z_norm, cb_norm)
+    idx = torch.argmin(dist, dim=1)                                               # :467
+    prob = F.softmax(-dist * 1.0, dim=1)                                          # :468
+    src = cb_norm if update_norm else state.weight                                # :473-476
+    q = F.embedding(idx, src)
+    out: Dict = {}
+    if training:
+        K = state.weight.shape[0]
+        onehot = F.one_hot(idx, K).to(z_flat.dtype)                               # :485
+        count = onehot.sum(dim=0)                                                 # :487
+        total = torch.matmul(onehot.t(), z_flat)                                  # :488 (raw z, not z_norm)
+        if allreduce is not None:
+            count, total = allreduce(count), allreduce(total)
+        exact_count += count                                                      # :493
+        out.update(histogram_percentiles(exact_count, "total"))                   # :496
+        out.update(histogram_percentiles(count, "current"))                       # :495
+        state.update(count, total)                                                # :504
+        unused = int((count == 0).sum())                                          # :509
+        out["codebook-usage"] = (K - unused) / K
+    commitment = F.mse_loss(z_norm, q)                                            # :514
+    out["loss"] = beta * commitment                                               # :526
+    out["commitment-loss"] = commitment
+    out["codebook-sum"] = torch.sum(torch.abs(state.weight))                      # :532
+    q_ste = z_norm + (q - z_norm)                                                 # :536 (value of the STE)
+    return q_ste, out, prob, idx
+
+
+def pq_forward_ema(z: torch.Tensor, states: Sequence[EmaState], exact_counts: Sequence[torch.Tensor], **kw
+                   ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """ProductQuantizerWrapper.forward over flat (n, D) input (model/quantizer.py:587-611).
+    Returns (z_q, outputs averaged over subspaces, distance_prob (n, K*M), indices (M, n))."""
+    M = len(states)
+    chunks = torch.chunk(z, chunks=M, dim=1)                                      # :589
+    qs, probs, idxs = [], [], []
+    outputs: Dict = {}
+    for i in range(M):
+        q, o, p, ix = ema_vq_forward(chunks[i], states[i], exact_counts[i], **kw)
+        qs.append(q); probs.append(p); idxs.append(ix)
+        for k, v in o.items():
+            outputs[k] = v if i == 0 else outputs[k] + v                          # :598-603
+    for k in outputs:
+        outputs[k] = outputs[k] / M                                               # :607-608
+    return torch.cat(qs, dim=1), outputs, torch.cat(probs, dim=-1), torch.stack(idxs)
+
+
+def param_vq_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, *, normalize: Optional[str], beta: float = 0.25,
+                     book: float = 1.0, gather_raw: bool = False, temperature: float = 1.0
+                     ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """One subspace of the learned-codebook quantiser on NCHW input: VectorQuantizer.forward
+    (model/quantizer.py:105-189) when ``gather_raw`` is False, dino_pqgo.Codebook.forward
+    (model/dino_pqgo.py:579-705) when True (gathers the raw embedding, `book` weight, softmax / jsd_ts)."""
+    b, d, h, w = z_nchw.shape
+    z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)                  # :112-115
+    z_norm, cb_norm = normalize_pair(z_flat, codebook, normalize, ema_style=False)
+    dist = sq_distance(z_norm, cb_norm)
+    idx = torch.argmin(dist, dim=1)                                               # :150
+    prob = F.softmax(-dist / temperature, dim=1)                                  # :151 / dino_pqgo.py:655
+    q = F.embedding(idx, codebook if gather_raw else cb_norm)                     # :153 / dino_pqgo.py:665
+    codebook_loss = F.mse_loss(q, z_norm)                                         # :175
+    commitment = F.mse_loss(z_norm, q)                                            # :176
+    out = {"loss": book * codebook_loss + beta * commitment, "codebook_loss": codebook_loss,
+           "commitment_loss": commitment}
+    q_ste = z_norm + (q - z_norm)                                                 # :184
+    return q_ste.view(b, h, w, d).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+def v2_ema_vq_forward(z_nchw: torch.Tensor, embeddings: torch.Tensor, beta: float = 0.25
+                      ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """Eval-mode quantizer_v2.EMAVectorQuantizer.forward (model/quantizer_v2.py:253-308): always l2, and
+    -- a quirk kept for parity -- the output rows are gathered from z_norm, not the codebook (:274)."""
+    b, d, h, w = z_nchw.shape
+    flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)
+    z_norm, cb_norm = F.normalize(flat, dim=1), F.normalize(embeddings, dim=1)
+    dist = sq_distance(z_norm, cb_norm)
+    prob = F.softmax(-dist * 1.0, dim=1)
+    idx = torch.argmin(dist, dim=1)
+    emb = F.embedding(idx, z_norm)                                                # :274
+    commitment = F.mse_loss(z_norm, emb)
+    out = {"commitment-loss": commitment, "loss": beta * commitment, "codebook-sum": torch.sum(torch.abs(embeddings))}
+    return emb.view(b, h, w, -1).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+# --------------------------------------------------------------------------------------------------
+# evaluation  (model/evaluator.py:46-111, model/metric.py:44-125)
+# --------------------------------------------------------------------------------------------------
+
+
+def evaluator_forward(out: torch.Tensor, label: torch.Tensor, clusters: torch.Tensor, lin_w: torch.Tensor,
+                      lin_b: torch.Tensor, num_classes: int
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """UnSegEvaluator.forward, non-CRF branch (model/evaluator.py:46-82) with ClusterLookup alpha=None
+    (:93-111).  Returns (linear_loss, linear_preds, cluster_loss, cluster_preds)."""
+    if out.shape[-2:] != label.shape[-2:]:
+        out = F.interpolate(out, label.shape[-2:], mode="bilinear", align_corners=False)   # :53-54
+    lin_logits = F.conv2d(out, lin_w.view(lin_w.shape[0], -1, 1, 1), lin_b)                # :67
+    lin_preds = lin_logits.argmax(1)                                                       # :68
+    nc = F.normalize(clusters, dim=1)                                                      # :95
+    nf = F.normalize(out, dim=1)                                                           # :96
+    inner = torch.einsum("bchw,nc->bnhw", nf, nc)                                          # :98
+    probs = F.one_hot(torch.argmax(inner, dim=1), clusters.shape[0]).permute(0, 3, 1, 2).to(torch.float32)
+    cluster_loss = -(probs * inner).sum(1).mean()                                          # :106
+    cluster_preds = probs.argmax(1)                                                        # :70
+    lab = label.reshape(-1)
+    mask = (lab >= 0) & (lab < num_classes)                                                # :73
+    flat = lin_logits.permute(0, 2, 3, 1).reshape(-1, num_classes)                         # :76
+    lin_loss = F.cross_entropy(flat[mask], lab[mask])                                      # :80
+    return lin_loss, lin_preds, cluster_loss, cluster_preds
+
+
+def confusion_update(confusion: torch.Tensor, preds: torch.Tensor, label: torch.Tensor, num_classes: int,
+                     extra_classes: int = 0) -> torch.Tensor:
+    """UnSegMetrics.update (model/metric.py:44-58): rows = prediction, cols = label; predictions >=
+    num_classes are dropped even when extra classes exist (:49)."""
+    p, l = preds.reshape(-1), label.reshape(-1)
+    m = (l >= 0) & (l < num_classes) & (p >= 0) & (p < num_classes)
+    rows = num_classes + extra_classes
+    binc = torch.bincount(l[m] * rows + p[m], minlength=num_classes * rows)
+    return confusion + binc.reshape(num_classes, rows).t()
+
+
+def metrics_compute(confusion: torch.Tensor, hungarian: bool) -> Dict[str, torch.Tensor]:
+    """UnSegMetrics.compute for extra_classes == 0 (model/metric.py:60-98) without the CSV side effect."""
+    from scipy.optimize import linear_sum_assignment
+    if hungarian:
+        assign = linear_sum_assignment(confusion.cpu(), maximize=True)                     # :66
+        hist = confusion[np.argsort(assign[1]), :]                                         # :72
+    else:
+        hist = confusion
+    tp = torch.diag(hist)
+    fp = hist.sum(0) - tp
+    fn = hist.sum(1) - tp
+    iou = tp / (tp + fp + fn)
+    iou = iou[~torch.isnan(iou)].mean()
+    accuracy = tp.sum() / hist.sum()                                                      # :94
+    return {"iou": 100 * iou, "accuracy": 100 * accuracy}
+
+
+# --------------------------------------------------------------------------------------------------
+# kNN  (data/precompute_knns.py:165-171, 305-319)
+# --------------------------------------------------------------------------------------------------
+
+
+def knn(normed_feats: torch.Tensor, k: int = 30, queries: Optional[torch.Tensor] = None
+        ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Indices (and values) of the k largest cosine similarities per query (precompute_knns.py:313-315)."""
+    q = normed_feats if queries is None else queries
+    sims = torch.einsum("nf,mf->nm", q, normed_feats)
+    vals, idx = torch.topk(sims, k)
+    return idx, vals
+
+
+# --------------------------------------------------------------------------------------------------
+# near-tie audit helpers used by the parity tests
+# --------------------------------------------------------------------------------------------------
+
+
+def top2_margin_fp64(z_norm: torch.Tensor, cb_norm: torch.Tensor, idx_a: torch.Tensor, idx_b: torch.Tensor
+                     ) -> torch.Tensor:
+    """For rows where two implementations picked different codes, the fp64 relative distance gap
+    |d(a) - d(b)| / max(d(a), d(b), tiny) between the two picks."""
+    zd, cd = z_norm.double(), cb_norm.double()
+    da = ((zd - cd[idx_a]) ** 2).sum(1)
+    db = ((zd - cd[idx_b]) ** 2).sum(1)
+    return (da - db).abs() / torch.clamp(torch.maximum(da, db), min=1e-300)

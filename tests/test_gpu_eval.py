@@ -1,0 +1,139 @@
+"""GPU parity of the cluster/linear probe + confusion histogram and the kNN against fixtures and oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import equss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from equss_b200 import ops
+    return ops
+
+
+def _probe(feat, clusters, lin_w, lin_b, label, C, rows=None):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    B, D, h, w = feat.shape
+    Cc = clusters.shape[0]
+    wmat = torch.cat([F.normalize(clusters, dim=1), lin_w], dim=0).to(dev)
+    bias = torch.cat([torch.zeros(Cc), lin_b]).to(dev)
+    logits = ops.probe_logits(feat.to(dev), wmat, bias)
+    conf_c = torch.zeros(rows or C, C, dtype=torch.long, device=dev)
+    conf_l = torch.zeros(C, C, dtype=torch.long, device=dev)
+    preds = ops.probe_argmax_confusion(logits, B, h, w, Cc + C, label.to(dev), C, [(0, Cc), (Cc, C)],
+                                       confusions=[conf_c, conf_l])
+    torch.cuda.synchronize()
+    return preds[0].cpu(), preds[1].cpu(), conf_c.cpu(), conf_l.cpu()
+
+
+def _audit_preds(pg, pr, logits_ref):
+    """Disagreements must be fp32 near-ties of the reference's own logits (relative gap < 1e-5 of the
+    logit scale: interpolate-then-dot vs dot-then-interpolate differ by fp32 reassociation only)."""
+    bad = (pg != pr)
+    nb = int(bad.sum())
+    if nb == 0:
+        return 0
+    lr = logits_ref.permute(0, 2, 3, 1)[bad]              # (nb, C)
+    a = lr.gather(1, pg[bad][:, None]).squeeze(1)
+    b = lr.gather(1, pr[bad][:, None]).squeeze(1)
+    gap = (a - b).abs() / lr.abs().max(dim=1)[0].clamp_min(1e-30)
+    assert float(gap.max()) < 1e-5, f"{nb} pred mismatches, worst relative logit gap {float(gap.max()):.3e}"
+    return nb
+
+
+def test_golden_probe_and_confusion(golden_dir):
+    g = np.load(os.path.join(golden_dir, "eval_probe.npz"))
+    C = 27
+    feat, label = torch.from_numpy(g["feat"]), torch.from_numpy(g["label"])
+    cp, lp, conf_c, conf_l = _probe(feat, torch.from_numpy(g["clusters"]), torch.from_numpy(g["lin_w"]),
+                                    torch.from_numpy(g["lin_b"]), label, C)
+    assert np.array_equal(cp.numpy(), g["cluster_preds"])
+    assert np.array_equal(lp.numpy(), g["linear_preds"])
+    assert np.array_equal(conf_c.numpy(), g["cluster_confusion"])
+    assert np.array_equal(conf_l.numpy(), g["linear_confusion"])
+    res = O.metrics_compute(conf_c, True)
+    assert float(res["iou"]) == pytest.approx(float(g["cluster_iou"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("B,D,h,w,H,W", [(2, 64, 28, 28, 224, 224), (3, 96, 7, 5, 23, 31), (1, 32, 10, 10, 10, 10)])
+def test_probe_vs_oracle(B, D, h, w, H, W):
+    torch.manual_seed(3)
+    C = 27
+    feat = torch.randn(B, D, h, w)
+    clusters, lin_w, lin_b = torch.randn(C, D), torch.randn(C, D) * 0.1, torch.randn(C) * 0.1
+    label = torch.randint(-1, C, (B, H, W))
+    ll, lp_ref, cl, cp_ref = O.evaluator_forward(feat, label, clusters, lin_w, lin_b, C)
+    cp, lp, conf_c, conf_l = _probe(feat, clusters, lin_w, lin_b, label, C)
+    up = F.interpolate(feat, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else feat
+    inner = torch.einsum("bchw,nc->bnhw", F.normalize(up, dim=1), F.normalize(clusters, dim=1))
+    lin = F.conv2d(up, lin_w.view(C, D, 1, 1), lin_b)
+    n1 = _audit_preds(cp, cp_ref, inner)
+    n2 = _audit_preds(lp, lp_ref, lin)
+    assert n1 + n2 <= max(2, int(2e-5 * B * H * W))
+    # the fused histogram must equal the reference bincount evaluated on the kernel's own predictions
+    assert torch.equal(conf_c, O.confusion_update(torch.zeros(C, C, dtype=torch.long), cp, label, C))
+    assert torch.equal(conf_l, O.confusion_update(torch.zeros(C, C, dtype=torch.long), lp, label, C))
+
+
+@pytest.mark.parametrize("n,C,extra", [(0, 27, 0), (1, 27, 0), (100003, 27, 0), (50000, 19, 3), (4096, 300, 0)])
+def test_confusion_update_vs_bincount(n, C, extra):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(n + C)
+    preds = torch.randint(-2, C + extra + 2, (n,))
+    label = torch.randint(-1, C + 1, (n,))
+    label[::7] = 255 if n else 0
+    conf = torch.zeros(C + extra, C, dtype=torch.long, device=dev)
+    ops.confusion_update(preds.to(dev), label.to(dev), C, conf)
+    ops.confusion_update(preds.to(dev), label.to(dev), C, conf)     # accumulates in place
+    ref = O.confusion_update(torch.zeros(C + extra, C, dtype=torch.long), preds, label, C, extra)
+    assert torch.equal(conf.cpu(), 2 * ref)
+
+
+def test_confusion_coherent_labels():
+    """Long runs of identical (pred, label) pairs exercise the warp run-length merge."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    C = 27
+    label = torch.arange(200000) // 997 % C
+    preds = torch.arange(200000) // 1500 % C
+    label[1000:1100] = -1
+    conf = torch.zeros(C, C, dtype=torch.long, device=dev)
+    ops.confusion_update(preds.to(dev), label.to(dev), C, conf)
+    assert torch.equal(conf.cpu(), O.confusion_update(torch.zeros(C, C, dtype=torch.long), preds, label, C))
+
+
+def test_knn_golden(golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "knn.npz"))
+    feats = torch.from_numpy(g["feats"]).cuda()
+    idx, sims = ops.knn_topk(feats, feats, 8, return_sims=True)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    np.testing.assert_allclose(sims.cpu().numpy(), g["vals"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("nq,n,Fd,k", [(257, 1000, 768, 30), (64, 5000, 100, 8), (5, 33, 7, 1), (130, 130, 64, 32)])
+def test_knn_vs_topk(nq, n, Fd, k):
+    ops = _ops()
+    torch.manual_seed(nq)
+    db = F.normalize(torch.randn(n, Fd), dim=1)
+    q = db[:nq] if nq <= n else F.normalize(torch.randn(nq, Fd), dim=1)
+    idx, sims = ops.knn_topk(q.cuda(), db.cuda(), k, return_sims=True)
+    ridx, rvals = O.knn(db, k, queries=q)
+    idx, sims = idx.cpu(), sims.cpu()
+    torch.testing.assert_close(sims, rvals, rtol=1e-5, atol=2e-6)
+    # identical neighbour sets, except members whose similarity ties the k-th value within fp32 noise
+    exact = torch.einsum("nf,mf->nm", q.double(), db.double())
+    kth = rvals[:, -1:].double()
+    for r in range(nq):
+        diff = set(idx[r].tolist()) ^ set(ridx[r].tolist())
+        for j in diff:
+            assert abs(float(exact[r, j] - kth[r])) < 5e-6, (r, j)
+    if nq <= n:
+        assert torch.equal(idx[:, 0], torch.arange(nq))     # column 0 is the query itself (dataset_aug.py:520)

@@ -1,0 +1,240 @@
+"""GPU parity of the PQ kernels (through the C-ABI) against the golden fixtures and the CPU oracle.
+
+Bar (BASELINE.json north_star): code indices and counts bit-exact, except fp32 near-ties whose fp64
+top-2 relative margin is below 1e-6 (audited); losses / EMA codebooks within 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import equss_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NEAR_TIE = 1e-6
+
+
+def _ops():
+    from equss_b200 import ops
+    return ops
+
+
+def _audit_indices(idx_gpu, idx_ref, zn, cbn):
+    """idx_*: (n,) long on CPU.  Every disagreement must be an fp32 near-tie.  Returns #near-ties."""
+    bad = (idx_gpu != idx_ref).nonzero().flatten()
+    if bad.numel() == 0:
+        return 0
+    marg = O.top2_margin_fp64(zn[bad], cbn, idx_ref[bad], idx_gpu[bad])
+    assert float(marg.max()) < NEAR_TIE, f"{bad.numel()} index mismatches, worst fp64 margin {float(marg.max()):.3e}"
+    return int(bad.numel())
+
+
+@pytest.mark.parametrize("mode", ["l2", "z_norm", "none"])
+@pytest.mark.parametrize("algo", [1, 0])   # exact SIMT kernel, then AUTO (tcgen05 when supported)
+def test_golden_ema_multi_step(golden_dir, mode, algo):
+    """Replays the reference's 3 training steps + 1 eval step (model/quantizer.py EMA PQ)."""
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, f"pq_ema_{mode}.npz"))
+    M, K = int(g["M"]), int(g["K"])
+    dev = torch.device("cuda:0")
+    weight = torch.from_numpy(g["weight0"]).to(dev).contiguous()
+    weight_avg = weight.clone()
+    vq_count = torch.zeros(M, K, device=dev)
+    exact = torch.zeros(M, K, device=dev)
+    d = weight.shape[2]
+    for s in range(4):
+        z = torch.from_numpy(g[f"z{s}"]).to(dev)
+        # codebook-side normalisation is host plumbing (M*K*d elements), same torch ops as the reference
+        cbn = torch.stack([O.normalize_pair(z[:1, :d], weight[m], mode)[1] for m in range(M)]).contiguous()
+        idx = ops.pq_assign(z, cbn, normalize=mode, algo=algo)
+        assert np.array_equal(idx.cpu().numpy(), g[f"idx{s}"]), f"step {s}: indices differ from the reference"
+        out, sqerr, _ = ops.pq_gather_loss(z, cbn, idx, normalize=mode)
+        np.testing.assert_allclose(out.cpu().numpy(), g[f"zq{s}"], rtol=1e-5, atol=1e-6)
+        n = z.shape[0]
+        commit = (sqerr / (n * d)).float().mean().item()
+        assert commit == pytest.approx(float(g[f"out{s}/commitment-loss"]), rel=1e-5)
+        if s < 3:
+            packed = ops.pq_accumulate(z, idx, K)
+            unused = ops.ema_update(packed, 0.99, 1e-5, vq_count, weight_avg, weight, exact)
+            np.testing.assert_allclose(weight.cpu().numpy(), g[f"weight_after{s}"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(weight_avg.cpu().numpy(), g[f"weight_avg_after{s}"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(vq_count.cpu().numpy(), g[f"vq_count_after{s}"], rtol=1e-6, atol=1e-7)
+            assert np.array_equal(exact.cpu().numpy(), g[f"exact_after{s}"])
+            usage = float(((K - unused.float()) / K).mean())
+            assert usage == pytest.approx(float(g[f"out{s}/codebook-usage"]), rel=1e-6)
+    prob = ops.pq_distance_prob(z, cbn, normalize=mode)
+    np.testing.assert_allclose(prob.cpu().numpy(), g["prob3"], rtol=2e-5, atol=1e-7)
+
+
+def test_golden_nchw_variants(golden_dir):
+    """Learned-codebook variants on NCHW input: V1 (quantizer.VectorQuantizer), V5 (dino_pqgo.Codebook)
+    and the quantizer_v2 quirk that gathers rows of z_norm."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(golden_dir, "pq_param_nchw.npz"))
+    z = torch.from_numpy(g["z"]).to(dev)
+    B, d, h, w = z.shape
+    cb = torch.from_numpy(g["v1_codebook"]).to(dev)
+    cbn = F.normalize(cb, dim=1)[None].contiguous()
+    idx = ops.pq_assign(z, cbn, normalize="l2")
+    assert np.array_equal(idx[0].cpu().numpy(), g["v1_idx"])
+    out, sqerr, _ = ops.pq_gather_loss(z, cbn, idx, normalize="l2")
+    np.testing.assert_allclose(out.cpu().numpy(), g["v1_q"], rtol=1e-5, atol=1e-6)
+    mse = float(sqerr[0] / (B * h * w * d))
+    assert mse == pytest.approx(float(g["v1_commitment_loss"]), rel=1e-5)
+    assert mse * 1.25 == pytest.approx(float(g["v1_loss"]), rel=1e-5)
+    cb5 = torch.from_numpy(g["v5_codebook"]).to(dev)[None].contiguous()
+    idx5 = ops.pq_assign(z, cb5, normalize="none")
+    assert np.array_equal(idx5[0].view(B, h, w).cpu().numpy(), g["v5_idx"])
+    out5, sq5, _ = ops.pq_gather_loss(z, cb5, idx5, normalize="none")
+    np.testing.assert_allclose(out5.cpu().numpy(), g["v5_q"], rtol=1e-5, atol=1e-6)
+    assert float(sq5[0] / (B * h * w * d)) * 1.25 == pytest.approx(float(g["v5_vq_loss"]), rel=1e-5)
+    g2 = np.load(os.path.join(golden_dir, "pq_v2_nchw.npz"))
+    emb = torch.from_numpy(g2["embeddings"]).to(dev)
+    cbn2 = F.normalize(emb, dim=1)[None].contiguous()
+    idx2 = ops.pq_assign(z, cbn2, normalize="l2")
+    assert np.array_equal(idx2[0].cpu().numpy(), g2["idx"])
+
+
+SHAPES = [
+    # (n_or_(B,h,w), M, K, d, mode)
+    (3136, 8, 256, 64, "l2"),          # BASELINE config 1 (pq_baseline, flat)
+    (1000, 64, 256, 16, "l2"),         # config-2 subspace shape, ragged N
+    (777, 16, 512, 64, "l2"),          # config-4 subspace shape, ragged N
+    (513, 4, 32, 32, "z_norm"),
+    (300, 3, 40, 12, "none"),          # d not a power of two, K not a multiple of 16: generic kernels
+    (1, 2, 8, 8, "l2"),                # single pixel
+    ((2, 28, 28), 8, 256, 64, "l2"),   # NCHW
+    ((3, 9, 7), 64, 256, 16, "l2"),    # NCHW, tiny odd grid
+    ((2, 5, 5), 2, 16, 128, "z_norm"),
+]
+
+
+@pytest.mark.parametrize("shape,M,K,d,mode", SHAPES)
+@pytest.mark.parametrize("algo", [1, 0])
+def test_assign_gather_accumulate_vs_oracle(shape, M, K, d, mode, algo):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1234)
+    D = M * d
+    if isinstance(shape, tuple):
+        B, h, w = shape
+        z = torch.randn(B, D, h, w)
+        z_flat = z.permute(0, 2, 3, 1).reshape(-1, D)
+    else:
+        z = torch.randn(shape, D)
+        z_flat = z
+    n = z_flat.shape[0]
+    cb = torch.randn(M, K, d) * (0.3 if mode == "none" else 1.0)
+    if mode == "none":
+        z, z_flat = z * 0.3, z_flat * 0.3
+    zg = z.to(dev)
+    cbn_list, zn_list = [], []
+    for m in range(M):
+        zn, cn = O.normalize_pair(z_flat[:, m * d:(m + 1) * d], cb[m], mode)
+        cbn_list.append(cn); zn_list.append(zn)
+    cbn = torch.stack(cbn_list).contiguous()
+    idx = ops.pq_assign(zg, cbn.to(dev), normalize=mode, algo=algo)
+    out, sqerr, znorm = ops.pq_gather_loss(zg, cbn.to(dev), idx, normalize=mode, want_znorm=True)
+    packed = ops.pq_accumulate(zg, idx, K)
+    packed_n = ops.pq_accumulate(zg, idx, K, use_norm=True, normalize=mode)
+    torch.cuda.synchronize()
+    idx_c = idx.cpu().long()
+    out_flat = out.cpu() if not isinstance(shape, tuple) else out.cpu().permute(0, 2, 3, 1).reshape(-1, D)
+    zn_flat = znorm.cpu() if not isinstance(shape, tuple) else znorm.cpu().permute(0, 2, 3, 1).reshape(-1, D)
+    ties = 0
+    for m in range(M):
+        dist = O.sq_distance(zn_list[m], cbn[m])
+        ref = torch.argmin(dist, dim=1)
+        ties += _audit_indices(idx_c[m], ref, zn_list[m], cbn[m])
+        # downstream quantities are checked against the oracle evaluated at the GPU's own indices
+        q = cbn[m][idx_c[m]]
+        ste = zn_list[m] + (q - zn_list[m])
+        torch.testing.assert_close(zn_flat[:, m * d:(m + 1) * d], zn_list[m], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(out_flat[:, m * d:(m + 1) * d], ste, rtol=1e-5, atol=1e-6)
+        mse_ref = F.mse_loss(zn_list[m], q).item()
+        assert float(sqerr[m] / (n * d)) == pytest.approx(mse_ref, rel=1e-5, abs=1e-9)
+        onehot = F.one_hot(idx_c[m], K).float()
+        assert torch.equal(packed[m, :, d].cpu(), onehot.sum(0))                      # counts: bit-exact
+        torch.testing.assert_close(packed[m, :, :d].cpu(), onehot.t() @ z_flat[:, m * d:(m + 1) * d],
+                                   rtol=1e-5, atol=2e-5)
+        torch.testing.assert_close(packed_n[m, :, :d].cpu(), onehot.t() @ zn_list[m], rtol=1e-5, atol=2e-5)
+    assert ties <= max(2, int(1e-4 * n * M)), f"too many near-ties: {ties}"
+
+
+def test_empty_input_is_a_noop():
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    cbn = F.normalize(torch.randn(4, 32, 16), dim=2).to(dev)
+    z = torch.zeros(0, 64, device=dev)
+    idx = ops.pq_assign(z, cbn, normalize="l2")
+    assert tuple(idx.shape) == (4, 0)
+    out, sqerr, _ = ops.pq_gather_loss(z, cbn, idx, normalize="l2")
+    assert out.numel() == 0 and float(sqerr.sum()) == 0.0
+    packed = ops.pq_accumulate(z, idx, 32)
+    assert float(packed.abs().sum()) == 0.0
+
+
+def test_collisions_all_pixels_one_code():
+    """Every pixel maps to the same code: the scatter-add is fully contended, counts must stay exact."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    M, K, d, n = 2, 64, 16, 20000
+    cb = F.normalize(torch.randn(M, K, d), dim=2)
+    z = cb[:, 5, :].reshape(1, M * d).repeat(n, 1) * 3.0
+    idx = ops.pq_assign(z.to(dev), cb.to(dev), normalize="l2")
+    assert int((idx != 5).sum()) == 0
+    packed = ops.pq_accumulate(z.to(dev), idx, K)
+    assert float(packed[0, 5, d]) == n and float(packed[:, :, d].sum()) == n * M
+    torch.testing.assert_close(packed[0, 5, :d].cpu(), z[:, :d].sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_first_index_wins_on_exact_ties():
+    """Duplicate codewords: torch.argmin returns the first minimal index."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    cb = F.normalize(torch.randn(1, 32, 16), dim=2)
+    cb[0, 20] = cb[0, 3]
+    cb[0, 31] = cb[0, 3]
+    z = cb[0, 3].reshape(1, 16).repeat(300, 1) * 2.0
+    for algo in (1, 0):
+        idx = ops.pq_assign(z.to(dev), cb.to(dev), normalize="l2", algo=algo)
+        assert int((idx != 3).sum()) == 0
+
+
+@pytest.mark.parametrize("mode", ["l2", "none", "z_norm"])
+@pytest.mark.parametrize("nchw", [False, True])
+def test_backward_matches_autograd(mode, nchw):
+    """K3' against torch autograd on the oracle's formulation of the STE output + losses."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    M, K, d, beta = 4, 32, 16, 0.25
+    D = M * d
+    z = (torch.randn(2, D, 6, 5) if nchw else torch.randn(60, D)).double().requires_grad_(True)
+    cb = torch.randn(M, K, d).double()
+    z_flat = z.permute(0, 2, 3, 1).reshape(-1, D) if nchw else z
+    n = z_flat.shape[0]
+    idx = ops.pq_assign(z.detach().float().to(dev),
+                        torch.stack([O.normalize_pair(z_flat[:1, :d].float(), cb[m].float(), mode)[1] for m in range(M)]).to(dev),
+                        normalize=mode)
+    idx_c = idx.cpu().long()
+    go = torch.randn_like(z_flat)
+    total = 0.0
+    cbn_all = []
+    for m in range(M):
+        zn, cn = O.normalize_pair(z_flat[:, m * d:(m + 1) * d], cb[m], mode)
+        cbn_all.append(cn)
+        q = cn[idx_c[m]].detach()
+        ste = zn + (q - zn).detach()
+        total = total + (ste * go[:, m * d:(m + 1) * d]).sum() + beta * F.mse_loss(zn, q)
+    total.backward()
+    go_dev = go.float()
+    if nchw:
+        go_dev = go_dev.view(2, 6, 5, D).permute(0, 3, 1, 2).contiguous()
+    coef = torch.full((M,), 2.0 * beta / (n * d))
+    gz, _ = ops.pq_gather_loss_bwd(z.detach().float().to(dev), torch.stack(cbn_all).float().to(dev), idx, mode,
+                                   go_dev.to(dev), coef.to(dev))
+    torch.testing.assert_close(gz.cpu().double(), z.grad, rtol=2e-4, atol=2e-5)
