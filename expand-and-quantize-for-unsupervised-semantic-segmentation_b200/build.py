@@ -55,7 +55,7 @@ def build(verbose=True, force=False):
         results = list(ex.map(lambda s: _compile(s, hm, verbose), srcs))
     objs = [o for o, _ in results]
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB, *objs]   # static cudart; driver API resolved at run time
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -301,10 +301,10 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
 
 extern "C" int equss_confusion_update(const int64_t* preds, const int64_t* label, int64_t n, int num_classes,
                                       int rows, int64_t* confusion, void* stream) {
-  EQUSS_REQUIRE(preds && label && confusion, EQUSS_ERR_INVALID_ARG, "equss_confusion_update: null pointer");
   EQUSS_REQUIRE(n >= 0 && num_classes > 0 && rows >= num_classes, EQUSS_ERR_INVALID_ARG,
                 "equss_confusion_update: bad shape n=%lld C=%d rows=%d", (long long)n, num_classes, rows);
-  if (n == 0) return EQUSS_OK;
+  if (n == 0) return EQUSS_OK;   // empty tensors have null data pointers
+  EQUSS_REQUIRE(preds && label && confusion, EQUSS_ERR_INVALID_ARG, "equss_confusion_update: null pointer");
   const int threads = 256;
   size_t smem = (size_t)(threads / 32) * rows * num_classes * sizeof(int);
   int use_smem = smem <= 96 * 1024;

@@ -204,6 +204,7 @@ extern "C" int equss_pq_assign(const float* z, const equss_zdesc* zd, const floa
                                const float* norm_a, const float* norm_b, int32_t* idx_out,
                                float* margin_out, void* workspace, int64_t workspace_bytes, int algo,
                                void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;   // empty tensors have null data pointers
   EQUSS_REQUIRE(z && zd && codebook_norm && cnorm2 && idx_out, EQUSS_ERR_INVALID_ARG, "equss_pq_assign: null pointer");
   int rc = validate_zdesc(zd, M, d); if (rc) return rc;
   EQUSS_REQUIRE(K > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_assign: K=%d", K);
@@ -232,6 +233,7 @@ extern "C" int equss_pq_distance_prob(const float* z, const equss_zdesc* zd, con
                                       const float* cnorm2, int M, int K, int d, int norm_mode,
                                       const float* norm_a, const float* norm_b, float temperature,
                                       float* prob, void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;
   EQUSS_REQUIRE(z && zd && codebook_norm && cnorm2 && prob, EQUSS_ERR_INVALID_ARG, "equss_pq_distance_prob: null pointer");
   int rc = validate_zdesc(zd, M, d); if (rc) return rc;
   EQUSS_REQUIRE(K > 0 && K <= 2048, EQUSS_ERR_UNSUPPORTED, "equss_pq_distance_prob: K=%d outside (0,2048]", K);

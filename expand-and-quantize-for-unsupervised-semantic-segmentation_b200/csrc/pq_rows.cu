@@ -447,6 +447,7 @@ extern "C" int equss_pq_gather_loss(const float* z, const equss_zdesc* zd, const
                                     const int32_t* idx, int M, int K, int d, int norm_mode,
                                     const float* norm_a, const float* norm_b, float* out,
                                     float* znorm_out, double* sqerr, void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;   // empty tensors have null data pointers
   EQUSS_REQUIRE(z && zd && gather_src && idx && out && sqerr, EQUSS_ERR_INVALID_ARG,
                 "equss_pq_gather_loss: null pointer");
   int rc = validate_zdesc(zd, M, d); if (rc) return rc;
@@ -485,6 +486,7 @@ extern "C" int equss_pq_gather_loss_bwd(const float* z, const equss_zdesc* zd, c
                                         const float* norm_a, const float* norm_b,
                                         const float* grad_out, const float* coef, float* grad_z,
                                         const float* cb_coef, float* grad_codebook, void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;
   EQUSS_REQUIRE(z && zd && gather_src && idx, EQUSS_ERR_INVALID_ARG, "equss_pq_gather_loss_bwd: null pointer");
   EQUSS_REQUIRE(grad_z || grad_codebook, EQUSS_ERR_INVALID_ARG, "equss_pq_gather_loss_bwd: nothing to compute");
   int rc = validate_zdesc(zd, M, d); if (rc) return rc;
@@ -506,6 +508,7 @@ extern "C" int equss_pq_gather_loss_bwd(const float* z, const equss_zdesc* zd, c
 extern "C" int equss_pq_accumulate(const float* z, const equss_zdesc* zd, const int32_t* idx, int M, int K,
                                    int d, int use_norm, int norm_mode, const float* norm_a,
                                    const float* norm_b, float* packed, void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;
   EQUSS_REQUIRE(z && zd && idx && packed, EQUSS_ERR_INVALID_ARG, "equss_pq_accumulate: null pointer");
   int rc = validate_zdesc(zd, M, d); if (rc) return rc;
   rc = check_norm_args(norm_mode, norm_a, norm_b); if (rc) return rc;

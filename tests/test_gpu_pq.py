@@ -238,3 +238,40 @@ def test_backward_matches_autograd(mode, nchw):
     gz, _ = ops.pq_gather_loss_bwd(z.detach().float().to(dev), torch.stack(cbn_all).float().to(dev), idx, mode,
                                    go_dev.to(dev), coef.to(dev))
     torch.testing.assert_close(gz.cpu().double(), z.grad, rtol=2e-4, atol=2e-5)
+
+
+TC_SHAPES = [
+    # (shape, M, K, d, mode)  -- BASELINE.json shapes; the oracle is too slow here, the exact SIMT kernel
+    # (itself oracle-checked above) is the comparator: the two kernels must agree on EVERY index.
+    (3136, 8, 256, 64, "l2"),                 # config 1
+    (51200, 64, 256, 16, "l2"),               # config 2 (flat view)
+    ((32, 40, 40), 64, 256, 16, "l2"),        # config 2, NCHW as the evaluator receives it
+    (6272, 16, 512, 64, "l2"),                # config 4, one rank's shard
+    ((2, 56, 56), 16, 512, 64, "l2"),         # config 4 NCHW
+    (4099, 16, 1024, 32, "none"),             # cityscapes-yaml-like K=1024, ragged N
+    (2500, 32, 32, 32, "z_norm"),             # cityscapes yaml M=32,K=32
+    (1000, 4, 40, 8, "l2"),                   # K not a multiple of 16 -> padded columns
+]
+
+
+@pytest.mark.parametrize("shape,M,K,d,mode", TC_SHAPES)
+def test_tcgen05_assign_equals_exact_kernel(shape, M, K, d, mode):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(99)
+    D = M * d
+    z = torch.randn(*((shape[0], D, shape[1], shape[2]) if isinstance(shape, tuple) else (shape, D)), device=dev)
+    cb = torch.randn(M, K, d, device=dev)
+    if mode == "l2":
+        cbn = F.normalize(cb, dim=2)
+    elif mode == "z_norm":
+        s, mu = torch.std_mean(cb, dim=2, keepdim=True)
+        cbn = (cb - mu) / (s + 1e-5)
+    else:
+        cbn = cb * 0.5
+    idx_simt = ops.pq_assign(z, cbn, normalize=mode, algo=1)
+    idx_tc = ops.pq_assign(z, cbn, normalize=mode, algo=2)
+    torch.cuda.synchronize()
+    nbad = int((idx_simt != idx_tc).sum())
+    assert nbad == 0, f"{nbad} of {idx_tc.numel()} indices differ between the tcgen05 and the exact kernel"
+    assert int(idx_tc.min()) >= 0 and int(idx_tc.max()) < K
