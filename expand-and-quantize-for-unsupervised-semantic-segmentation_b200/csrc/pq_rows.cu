@@ -83,12 +83,17 @@ gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4
   __syncthreads();
   const long long total = n_pixels * D4;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < total; f += stride) {
-    long long n = f / D4;
-    int c4 = (int)(f - n * D4);
+  // warp-uniform trip count: the xor-shuffles below need every lane of the warp, so the bound is
+  // tested on the warp's first element and the tail is predicated instead of exiting the loop
+  for (long long f0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); f0 < total; f0 += stride) {
+    const long long f = f0 + (threadIdx.x & 31);
+    const bool live = f < total;
+    const long long fc = live ? f : total - 1;
+    long long n = fc / D4;
+    int c4 = (int)(fc - n * D4);
     int m = c4 / LPS;
     int l = c4 - m * LPS;
-    float4 v = __ldcs(z + f);
+    float4 v = __ldcs(z + fc);
     RowNorm r; r.shift = 0.f; r.denom = 1.f;
     if (mode == EQUSS_NORM_L2) {
       r = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v.x, v.y, v.z, v.w)));
@@ -109,11 +114,13 @@ gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4
     float4 dq, o;
     dq.x = q.x - zn.x; dq.y = q.y - zn.y; dq.z = q.z - zn.z; dq.w = q.w - zn.w;
     o.x = zn.x + dq.x; o.y = zn.y + dq.y; o.z = zn.z + dq.z; o.w = zn.w + dq.w;   // STE value (:536)
-    __stcs(out + f, o);
-    if (znorm_out) __stcs(znorm_out + f, zn);
+    if (live) {
+      __stcs(out + f, o);
+      if (znorm_out) __stcs(znorm_out + f, zn);
+    }
     float e = group_sumsq(dq.x, dq.y, dq.z, dq.w);
     e = butterfly_lanes<LPS>(e);
-    if (l == 0) atomicAdd(&s_sq[m], e);
+    if (l == 0 && live) atomicAdd(&s_sq[m], e);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
@@ -257,7 +264,10 @@ accumulate_flat_kernel(const float* __restrict__ z, long long n_pixels, int D, i
   const int rows_per_iter = blockDim.x / LPS;
   const int rl = threadIdx.x / LPS, l = threadIdx.x % LPS;
   const int32_t* idxm = idx + (long long)m * n_pixels;
-  for (long long n = n0 + rl; n < n1; n += rows_per_iter) {
+  for (long long nb0 = n0; nb0 < n1; nb0 += rows_per_iter) {   // block-uniform trip count (shuffles inside)
+    const long long nr = nb0 + rl;
+    const bool live = nr < n1;
+    const long long n = live ? nr : n1 - 1;
     float4 v = __ldcs(reinterpret_cast<const float4*>(z + n * D + (long long)m * d) + l);
     if (use_norm && mode != EQUSS_NORM_NONE) {
       RowNorm r; r.shift = 0.f; r.denom = 1.f;
@@ -274,6 +284,7 @@ accumulate_flat_kernel(const float* __restrict__ z, long long n_pixels, int D, i
       v.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
       v.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
     }
+    if (!live) continue;
     int code = __ldg(idxm + n);
     float* a = s_acc + code * ld + l * 4;
     atomicAdd(a + 0, v.x);

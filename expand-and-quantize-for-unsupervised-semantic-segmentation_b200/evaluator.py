@@ -1,0 +1,158 @@
+"""Drop-in mirror of the reference's ``model/evaluator.py`` (UnSegEvaluator, ClusterLookup).
+
+The reference bilinearly upsamples the (B, D, h, w) features to label resolution and runs both probes
+there (model/evaluator.py:53-54,67-70,95-106).  Here both probes run at TOKEN resolution in one kernel
+(K8 step 1) and a second kernel interpolates the 27+27 logits per label pixel, takes both argmaxes and
+(optionally) feeds the confusion histograms (K8 step 2 + K9), see csrc/eval_probe.cu.
+
+The two training losses are "next" rows: they are evaluated from the low-resolution
+logits with differentiable PyTorch ops (interpolation of logits instead of features; the per-pixel
+feature norm from 2x2 Gram terms), never materialising the upsampled feature map.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa
+
+from . import ops
+
+__all__ = ["UnSegEvaluator", "ClusterLookup"]
+
+
+class ClusterLookup(nn.Module):
+    """model/evaluator.py:85-111 (kept for the CRF / soft-assignment branches and API parity)."""
+
+    def __init__(self, dim: int, n_classes: int):
+        super().__init__()
+        self.n_classes = n_classes
+        self.dim = dim
+        self.clusters = torch.nn.Parameter(torch.randn(n_classes, dim))
+
+    def forward(self, x: torch.Tensor, alpha: Optional[float] = 2.0, log_probs: bool = False):
+        normed_clusters = F.normalize(self.clusters, dim=1)
+        normed_features = F.normalize(x, dim=1)
+        inner_products = torch.einsum("bchw,nc->bnhw", normed_features, normed_clusters)
+        if alpha is None:
+            cluster_probs = F.one_hot(torch.argmax(inner_products, dim=1), self.n_classes)
+            cluster_probs = cluster_probs.permute(0, 3, 1, 2).contiguous().to(torch.float32)
+        else:
+            cluster_probs = F.softmax(inner_products * alpha, dim=1)
+        cluster_loss = -torch.sum(cluster_probs * inner_products, dim=1).mean()
+        if log_probs:
+            return cluster_loss, F.log_softmax(inner_products * alpha, dim=1)
+        return cluster_loss, cluster_probs
+
+
+def _taps(out_size: int, in_size: int, device):
+    """Source indices / weights of torch's bilinear upsampling, align_corners=False."""
+    scale = float(in_size) / float(out_size)
+    dst = torch.arange(out_size, dtype=torch.float32, device=device)
+    src = torch.clamp((dst + 0.5) * torch.tensor(scale, dtype=torch.float32, device=device) - 0.5, min=0.0)
+    i0 = src.floor().long().clamp_(max=in_size - 1)
+    i1 = torch.clamp(i0 + 1, max=in_size - 1)
+    l1 = src - i0.float()
+    return i0, i1, 1.0 - l1, l1
+
+
+@torch.no_grad()
+def _upsampled_feature_norm(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """|| bilinear_upsample(x)[b, :, Y, X] ||_2 for every label pixel, shape (B, H, W), from the 2x2 Gram
+    terms of the token grid: |sum_t w_t x_t|^2 = sum_{t,t'} w_t w_t' <x_t, x_t'>."""
+    B, D, h, w = x.shape
+    y0, y1, wy0, wy1 = _taps(H, h, x.device)
+    x0, x1, wx0, wx1 = _taps(W, w, x.device)
+    g_self = (x * x).sum(1)                                             # (B,h,w)
+    g_h = F.pad((x[..., :, :-1] * x[..., :, 1:]).sum(1), (0, 1))        # <x[y,x], x[y,x+1]>
+    g_v = F.pad((x[..., :-1, :] * x[..., 1:, :]).sum(1), (0, 0, 0, 1))  # <x[y,x], x[y+1,x]>
+    g_d = F.pad((x[..., :-1, :-1] * x[..., 1:, 1:]).sum(1), (0, 1, 0, 1))   # <x[y,x], x[y+1,x+1]>
+    g_a = F.pad((x[..., :-1, 1:] * x[..., 1:, :-1]).sum(1), (1, 0, 0, 1))   # <x[y,x], x[y+1,x-1]> stored at [y, x]
+    Y0, X0 = y0[:, None], x0[None, :]
+    Y1, X1 = y1[:, None], x1[None, :]
+    sx, sy = (X1 != X0), (Y1 != Y0)                                     # taps distinct (not clamped at the border)?
+
+    def at(g, yy, xx):
+        return g[:, yy, xx]
+    a, b_, c, e = wy0[:, None] * wx0[None, :], wy0[:, None] * wx1[None, :], wy1[:, None] * wx0[None, :], wy1[:, None] * wx1[None, :]
+    s00, s01, s10, s11 = at(g_self, Y0, X0), at(g_self, Y0, X1), at(g_self, Y1, X0), at(g_self, Y1, X1)
+    h0 = torch.where(sx, at(g_h, Y0, X0), s00)                          # <(y0,x0),(y0,x1)>
+    h1 = torch.where(sx, at(g_h, Y1, X0), s10)                          # <(y1,x0),(y1,x1)>
+    v0 = torch.where(sy, at(g_v, Y0, X0), s00)                          # <(y0,x0),(y1,x0)>
+    v1 = torch.where(sy, at(g_v, Y0, X1), s01)                          # <(y0,x1),(y1,x1)>
+    dd = torch.where(sx & sy, at(g_d, Y0, X0), torch.where(sx, h0, torch.where(sy, v0, s00)))   # <(y0,x0),(y1,x1)>
+    aa = torch.where(sx & sy, at(g_a, Y0, X1), torch.where(sx, h0, torch.where(sy, v1, s01)))   # <(y0,x1),(y1,x0)>
+    n2 = (a * a * s00 + b_ * b_ * s01 + c * c * s10 + e * e * s11 +
+          2 * (a * b_ * h0 + c * e * h1 + a * c * v0 + b_ * e * v1 + a * e * dd + b_ * c * aa))
+    return n2.clamp_min(0).sqrt()
+
+
+class UnSegEvaluator(nn.Module):
+    """model/evaluator.py:11-82."""
+
+    def __init__(self, embed_dim: int, num_classes: int, extra_classes: int = 0, num_pq: int = 1) -> None:
+        super().__init__()
+        self.num_classes = num_classes
+        self.linear_probe = nn.Conv2d(embed_dim, num_classes, kernel_size=1, stride=1)
+        self.cluster_probe = ClusterLookup(embed_dim, num_classes + extra_classes)
+        self.linear_loss = nn.CrossEntropyLoss()
+        self.compute_losses = True   # set False to skip the two (training-only) loss scalars
+
+    # -- K8: predictions (and optionally K9 confusion matrices) -----------------------------------
+    @torch.no_grad()
+    def predict(self, out: torch.Tensor, label: torch.Tensor, cluster_confusion: Optional[torch.Tensor] = None,
+                linear_confusion: Optional[torch.Tensor] = None, want_preds: bool = True):
+        """Fused probe: returns (linear_preds, cluster_preds) at label resolution (None if not wanted) and
+        accumulates the int64 confusion buffers in place when given (rows = prediction, cols = label)."""
+        B, D, h, w = out.shape
+        Cc = self.cluster_probe.n_classes
+        C = self.num_classes
+        wmat = torch.cat([F.normalize(self.cluster_probe.clusters.detach().float(), dim=1),
+                          self.linear_probe.weight.detach().float().view(C, D)], dim=0)
+        bias = torch.cat([torch.zeros(Cc, device=out.device), self.linear_probe.bias.detach().float()])
+        logits = ops.probe_logits(out, wmat, bias)
+        confs = None
+        if cluster_confusion is not None or linear_confusion is not None:
+            confs = [cluster_confusion, linear_confusion]
+        preds = ops.probe_argmax_confusion(logits, B, h, w, Cc + C, label, C, [(0, Cc), (Cc, C)],
+                                           want_preds=want_preds, confusions=confs)
+        return preds[1], preds[0]
+
+    def _losses(self, out: torch.Tensor, label: torch.Tensor, cluster_preds: torch.Tensor):
+        B, D, h, w = out.shape
+        H, W = label.shape[-2:]
+        lin_low = self.linear_probe(out)                                                   # :67 at token resolution
+        lin_up = F.interpolate(lin_low, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else lin_low
+        label_flat = label.reshape(-1)
+        mask = torch.logical_and(label_flat >= 0, label_flat < self.num_classes)           # :73
+        logit_flat = lin_up.permute(0, 2, 3, 1).reshape(-1, self.num_classes)
+        linear_loss = self.linear_loss(logit_flat[mask], label_flat[mask]).mean()          # :80
+        nc = F.normalize(self.cluster_probe.clusters, dim=1)
+        inner_low = F.conv2d(out, nc[:, :, None, None])
+        inner_up = F.interpolate(inner_low, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else inner_low
+        norm = _upsampled_feature_norm(out, H, W).clamp_min(1e-12)
+        picked = inner_up.gather(1, cluster_preds.unsqueeze(1)).squeeze(1) / norm
+        cluster_loss = -picked.mean()                                                      # :106
+        return linear_loss, cluster_loss
+
+    def forward(self, out: torch.Tensor, img: torch.Tensor, label: Optional[torch.Tensor] = None,
+                is_crf: bool = False) -> Tuple[torch.Tensor, ...]:
+        if is_crf:
+            # final-eval CRF branch (CPU pydensecrf, SURVEY out of scope): reference formulation
+            from utils.crf_utils import batched_crf  # provided by the reference checkout
+            if out.shape[-2:] != label.shape[-2:]:
+                out = F.interpolate(out, label.shape[-2:], mode="bilinear", align_corners=False)
+            linear_log_prob = torch.log_softmax(self.linear_probe(out), dim=1)
+            cluster_loss, cluster_log_prob = self.cluster_probe(out, 2, log_probs=True)
+            linear_preds = batched_crf(img, linear_log_prob).argmax(1)
+            cluster_preds = batched_crf(img, cluster_log_prob).argmax(1)
+            return torch.zeros_like(cluster_loss), linear_preds, cluster_loss, cluster_preds
+        assert label is not None
+        out32 = out.float()
+        linear_preds, cluster_preds = self.predict(out32, label)
+        if self.compute_losses:
+            linear_loss, cluster_loss = self._losses(out32, label, cluster_preds)
+        else:
+            linear_loss = cluster_loss = torch.zeros((), device=out.device)
+        return linear_loss, linear_preds, cluster_loss, cluster_preds

@@ -1,0 +1,414 @@
+"""Drop-in mirror of the reference's ``model/quantizer.py`` running on the sm_100a kernels.
+
+Same class names, constructor arguments, forward signatures, output-dict keys and state-dict keys
+(``quantizers.{i}.codebook.{weight,weight_avg,vq_count}``) as the reference, so wrappers, ``build.py``'s
+isinstance checks and ``load_state_dict(strict=True)`` keep working.  Differences that are
+visible to a caller are deliberate and small:
+
+* all ``num_pq`` subspaces are quantised by one kernel per stage instead of a Python loop; the per-
+  subspace modules still exist (``.quantizers[i]``) and can be called on their own;
+* logging statistics (usage percentiles, ``codebook-usage``) come back as 0-dim tensors instead of
+  Python floats, which removes ~6K host synchronisations per subspace per step (quantizer.py:23-29);
+* the arithmetic always runs in fp32, also under autocast;
+* ``use_gumbel`` / ``use_weighted_sum`` (stochastic / soft assignment research flags) are not part of
+  the accelerated path and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F  # noqa
+
+from . import _pq_core as core
+from . import ops
+from .dist_utils import all_reduce_tensor
+
+__all__ = ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper", "get_histogram_count"]
+
+
+@torch.no_grad()
+def get_histogram_count(count: torch.Tensor, prefix: str = "") -> Dict:
+    """model/quantizer.py:15-30 for a single (K,) count vector (values are 0-dim tensors)."""
+    return core.percentile_stats(count.reshape(1, -1), prefix)
+
+
+def _check_flags(use_gumbel: bool, use_weighted_sum: bool) -> None:
+    if use_gumbel or use_weighted_sum:
+        raise NotImplementedError("use_gumbel / use_weighted_sum are outside the accelerated PQ path "
+                                  "(SURVEY.md 7.5); use the reference module for those experiments.")
+
+
+class _RestartMixin:
+    """Dead-code restart shared by both quantiser flavours (model/quantizer.py:73-103, 298-328).
+    Rare host-side path: keeps the reference's use of Python's `random` so seeds behave the same."""
+
+    update_indices = None
+    update_candidates = None
+
+    @torch.no_grad()
+    def prepare_restart(self, vq_current_count: torch.Tensor, z_flat: torch.Tensor) -> None:
+        n_data = z_flat.shape[0]
+        update_indices = torch.nonzero(vq_current_count == 0, as_tuple=True)[0]
+        n_update = len(update_indices)
+        z_indices = list(range(n_data))
+        random.shuffle(z_indices)
+        if n_update <= n_data:
+            z_indices = z_indices[:n_update]
+        else:
+            update_indices = update_indices.tolist()
+            random.shuffle(update_indices)
+            update_indices = update_indices[:n_data]
+        self.update_indices = update_indices
+        self.update_candidates = z_flat[z_indices]
+
+
+class VectorQuantizer(nn.Module, _RestartMixin):
+    """Learned-codebook quantiser, NCHW in / NCHW out (model/quantizer.py:33-200)."""
+
+    def __init__(self, num_codebook: int, embed_dim: int, beta: float = 0.25, normalize: Optional[str] = None,
+                 use_restart: bool = False, use_gumbel: bool = False, use_split: bool = False,
+                 use_weighted_sum: bool = False, update_norm: bool = True, need_initialized: str = "none",
+                 **_ignored) -> None:
+        super().__init__()
+        self.num_codebook = num_codebook
+        self.embed_dim = embed_dim
+        self.beta = beta
+        self.normalize = normalize
+        if normalize == "z_trainable":
+            self.z_mean = nn.Parameter(torch.zeros(self.embed_dim))
+            self.z_log_var = nn.Parameter(torch.zeros(self.embed_dim))
+        self.codebook = nn.Embedding(self.num_codebook, self.embed_dim)
+        nn.init.xavier_normal_(self.codebook.weight)
+        self.register_buffer("vq_count", torch.zeros(self.num_codebook), persistent=False)
+        self.use_restart = use_restart
+        self.use_gumbel = use_gumbel
+        self.use_split = use_split
+        self.use_weighted_sum = use_weighted_sum
+        self.update_norm = update_norm
+        self.need_initialized = need_initialized
+        if use_split:
+            raise NotImplementedError("NOT YET implemented. Currently only for EMA.")
+        _check_flags(use_gumbel, use_weighted_sum)
+
+    @torch.no_grad()
+    def restart(self) -> None:
+        if (self.update_indices is not None) and (self.update_candidates is not None):
+            # NB: the reference indexes a copy here (quantizer.py:99), so its restart never changes the
+            # codebook; only the exact-count reset has an effect.  Kept as is.
+            self.codebook.weight.data[self.update_indices].copy_(self.update_candidates)
+            self.vq_count.fill_(0)
+            self.update_indices = None
+            self.update_candidates = None
+
+    def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor], torch.Tensor]:
+        return _param_group_forward([self], z)
+
+    def extra_repr(self) -> str:
+        return (f"embed_dim={self.embed_dim}, num_codebook={self.num_codebook}, normalize={self.normalize}, "
+                f"use_restart={self.use_restart}, update_norm={self.update_norm}")
+
+
+class EmbeddingEMA(nn.Module):
+    """EMA codebook state (model/quantizer.py:203-254)."""
+
+    def __init__(self, num_codebook: int, embed_dim: int, decay: float = 0.99, eps: float = 1e-5) -> None:
+        super().__init__()
+        self.decay = decay
+        self.eps = eps
+        self.num_codebook = num_codebook
+        weight = torch.randn(num_codebook, embed_dim)
+        nn.init.uniform_(weight, -1.0 / num_codebook, 1.0 / num_codebook)
+        self.register_buffer("weight", weight)
+        self.register_buffer("weight_avg", weight.clone())
+        self.register_buffer("vq_count", torch.zeros(num_codebook))
+
+    @torch.no_grad()
+    def reset(self) -> None:
+        self.weight_avg.data.copy_(self.weight.data)
+        self.vq_count.fill_(0)
+
+    def forward(self, indices: torch.Tensor) -> torch.Tensor:
+        return F.embedding(indices, self.weight)
+
+    @torch.no_grad()
+    def update(self, vq_current_count, vq_current_sum) -> None:
+        """EMA count / average update and renormalisation (quantizer.py:233-254) through K6."""
+        K, d = self.weight.shape
+        packed = torch.cat([vq_current_sum.float(), vq_current_count.float().unsqueeze(1)], dim=1).unsqueeze(0).contiguous()
+        ops.ema_update(packed, self.decay, self.eps, self.vq_count.view(1, K), self.weight_avg.view(1, K, d),
+                       self.weight.view(1, K, d))
+
+    # kept for API parity with the reference (quantizer.py:241-254)
+    def vq_count_ema_update(self, vq_current_count) -> None:
+        self.vq_count.data.mul_(self.decay).add_(vq_current_count, alpha=1 - self.decay)
+
+    def weight_avg_ema_update(self, vq_current_sum) -> None:
+        self.weight_avg.data.mul_(self.decay).add_(vq_current_sum, alpha=1 - self.decay)
+
+    def weight_update(self) -> None:
+        n = self.vq_count.sum()
+        smoothed = (self.vq_count + self.eps) / (n + self.num_codebook * self.eps) * n
+        self.weight.data.copy_(self.weight_avg / smoothed.unsqueeze(1))
+
+
+class EMAVectorQuantizer(nn.Module, _RestartMixin):
+    """EMA quantiser on flat (n, d) input (model/quantizer.py:257-551)."""
+
+    def __init__(self, num_codebook: int, embed_dim: int, beta: float = 0.25, normalize: Optional[str] = None,
+                 decay: float = 0.99, eps: float = 1e-5, use_restart: bool = False, use_gumbel: bool = False,
+                 use_split: bool = False, use_weighted_sum: bool = False, update_norm: bool = True,
+                 need_initialized: str = "none") -> None:
+        super().__init__()
+        self.num_codebook = num_codebook
+        self.embed_dim = embed_dim
+        self.beta = beta
+        self.decay = decay
+        self.normalize = normalize
+        if normalize == "z_trainable":
+            self.register_buffer("z_mean", torch.zeros(self.embed_dim))
+            self.register_buffer("z_log_var", torch.zeros(self.embed_dim))
+        self.codebook = EmbeddingEMA(self.num_codebook, self.embed_dim, decay=decay, eps=eps)
+        self.register_buffer("vq_count", torch.zeros(self.num_codebook), persistent=False)
+        self.use_restart = use_restart
+        self.use_split = use_split
+        self.use_gumbel = use_gumbel
+        self.need_initialized = need_initialized
+        self.use_weighted_sum = use_weighted_sum
+        self.update_norm = update_norm
+        _check_flags(use_gumbel, use_weighted_sum)
+
+    @torch.no_grad()
+    def restart(self) -> None:
+        if (self.update_indices is not None) and (self.update_candidates is not None):
+            self.codebook.weight.data[self.update_indices] = self.update_candidates
+            self.codebook.reset()
+            self.update_indices = None
+            self.update_candidates = None
+
+    @torch.no_grad()
+    def split(self, vq_current_count: torch.Tensor) -> int:
+        """Replace unused codes by perturbed copies of the most used ones (quantizer.py:330-381)."""
+        update_indices = torch.nonzero(vq_current_count == 0, as_tuple=True)[0]
+        if len(update_indices) == 0:
+            return 0
+        n_update = len(update_indices)
+        update_indices = update_indices[torch.randperm(n_update, device=update_indices.device)]
+        total, weight, weight_avg = self.codebook.vq_count, self.codebook.weight, self.codebook.weight_avg
+        order = torch.sort(total, dim=0, descending=True)[1][:n_update]
+        total_c, weight_c, avg_c = total.clone(), weight.clone(), weight_avg.clone()
+        noise = torch.randn(n_update, self.embed_dim, dtype=weight.dtype, device=weight.device).mul_(0.02)
+        weight_c[update_indices] = weight[order] + noise
+        weight_c[order] = weight[order] - noise
+        total_c[update_indices] = total[order] / 2.0
+        total_c[order] = total[order] / 2.0
+        avg_c[update_indices] = weight_avg[order] / 2.0
+        avg_c[order] = weight_avg[order] / 2.0
+        total.copy_(total_c); weight.copy_(weight_c); weight_avg.copy_(avg_c)
+        self.vq_count.fill_(0)
+        return n_update
+
+    @torch.no_grad()
+    def _maybe_initialize(self, z_flat: torch.Tensor) -> None:
+        """First-training-call codebook initialisation (quantizer.py:399-414); host-side, runs once."""
+        if self.need_initialized != "none" and self.training:
+            if self.need_initialized == "rand":
+                self.prepare_restart(torch.zeros(self.num_codebook, dtype=torch.long, device=z_flat.device), z_flat)
+                self.restart()
+            elif self.need_initialized == "kmeans":
+                from sklearn.cluster import KMeans
+                clustering = KMeans(init="k-means++", n_clusters=self.num_codebook, random_state=0)
+                clustering.fit(z_flat.detach().cpu().numpy())
+                centroids = torch.from_numpy(np.array(clustering.cluster_centers_)).float().to(z_flat.device)
+                self.codebook.weight.data.copy_(centroids)
+                self.codebook.weight_avg.data.copy_(centroids)
+            self.need_initialized = False
+
+    def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor], torch.Tensor]:
+        return _ema_group_forward([self], z)
+
+    def extra_repr(self) -> str:
+        return (f"embed_dim={self.embed_dim}, num_codebook={self.num_codebook}, normalize={self.normalize}, "
+                f"use_split={self.use_split}, use_restart={self.use_restart}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused group forwards (one call for all subspaces)
+# ---------------------------------------------------------------------------------------------------
+def _stack(ts: List[torch.Tensor]) -> torch.Tensor:
+    """[M, ...] tensor of the per-subspace tensors WITHOUT a copy when they are consecutive slices of one
+    storage (the wrapper arranges that for EMA buffers), else torch.stack."""
+    t0 = ts[0]
+    if len(ts) == 1:
+        return t0.unsqueeze(0)
+    step = t0.numel()
+    base = t0.untyped_storage().data_ptr()
+    if all(t.is_contiguous() and t.untyped_storage().data_ptr() == base and
+           t.storage_offset() == t0.storage_offset() + i * step for i, t in enumerate(ts)):
+        return torch.as_strided(t0, (len(ts),) + tuple(t0.shape), (step,) + tuple(t0.stride()), t0.storage_offset())
+    return torch.stack(ts)
+
+
+def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_prob: bool = True):
+    """EMAVectorQuantizer.forward (quantizer.py:383-542) for M = len(mods) subspaces at once; z is flat
+    (n, M*d)."""
+    q0 = mods[0]
+    M, K, mode, beta = len(mods), q0.num_codebook, q0.normalize, q0.beta
+    if z.dim() != 2:
+        raise ValueError("EMAVectorQuantizer expects a flat (n, d) input (model/quantizer.py:396)")
+    d = z.shape[1] // M
+    training = q0.training
+    if q0.need_initialized != "none" and training:
+        for i, q in enumerate(mods):
+            q._maybe_initialize(z[:, i * d:(i + 1) * d])
+    weight = _stack([q.codebook.weight for q in mods])
+    norm_a = norm_b = None
+    if mode == "z_trainable":
+        if training:
+            with torch.no_grad():     # running statistics of z (quantizer.py:432-444)
+                zm = all_reduce_tensor(z.mean(dim=0), op="mean")
+                zsq = all_reduce_tensor((z * z).mean(dim=0), op="mean")
+                logvar = (zsq - zm * zm).log()
+                for i, q in enumerate(mods):
+                    q.z_mean.data.mul_(q.decay).add_(zm[i * d:(i + 1) * d], alpha=1 - q.decay)
+                    q.z_log_var.data.mul_(q.decay).add_(logvar[i * d:(i + 1) * d], alpha=1 - q.decay)
+        norm_a = torch.cat([q.z_mean for q in mods])
+        norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
+    with torch.no_grad():
+        cbn = core.normalize_codebook(weight, mode, ema_style=True)
+        src = cbn if q0.update_norm else weight.clone()
+    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob)
+    output: Dict[str, torch.Tensor] = {}
+    if training:
+        with torch.no_grad():
+            packed = core.ema_statistics(z, idx, K)                                    # :485-491
+            count = packed[:, :, d]
+            # in-place EMA update on the stacked state; zero-copy when the buffers are slices of one
+            # storage (ProductQuantizerWrapper._restack), otherwise stack -> update -> write back
+            state = [[q.vq_count for q in mods], [q.codebook.vq_count for q in mods],
+                     [q.codebook.weight_avg for q in mods], [q.codebook.weight for q in mods]]
+            stacked = [_stack(ts) for ts in state]
+            exact_c, vqc_c, wavg_c, w_c = (t.contiguous() for t in stacked)
+            unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
+            for ts, st in zip(state, (exact_c, vqc_c, wavg_c, w_c)):
+                if st.data_ptr() != ts[0].data_ptr():
+                    for i, t in enumerate(ts):
+                        t.copy_(st[i])
+            output.update(core.percentile_stats(exact_c, "total"))                      # :496
+            output.update(core.percentile_stats(count, "current"))                      # :495
+            if q0.use_restart:
+                for i, q in enumerate(mods):
+                    q.prepare_restart(count[i], z[:, i * d:(i + 1) * d])                # :500-501
+            if q0.use_split:
+                n_split = torch.tensor([float(q.split(count[i])) for i, q in enumerate(mods)], device=z.device)
+            else:
+                n_split = unused.float()
+            output["codebook-usage"] = ((K - n_split) / K).mean()                       # :510
+    commitment = mse_commit.mean()
+    output["loss"] = beta * commitment                                                  # :526
+    output["commitment-loss"] = commitment
+    output["codebook-sum"] = torch.sum(torch.abs(_stack([q.codebook.weight for q in mods]))) / M   # :532
+    return out, output, prob
+
+
+def _param_group_forward(mods: List[VectorQuantizer], z: torch.Tensor, want_prob: bool = True):
+    """VectorQuantizer.forward (quantizer.py:105-189) for M subspaces at once; z is NCHW (B, M*d, h, w)."""
+    q0 = mods[0]
+    M, K, mode, beta = len(mods), q0.num_codebook, q0.normalize, q0.beta
+    if z.dim() != 4:
+        raise ValueError("VectorQuantizer expects a (batch, embed_dim, h, w) input (model/quantizer.py:107)")
+    d = z.shape[1] // M
+    codebook = torch.stack([q.codebook.weight for q in mods])                 # autograd splits the grads back
+    norm_a = norm_b = z_std = None
+    if mode == "z_trainable":
+        norm_a = torch.cat([q.z_mean for q in mods])
+        z_std = torch.stack([q.z_log_var for q in mods]).exp().sqrt()
+        norm_b = z_std.reshape(-1) + 1e-5
+    cbn = core.normalize_codebook(codebook, mode, ema_style=False,
+                                  z_mean=torch.stack([q.z_mean for q in mods]) if mode == "z_trainable" else None,
+                                  z_std=z_std)
+    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, cbn, mode, norm_a, norm_b, want_prob=want_prob)
+    output: Dict[str, torch.Tensor] = {}
+    with torch.no_grad():                                                     # counts are updated in eval too (:158)
+        packed = ops.pq_accumulate(z.detach().float(), idx, K)
+        count = all_reduce_tensor(packed[:, :, d].contiguous(), op="sum")
+        for i, q in enumerate(mods):
+            q.vq_count += count[i]
+        output.update(core.percentile_stats(torch.stack([q.vq_count for q in mods]), "total"))
+        output.update(core.percentile_stats(count, "current"))
+        if q0.use_restart:
+            zf = z.detach().permute(0, 2, 3, 1).reshape(-1, z.shape[1])
+            for i, q in enumerate(mods):
+                q.prepare_restart(count[i], zf[:, i * d:(i + 1) * d])
+    codebook_loss, commitment_loss = mse_cb.mean(), mse_commit.mean()
+    output["loss"] = codebook_loss + beta * commitment_loss                   # :177
+    output["codebook_loss"] = codebook_loss
+    output["commitment_loss"] = commitment_loss
+    return out, output, prob
+
+
+class ProductQuantizerWrapper(nn.Module):
+    """model/quantizer.py:554-614.  ``materialize_prob`` (default True, as the reference always returns
+    it) controls whether the N x (K*num_pq) soft-assignment tensor is produced; set it to False when the
+    caller ignores the third return value (e.g. DIONPQGO, model/dino_pqgo.py:140-154)."""
+
+    def __init__(self, num_pq: int, num_codebook: int, embed_dim: int, beta: float = 0.25,
+                 normalize: Optional[str] = None, decay: float = 0.99, eps: float = 1e-5, use_restart: bool = False,
+                 use_gumbel: bool = False, use_split: bool = False, use_weighted_sum: bool = False,
+                 update_norm: bool = True, need_initialized: str = "none", quantizer_cls=EMAVectorQuantizer) -> None:
+        super().__init__()
+        if embed_dim % num_pq != 0:
+            raise ValueError(f"Embed dim {embed_dim} should be divisible by #PQ {num_pq}.")
+        self.num_pq = num_pq
+        self.pq_dim = embed_dim // num_pq
+        self.materialize_prob = True
+        self.quantizers = nn.ModuleList([
+            quantizer_cls(num_codebook, self.pq_dim, beta=beta, normalize=normalize, decay=decay, eps=eps,
+                          use_restart=use_restart, use_gumbel=use_gumbel, use_split=use_split,
+                          use_weighted_sum=use_weighted_sum, update_norm=update_norm, need_initialized=need_initialized)
+            for _ in range(self.num_pq)
+        ])
+        self._restack()
+
+    # EMA buffers of all subspaces live in one [M, ...] storage each; the per-subspace buffers the state
+    # dict exposes are views into it, so the kernels update every subspace in place with one launch.
+    def _restack(self) -> None:
+        qs = list(self.quantizers)
+        if not qs or not all(isinstance(q, EMAVectorQuantizer) for q in qs):
+            return
+        with torch.no_grad():
+            for owner, name in ((lambda q: q.codebook, "weight"), (lambda q: q.codebook, "weight_avg"),
+                                (lambda q: q.codebook, "vq_count"), (lambda q: q, "vq_count")):
+                stacked = torch.stack([owner(q)._buffers[name] for q in qs]).contiguous()
+                for i, q in enumerate(qs):
+                    owner(q)._buffers[name] = stacked[i]
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._restack()
+        return out
+
+    def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor], torch.Tensor]:
+        qs = list(self.quantizers)
+        if all(isinstance(q, EMAVectorQuantizer) for q in qs):
+            return _ema_group_forward(qs, z, want_prob=self.materialize_prob)
+        if all(isinstance(q, VectorQuantizer) for q in qs):
+            return _param_group_forward(qs, z, want_prob=self.materialize_prob)
+        # heterogeneous / user-supplied quantiser classes: the reference's loop (quantizer.py:589-611)
+        z_split = torch.chunk(z, chunks=self.num_pq, dim=1)
+        z_quantized, distance_prob, outputs = [], [], {}
+        for i in range(self.num_pq):
+            q_i, output_i, prob_i = self.quantizers[i](z_split[i])
+            z_quantized.append(q_i)
+            for k, v in output_i.items():
+                outputs[k] = v if i == 0 else outputs[k] + v
+            distance_prob.append(prob_i)
+        for k in outputs:
+            outputs[k] = outputs[k] / self.num_pq
+        return torch.cat(z_quantized, dim=1), outputs, torch.cat(distance_prob, dim=-1)
+
+    def extra_repr(self) -> str:
+        return f"num_pq={self.num_pq}"

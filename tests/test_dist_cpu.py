@@ -1,0 +1,92 @@
+"""Host-side data-parallel logic on CPU with gloo, world_size 2 (no GPU needed).
+
+The kernels themselves need a B200; what is covered here is the plumbing around them: pixel sharding,
+the clone-and-return contract of all_reduce_tensor, and that ONE all-reduce of the packed [M, K, d+1]
+statistics buffer reproduces the single-process statistics (counts exactly, sums up to fp32 add order),
+so every rank applies an identical EMA update."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import equss_oracle as O
+        from equss_b200 import dist_utils as DU
+        torch.manual_seed(0)                       # same data on every rank, each takes its shard
+        M, K, d, n = 3, 16, 8, 203                 # ragged: 203 pixels over 2 ranks
+        z = torch.randn(n, M * d)
+        w0 = torch.randn(M, K, d)
+        lo, hi = DU.shard_range(n)
+        assert (lo, hi) == ((0, 102) if rank == 0 else (102, 203))
+        # all_reduce_tensor returns a reduced clone and leaves its input alone (utils/dist_utils.py:98-113)
+        t = torch.full((4,), float(rank + 1))
+        r = DU.all_reduce_tensor(t, op="sum")
+        assert torch.equal(t, torch.full((4,), float(rank + 1))) and torch.equal(r, torch.full((4,), 3.0))
+        assert torch.equal(DU.all_reduce_tensor(t, op="mean"), torch.full((4,), 1.5))
+        with pytest.raises(RuntimeError):
+            DU.all_reduce_tensor(t, op="max")
+        # per-rank packed statistics on the shard (oracle arithmetic stands in for K4), one all-reduce (K5)
+        packed = torch.zeros(M, K, d + 1)
+        idx_full = []
+        for m in range(M):
+            zn, cn = O.normalize_pair(z[:, m * d:(m + 1) * d], w0[m], "l2")
+            idx = torch.argmin(O.sq_distance(zn, cn), dim=1)
+            idx_full.append(idx)
+            oh = torch.nn.functional.one_hot(idx[lo:hi], K).float()
+            packed[m, :, :d] = oh.t() @ z[lo:hi, m * d:(m + 1) * d]
+            packed[m, :, d] = oh.sum(0)
+        DU.all_reduce_packed_(packed)
+        for m in range(M):
+            oh = torch.nn.functional.one_hot(idx_full[m], K).float()
+            assert torch.equal(packed[m, :, d], oh.sum(0))                                     # counts: exact
+            torch.testing.assert_close(packed[m, :, :d], oh.t() @ z[:, m * d:(m + 1) * d], rtol=1e-5, atol=1e-5)
+        # identical EMA update on every rank -> replicas stay bit-identical
+        st = O.EmaState(w0[0])
+        st.update(packed[0, :, d], packed[0, :, :d])
+        gathered = [torch.empty_like(st.weight) for _ in range(world)]
+        dist.all_gather(gathered, st.weight)
+        assert torch.equal(gathered[0], gathered[1])
+        ret[rank] = "ok"
+    except BaseException as e:   # noqa
+        ret[rank] = f"{type(e).__name__}: {e}"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
+
+
+def test_single_process_helpers_are_identity():
+    sys.path.insert(0, ROOT)
+    from equss_b200 import dist_utils as DU
+    t = torch.arange(4.0)
+    assert DU.all_reduce_tensor(t) is t                    # reference returns the input itself (dist_utils.py:99-100)
+    assert DU.all_reduce_packed_(t) is t
+    assert DU.get_world_size() == 1 and DU.get_rank() == 0
+    assert DU.shard_range(10, 1, 4) == (3, 6) and DU.shard_range(10, 3, 4) == (9, 10)
