@@ -91,7 +91,7 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    n_img = 1
+    n_img = 4
     step, px = cpu_pipeline_factory(n_img)
     ts = time_cpu(step, args.warmup, args.steps)
     total = sum(ts)
@@ -343,10 +343,11 @@ def run_equss(args):
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline and not train:
         torch.set_num_threads(os.cpu_count() or 1)
-        cstep, px = cpu_pipeline_factory(1)
-        ts = time_cpu(cstep, 1, 2)
+        n_img = 8
+        cstep, px = cpu_pipeline_factory(n_img)
+        ts = time_cpu(cstep, 1, 8)
         cpu_base = {"value": px * len(ts) / sum(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                    "sample": f"1 of {B} images ({px} pixels) x {len(ts)} timed runs of the oracle port "
+                    "sample": f"{n_img} of {B} images ({px} pixels) x {len(ts)} timed runs of the oracle port "
                               f"(PQ loop + evaluator + 2 confusion updates), {sum(ts):.1f} s of CPU work"}
 
     line = {
@@ -370,8 +371,8 @@ def run_equss(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="equss", choices=["equss", "reference"])
     ap.add_argument("--workload", default="cocostuff27_eval", choices=["cocostuff27_eval", "pq_train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -122,14 +122,17 @@ class UnSegEvaluator(nn.Module):
     def _losses(self, out: torch.Tensor, label: torch.Tensor, cluster_preds: torch.Tensor):
         B, D, h, w = out.shape
         H, W = label.shape[-2:]
-        lin_low = self.linear_probe(out)                                                   # :67 at token resolution
+        C = self.num_classes
+        # fp32 contraction (cuDNN convolutions default to TF32, which is not within the 1e-5 parity bar)
+        lin_low = torch.einsum("bchw,nc->bnhw", out, self.linear_probe.weight.view(C, D)) + \
+            self.linear_probe.bias.view(1, C, 1, 1)                                         # :67 at token resolution
         lin_up = F.interpolate(lin_low, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else lin_low
         label_flat = label.reshape(-1)
         mask = torch.logical_and(label_flat >= 0, label_flat < self.num_classes)           # :73
         logit_flat = lin_up.permute(0, 2, 3, 1).reshape(-1, self.num_classes)
         linear_loss = self.linear_loss(logit_flat[mask], label_flat[mask]).mean()          # :80
         nc = F.normalize(self.cluster_probe.clusters, dim=1)
-        inner_low = F.conv2d(out, nc[:, :, None, None])
+        inner_low = torch.einsum("bchw,nc->bnhw", out, nc)
         inner_up = F.interpolate(inner_low, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else inner_low
         norm = _upsampled_feature_norm(out, H, W).clamp_min(1e-12)
         picked = inner_up.gather(1, cluster_preds.unsqueeze(1)).squeeze(1) / norm
