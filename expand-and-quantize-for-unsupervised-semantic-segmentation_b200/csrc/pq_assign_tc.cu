@@ -11,10 +11,11 @@
 //   s_k with an absolute error below ~1e-6 * R,  R = |z| max|c| + max|c|^2/2.
 //
 // Exact argmin from an approximate GEMM
-//   Each accumulator is mapped to a fixed-point key  (round(s_k * 2^20 / R) << 8) | (255 - column)
+//   Each accumulator is mapped to a fixed-point key  (round(s_k * 2^20 / R) << 8) | (255 - column/16)
 //   with one FFMA (magic-number rounding) and one IMAD; keys are positive normal floats as bit patterns,
-//   so "largest s, lowest index on ties" is a plain float max (3-input FMNMX3).  Two orthogonal column
-//   partitions (column mod 16 and column div 16) give the exact runner-up key at ~1.2 ALU ops/element.
+//   so "largest s, lowest group on ties" is a plain float max (3-input FMNMX3).  Two orthogonal column
+//   partitions (column mod 16: 16 running class maxima; column div 16: group maxima, id in the key's
+//   low byte) identify the winning column and give the exact runner-up key at ~1.2 ALU ops/element.
 //   If the best and the runner-up differ by more than 16 quanta (>> the error bound) the winner is the
 //   fp32 argmin with certainty; otherwise (about 1e-4 of the rows) the thread re-scores the candidate
 //   columns with the exact fp32 expression in the reference's association order -- the same code path
@@ -91,6 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);                         // do not steal issue slots from the working warps of this SMSP
     if (clock64() - t0 > 4000000000LL) {   // ~2 s
       printf("equss tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", blockIdx.x, threadIdx.x, tag,
              parity);
@@ -182,6 +184,37 @@ __host__ __device__ constexpr uint32_t make_idesc(int N) {
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// 2^20 / R with R >= |z| max|c| + max|c|^2 / 2 (a bound on |s_k|).  Only monotonicity and the bound matter,
+// so approximate sqrt / reciprocal are fine; 2% slack covers their error.
+__device__ __forceinline__ float key_scale(float zn2, float cmax, float cmax2) {
+  float R = 1.02f * (__fsqrt_rn(zn2) * cmax + 0.5f * cmax2);
+  return (R > 0.f) ? __fdividef((float)(1 << kQuantBits), R) : 0.f;
+}
+
+// One 32-column chunk of accumulators -> keys -> class maxima (column mod 16) and top-2 group maxima.
+// `gid` is the index of the chunk's first 16-column group; the key's low byte is 255 - group.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float scale, int gid, float (&cls)[16], float& m1,
+                                          float& m2) {
+  float key[32];
+  const uint32_t a0 = (uint32_t)(255 - gid), a1 = a0 - 1u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    key[j] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j]), scale, kMagic)) * 256u + a0);
+    key[j + 16] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j + 16]), scale, kMagic)) * 256u + a1);
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], key[r], key[r + 16]);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const float* k = key + 16 * g;
+    float t0 = max3f(k[0], k[1], k[2]), t1 = max3f(k[3], k[4], k[5]), t2 = max3f(k[6], k[7], k[8]);
+    float t3 = max3f(k[9], k[10], k[11]), t4 = max3f(k[12], k[13], k[14]);
+    float gm = max3f(max3f(t0, t1, t2), max3f(t3, t4, k[15]), 0.f);
+    m2 = fmaxf(m2, fminf(m1, gm));
+    m1 = fmaxf(m1, gm);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // B operand image builder: one block per (subspace, code chunk)
@@ -435,8 +468,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         // flat: raw[row][D]; LPS lanes per row, one float4 each
         constexpr int ROWS_PER_PASS = 128 / LPS;
         const int l = ct % LPS;
-#pragma unroll
-        for (int pass = 0; pass < kTileM / ROWS_PER_PASS; ++pass) {
+#pragma unroll 1
+        for (int pass = 0; pass < kTileM / ROWS_PER_PASS; ++pass) {   // rolled: keeps the role's code in the I-cache
           const int row = pass * ROWS_PER_PASS + ct / LPS;
           float4 v = *reinterpret_cast<const float4*>(raw + row * D + l * 4);
           RowNorm rn; rn.shift = 0.f; rn.denom = 1.f;
@@ -467,8 +500,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           *reinterpret_cast<float4*>(rowp + (LPS + l) * 128) = lo;
           if (l == 0) {
             s_zn2[a * kTileM + row] = zn2;
-            float R = sqrtf(zn2) * cmax + 0.5f * cmax2;
-            s_scale[a * kTileM + row] = (R > 0.f) ? (float)(1 << kQuantBits) / R : 0.f;
+            s_scale[a * kTileM + row] = key_scale(zn2, cmax, cmax2);
           }
         }
       } else {
@@ -513,8 +545,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           *reinterpret_cast<float4*>(rowp + (LPS + q) * 128) = lo;
         }
         s_zn2[a * kTileM + row] = zn2;
-        float R = sqrtf(zn2) * cmax + 0.5f * cmax2;
-        s_scale[a * kTileM + row] = (R > 0.f) ? (float)(1 << kQuantBits) / R : 0.f;
+        s_scale[a * kTileM + row] = key_scale(zn2, cmax, cmax2);
       }
       fence_proxy_async();     // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -545,28 +576,20 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) cls[r] = 0.f;
       float m1 = 0.f, m2 = 0.f;                   // best / second-best 16-column group maxima
-      uint32_t v[2][32];
-      tmem_ld32(taddr, v[0]);
-#pragma unroll
-      for (int c = 0; c < NC / 32; ++c) {
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+      if constexpr (NC == 32) {
         tmem_ld_wait();
-        if (c + 1 < NC / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-        float key[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float uq = fmaf(__uint_as_float(v[c & 1][j]), scale, kMagic);
-          key[j] = __uint_as_float(__float_as_uint(uq) * 256u + (uint32_t)(255 - (c * 32 + j)));
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], key[r], key[r + 16]);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const float* k = key + 16 * g;
-          float t0 = max3f(k[0], k[1], k[2]), t1 = max3f(k[3], k[4], k[5]), t2 = max3f(k[6], k[7], k[8]);
-          float t3 = max3f(k[9], k[10], k[11]), t4 = max3f(k[12], k[13], k[14]);
-          float gm = max3f(max3f(t0, t1, t2), max3f(t3, t4, k[15]), 0.f);
-          m2 = fmaxf(m2, fminf(m1, gm));
-          m1 = fmaxf(m1, gm);
+        epi_chunk(va, scale, 0, cls, m1, m2);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NC / 32; c += 2) {      // rolled (two chunks per trip): small I-cache footprint
+          tmem_ld_wait();
+          tmem_ld32(taddr + (c + 1) * 32, vb);
+          epi_chunk(va, scale, 2 * c, cls, m1, m2);
+          tmem_ld_wait();
+          if (c + 2 < NC / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+          epi_chunk(vb, scale, 2 * c + 2, cls, m1, m2);
         }
       }
       // accumulator fully consumed -> hand the TMEM buffer back to the MMA warp
@@ -575,10 +598,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if (lane == 0) mbar_arrive(t_empty + t);
 
       const uint32_t k1 = __float_as_uint(m1);
-      const int col1 = 255 - (int)(k1 & 0xFFu);
+      // winning column = (group from the key's low byte) * 16 + (class whose running maximum is the key)
+      int r1 = 0;
+#pragma unroll
+      for (int r = 15; r >= 0; --r) r1 = (cls[r] == m1) ? r : r1;
+      const int col1 = (255 - (int)(k1 & 0xFFu)) * 16 + r1;
       float runner = m2;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) runner = fmaxf(runner, ((col1 & 15) == r) ? 0.f : cls[r]);
+      for (int r = 0; r < 16; ++r) runner = fmaxf(runner, (r1 == r) ? 0.f : cls[r]);
       const int gap = (int)(k1 >> 8) - (int)(__float_as_uint(runner) >> 8);
       const int kvalid = min(NC, p.K - chunk * NC);
       int best_col = col1;
@@ -747,8 +774,11 @@ int assign_tc_launch(const float* z, const equss_zdesc* zd, const float* codeboo
     cuuint64_t gstr[1] = {(cuuint64_t)zd->dim * 4};
     cuuint32_t box[2] = {(cuuint32_t)d, (cuuint32_t)kTileM};
     cuuint32_t estr[2] = {1, 1};
+    // rows of a box are d*4 bytes; promoting 64-byte rows to 128-byte L2 fetches doubles the DRAM traffic
+    // (the other half of the line belongs to the neighbouring subspace, read much later by another CTA)
     cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)z, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                CU_TENSOR_MAP_SWIZZLE_NONE, d * 4 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const long long B = zd->n_pixels / zd->hw;
     cuuint64_t gdim[3] = {(cuuint64_t)zd->hw, (cuuint64_t)zd->dim, (cuuint64_t)B};
