@@ -45,6 +45,13 @@ constexpr int kConvWarp0 = 2, kEpiWarp0 = 6;
 constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23: float spacing 1 -> fma(v, S, kMagic) rounds v*S
 constexpr int kQuantBits = 20;              // keys resolve R / 2^20
 constexpr int kTolQuanta = 16;              // ambiguity threshold in quanta
+// key = bits(fma(v, S, kMagic)) * 257 + addend  (mod 2^32).  257 is not a power of two, so ptxas keeps the
+// multiply-add on the FMA pipe (IMAD) instead of an ALU-pipe LEA; with bits = 0x4B400000 + n the product is
+// 0x8B400000 + 257 n, and kKeyBias recentres it to 0x40000000 + 257 n + (255 - group): positive normal
+// floats whose float order is (n, lower group first).  n = (key - 0x40000000) / 257, group byte = remainder.
+constexpr uint32_t kKeyMul = 257u;
+constexpr uint32_t kKeyBias = 0x40000000u - 0x8B400000u;
+constexpr uint32_t kKeyBase = 0x40000000u;
 
 __host__ __device__ constexpr int kch(int D) { return (2 * D + 8) / 4; }          // 16-byte K chunks per row
 __host__ __device__ constexpr int sbo_bytes(int D) { return kch(D) * 128 + 16; }  // 8-row group stride (padded)
@@ -161,6 +168,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// quanta (signed) encoded in a key; key 0 (the "empty" initial value) maps far below every real key
+__device__ __forceinline__ int key_quanta(uint32_t key) {
+  return (key == 0u) ? -(1 << 30) : (int)((key - kKeyBase + (kKeyMul << 22)) / kKeyMul) - (1 << 22);
+}
+
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -197,11 +209,12 @@ __device__ __forceinline__ float key_scale(float zn2, float cmax, float cmax2) {
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float scale, int gid, float (&cls)[16], float& m1,
                                           float& m2) {
   float key[32];
-  const uint32_t a0 = (uint32_t)(255 - gid), a1 = a0 - 1u;
+  uint32_t a0 = kKeyBias + (uint32_t)(255 - gid), a1 = a0 - 1u;
+  asm volatile("" : "+r"(a0), "+r"(a1));      // opaque: one addend register per 16-column group, no re-basing
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    key[j] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j]), scale, kMagic)) * 256u + a0);
-    key[j + 16] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j + 16]), scale, kMagic)) * 256u + a1);
+    key[j] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j]), scale, kMagic)) * kKeyMul + a0);
+    key[j + 16] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j + 16]), scale, kMagic)) * kKeyMul + a1);
   }
 #pragma unroll
   for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], key[r], key[r + 16]);
@@ -298,6 +311,24 @@ struct Params {
   unsigned long long* merged;   // nullptr when nchunks == 1
 };
 
+// Walks the CTA's contiguous unit range without per-unit divisions.
+struct UnitIter {
+  int slot, tile, m, chunk, n_tiles, nchunks;
+  __device__ __forceinline__ void init(long long u0, int n_tiles_, int nchunks_) {
+    n_tiles = n_tiles_; nchunks = nchunks_;
+    slot = (int)(u0 / n_tiles_);
+    tile = (int)(u0 - (long long)slot * n_tiles_);
+    m = slot / nchunks_;
+    chunk = slot - m * nchunks_;
+  }
+  __device__ __forceinline__ void next() {
+    if (++tile == n_tiles) {
+      tile = 0; ++slot;
+      if (++chunk == nchunks) { chunk = 0; ++m; }
+    }
+  }
+};
+
 // exact fp32 distance of code row r (chunk-local) for pixel row `row`, both reconstructed from hi+lo
 template <int D>
 __device__ __forceinline__ float exact_distance(const uint8_t* a_tile, const uint8_t* b_tile, int row, int r, float zn2) {
@@ -335,7 +366,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   static_assert(D % 8 == 0 && D <= 64, "D must be a multiple of 8, at most 64");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align inside the shared window without laundering the pointer through an integer (which would turn
+  // every shared-memory access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_b = smem;
   uint8_t* s_a = s_b + B_BYTES;
   uint8_t* s_rawt = s_a + ABUFS * A_BYTES;
@@ -383,19 +416,17 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      for (int i = 0; i < n_units; ++i) {
-        const long long u = u0 + i;
-        const int slot = (int)(u / p.n_tiles);
-        const long long tile = u - (long long)slot * p.n_tiles;
-        const int m = slot / p.nchunks;
+      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
+      for (int i = 0; i < n_units; ++i, it.next()) {
+        const int tile = it.tile, m = it.m;
         const int s = i % STAGES;
         mbar_wait(raw_empty + s, ((i / STAGES) & 1) ^ 1, 10 + s);
         mbar_expect_tx(raw_full + s, RAW_BYTES);
         if (!p.nchw) {
-          tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, (int)(tile * kTileM), raw_full + s);
+          tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, tile * kTileM, raw_full + s);
         } else {
-          const int b = (int)(tile / p.tiles_per_image);
-          const int t = (int)(tile - (long long)b * p.tiles_per_image);
+          const int b = tile / p.tiles_per_image;
+          const int t = tile - b * p.tiles_per_image;
           tma_load_3d(s_rawt + s * RAW_BYTES, &tmap, t * kTileM, m * D, b, raw_full + s);
         }
       }
@@ -403,9 +434,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     int b_loads = 0, cur_slot = -1;
-    for (int i = 0; i < n_units; ++i) {
-      const long long u = u0 + i;
-      const int slot = (int)(u / p.n_tiles);
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
+    for (int i = 0; i < n_units; ++i, it.next()) {
+      const int slot = it.slot;
       const int a = i % ABUFS, t = i & 1;
       if (slot != cur_slot) {
         mbar_wait(b_full, b_loads & 1, 20);
@@ -442,10 +473,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int ct = threadIdx.x - kConvWarp0 * 32;   // 0..127
     int b_loads = 0, cur_slot = -1;
     float cmax = 0.f, cmax2 = 0.f;
-    for (int i = 0; i < n_units; ++i) {
-      const long long u = u0 + i;
-      const int slot = (int)(u / p.n_tiles);
-      const int m = slot / p.nchunks;
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
+    for (int i = 0; i < n_units; ++i, it.next()) {
+      const int slot = it.slot, m = it.m;
       const int a = i % ABUFS, s = i % STAGES;
       mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (slot != cur_slot) {
@@ -556,11 +586,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     int b_loads = 0, cur_slot = -1;
-    for (int i = 0; i < n_units; ++i) {
-      const long long u = u0 + i;
-      const int slot = (int)(u / p.n_tiles);
-      const long long tile = u - (long long)slot * p.n_tiles;
-      const int m = slot / p.nchunks, chunk = slot % p.nchunks;
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
+    for (int i = 0; i < n_units; ++i, it.next()) {
+      const int slot = it.slot, tile = it.tile, m = it.m, chunk = it.chunk;
       const int a = i % ABUFS, t = i & 1;
       if (slot != cur_slot) {
         mbar_wait(b_full, b_loads & 1, 40);
@@ -602,11 +630,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       int r1 = 0;
 #pragma unroll
       for (int r = 15; r >= 0; --r) r1 = (cls[r] == m1) ? r : r1;
-      const int col1 = (255 - (int)(k1 & 0xFFu)) * 16 + r1;
+      const uint32_t t1 = k1 - kKeyBase + (kKeyMul << 22);           // 257 * (n + 2^22) + group byte, positive
+      const int col1 = (255 - (int)(t1 - (t1 / kKeyMul) * kKeyMul)) * 16 + r1;
       float runner = m2;
 #pragma unroll
       for (int r = 0; r < 16; ++r) runner = fmaxf(runner, (r1 == r) ? 0.f : cls[r]);
-      const int gap = (int)(k1 >> 8) - (int)(__float_as_uint(runner) >> 8);
+      const int gap = key_quanta(k1) - key_quanta(__float_as_uint(runner));
       const int kvalid = min(NC, p.K - chunk * NC);
       int best_col = col1;
       const uint8_t* a_tile = s_a + a * A_BYTES;
@@ -615,14 +644,14 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       bool have_dist = false;
       if (gap < kTolQuanta || col1 >= kvalid) {
         // ambiguous row: exact fp32 re-score of every column whose class maximum is within tolerance
-        const uint32_t thr = (k1 >> 8) - (uint32_t)kTolQuanta;
+        const int thr = key_quanta(k1) - kTolQuanta;
         best_dist = INFINITY; best_col = 0;
 #pragma unroll 1
         for (int r = 0; r < 16; ++r) {
           float cr = 0.f;
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) cr = (rr == r) ? cls[rr] : cr;
-          if ((__float_as_uint(cr) >> 8) + 0u < thr && col1 < kvalid) continue;
+          if (key_quanta(__float_as_uint(cr)) < thr && col1 < kvalid) continue;
 #pragma unroll 1
           for (int col = r; col < kvalid; col += 16) {
             float dd = exact_distance<D>(a_tile, s_b, row, col, zn2);
@@ -635,11 +664,11 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       long long n;
       bool live;
       if (!p.nchw) {
-        n = tile * kTileM + row;
+        n = (long long)tile * kTileM + row;
         live = n < p.n_pixels;
       } else {
         const long long b = tile / p.tiles_per_image;
-        const long long sidx = (tile - b * p.tiles_per_image) * kTileM + row;
+        const long long sidx = (long long)(tile - (int)b * p.tiles_per_image) * kTileM + row;
         live = sidx < p.hw;
         n = b * p.hw + sidx;
       }
