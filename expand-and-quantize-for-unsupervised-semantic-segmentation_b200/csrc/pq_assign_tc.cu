@@ -329,6 +329,23 @@ struct UnitIter {
   }
 };
 
+// canonical sum z_norm^2 of pixel row `row`, reconstructed from the hi/lo A tile (same association order as
+// every other kernel: group-of-four fma chains combined by a butterfly)
+template <int D>
+__device__ __forceinline__ float exact_zn2(const uint8_t* a_tile, int row) {
+  constexpr int SBO = sbo_bytes(D);
+  constexpr int G = D / 4;
+  const uint8_t* ap = a_tile + (row / 8) * SBO + (row % 8) * 16;
+  float g[G];
+#pragma unroll
+  for (int jc = 0; jc < G; ++jc) {
+    float4 zh = *reinterpret_cast<const float4*>(ap + jc * 128);
+    float4 zl = *reinterpret_cast<const float4*>(ap + (G + jc) * 128);
+    g[jc] = group_sumsq(zh.x + zl.x, zh.y + zl.y, zh.z + zl.z, zh.w + zl.w);
+  }
+  return butterfly_array<G>(g);
+}
+
 // exact fp32 distance of code row r (chunk-local) for pixel row `row`, both reconstructed from hi+lo
 template <int D>
 __device__ __forceinline__ float exact_distance(const uint8_t* a_tile, const uint8_t* b_tile, int row, int r, float zn2) {
@@ -480,7 +497,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (slot != cur_slot) {
         // every earlier unit must be fully retired before the B image is overwritten
-        if (ABUFS == 2 && i >= 1) mbar_wait(a_empty + ((i - 1) % ABUFS), ((i - 1) / ABUFS) & 1, 31);
+#pragma unroll
+        for (int back = 1; back < ABUFS; ++back)
+          if (i >= back) mbar_wait(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
         if (ct == 0) {
           mbar_expect_tx(b_full, (uint32_t)p.img_bytes);
           bulk_load_1d(s_b, p.images + (size_t)slot * p.img_bytes, (uint32_t)p.img_bytes, b_full);
@@ -498,8 +517,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         // flat: raw[row][D]; LPS lanes per row, one float4 each
         constexpr int ROWS_PER_PASS = 128 / LPS;
         const int l = ct % LPS;
-#pragma unroll 1
-        for (int pass = 0; pass < kTileM / ROWS_PER_PASS; ++pass) {   // rolled: keeps the role's code in the I-cache
+#pragma unroll
+        for (int pass = 0; pass < kTileM / ROWS_PER_PASS; ++pass) {   // independent passes: unrolled for ILP
           const int row = pass * ROWS_PER_PASS + ct / LPS;
           float4 v = *reinterpret_cast<const float4*>(raw + row * D + l * 4);
           RowNorm rn; rn.shift = 0.f; rn.denom = 1.f;
@@ -521,17 +540,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             zn.x = apply_norm(v.x, rn, p.norm_mode); zn.y = apply_norm(v.y, rn, p.norm_mode);
             zn.z = apply_norm(v.z, rn, p.norm_mode); zn.w = apply_norm(v.w, rn, p.norm_mode);
           }
-          float zn2 = butterfly_lanes<LPS>(group_sumsq(zn.x, zn.y, zn.z, zn.w));
           float4 hi, lo;
           hi.x = tf32_hi(zn.x); hi.y = tf32_hi(zn.y); hi.z = tf32_hi(zn.z); hi.w = tf32_hi(zn.w);
           lo.x = zn.x - hi.x; lo.y = zn.y - hi.y; lo.z = zn.z - hi.z; lo.w = zn.w - hi.w;
           uint8_t* rowp = a_tile + (row / 8) * SBO + (row % 8) * 16;
           *reinterpret_cast<float4*>(rowp + l * 128) = hi;
           *reinterpret_cast<float4*>(rowp + (LPS + l) * 128) = lo;
-          if (l == 0) {
-            s_zn2[a * kTileM + row] = zn2;
-            s_scale[a * kTileM + row] = key_scale(zn2, cmax, cmax2);
-          }
+          // |z_norm|^2 for the key scale only needs to be an upper bound (exact value: lazily in the
+          // ambiguous path); 1 for l2, else a cheap butterfly
+          float zn2b;
+          if (p.norm_mode == EQUSS_NORM_L2) zn2b = 1.0001f;
+          else zn2b = 1.0001f * butterfly_lanes<LPS>(group_sumsq(zn.x, zn.y, zn.z, zn.w));
+          if (l == 0) s_scale[a * kTileM + row] = key_scale(zn2b, cmax, cmax2);
         }
       } else {
         // NCHW: raw[channel][128 pixels]; one thread per pixel row
@@ -574,8 +594,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           *reinterpret_cast<float4*>(rowp + q * 128) = hi;
           *reinterpret_cast<float4*>(rowp + (LPS + q) * 128) = lo;
         }
-        s_zn2[a * kTileM + row] = zn2;
-        s_scale[a * kTileM + row] = key_scale(zn2, cmax, cmax2);
+        s_scale[a * kTileM + row] = key_scale(1.0001f * zn2, cmax, cmax2);
       }
       fence_proxy_async();     // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -639,12 +658,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const int kvalid = min(NC, p.K - chunk * NC);
       int best_col = col1;
       const uint8_t* a_tile = s_a + a * A_BYTES;
-      const float zn2 = s_zn2[a * kTileM + row];
+      float zn2 = 0.f;
       float best_dist = 0.f;
       bool have_dist = false;
       if (gap < kTolQuanta || col1 >= kvalid) {
         // ambiguous row: exact fp32 re-score of every column whose class maximum is within tolerance
         const int thr = key_quanta(k1) - kTolQuanta;
+        zn2 = exact_zn2<D>(a_tile, row);
         best_dist = INFINITY; best_col = 0;
 #pragma unroll 1
         for (int r = 0; r < 16; ++r) {
@@ -675,7 +695,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if (p.merged == nullptr) {
         if (live) p.idx_out[(long long)m * p.n_pixels + n] = best_col;
       } else {
-        if (!have_dist) best_dist = exact_distance<D>(a_tile, s_b, row, best_col, zn2);
+        if (!have_dist) best_dist = exact_distance<D>(a_tile, s_b, row, best_col, exact_zn2<D>(a_tile, row));
         if (live) {
           unsigned long long packed = ((unsigned long long)sortable(best_dist) << 32) |
                                       (unsigned long long)(uint32_t)(chunk * NC + best_col);
@@ -730,7 +750,7 @@ static Plan make_plan(int K, int d) {
   while (nc < pl.NC) nc <<= 1;
   pl.NC = nc;
   pl.nchunks = (K + pl.NC - 1) / pl.NC;
-  pl.abufs = (d == 64) ? 1 : 2;
+  pl.abufs = (d == 64) ? 1 : (d == 32) ? 2 : 3;
   pl.stages = (d == 8) ? 8 : (d == 16) ? 8 : (d == 32) ? 4 : 2;
   pl.ok = true;
   return pl;
@@ -833,8 +853,8 @@ int assign_tc_launch(const float* z, const equss_zdesc* zd, const float* codeboo
   int rc = EQUSS_ERR_UNSUPPORTED;
 #define EQUSS_TC_CASE(DV, NCV, STV, ABV) \
   if (d == DV && pl.NC == NCV) rc = launch_instance<DV, NCV, STV, ABV>(tmap, p, grid, st);
-  EQUSS_TC_CASE(8, 32, 8, 2) EQUSS_TC_CASE(8, 64, 8, 2) EQUSS_TC_CASE(8, 128, 8, 2) EQUSS_TC_CASE(8, 256, 8, 2)
-  EQUSS_TC_CASE(16, 32, 8, 2) EQUSS_TC_CASE(16, 64, 8, 2) EQUSS_TC_CASE(16, 128, 8, 2) EQUSS_TC_CASE(16, 256, 8, 2)
+  EQUSS_TC_CASE(8, 32, 8, 3) EQUSS_TC_CASE(8, 64, 8, 3) EQUSS_TC_CASE(8, 128, 8, 3) EQUSS_TC_CASE(8, 256, 8, 3)
+  EQUSS_TC_CASE(16, 32, 8, 3) EQUSS_TC_CASE(16, 64, 8, 3) EQUSS_TC_CASE(16, 128, 8, 3) EQUSS_TC_CASE(16, 256, 8, 3)
   EQUSS_TC_CASE(32, 32, 4, 2) EQUSS_TC_CASE(32, 64, 4, 2) EQUSS_TC_CASE(32, 128, 4, 2) EQUSS_TC_CASE(32, 256, 4, 2)
   EQUSS_TC_CASE(64, 32, 2, 1) EQUSS_TC_CASE(64, 64, 2, 1) EQUSS_TC_CASE(64, 128, 2, 1)
 #undef EQUSS_TC_CASE
