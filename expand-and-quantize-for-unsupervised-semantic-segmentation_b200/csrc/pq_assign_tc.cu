@@ -1,233 +1,14 @@
-// pq_assign_tc.cu -- K1 on the 5th-generation tensor cores: per-subspace squared-L2 argmin as a
-// tcgen05 / TMEM GEMM with a fused, exact argmin epilogue (model/quantizer.py:457-467).
-//
-// Arithmetic
-//   argmin_k (|z|^2 + |c_k|^2) - 2<z,c_k>  ==  argmax_k  s_k := <z,c_k> - |c_k|^2/2.
-//   tcgen05 has no fp32-input MMA, so the contraction runs as split-tf32 ("3xTF32"):
-//     x = x_hi + x_lo,  x_hi = x & 0xffffe000 (exact tf32),  x_lo = x - x_hi (exact in fp32)
-//     <z,c> ~= z_hi.c_hi + z_lo.c_hi + z_hi.c_lo          (dropped term and tf32 rounding of x_lo: 2^-21)
-//   and -|c_k|^2/2 enters the same accumulator through 8 augmented K columns: the A row carries
-//   (1,1,1,0,..), the B row three exact tf32 pieces h+m+l = -cn2/2.  The accumulator therefore holds
-//   s_k with an absolute error below ~1e-6 * R,  R = |z| max|c| + max|c|^2/2.
-//
-// Exact argmin from an approximate GEMM
-//   Each accumulator is mapped to a fixed-point key  (round(s_k * 2^20 / R) << 8) | (255 - column/16)
-//   with one FFMA (magic-number rounding) and one IMAD; keys are positive normal floats as bit patterns,
-//   so "largest s, lowest group on ties" is a plain float max (3-input FMNMX3).  Two orthogonal column
-//   partitions (column mod 16: 16 running class maxima; column div 16: group maxima, id in the key's
-//   low byte) identify the winning column and give the exact runner-up key at ~1.2 ALU ops/element.
-//   If the best and the runner-up differ by more than 16 quanta (>> the error bound) the winner is the
-//   fp32 argmin with certainty; otherwise (about 1e-4 of the rows) the thread re-scores the candidate
-//   columns with the exact fp32 expression in the reference's association order -- the same code path
-//   as the SIMT kernel, so both kernels return identical indices.
-//
-// Structure (one persistent CTA per SM, 10 warps):
-//   warp 0      TMA producer: 128-pixel x d-float boxes of z into a ring of raw stages
-//   warp 1      MMA issuer (one elected lane): 3*d/8+1 tcgen05.mma.kind::tf32 per tile, 128 x NC x 8
-//   warps 2-5   convert: raw tile -> normalise (canonical order) -> hi/lo split -> UMMA K-major,
-//               no-swizzle core-matrix layout; per-row |z_norm|^2 and key scale
-//   warps 6-9   epilogue: tcgen05.ld 32 columns at a time, keys, partitions, ambiguity check, index
-//   Accumulators are double-buffered in TMEM (2 x NC columns), the A operand in shared memory.
-//   A CTA walks a contiguous range of units ordered (subspace, code chunk, pixel tile), so the
-//   prepared B operand image (built once per call by a small kernel) is bulk-copied only when the
-//   (subspace, chunk) slot changes.
-#include <cuda.h>
-#include <cstdio>
-#include "equss_common.cuh"
-#include "pq_assign.h"
+// pq_assign_tc.cu -- host side of the tcgen05 assign kernel (see pq_assign_tc_kernel.cuh for the design):
+// shape planning, B-operand image construction, TMA descriptor, dispatch to the per-d translation units.
+#include "pq_assign_tc_kernel.cuh"
 
 namespace equss {
 namespace tc {
 
-constexpr int kTileM = 128;                 // pixels per tile (= TMEM lanes)
-constexpr int kThreads = 320;
-constexpr int kConvWarp0 = 2, kEpiWarp0 = 6;
-constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23: float spacing 1 -> fma(v, S, kMagic) rounds v*S
-constexpr int kQuantBits = 20;              // keys resolve R / 2^20
-constexpr int kTolQuanta = 16;              // ambiguity threshold in quanta
-// key = bits(fma(v, S, kMagic)) * 257 + addend  (mod 2^32).  257 is not a power of two, so ptxas keeps the
-// multiply-add on the FMA pipe (IMAD) instead of an ALU-pipe LEA; with bits = 0x4B400000 + n the product is
-// 0x8B400000 + 257 n, and kKeyBias recentres it to 0x40000000 + 257 n + (255 - group): positive normal
-// floats whose float order is (n, lower group first).  n = (key - 0x40000000) / 257, group byte = remainder.
-constexpr uint32_t kKeyMul = 257u;
-constexpr uint32_t kKeyBias = 0x40000000u - 0x8B400000u;
-constexpr uint32_t kKeyBase = 0x40000000u;
-
-__host__ __device__ constexpr int kch(int D) { return (2 * D + 8) / 4; }          // 16-byte K chunks per row
-__host__ __device__ constexpr int sbo_bytes(int D) { return kch(D) * 128 + 16; }  // 8-row group stride (padded)
-
-struct Cfg {
-  int D, NC, stages, a_bufs;
-};
-// shared-memory plan (bytes) -- must match the carve-up in the kernel
-__host__ __device__ constexpr int b_bytes(int D, int NC) { return (NC / 8) * sbo_bytes(D) + 128; }
-__host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * sbo_bytes(D); }
-__host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
-__host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
-__host__ __device__ constexpr int smem_bytes(int D, int NC, int stages, int a_bufs) {
-  return 1024 /*alignment slack*/ + align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) +
-         stages * raw_bytes(D) + a_bufs * kTileM * 8 /*zn2 + scale*/ + 256 /*barriers*/;
-}
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(32);                         // do not steal issue slots from the working warps of this SMSP
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s
-      printf("equss tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", blockIdx.x, threadIdx.x, tag,
-             parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// quanta (signed) encoded in a key; key 0 (the "empty" initial value) maps far below every real key
-__device__ __forceinline__ int key_quanta(uint32_t key) {
-  return (key == 0u) ? -(1 << 30) : (int)((key - kKeyBase + (kKeyMul << 22)) / kKeyMul) - (1 << 22);
-}
-
-__device__ __forceinline__ float max3f(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// rows of one 8 x 16-byte core matrix are 16 bytes apart, LBO = distance between the two 16-byte K
-// chunks of one MMA (128 B), SBO = distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
-  return d;
-}
-// kind::tf32 instruction descriptor: fp32 accumulate, tf32 A/B, both K-major, M=128, N=NC.
-__host__ __device__ constexpr uint32_t make_idesc(int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-// 2^20 / R with R >= |z| max|c| + max|c|^2 / 2 (a bound on |s_k|).  Only monotonicity and the bound matter,
-// so approximate sqrt / reciprocal are fine; 2% slack covers their error.
-__device__ __forceinline__ float key_scale(float zn2, float cmax, float cmax2) {
-  float R = 1.02f * (__fsqrt_rn(zn2) * cmax + 0.5f * cmax2);
-  return (R > 0.f) ? __fdividef((float)(1 << kQuantBits), R) : 0.f;
-}
-
-// One 32-column chunk of accumulators -> keys -> class maxima (column mod 16) and top-2 group maxima.
-// `gid` is the index of the chunk's first 16-column group; the key's low byte is 255 - group.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float scale, int gid, float (&cls)[16], float& m1,
-                                          float& m2) {
-  float key[32];
-  uint32_t a0 = kKeyBias + (uint32_t)(255 - gid), a1 = a0 - 1u;
-  asm volatile("" : "+r"(a0), "+r"(a1));      // opaque: one addend register per 16-column group, no re-basing
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    key[j] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j]), scale, kMagic)) * kKeyMul + a0);
-    key[j + 16] = __uint_as_float(__float_as_uint(fmaf(__uint_as_float(v[j + 16]), scale, kMagic)) * kKeyMul + a1);
-  }
-#pragma unroll
-  for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], key[r], key[r + 16]);
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const float* k = key + 16 * g;
-    float t0 = max3f(k[0], k[1], k[2]), t1 = max3f(k[3], k[4], k[5]), t2 = max3f(k[6], k[7], k[8]);
-    float t3 = max3f(k[9], k[10], k[11]), t4 = max3f(k[12], k[13], k[14]);
-    float gm = max3f(max3f(t0, t1, t2), max3f(t3, t4, k[15]), 0.f);
-    m2 = fmaxf(m2, fminf(m1, gm));
-    m1 = fmaxf(m1, gm);
-  }
-}
+int launch_tc_d8(int NC, int norm_mode, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tc_d16(int NC, int norm_mode, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tc_d32(int NC, int norm_mode, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tc_d64(int NC, int norm_mode, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // B operand image builder: one block per (subspace, code chunk)
@@ -290,431 +71,6 @@ __global__ void finalize_merge_kernel(const unsigned long long* __restrict__ mer
   if (i < total) idx_out[i] = (int32_t)(merged[i] & 0xFFFFFFFFull);
 }
 
-__device__ __forceinline__ unsigned int sortable(float f) {
-  unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-struct Params {
-  long long n_pixels;
-  long long hw;
-  int M, K, D, NC, nchunks;
-  int tiles_per_image;   // NCHW: ceil(hw/128); flat: unused
-  long long n_tiles;     // pixel tiles (flat: ceil(N/128); NCHW: B * tiles_per_image)
-  int nchw;
-  int norm_mode;
-  const float* na;
-  const float* nb;
-  const uint8_t* images;
-  int img_bytes;
-  int32_t* idx_out;
-  unsigned long long* merged;   // nullptr when nchunks == 1
-};
-
-// Walks the CTA's contiguous unit range without per-unit divisions.
-struct UnitIter {
-  int slot, tile, m, chunk, n_tiles, nchunks;
-  __device__ __forceinline__ void init(long long u0, int n_tiles_, int nchunks_) {
-    n_tiles = n_tiles_; nchunks = nchunks_;
-    slot = (int)(u0 / n_tiles_);
-    tile = (int)(u0 - (long long)slot * n_tiles_);
-    m = slot / nchunks_;
-    chunk = slot - m * nchunks_;
-  }
-  __device__ __forceinline__ void next() {
-    if (++tile == n_tiles) {
-      tile = 0; ++slot;
-      if (++chunk == nchunks) { chunk = 0; ++m; }
-    }
-  }
-};
-
-// canonical sum z_norm^2 of pixel row `row`, reconstructed from the hi/lo A tile (same association order as
-// every other kernel: group-of-four fma chains combined by a butterfly)
-template <int D>
-__device__ __forceinline__ float exact_zn2(const uint8_t* a_tile, int row) {
-  constexpr int SBO = sbo_bytes(D);
-  constexpr int G = D / 4;
-  const uint8_t* ap = a_tile + (row / 8) * SBO + (row % 8) * 16;
-  float g[G];
-#pragma unroll
-  for (int jc = 0; jc < G; ++jc) {
-    float4 zh = *reinterpret_cast<const float4*>(ap + jc * 128);
-    float4 zl = *reinterpret_cast<const float4*>(ap + (G + jc) * 128);
-    g[jc] = group_sumsq(zh.x + zl.x, zh.y + zl.y, zh.z + zl.z, zh.w + zl.w);
-  }
-  return butterfly_array<G>(g);
-}
-
-// exact fp32 distance of code row r (chunk-local) for pixel row `row`, both reconstructed from hi+lo
-template <int D>
-__device__ __forceinline__ float exact_distance(const uint8_t* a_tile, const uint8_t* b_tile, int row, int r, float zn2) {
-  constexpr int SBO = sbo_bytes(D);
-  const uint8_t* ap = a_tile + (row / 8) * SBO + (row % 8) * 16;
-  const uint8_t* bp = b_tile + (r / 8) * SBO + (r % 8) * 16;
-  float dot = 0.f;
-#pragma unroll 4
-  for (int jc = 0; jc < D / 4; ++jc) {
-    float4 zh = *reinterpret_cast<const float4*>(ap + jc * 128);
-    float4 zl = *reinterpret_cast<const float4*>(ap + (D / 4 + jc) * 128);
-    float4 ch = *reinterpret_cast<const float4*>(bp + jc * 128);
-    float4 cl = *reinterpret_cast<const float4*>(bp + (D / 4 + jc) * 128);
-    dot = fmaf(zh.x + zl.x, ch.x + cl.x, dot);
-    dot = fmaf(zh.y + zl.y, ch.y + cl.y, dot);
-    dot = fmaf(zh.z + zl.z, ch.z + cl.z, dot);
-    dot = fmaf(zh.w + zl.w, ch.w + cl.w, dot);
-  }
-  float cn2 = reinterpret_cast<const float4*>(bp + (2 * (D / 4)) * 128)->w;
-  return ref_distance(zn2, cn2, dot);
-}
-
-template <int D, int NC, int STAGES, int ABUFS>
-__global__ void __launch_bounds__(kThreads, 1)
-assign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  constexpr int SBO = sbo_bytes(D);
-  constexpr int KCH = kch(D);
-  constexpr int B_BYTES = align_up(b_bytes(D, NC), 128);
-  constexpr int A_BYTES = align_up(a_bytes(D), 128);
-  constexpr int RAW_BYTES = raw_bytes(D);
-  constexpr int TMEM_COLS = (2 * NC <= 32) ? 32 : (2 * NC <= 64) ? 64 : (2 * NC <= 128) ? 128 : (2 * NC <= 256) ? 256 : 512;
-  constexpr int LPS = D / 4;                    // lanes per pixel row in the flat convert
-  constexpr uint32_t IDESC = make_idesc(NC);
-  static_assert(NC % 32 == 0 && NC <= 256, "NC must be a multiple of 32, at most 256");
-  static_assert(D % 8 == 0 && D <= 64, "D must be a multiple of 8, at most 64");
-
-  extern __shared__ uint8_t smem_raw[];
-  // align inside the shared window without laundering the pointer through an integer (which would turn
-  // every shared-memory access into a generic LD/ST)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* s_b = smem;
-  uint8_t* s_a = s_b + B_BYTES;
-  uint8_t* s_rawt = s_a + ABUFS * A_BYTES;
-  float* s_zn2 = reinterpret_cast<float*>(s_rawt + STAGES * RAW_BYTES);   // [ABUFS][128]
-  float* s_scale = s_zn2 + ABUFS * kTileM;                                 // [ABUFS][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scale + ABUFS * kTileM);
-  uint64_t* raw_full = bars;                    // [STAGES]
-  uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
-  uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
-  uint64_t* a_empty = a_full + ABUFS;           // [ABUFS]
-  uint64_t* t_full = a_empty + ABUFS;           // [2]
-  uint64_t* t_empty = t_full + 2;               // [2]
-  uint64_t* b_full = t_empty + 2;               // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // contiguous unit range of this CTA; unit u -> (slot = u / n_tiles, tile = u % n_tiles), slot = m*nchunks + c
-  const long long total_units = (long long)p.M * p.nchunks * p.n_tiles;
-  const long long u0 = total_units * blockIdx.x / gridDim.x;
-  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
-  const int n_units = (int)(u1 - u0);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 4); }
-    for (int i = 0; i < ABUFS; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
-    mbar_init(b_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(s_tmem);
-  // constant augmented K chunks of the A operand: (1,1,1,0) and (0,0,0,0)
-  for (int i = threadIdx.x; i < ABUFS * kTileM; i += blockDim.x) {
-    int a = i / kTileM, row = i % kTileM;
-    uint8_t* rowp = s_a + a * A_BYTES + (row / 8) * SBO + (row % 8) * 16;
-    *reinterpret_cast<float4*>(rowp + (2 * LPS) * 128) = make_float4(1.f, 1.f, 1.f, 0.f);
-    *reinterpret_cast<float4*>(rowp + (2 * LPS + 1) * 128) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
-      for (int i = 0; i < n_units; ++i, it.next()) {
-        const int tile = it.tile, m = it.m;
-        const int s = i % STAGES;
-        mbar_wait(raw_empty + s, ((i / STAGES) & 1) ^ 1, 10 + s);
-        mbar_expect_tx(raw_full + s, RAW_BYTES);
-        if (!p.nchw) {
-          tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, tile * kTileM, raw_full + s);
-        } else {
-          const int b = tile / p.tiles_per_image;
-          const int t = tile - b * p.tiles_per_image;
-          tma_load_3d(s_rawt + s * RAW_BYTES, &tmap, t * kTileM, m * D, b, raw_full + s);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    int b_loads = 0, cur_slot = -1;
-    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
-    for (int i = 0; i < n_units; ++i, it.next()) {
-      const int slot = it.slot;
-      const int a = i % ABUFS, t = i & 1;
-      if (slot != cur_slot) {
-        mbar_wait(b_full, b_loads & 1, 20);
-        ++b_loads;
-        cur_slot = slot;
-      }
-      mbar_wait(a_full + a, (i / ABUFS) & 1, 21);
-      mbar_wait(t_empty + t, ((i >> 1) & 1) ^ 1, 22);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(s_a + a * A_BYTES);
-        const uint32_t b_addr = smem_u32(s_b);
-        const uint32_t d_addr = tmem_base + (uint32_t)(t * NC);
-        uint32_t acc = 0;
-        // hi.hi, lo.hi, hi.lo : operand K-slice kk starts 2*kk chunks (256 B) into its region
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          const int a_off = (part == 1) ? LPS : 0;     // z_lo for the middle product
-          const int b_off = (part == 2) ? LPS : 0;     // c_lo for the last product
-#pragma unroll
-          for (int kk = 0; kk < D / 8; ++kk) {
-            umma_tf32(d_addr, make_desc(a_addr + (a_off + 2 * kk) * 128, SBO),
-                      make_desc(b_addr + (b_off + 2 * kk) * 128, SBO), IDESC, acc);
-            acc = 1;
-          }
-        }
-        umma_tf32(d_addr, make_desc(a_addr + (2 * LPS) * 128, SBO), make_desc(b_addr + (2 * LPS) * 128, SBO), IDESC, 1);
-        umma_commit(t_full + t);
-      }
-      __syncwarp();
-    }
-  } else if (warp < kEpiWarp0) {
-    // ===================================== convert warps ====================================
-    const int ct = threadIdx.x - kConvWarp0 * 32;   // 0..127
-    int b_loads = 0, cur_slot = -1;
-    float cmax = 0.f, cmax2 = 0.f;
-    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
-    for (int i = 0; i < n_units; ++i, it.next()) {
-      const int slot = it.slot, m = it.m;
-      const int a = i % ABUFS, s = i % STAGES;
-      mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
-      if (slot != cur_slot) {
-        // every earlier unit must be fully retired before the B image is overwritten
-#pragma unroll
-        for (int back = 1; back < ABUFS; ++back)
-          if (i >= back) mbar_wait(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
-        if (ct == 0) {
-          mbar_expect_tx(b_full, (uint32_t)p.img_bytes);
-          bulk_load_1d(s_b, p.images + (size_t)slot * p.img_bytes, (uint32_t)p.img_bytes, b_full);
-        }
-        mbar_wait(b_full, b_loads & 1, 32);
-        ++b_loads;
-        cur_slot = slot;
-        const float* tr = reinterpret_cast<const float*>(s_b + (NC / 8) * SBO);
-        cmax = tr[0]; cmax2 = tr[1];
-      }
-      mbar_wait(raw_full + s, (i / STAGES) & 1, 33);
-      uint8_t* a_tile = s_a + a * A_BYTES;
-      const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
-      if (!p.nchw) {
-        // flat: raw[row][D]; LPS lanes per row, one float4 each
-        constexpr int ROWS_PER_PASS = 128 / LPS;
-        const int l = ct % LPS;
-#pragma unroll
-        for (int pass = 0; pass < kTileM / ROWS_PER_PASS; ++pass) {   // independent passes: unrolled for ILP
-          const int row = pass * ROWS_PER_PASS + ct / LPS;
-          float4 v = *reinterpret_cast<const float4*>(raw + row * D + l * 4);
-          RowNorm rn; rn.shift = 0.f; rn.denom = 1.f;
-          if (p.norm_mode == EQUSS_NORM_L2) {
-            rn = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v.x, v.y, v.z, v.w)));
-          } else if (p.norm_mode == EQUSS_NORM_ZNORM) {
-            float mean = butterfly_lanes<LPS>(group_sum(v.x, v.y, v.z, v.w)) / (float)D;
-            float ssd = butterfly_lanes<LPS>(group_sumsq(v.x - mean, v.y - mean, v.z - mean, v.w - mean));
-            rn.shift = mean; rn.denom = sqrtf(ssd / (float)(D - 1)) + kStdEps;
-          }
-          float4 zn;
-          if (p.norm_mode == EQUSS_NORM_AFFINE) {
-            const int ch = m * D + l * 4;
-            zn.x = (v.x - __ldg(p.na + ch)) / __ldg(p.nb + ch);
-            zn.y = (v.y - __ldg(p.na + ch + 1)) / __ldg(p.nb + ch + 1);
-            zn.z = (v.z - __ldg(p.na + ch + 2)) / __ldg(p.nb + ch + 2);
-            zn.w = (v.w - __ldg(p.na + ch + 3)) / __ldg(p.nb + ch + 3);
-          } else {
-            zn.x = apply_norm(v.x, rn, p.norm_mode); zn.y = apply_norm(v.y, rn, p.norm_mode);
-            zn.z = apply_norm(v.z, rn, p.norm_mode); zn.w = apply_norm(v.w, rn, p.norm_mode);
-          }
-          float4 hi, lo;
-          hi.x = tf32_hi(zn.x); hi.y = tf32_hi(zn.y); hi.z = tf32_hi(zn.z); hi.w = tf32_hi(zn.w);
-          lo.x = zn.x - hi.x; lo.y = zn.y - hi.y; lo.z = zn.z - hi.z; lo.w = zn.w - hi.w;
-          uint8_t* rowp = a_tile + (row / 8) * SBO + (row % 8) * 16;
-          *reinterpret_cast<float4*>(rowp + l * 128) = hi;
-          *reinterpret_cast<float4*>(rowp + (LPS + l) * 128) = lo;
-          // |z_norm|^2 for the key scale only needs to be an upper bound (exact value: lazily in the
-          // ambiguous path); 1 for l2, else a cheap butterfly
-          float zn2b;
-          if (p.norm_mode == EQUSS_NORM_L2) zn2b = 1.0001f;
-          else zn2b = 1.0001f * butterfly_lanes<LPS>(group_sumsq(zn.x, zn.y, zn.z, zn.w));
-          if (l == 0) s_scale[a * kTileM + row] = key_scale(zn2b, cmax, cmax2);
-        }
-      } else {
-        // NCHW: raw[channel][128 pixels]; one thread per pixel row
-        const int row = ct;
-        float x[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) x[j] = raw[j * kTileM + row];
-        RowNorm rn; rn.shift = 0.f; rn.denom = 1.f;
-        {
-          float g[LPS];
-          if (p.norm_mode == EQUSS_NORM_L2) {
-#pragma unroll
-            for (int q = 0; q < LPS; ++q) g[q] = group_sumsq(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            rn = l2_from_sumsq(butterfly_array<LPS>(g));
-          } else if (p.norm_mode == EQUSS_NORM_ZNORM) {
-#pragma unroll
-            for (int q = 0; q < LPS; ++q) g[q] = group_sum(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            float mean = butterfly_array<LPS>(g) / (float)D;
-#pragma unroll
-            for (int q = 0; q < LPS; ++q)
-              g[q] = group_sumsq(x[4 * q] - mean, x[4 * q + 1] - mean, x[4 * q + 2] - mean, x[4 * q + 3] - mean);
-            rn.shift = mean; rn.denom = sqrtf(butterfly_array<LPS>(g) / (float)(D - 1)) + kStdEps;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          if (p.norm_mode == EQUSS_NORM_AFFINE) x[j] = (x[j] - __ldg(p.na + m * D + j)) / __ldg(p.nb + m * D + j);
-          else x[j] = apply_norm(x[j], rn, p.norm_mode);
-        }
-        float g2[LPS];
-#pragma unroll
-        for (int q = 0; q < LPS; ++q) g2[q] = group_sumsq(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-        float zn2 = butterfly_array<LPS>(g2);
-        uint8_t* rowp = a_tile + (row / 8) * SBO + (row % 8) * 16;
-#pragma unroll
-        for (int q = 0; q < LPS; ++q) {
-          float4 hi, lo;
-          hi.x = tf32_hi(x[4 * q]); hi.y = tf32_hi(x[4 * q + 1]); hi.z = tf32_hi(x[4 * q + 2]); hi.w = tf32_hi(x[4 * q + 3]);
-          lo.x = x[4 * q] - hi.x; lo.y = x[4 * q + 1] - hi.y; lo.z = x[4 * q + 2] - hi.z; lo.w = x[4 * q + 3] - hi.w;
-          *reinterpret_cast<float4*>(rowp + q * 128) = hi;
-          *reinterpret_cast<float4*>(rowp + (LPS + q) * 128) = lo;
-        }
-        s_scale[a * kTileM + row] = key_scale(1.0001f * zn2, cmax, cmax2);
-      }
-      fence_proxy_async();     // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
-    }
-  } else {
-    // ===================================== epilogue warps ===================================
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    int b_loads = 0, cur_slot = -1;
-    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks);
-    for (int i = 0; i < n_units; ++i, it.next()) {
-      const int slot = it.slot, tile = it.tile, m = it.m, chunk = it.chunk;
-      const int a = i % ABUFS, t = i & 1;
-      if (slot != cur_slot) {
-        mbar_wait(b_full, b_loads & 1, 40);
-        ++b_loads;
-        cur_slot = slot;
-      }
-      mbar_wait(t_full + t, (i >> 1) & 1, 41);
-      tc_fence_after();
-      const float scale = s_scale[a * kTileM + row];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NC);
-
-      float cls[16];                              // running max key per (column mod 16)
-#pragma unroll
-      for (int r = 0; r < 16; ++r) cls[r] = 0.f;
-      float m1 = 0.f, m2 = 0.f;                   // best / second-best 16-column group maxima
-      uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
-      if constexpr (NC == 32) {
-        tmem_ld_wait();
-        epi_chunk(va, scale, 0, cls, m1, m2);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < NC / 32; c += 2) {      // rolled (two chunks per trip): small I-cache footprint
-          tmem_ld_wait();
-          tmem_ld32(taddr + (c + 1) * 32, vb);
-          epi_chunk(va, scale, 2 * c, cls, m1, m2);
-          tmem_ld_wait();
-          if (c + 2 < NC / 32) tmem_ld32(taddr + (c + 2) * 32, va);
-          epi_chunk(vb, scale, 2 * c + 2, cls, m1, m2);
-        }
-      }
-      // accumulator fully consumed -> hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty + t);
-
-      const uint32_t k1 = __float_as_uint(m1);
-      // winning column = (group from the key's low byte) * 16 + (class whose running maximum is the key)
-      int r1 = 0;
-#pragma unroll
-      for (int r = 15; r >= 0; --r) r1 = (cls[r] == m1) ? r : r1;
-      const uint32_t t1 = k1 - kKeyBase + (kKeyMul << 22);           // 257 * (n + 2^22) + group byte, positive
-      const int col1 = (255 - (int)(t1 - (t1 / kKeyMul) * kKeyMul)) * 16 + r1;
-      float runner = m2;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) runner = fmaxf(runner, (r1 == r) ? 0.f : cls[r]);
-      const int gap = key_quanta(k1) - key_quanta(__float_as_uint(runner));
-      const int kvalid = min(NC, p.K - chunk * NC);
-      int best_col = col1;
-      const uint8_t* a_tile = s_a + a * A_BYTES;
-      float zn2 = 0.f;
-      float best_dist = 0.f;
-      bool have_dist = false;
-      if (gap < kTolQuanta || col1 >= kvalid) {
-        // ambiguous row: exact fp32 re-score of every column whose class maximum is within tolerance
-        const int thr = key_quanta(k1) - kTolQuanta;
-        zn2 = exact_zn2<D>(a_tile, row);
-        best_dist = INFINITY; best_col = 0;
-#pragma unroll 1
-        for (int r = 0; r < 16; ++r) {
-          float cr = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 16; ++rr) cr = (rr == r) ? cls[rr] : cr;
-          if (key_quanta(__float_as_uint(cr)) < thr && col1 < kvalid) continue;
-#pragma unroll 1
-          for (int col = r; col < kvalid; col += 16) {
-            float dd = exact_distance<D>(a_tile, s_b, row, col, zn2);
-            if (dd < best_dist || (dd == best_dist && col < best_col)) { best_dist = dd; best_col = col; }
-          }
-        }
-        have_dist = true;
-      }
-      // global pixel index of this row
-      long long n;
-      bool live;
-      if (!p.nchw) {
-        n = (long long)tile * kTileM + row;
-        live = n < p.n_pixels;
-      } else {
-        const long long b = tile / p.tiles_per_image;
-        const long long sidx = (long long)(tile - (int)b * p.tiles_per_image) * kTileM + row;
-        live = sidx < p.hw;
-        n = b * p.hw + sidx;
-      }
-      if (p.merged == nullptr) {
-        if (live) p.idx_out[(long long)m * p.n_pixels + n] = best_col;
-      } else {
-        if (!have_dist) best_dist = exact_distance<D>(a_tile, s_b, row, best_col, exact_zn2<D>(a_tile, row));
-        if (live) {
-          unsigned long long packed = ((unsigned long long)sortable(best_dist) << 32) |
-                                      (unsigned long long)(uint32_t)(chunk * NC + best_col);
-          atomicMin(p.merged + (long long)m * p.n_pixels + n, packed);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_empty + a);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -742,28 +98,13 @@ struct Plan {
 static Plan make_plan(int K, int d) {
   Plan pl{d, 0, 0, 2, 0, false};
   if (!(d == 8 || d == 16 || d == 32 || d == 64)) return pl;
-  pl.NC = (d == 64) ? 128 : 256;
-  int kpad = (K + 31) / 32 * 32;
-  if (kpad < pl.NC) pl.NC = kpad;                 // small codebooks: one narrower chunk
-  // supported instantiations: NC in {32, 64, 128, 256}
-  int nc = 32;
-  while (nc < pl.NC) nc <<= 1;
-  pl.NC = nc;
+  // instantiated chunk widths: 32 (small codebooks, e.g. the cityscapes yaml's K=32) or 256 (128 for d=64)
+  pl.NC = (K <= 32) ? 32 : (d == 64) ? 128 : 256;
   pl.nchunks = (K + pl.NC - 1) / pl.NC;
   pl.abufs = (d == 64) ? 1 : (d == 32) ? 2 : 3;
   pl.stages = (d == 8) ? 8 : (d == 16) ? 8 : (d == 32) ? 4 : 2;
   pl.ok = true;
   return pl;
-}
-
-template <int D, int NC, int STAGES, int ABUFS>
-static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = smem_bytes(D, NC, STAGES, ABUFS) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, STAGES, ABUFS);
-  static_assert(SMEM <= 227 * 1024, "shared-memory plan exceeds 227 KB");
-  EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_tc_kernel<D, NC, STAGES, ABUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  assign_tc_kernel<D, NC, STAGES, ABUFS><<<grid, kThreads, SMEM, st>>>(tmap, p);
-  EQUSS_LAUNCH_OK("assign_tc_kernel");
-  return EQUSS_OK;
 }
 
 }  // namespace tc
@@ -850,15 +191,13 @@ int assign_tc_launch(const float* z, const equss_zdesc* zd, const float* codeboo
   int grid = num_sms();
   if (total_units < grid) grid = (int)total_units;
 
-  int rc = EQUSS_ERR_UNSUPPORTED;
-#define EQUSS_TC_CASE(DV, NCV, STV, ABV) \
-  if (d == DV && pl.NC == NCV) rc = launch_instance<DV, NCV, STV, ABV>(tmap, p, grid, st);
-  EQUSS_TC_CASE(8, 32, 8, 3) EQUSS_TC_CASE(8, 64, 8, 3) EQUSS_TC_CASE(8, 128, 8, 3) EQUSS_TC_CASE(8, 256, 8, 3)
-  EQUSS_TC_CASE(16, 32, 8, 3) EQUSS_TC_CASE(16, 64, 8, 3) EQUSS_TC_CASE(16, 128, 8, 3) EQUSS_TC_CASE(16, 256, 8, 3)
-  EQUSS_TC_CASE(32, 32, 4, 2) EQUSS_TC_CASE(32, 64, 4, 2) EQUSS_TC_CASE(32, 128, 4, 2) EQUSS_TC_CASE(32, 256, 4, 2)
-  EQUSS_TC_CASE(64, 32, 2, 1) EQUSS_TC_CASE(64, 64, 2, 1) EQUSS_TC_CASE(64, 128, 2, 1)
-#undef EQUSS_TC_CASE
-  if (rc == EQUSS_ERR_UNSUPPORTED) set_error("tcgen05 assign: no instantiation for d=%d NC=%d", d, pl.NC);
+  int rc;
+  switch (d) {
+    case 8: rc = launch_tc_d8(pl.NC, norm_mode, nchw, tmap, p, grid, st); break;
+    case 16: rc = launch_tc_d16(pl.NC, norm_mode, nchw, tmap, p, grid, st); break;
+    case 32: rc = launch_tc_d32(pl.NC, norm_mode, nchw, tmap, p, grid, st); break;
+    default: rc = launch_tc_d64(pl.NC, norm_mode, nchw, tmap, p, grid, st); break;
+  }
   if (rc != EQUSS_OK) return rc;
   if (merged) {
     long long total = (long long)M * zd->n_pixels;
