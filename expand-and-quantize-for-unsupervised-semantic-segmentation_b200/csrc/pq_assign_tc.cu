@@ -101,7 +101,7 @@ static Plan make_plan(int K, int d) {
   // instantiated chunk widths: 32 (small codebooks, e.g. the cityscapes yaml's K=32) or 256 (128 for d=64)
   pl.NC = (K <= 32) ? 32 : (d == 64) ? 128 : 256;
   pl.nchunks = (K + pl.NC - 1) / pl.NC;
-  pl.abufs = (d == 64) ? 1 : (d == 32) ? 2 : 5;
+  pl.abufs = (d == 64) ? 1 : (d == 32) ? 2 : 4;
   pl.stages = (d == 8) ? 8 : (d == 16) ? 6 : (d == 32) ? 4 : 2;
   pl.ok = true;
   return pl;

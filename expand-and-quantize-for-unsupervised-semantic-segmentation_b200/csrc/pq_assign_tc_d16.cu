@@ -2,6 +2,6 @@
 #include "pq_assign_tc_kernel.cuh"
 namespace equss {
 namespace tc {
-EQUSS_TC_DISPATCH(16, 256, 6, 5)
+EQUSS_TC_DISPATCH(16, 256, 6, 4)
 }  // namespace tc
 }  // namespace equss

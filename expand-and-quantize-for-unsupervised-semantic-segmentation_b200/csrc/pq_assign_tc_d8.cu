@@ -2,6 +2,6 @@
 #include "pq_assign_tc_kernel.cuh"
 namespace equss {
 namespace tc {
-EQUSS_TC_DISPATCH(8, 256, 8, 5)
+EQUSS_TC_DISPATCH(8, 256, 8, 4)
 }  // namespace tc
 }  // namespace equss
