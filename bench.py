@@ -201,8 +201,11 @@ def run_equss(args):
         codebook = torch.randn(M, K, d, device=dev)
         clusters = torch.randn(C, D, device=dev)
         lin_w = torch.randn(C, D, device=dev) * 0.03
-        wmat = torch.cat([F.normalize(clusters, dim=1), lin_w]).contiguous()
-        bias = torch.zeros(2 * C, device=dev)
+        Cp = (C + 3) // 4 * 4                      # each probe head starts at a multiple of four channels
+        wmat = torch.zeros(Cp + C, D, device=dev)
+        wmat[:C] = F.normalize(clusters, dim=1)
+        wmat[Cp:] = lin_w
+        bias = torch.zeros(Cp + C, device=dev)
         conf_c = torch.zeros(C, C, dtype=torch.long, device=dev)
         conf_l = torch.zeros(C, C, dtype=torch.long, device=dev)
         cbn = F.normalize(codebook, dim=2).contiguous()
@@ -218,7 +221,7 @@ def run_equss(args):
             if ev: ev[2].record()
             logits = ops.probe_logits(zq, wmat, bias)
             if ev: ev[3].record()
-            ops.probe_argmax_confusion(logits, B, h, w, 2 * C, lab, C, [(0, C), (C, C)], want_preds=False,
+            ops.probe_argmax_confusion(logits, B, h, w, Cp + C, lab, C, [(0, C), (Cp, C)], want_preds=False,
                                        confusions=[conf_c, conf_l])
             if ev: ev[4].record()
 

@@ -23,15 +23,15 @@ constexpr int kProbeMaxHeads = 4;
 //   weights staged transposed in shared memory ([DC][CT]) so each feature value meets CT/4 broadcast
 //   LDS.128.
 // ------------------------------------------------------------------------------------------------
-template <int CT, int PT>
-__global__ void __launch_bounds__(128)
+template <int CT, int PT, int TB>
+__global__ void __launch_bounds__(TB)
 probe_logits_kernel(const float* __restrict__ feat, int D, int hw, const float* __restrict__ wmat,
                     const float* __restrict__ bias, int c_total, int c_pad, float* __restrict__ logits) {
   constexpr int DC = 128;                       // feature channels per shared-memory chunk
   __shared__ __align__(16) float s_w[DC * CT];  // [c][j]
   const int b = blockIdx.y;
   const int j0 = blockIdx.z * CT;               // first output channel of this block
-  const int s0 = blockIdx.x * (128 * PT);
+  const int s0 = blockIdx.x * (TB * PT);
   const float* fb = feat + (long long)b * D * hw;
   float acc[PT][CT];
 #pragma unroll
@@ -41,30 +41,36 @@ probe_logits_kernel(const float* __restrict__ feat, int D, int hw, const float* 
   int s[PT];
   bool live[PT];
 #pragma unroll
-  for (int p = 0; p < PT; ++p) { s[p] = s0 + threadIdx.x + p * 128; live[p] = s[p] < hw; }
+  for (int p = 0; p < PT; ++p) { s[p] = s0 + threadIdx.x + p * TB; live[p] = s[p] < hw; }
   for (int c0 = 0; c0 < D; c0 += DC) {
     const int dc = min(DC, D - c0);
     __syncthreads();
-    for (int i = threadIdx.x; i < dc * CT; i += 128) {
+    for (int i = threadIdx.x; i < dc * CT; i += TB) {
       int c = i / CT, j = i - c * CT;
       s_w[i] = (j0 + j < c_total) ? __ldg(wmat + (long long)(j0 + j) * D + c0 + c) : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int c = 0; c < dc; ++c) {
-      float x[PT];
+    constexpr int U = 4;                        // feature channels in flight per thread
+    for (int c = 0; c < dc; c += U) {
+      float x[U][PT];
 #pragma unroll
-      for (int p = 0; p < PT; ++p) x[p] = live[p] ? __ldcs(fb + (long long)(c0 + c) * hw + s[p]) : 0.f;
-      const float4* w4 = reinterpret_cast<const float4*>(s_w + c * CT);
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-      for (int j4 = 0; j4 < CT / 4; ++j4) {
-        float4 w = w4[j4];
+        for (int p = 0; p < PT; ++p)
+          x[u][p] = (live[p] && c + u < dc) ? __ldcs(fb + (long long)(c0 + c + u) * hw + s[p]) : 0.f;
 #pragma unroll
-        for (int p = 0; p < PT; ++p) {
-          acc[p][4 * j4 + 0] = fmaf(x[p], w.x, acc[p][4 * j4 + 0]);
-          acc[p][4 * j4 + 1] = fmaf(x[p], w.y, acc[p][4 * j4 + 1]);
-          acc[p][4 * j4 + 2] = fmaf(x[p], w.z, acc[p][4 * j4 + 2]);
-          acc[p][4 * j4 + 3] = fmaf(x[p], w.w, acc[p][4 * j4 + 3]);
+      for (int u = 0; u < U; ++u) {
+        const float4* w4 = reinterpret_cast<const float4*>(s_w + (c + u < dc ? c + u : c) * CT);
+#pragma unroll
+        for (int j4 = 0; j4 < CT / 4; ++j4) {
+          float4 w = w4[j4];
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            acc[p][4 * j4 + 0] = fmaf(x[u][p], w.x, acc[p][4 * j4 + 0]);
+            acc[p][4 * j4 + 1] = fmaf(x[u][p], w.y, acc[p][4 * j4 + 1]);
+            acc[p][4 * j4 + 2] = fmaf(x[u][p], w.z, acc[p][4 * j4 + 2]);
+            acc[p][4 * j4 + 3] = fmaf(x[u][p], w.w, acc[p][4 * j4 + 3]);
+          }
         }
       }
     }
@@ -158,11 +164,32 @@ probe_argmax_confusion_kernel(const float* __restrict__ logits, int B, int h, in
         float best = -INFINITY;
         int bj = 0;
         const int off = heads.off[hd], cnt = heads.cnt[hd];
-        for (int j = 0; j < cnt; ++j) {
-          float v00 = __ldg(p00 + off + j), v01 = __ldg(p01 + off + j);
-          float v10 = __ldg(p10 + off + j), v11 = __ldg(p11 + off + j);
-          float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-          if (v > best) { best = v; bj = j; }     // first maximal index wins (torch.argmax)
+        if ((off & 3) == 0) {
+          // vector path: four channels per 16-byte load from each of the four neighbouring tokens
+          const float4* q00 = reinterpret_cast<const float4*>(p00 + off);
+          const float4* q01 = reinterpret_cast<const float4*>(p01 + off);
+          const float4* q10 = reinterpret_cast<const float4*>(p10 + off);
+          const float4* q11 = reinterpret_cast<const float4*>(p11 + off);
+          const int n4 = (cnt + 3) >> 2;
+          for (int g = 0; g < n4; ++g) {
+            float4 a = __ldg(q00 + g), bq = __ldg(q01 + g), c = __ldg(q10 + g), dq = __ldg(q11 + g);
+            float v0 = ly0 * (lx0 * a.x + lx1 * bq.x) + ly1 * (lx0 * c.x + lx1 * dq.x);
+            float v1 = ly0 * (lx0 * a.y + lx1 * bq.y) + ly1 * (lx0 * c.y + lx1 * dq.y);
+            float v2 = ly0 * (lx0 * a.z + lx1 * bq.z) + ly1 * (lx0 * c.z + lx1 * dq.z);
+            float v3 = ly0 * (lx0 * a.w + lx1 * bq.w) + ly1 * (lx0 * c.w + lx1 * dq.w);
+            const int j = 4 * g;
+            if (v0 > best) { best = v0; bj = j; }                      // first maximal index wins (torch.argmax)
+            if (j + 1 < cnt && v1 > best) { best = v1; bj = j + 1; }
+            if (j + 2 < cnt && v2 > best) { best = v2; bj = j + 2; }
+            if (j + 3 < cnt && v3 > best) { best = v3; bj = j + 3; }
+          }
+        } else {
+          for (int j = 0; j < cnt; ++j) {
+            float v00 = __ldg(p00 + off + j), v01 = __ldg(p01 + off + j);
+            float v10 = __ldg(p10 + off + j), v11 = __ldg(p11 + off + j);
+            float v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+            if (v > best) { best = v; bj = j; }     // first maximal index wins (torch.argmax)
+          }
         }
         if (heads.preds[hd]) __stcs(heads.preds[hd] + p, (long long)bj);
         if (heads.conf[hd] && lab >= 0 && lab < C && bj < C) bins[hd] = bj * C + (int)lab;
@@ -241,12 +268,19 @@ extern "C" int equss_probe_logits(const float* feat, int B, int D, int h, int w,
   const int hw = h * w;
   const int c_pad = equss_probe_cpad(c_total);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c_pad <= 32) {
+  // CT output channels x PT pixels of accumulators per thread; 64-thread blocks keep the tail of hw small
+  if (c_pad <= 28) {
     dim3 grid((hw + 255) / 256, B, 1);
-    probe_logits_kernel<32, 2><<<grid, 128, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+    probe_logits_kernel<28, 4, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+  } else if (c_pad <= 32) {
+    dim3 grid((hw + 255) / 256, B, 1);
+    probe_logits_kernel<32, 4, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+  } else if (c_pad <= 56) {
+    dim3 grid((hw + 127) / 128, B, 1);
+    probe_logits_kernel<56, 2, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
   } else {
     dim3 grid((hw + 127) / 128, B, (c_pad + 63) / 64);
-    probe_logits_kernel<64, 1><<<grid, 128, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+    probe_logits_kernel<64, 2, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
   }
   EQUSS_LAUNCH_OK("probe_logits_kernel");
   return EQUSS_OK;

@@ -153,10 +153,18 @@ gather_loss_scalar_kernel(const float* __restrict__ z, ZView zv, int M, int K, i
     const int dd = DT > 0 ? DT : d;
     // error accumulated in the canonical group order so both paths agree
     float g = 0.f;
+    float qr[DT > 0 ? DT : 1];
+    if (DT >= 4) {            // codebook row: 16-byte loads (rows are d*4 bytes, d % 4 == 0 -> aligned)
+#pragma unroll
+      for (int j = 0; j < (DT >= 4 ? DT : 0); j += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(q + j));
+        qr[j] = t.x; qr[j + 1] = t.y; qr[j + 2] = t.z; qr[j + 3] = t.w;
+      }
+    }
 #pragma unroll 4
     for (int j = 0; j < dd; ++j) {
       float zn = norm_elem(row.raw(j), r, mode, na, nb, m * d + j);
-      float dq = __ldg(q + j) - zn;
+      float dq = (DT >= 4 ? qr[j] : __ldg(q + j)) - zn;
       out[base + j * zv.stride_c] = zn + dq;
       if (znorm_out) znorm_out[base + j * zv.stride_c] = zn;
       g = ((j & 3) == 0) ? dq * dq : fmaf(dq, dq, g);

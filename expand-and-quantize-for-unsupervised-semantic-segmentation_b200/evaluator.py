@@ -108,14 +108,20 @@ class UnSegEvaluator(nn.Module):
         B, D, h, w = out.shape
         Cc = self.cluster_probe.n_classes
         C = self.num_classes
-        wmat = torch.cat([F.normalize(self.cluster_probe.clusters.detach().float(), dim=1),
-                          self.linear_probe.weight.detach().float().view(C, D)], dim=0)
-        bias = torch.cat([torch.zeros(Cc, device=out.device), self.linear_probe.bias.detach().float()])
+        # both probes share one weight matrix; each head starts at a multiple of four channels so the second
+        # kernel can read four logits per 16-byte load (padding rows are zero and never compete in the argmax)
+        Cp = (Cc + 3) // 4 * 4
+        dev = out.device
+        wmat = torch.zeros(Cp + C, D, device=dev)
+        wmat[:Cc] = F.normalize(self.cluster_probe.clusters.detach().float(), dim=1)
+        wmat[Cp:] = self.linear_probe.weight.detach().float().view(C, D)
+        bias = torch.zeros(Cp + C, device=dev)
+        bias[Cp:] = self.linear_probe.bias.detach().float()
         logits = ops.probe_logits(out, wmat, bias)
         confs = None
         if cluster_confusion is not None or linear_confusion is not None:
             confs = [cluster_confusion, linear_confusion]
-        preds = ops.probe_argmax_confusion(logits, B, h, w, Cc + C, label, C, [(0, Cc), (Cc, C)],
+        preds = ops.probe_argmax_confusion(logits, B, h, w, Cp + C, label, C, [(0, Cc), (Cp, C)],
                                            want_preds=want_preds, confusions=confs)
         return preds[1], preds[0]
 
