@@ -206,6 +206,7 @@ def run_equss(args):
         wmat[:C] = F.normalize(clusters, dim=1)
         wmat[Cp:] = lin_w
         bias = torch.zeros(Cp + C, device=dev)
+        wpack = ops.probe_pack(wmat)
         conf_c = torch.zeros(C, C, dtype=torch.long, device=dev)
         conf_l = torch.zeros(C, C, dtype=torch.long, device=dev)
         cbn = F.normalize(codebook, dim=2).contiguous()
@@ -219,7 +220,7 @@ def run_equss(args):
             if ev: ev[1].record()
             zq, sqerr, _ = ops.pq_gather_loss(z, cbn, idx, "l2")
             if ev: ev[2].record()
-            logits = ops.probe_logits(zq, wmat, bias)
+            logits = ops.probe_logits(zq, wpack, bias)
             if ev: ev[3].record()
             ops.probe_argmax_confusion(logits, B, h, w, Cp + C, lab, C, [(0, C), (Cp, C)], want_preds=False,
                                        confusions=[conf_c, conf_l])

@@ -9,6 +9,7 @@
 // K8 therefore runs in two HBM-friendly steps: token-resolution logits (reads x once), then one pass
 // over the label pixels that interpolates 27 logits from an L2-resident table, takes the argmax and
 // feeds warp-privatised shared-memory confusion bins.
+#include <cstdlib>
 #include <cstring>
 #include "equss_common.cuh"
 
@@ -47,7 +48,7 @@ probe_logits_kernel(const float* __restrict__ feat, int D, int hw, const float* 
     __syncthreads();
     for (int i = threadIdx.x; i < dc * CT; i += TB) {
       int c = i / CT, j = i - c * CT;
-      s_w[i] = (j0 + j < c_total) ? __ldg(wmat + (long long)(j0 + j) * D + c0 + c) : 0.f;
+      s_w[i] = (j0 + j < c_pad) ? __ldg(wmat + (long long)(c0 + c) * c_pad + j0 + j) : 0.f;   // K-major weights
     }
     __syncthreads();
     constexpr int U = 4;                        // feature channels in flight per thread
@@ -89,6 +90,109 @@ probe_logits_kernel(const float* __restrict__ feat, int D, int hw, const float* 
       v.w = acc[p][4 * j4 + 3] + ((bias && j0 + 4 * j4 + 3 < c_total) ? __ldg(bias + j0 + 4 * j4 + 3) : 0.f);
       *reinterpret_cast<float4*>(o + 4 * j4) = v;
     }
+  }
+}
+
+// K-split variant (the one used for the common head sizes): 256 threads = 4 k-groups x 64 pixels.  Each
+// k-group contracts a quarter of the D feature channels for the same 64 pixels (one pixel per thread, CT
+// accumulators), partial sums are combined through shared memory in a fixed order (deterministic).  Compared
+// with one thread per pixel over all of D this gives 4x the warps (~16 per SM) to hide the feature-load
+// latency, which is what bounds this kernel (the arithmetic is 1.5 % of fp32 peak).
+template <int CT, int PT>
+__global__ void __launch_bounds__(256, (PT == 1) ? 2 : 1)
+probe_logits_ksplit_kernel(const float* __restrict__ feat, int D, int hw, const float* __restrict__ wmat_t,
+                           const float* __restrict__ bias, int c_total, int c_pad, float* __restrict__ logits) {
+  constexpr int KG = 4, PX = 64 * PT, DC = 32;
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                          // [KG][DC][CT]
+  float* s_red = s_dyn + KG * DC * CT;         // [KG-1][CT][PX]
+  const int kg = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int b = blockIdx.y;
+  int s[PT];
+  bool live[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) { s[p] = blockIdx.x * PX + t + 64 * p; live[p] = s[p] < hw; }
+  const int dper = (D + KG - 1) / KG;          // channels per k-group
+  const int cbeg = kg * dper, cend = min(D, cbeg + dper);
+  const float* fb = feat + (long long)b * D * hw;
+  float acc[PT][CT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[p][j] = 0.f;
+  for (int c0 = 0; c0 < dper; c0 += DC) {
+    __syncthreads();
+    // weights arrive K-major ([D][c_pad]): every k-group's chunk is DC contiguous rows -> 16-byte copies
+    {
+      const int r4 = c_pad >> 2;                               // float4 per weight row
+      for (int i = threadIdx.x; i < KG * DC * r4; i += 256) {
+        const int g = i / (DC * r4), r = i - g * (DC * r4);
+        const int c = r / r4, j4 = r - c * r4;
+        const int ch = g * dper + c0 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < dper && ch < D) v = __ldg(reinterpret_cast<const float4*>(wmat_t + (long long)ch * c_pad) + j4);
+        *reinterpret_cast<float4*>(s_w + (g * DC + c) * CT + 4 * j4) = v;
+      }
+      if (c0 == 0 && c_pad < CT)                                // unused accumulator columns stay zero
+        for (int i = threadIdx.x; i < KG * DC * (CT - c_pad); i += 256) {
+          const int row = i / (CT - c_pad), j = c_pad + i % (CT - c_pad);
+          s_w[row * CT + j] = 0.f;
+        }
+    }
+    __syncthreads();
+    const float* wg = s_w + kg * DC * CT;
+    constexpr int U = (PT == 1) ? 8 : 4;
+#pragma unroll 1
+    for (int c = 0; c < DC; c += U) {
+      float x[U][PT];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ch = cbeg + c0 + c + u;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) x[u][p] = (live[p] && ch < cend) ? __ldcs(fb + (long long)ch * hw + s[p]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4* w4 = reinterpret_cast<const float4*>(wg + (c + u) * CT);
+#pragma unroll
+        for (int j4 = 0; j4 < CT / 4; ++j4) {
+          float4 w = w4[j4];
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            acc[p][4 * j4 + 0] = fmaf(x[u][p], w.x, acc[p][4 * j4 + 0]);
+            acc[p][4 * j4 + 1] = fmaf(x[u][p], w.y, acc[p][4 * j4 + 1]);
+            acc[p][4 * j4 + 2] = fmaf(x[u][p], w.z, acc[p][4 * j4 + 2]);
+            acc[p][4 * j4 + 3] = fmaf(x[u][p], w.w, acc[p][4 * j4 + 3]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    // fixed-order reduction over the k-groups through shared memory, one pixel slot at a time
+    if (kg > 0) {
+#pragma unroll
+      for (int j = 0; j < CT; ++j) s_red[((kg - 1) * CT + j) * 64 + t] = acc[p][j];
+    }
+    __syncthreads();
+    if (kg == 0 && live[p]) {
+      float* o = logits + ((long long)b * hw + s[p]) * c_pad;
+#pragma unroll
+      for (int j4 = 0; j4 < CT / 4; ++j4) {
+        if (4 * j4 >= c_pad) break;
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = 4 * j4 + e;
+          r[e] = ((acc[p][j] + s_red[(0 * CT + j) * 64 + t]) + s_red[(1 * CT + j) * 64 + t]) + s_red[(2 * CT + j) * 64 + t];
+          if (bias && j < c_total) r[e] += __ldg(bias + j);
+        }
+        *reinterpret_cast<float4*>(o + 4 * j4) = make_float4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -268,16 +372,22 @@ extern "C" int equss_probe_logits(const float* feat, int B, int D, int h, int w,
   const int hw = h * w;
   const int c_pad = equss_probe_cpad(c_total);
   cudaStream_t st = (cudaStream_t)stream;
-  // CT output channels x PT pixels of accumulators per thread; 64-thread blocks keep the tail of hw small
-  if (c_pad <= 28) {
-    dim3 grid((hw + 255) / 256, B, 1);
-    probe_logits_kernel<28, 4, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
-  } else if (c_pad <= 32) {
-    dim3 grid((hw + 255) / 256, B, 1);
-    probe_logits_kernel<32, 4, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
-  } else if (c_pad <= 56) {
-    dim3 grid((hw + 127) / 128, B, 1);
-    probe_logits_kernel<56, 2, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);
+  if (c_pad <= 56) {
+    const int ptv = (getenv("EQUSS_PROBE_PT") ? atoi(getenv("EQUSS_PROBE_PT")) : 2);
+    dim3 grid((hw + 64 * ptv - 1) / (64 * ptv), B, 1);
+#define EQUSS_KSPLIT(CTV, PTV)                                                                                   \
+    {                                                                                                         \
+      const size_t smem = (size_t)(4 * 32 * CTV + 3 * CTV * 64) * sizeof(float);                              \
+      EQUSS_CUDA_OK(cudaFuncSetAttribute(probe_logits_ksplit_kernel<CTV, PTV>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      probe_logits_ksplit_kernel<CTV, PTV><<<grid, 256, smem, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits); \
+    }
+    if (ptv == 1) {
+      if (c_pad <= 28) EQUSS_KSPLIT(28, 1) else if (c_pad <= 32) EQUSS_KSPLIT(32, 1) else EQUSS_KSPLIT(56, 1)
+    } else {
+      if (c_pad <= 28) EQUSS_KSPLIT(28, 2) else if (c_pad <= 32) EQUSS_KSPLIT(32, 2) else EQUSS_KSPLIT(56, 2)
+    }
+#undef EQUSS_KSPLIT
   } else {
     dim3 grid((hw + 127) / 128, B, (c_pad + 63) / 64);
     probe_logits_kernel<64, 2, 64><<<grid, 64, 0, st>>>(feat, D, hw, wmat, bias, c_total, c_pad, logits);

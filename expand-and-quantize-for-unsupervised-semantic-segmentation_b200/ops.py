@@ -14,7 +14,7 @@ from . import _native as N
 
 __all__ = [
     "pq_cnorm2", "pq_assign", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
-    "pq_distance_prob", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "pq_distance_prob", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
     "launch_count",
 ]
 
@@ -186,20 +186,32 @@ def pq_distance_prob(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optio
     return prob
 
 
-def probe_logits(feat: torch.Tensor, wmat: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Token-resolution probe logits [B*h*w, C_pad] from NCHW features (model/evaluator.py:67,98-100)."""
-    dev = N.require_cuda(feat, wmat, bias)
+def probe_pack(wmat: torch.Tensor):
+    """Pack probe weights [C_total, D] into the K-major, zero-padded [D, C_pad] layout the kernel reads.
+    Do this once per weight update; pass the result to :func:`probe_logits` instead of the raw matrix."""
+    dev = N.require_cuda(wmat)
+    wmat = N.f32c(wmat.detach())
+    Ct, D = wmat.shape
+    cpad = int(N.lib().equss_probe_cpad(Ct))
+    wmat_t = torch.zeros((D, cpad), dtype=torch.float32, device=dev)
+    wmat_t[:, :Ct] = wmat.t()
+    return wmat_t, Ct
+
+
+def probe_logits(feat: torch.Tensor, wmat, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Token-resolution probe logits [B*h*w, C_pad] from NCHW features (model/evaluator.py:67,98-100).
+    ``wmat`` is either the [C_total, D] weight matrix or the result of :func:`probe_pack`."""
+    wmat_t, Ct = wmat if isinstance(wmat, tuple) else probe_pack(wmat)
+    dev = N.require_cuda(feat, wmat_t, bias)
     N.ensure_device(dev)
     feat = N.f32c(feat.detach())
-    wmat = N.f32c(wmat.detach())
     B, D, h, w = feat.shape
-    Ct, D2 = wmat.shape
-    if D2 != D:
-        raise ValueError(f"probe weight has {D2} input channels, features have {D}")
+    if wmat_t.shape[0] != D:
+        raise ValueError(f"probe weight has {wmat_t.shape[0]} input channels, features have {D}")
     b = N.f32c(bias.detach()).reshape(-1) if bias is not None else None
-    cpad = int(N.lib().equss_probe_cpad(Ct))
+    cpad = wmat_t.shape[1]
     logits = torch.empty((B * h * w, cpad), dtype=torch.float32, device=dev)
-    rc = N.lib().equss_probe_logits(feat.data_ptr(), B, D, h, w, wmat.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
+    rc = N.lib().equss_probe_logits(feat.data_ptr(), B, D, h, w, wmat_t.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
                                     N.stream_ptr(dev))
     N.check(rc, "equss_probe_logits")
     return logits

@@ -158,8 +158,9 @@ int equss_pq_distance_prob(const float* z, const equss_zdesc* zd,
 /* ---------------------------------------------------------------------------------------------
  * K8  cluster / linear probe at label resolution   replaces model/evaluator.py:53-54,67-70,95-106
  *   step 1 (token resolution):  logits[b][s][j] = <feat[b,:,s], w[j,:]> + bias[j]
- *           feat: NCHW (B, D, h, w);  w: [C_total][D] (rows 0..C'-1 = L2-normalised cluster centres,
- *           optional rows C'.. = linear-probe weights); bias: [C_total] or NULL;
+ *           feat: NCHW (B, D, h, w);  wmat_t: K-major weights [D][C_pad] (column j = probe channel j: columns
+ *           0..C'-1 = L2-normalised cluster centres, further columns = linear-probe weights, padding
+ *           columns zero); bias: [C_total] or NULL;
  *           logits: [B*h*w][C_pad] with C_pad = equss_probe_cpad(C_total).
  *   step 2 (label resolution):  bilinear (align_corners=False) interpolation of the token logits,
  *           argmax over each head's channel range, int64 predictions, fused confusion histogram.
@@ -172,7 +173,7 @@ int equss_pq_distance_prob(const float* z, const equss_zdesc* zd,
  * ------------------------------------------------------------------------------------------- */
 int equss_probe_cpad(int c_total);
 int equss_probe_logits(const float* feat, int B, int D, int h, int w,
-                       const float* wmat, const float* bias, int c_total,
+                       const float* wmat_t, const float* bias, int c_total,
                        float* logits, void* stream);
 int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
                                  const int64_t* label, int H, int W, int num_classes,

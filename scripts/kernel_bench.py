@@ -51,11 +51,11 @@ if __name__ == "__main__":
     if not only:
         B, D, h, w, H, W, C = 32, 1024, 40, 40, 320, 320, 27
         feats = [torch.randn(B, D, h, w, device=dev) for _ in range(3)]
-        Cp = 28; wmat = torch.randn(Cp + C, D, device=dev); bias = torch.zeros(Cp + C, device=dev)
+        Cp = 28; wmat = torch.randn(Cp + C, D, device=dev); bias = torch.zeros(Cp + C, device=dev); wpack = ops.probe_pack(wmat)
         label = torch.randint(-1, C, (B, H, W), device=dev)
-        ms = timeit(lambda f: ops.probe_logits(f, wmat, bias), feats)
+        ms = timeit(lambda f: ops.probe_logits(f, wpack, bias), feats)
         print(f"probe_logits {ms*1e3:.1f} us  {4*B*D*h*w/ms/1e6:.1f} GB/s")
-        logits = ops.probe_logits(feats[0], wmat, bias)
+        logits = ops.probe_logits(feats[0], wpack, bias)
         cc = torch.zeros(C, C, dtype=torch.long, device=dev); lc = torch.zeros(C, C, dtype=torch.long, device=dev)
         ms = timeit(lambda f: ops.probe_argmax_confusion(logits, B, h, w, Cp + C, label, C, [(0, C), (Cp, C)], want_preds=False, confusions=[cc, lc]), feats)
         print(f"probe_argmax_confusion(no preds) {ms*1e3:.1f} us  {8*B*H*W/ms/1e6:.1f} GB/s")
