@@ -295,24 +295,50 @@ def run_equss(args):
         hl = [torch.randint(-1, C, (B, H, W)).pin_memory() for _ in range(2)]
         out_host = torch.empty(2, C, C, dtype=torch.long).pin_memory()
 
-        def e2e_step(i):
-            z = hz[i % 2].to(dev, non_blocking=True)
-            lab = hl[i % 2].to(dev, non_blocking=True)
+        # Host->device copies run on a side stream one batch ahead of the compute stream (what a prefetching
+        # data loader does); every step still pays its own H2D copy and D2H read inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        dz = [torch.empty(B, D, h, w, device=dev) for _ in range(2)]
+        dl = [torch.empty(B, H, W, dtype=torch.long, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            k = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[k])
+                dz[k].copy_(hz[k], non_blocking=True)
+                dl[k].copy_(hl[k], non_blocking=True)
+                ready[k].record(copy_stream)
+
+        def e2e_step(i, n_total):
+            k = i % 2
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[k])
             with torch.no_grad():
-                zq, _, _, _ = pqm(z)
-                evalr.predict(zq, lab, cm.confusion_matrix, lm.confusion_matrix, want_preds=False)
+                zq, _, _, _ = pqm(dz[k])
+                evalr.predict(zq, dl[k], cm.confusion_matrix, lm.confusion_matrix, want_preds=False)
+            freed[k].record(cur)
+            if i + 2 < n_total:
+                prefetch(i + 2)
             out_host[0].copy_(cm.confusion_matrix, non_blocking=True)
             out_host[1].copy_(lm.confusion_matrix, non_blocking=True)
-            torch.cuda.current_stream().synchronize()     # the step's result is on the host
+            cur.synchronize()                              # the step's result is on the host
 
-        n_e2e = max(3, min(args.steps, 10))
-        for i in range(2):
-            e2e_step(i)
+        def e2e_run(n):
+            for k in range(2):
+                freed[k].record(torch.cuda.current_stream())
+            for i in range(min(2, n)):
+                prefetch(i)
+            for i in range(n):
+                e2e_step(i, n)
+
+        n_e2e = max(4, min(args.steps, 20))
+        e2e_run(3)
         sync_all()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for i in range(n_e2e):
-            e2e_step(i)
+        e2e_run(n_e2e)
         s1.record()
         sync_all()
         t = torch.tensor([s0.elapsed_time(s1)], device=dev)
@@ -320,7 +346,7 @@ def run_equss(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * N * n_e2e / (float(t.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": 4 * N * D + 8 * P, "d2h_bytes_per_step": 2 * C * C * 8, "steps": n_e2e,
-               "api": "PQGOProductQuantizerWrapper.forward + UnSegEvaluator.predict (fused UnSegMetrics buffers)"}
+               "api": "PQGOProductQuantizerWrapper.forward + UnSegEvaluator.predict (fused UnSegMetrics buffers); H2D of batch i+1 overlaps compute of batch i on a copy stream"}
 
     if rank != 0:
         if world > 1:
