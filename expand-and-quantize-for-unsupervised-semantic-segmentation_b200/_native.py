@@ -15,14 +15,14 @@ import torch
 
 __all__ = [
     "EqussNativeError", "lib", "lib_path", "load", "NORM_MODES", "ZDesc", "zdesc_for",
-    "ASSIGN_AUTO", "ASSIGN_SIMT", "ASSIGN_TCGEN05", "EXPORTS",
+    "ASSIGN_AUTO", "ASSIGN_SIMT", "ASSIGN_TCGEN05", "ASSIGN_TCGEN05_TF32", "EXPORTS",
 ]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libequss_b200.so"
 
 NORM_MODES = {"none": 0, None: 0, "l2": 1, "z_norm": 2, "z_trainable": 3, "affine": 3}
-ASSIGN_AUTO, ASSIGN_SIMT, ASSIGN_TCGEN05 = 0, 1, 2
+ASSIGN_AUTO, ASSIGN_SIMT, ASSIGN_TCGEN05, ASSIGN_TCGEN05_TF32 = 0, 1, 2, 3
 LAYOUT_FLAT, LAYOUT_NCHW = 0, 1
 
 # every symbol include/equss_b200.h declares (checked by tests/test_abi.py)

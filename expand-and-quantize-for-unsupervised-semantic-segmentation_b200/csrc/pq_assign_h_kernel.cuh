@@ -1,0 +1,582 @@
+// pq_assign_h_kernel.cuh -- K1 for l2-normalised rows on the 5th-generation tensor cores, second design:
+// kind::f16 MMAs on a two-piece fp16 split of both operands, float-domain argmax epilogue, exact fp32
+// re-score of rows whose top-2 gap is inside the error bound (model/quantizer.py:457-467).
+//
+// Arithmetic
+//   argmin_k (|z|^2 + |c_k|^2) - 2<z,c_k>  ==  argmax_k  s_k := <z,c_k> - |c_k|^2/2       (z = l2-normalised row)
+//   x = z (|x_i| <= 1),  y = beta*c  with beta a power of two such that max|y| in [1/2, 1]  (per subspace)
+//   x = x1 + x2 + O(2^-22|x| + 2^-25),  x1 = fp16(x), x2 = fp16(x - x1);  same for y
+//   beta*s_k ~= x1.y1 + x2.y1 + x1.y2 + 1*(b1+b2+b3),   b = -beta*|c_k|^2/2 in three fp16 pieces
+//   -> 3*d/16 + 1 MMAs of K = 16 per tile (the split-tf32 kernel needs 3*d/8 + 1 of K = 8: 7 vs 4 at d = 16,
+//   25 vs 13 at d = 64), operand tiles half the bytes.  The normalisation feeding the GEMM is a single
+//   rsqrt + multiply; only the exact path uses the canonical division.
+//
+// Exact argmin from an approximate GEMM
+//   The accumulators are compared as plain floats.  Two orthogonal column partitions -- 16 running class
+//   maxima (column mod 16) and the top-2 of the 16-column group maxima -- give the winning column and the exact
+//   runner-up score at 1.3 ALU-pipe operations per element (FMNMX3).  A row whose gap exceeds the slot's
+//   tolerance (2^-16 R + absolute floor, R >= max|beta s|; the GEMM error is below ~1e-6 R) has a certain
+//   winner.  The others (~3e-4 of the rows) are re-scored in the reference's fp32 arithmetic -- canonical z_norm,
+//   sequential fma dot, (sum z^2 + sum c^2) - 2 dot, first minimal index -- from global memory, i.e. the same
+//   code path as the SIMT kernel, so both kernels return identical indices.
+//
+// Structure (one persistent CTA per SM, 15 warps): warps 0-3 convert (raw tile -> normalise -> fp16 split ->
+// UMMA K-major core-matrix layout), 4-11 epilogue (two groups of four, alternating tiles, TMEM lane quarter =
+// warp % 4), 12 TMA producer, 13/14 MMA issuers (one per accumulator half).  A CTA walks a contiguous range of
+// units ordered (subspace group, code chunk, pixel tile, subspace in group): the G = 128/(4d) subspaces that
+// share a 128-byte line of a flat row are processed back to back, so the second half of every line is an L2 hit,
+// and the G operand images stay resident in shared memory.  Codebooks with K > NC are split into chunks whose
+// winners are merged with a 64-bit atomicMax on (score, index); cross-chunk near-ties are appended to a list and
+// resolved by a full exact scan (one warp per listed row) after the main kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cstdio>
+#include "equss_common.cuh"
+#include "equss_tcgen05.cuh"
+#include "pq_assign.h"
+
+namespace equss {
+namespace tch {
+
+using namespace ::equss::ptx;
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 480;
+// The SMSP arbiter prefers the highest warp id among eligible warps: the convert warps (the pipeline's critical
+// stage) get the highest ids, the epilogue warps (ALU-pipe heavy, plenty of slack) the lowest.
+constexpr int kEpiWarp0 = 0, kProducerWarp = 8, kMmaWarp = 9, kConvWarp0 = 11;
+constexpr float kTolRel = 1.52587890625e-5f;     // 2^-16
+
+#ifdef EQUSS_TRACE   // scripts/trace_assign.cu: per-unit clock64 stamps of CTA 0 (pipeline timeline)
+__device__ long long g_trace[256 * 8];
+#define EQUSS_TR(slot, i) do { if (blockIdx.x == 0 && (i) < 256 && lane == 0) g_trace[(i) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define EQUSS_TR(slot, i) do { } while (0)
+#endif
+
+__host__ __device__ constexpr int kch(int D) { return 2 * (D / 8) + 2; }           // 16-byte K chunks per row
+__host__ __device__ constexpr int b_sbo(int D) { return kch(D) * 128; }
+__host__ __device__ constexpr int b_bytes(int D, int NC) { return (NC / 8) * b_sbo(D) + 128; }   // + trailer
+// A operand: stride between K chunks chosen so that one convert store instruction (8-byte pieces of 32/(D/4)
+// rows x D/4 lanes) touches every bank at most twice
+__host__ __device__ constexpr int a_lbo(int D) { return D == 16 ? 128 : D == 32 ? 160 : 144; }
+__host__ __device__ constexpr int a_sbo(int D) { return kch(D) * a_lbo(D); }
+__host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * a_sbo(D); }
+__host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
+__host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
+__host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs) {
+  return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) + 512;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, both K-major, M = 128, N
+__host__ __device__ constexpr uint32_t make_idesc(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct Params {
+  long long n_pixels, hw;
+  int M, K, D, NC, nchunks, G;
+  int tiles_per_image;
+  long long n_tiles;
+  const float* z;
+  ZView zv;
+  const float* cb;            // codebook_norm [M][K][d]
+  const float* cn2;           // [M][K]
+  const uint8_t* images;      // [M/G][nchunks][G] operand images
+  int img_bytes;
+  int32_t* idx_out;
+  unsigned long long* merged; // nchunks > 1: [M][N] (sortable score << 32 | index), zero-initialised
+  uint32_t* flag_list;        // nchunks > 1: [M*N] rows (m*N + n) with a cross-chunk near-tie (duplicates allowed)
+  unsigned int* flag_count;   // nchunks > 1: number of entries in flag_list, zero-initialised
+};
+
+// Walks the CTA's contiguous unit range (sslot-major, then tile, then subspace-in-group) without divisions.
+struct UnitIter {
+  int sslot, tile, g, sg, chunk, n_tiles, nchunks, G;
+  __device__ __forceinline__ void init(long long u0, int n_tiles_, int nchunks_, int G_) {
+    n_tiles = n_tiles_; nchunks = nchunks_; G = G_;
+    const long long per = (long long)n_tiles_ * G_;
+    sslot = (int)(u0 / per);
+    const int rem = (int)(u0 - (long long)sslot * per);
+    tile = rem / G_; g = rem - tile * G_;
+    sg = sslot / nchunks_; chunk = sslot - sg * nchunks_;
+  }
+  __device__ __forceinline__ void next() {
+    if (++g == G) {
+      g = 0;
+      if (++tile == n_tiles) {
+        tile = 0; ++sslot;
+        if (++chunk == nchunks) { chunk = 0; ++sg; }
+      }
+    }
+  }
+  __device__ __forceinline__ int m() const { return sg * G + g; }
+};
+
+__device__ __forceinline__ unsigned int sortable(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unsortable(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// One 32-column chunk of accumulators: class maxima (column mod 16), top-2 of the 16-column group maxima and
+// the id of the best group.  `gid` = index of the chunk's first group.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int gid, float (&cls)[16], float& m1, float& m2, int& g1) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], __uint_as_float(v[r]), __uint_as_float(v[r + 16]));
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const uint32_t* k = v + 16 * g;
+#define F(i) __uint_as_float(k[i])
+    float t0 = max3f(F(0), F(1), F(2)), t1 = max3f(F(3), F(4), F(5)), t2 = max3f(F(6), F(7), F(8));
+    float t3 = max3f(F(9), F(10), F(11)), t4 = max3f(F(12), F(13), F(14));
+    float gm = fmaxf(max3f(t0, t1, t2), max3f(t3, t4, F(15)));
+#undef F
+    m2 = fmaxf(m2, fminf(m1, gm));
+    g1 = (gm > m1) ? (gid + g) : g1;
+    m1 = fmaxf(m1, gm);
+  }
+}
+
+// Exact fp32 re-score of the chunk-local columns {r + 16 j : bit r of cmask set, column < kvalid} of row n,
+// subspace m, by the whole warp: every lane builds the canonical z_norm from global memory (the SIMT kernel's
+// arithmetic), lanes split the candidate columns, the minimum (lowest column on ties) is combined by shuffles.
+// Returns the chunk-local column to all lanes.
+template <int D>
+__device__ __noinline__ int exact_rescore_warp(const Params& p, int m, long long n, int k0, int kvalid, uint32_t cmask, int lane) {
+  constexpr int LPS = D / 4;
+  // candidate of this lane (first round) -- its loads are issued together with the row's, one memory round trip
+  const int ncand = __popc(cmask) * 16;
+  const float* cbm = p.cb + ((long long)m * p.K + k0) * D;
+  const float* cn2m = p.cn2 + (long long)m * p.K + k0;
+  int c = lane;
+  int col = (c < ncand) ? (int)__fns(cmask, 0, (c >> 4) + 1) + 16 * (c & 15) : kvalid;
+  constexpr bool kPrefetch = (D <= 32);      // d = 64: the row alone fills the register file
+  float4 cv[LPS];
+  float c2 = 0.f;
+  if (kPrefetch && col < kvalid) {
+    const float4* c4 = reinterpret_cast<const float4*>(cbm + (long long)col * D);
+#pragma unroll
+    for (int q = 0; q < LPS; ++q) cv[q] = __ldg(c4 + q);
+    c2 = __ldg(cn2m + col);
+  }
+  float x[D];
+  const long long base = pixel_base(p.zv, n) + (long long)m * D * p.zv.stride_c;
+#pragma unroll
+  for (int j = 0; j < D; ++j) x[j] = __ldg(p.z + base + j * p.zv.stride_c);
+  float gsum[LPS];
+#pragma unroll
+  for (int q = 0; q < LPS; ++q) gsum[q] = group_sumsq(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+  const RowNorm rn = l2_from_sumsq(butterfly_array<LPS>(gsum));
+#pragma unroll
+  for (int j = 0; j < D; ++j) x[j] = x[j] / rn.denom;
+#pragma unroll
+  for (int q = 0; q < LPS; ++q) gsum[q] = group_sumsq(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+  const float zn2 = butterfly_array<LPS>(gsum);
+  float best = INFINITY;
+  int best_col = 0x7fffffff;
+#pragma unroll 1
+  while (true) {
+    if (col < kvalid) {
+      if (!kPrefetch) {
+        const float4* c4 = reinterpret_cast<const float4*>(cbm + (long long)col * D);
+#pragma unroll
+        for (int q = 0; q < LPS; ++q) cv[q] = __ldg(c4 + q);
+        c2 = __ldg(cn2m + col);
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < LPS; ++q) {
+        dot = fmaf(x[4 * q], cv[q].x, dot);
+        dot = fmaf(x[4 * q + 1], cv[q].y, dot);
+        dot = fmaf(x[4 * q + 2], cv[q].z, dot);
+        dot = fmaf(x[4 * q + 3], cv[q].w, dot);
+      }
+      const float dd = ref_distance(zn2, c2, dot);
+      if (dd < best || (dd == best && col < best_col)) { best = dd; best_col = col; }
+    }
+    c += 32;
+    if (c >= ncand) break;
+    col = (int)__fns(cmask, 0, (c >> 4) + 1) + 16 * (c & 15);
+    if (kPrefetch && col < kvalid) {
+      const float4* c4 = reinterpret_cast<const float4*>(cbm + (long long)col * D);
+#pragma unroll
+      for (int q = 0; q < LPS; ++q) cv[q] = __ldg(c4 + q);
+      c2 = __ldg(cn2m + col);
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, s);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_col, s);
+    if (ob < best || (ob == best && oc < best_col)) { best = ob; best_col = oc; }
+  }
+  return best_col == 0x7fffffff ? 0 : best_col;
+}
+
+template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW>
+__global__ void __launch_bounds__(kThreads, 1)
+assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  constexpr int SBO = b_sbo(D);
+  constexpr int ASBO = a_sbo(D), ALBO = a_lbo(D);
+  constexpr int B_BYTES = align_up(b_bytes(D, NC), 128);
+  constexpr int A_BYTES = align_up(a_bytes(D), 128);
+  constexpr int RAW_BYTES = raw_bytes(D);
+  constexpr int TMEM_COLS = (2 * NC <= 32) ? 32 : (2 * NC <= 64) ? 64 : (2 * NC <= 128) ? 128 : (2 * NC <= 256) ? 256 : 512;
+  constexpr int LPS = D / 4;                   // lanes per pixel row in the flat convert
+  constexpr int C8 = D / 8;                    // 16-byte chunks per operand piece
+  constexpr int HALVES = (NC >= 64) ? 2 : 1;   // accumulator halves with their own barriers / issuer warps
+  constexpr int NH = NC / HALVES;
+  constexpr uint32_t IDESC = make_idesc(NH);
+  static_assert(NC % 32 == 0 && NC <= 256, "NC must be a multiple of 32, at most 256");
+  static_assert(D == 16 || D == 32 || D == 64, "D must be 16, 32 or 64");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* s_b = smem;                                   // [G][B_BYTES]
+  uint8_t* s_a = s_b + G * B_BYTES;                      // [ABUFS][A_BYTES]
+  uint8_t* s_rawt = s_a + ABUFS * A_BYTES;               // [STAGES][RAW_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES);
+  uint64_t* raw_full = bars;                    // [STAGES]
+  uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
+  uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
+  uint64_t* a_empty = a_full + ABUFS;           // [ABUFS]   arrived by tcgen05.commit: the MMAs have read A (and B)
+  uint64_t* t_full = a_empty + ABUFS;           // [4]  (unit parity, half)
+  uint64_t* t_empty = t_full + 4;               // [4]
+  uint64_t* b_full = t_empty + 4;               // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const long long total_units = (long long)p.M * p.nchunks * p.n_tiles;
+  const long long u0 = total_units * blockIdx.x / gridDim.x;
+  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  const int n_units = (int)(u1 - u0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 4); }
+    for (int i = 0; i < ABUFS; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, HALVES); }
+    for (int i = 0; i < 4; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<TMEM_COLS>(s_tmem);
+  // constant bias chunks of the A operand: fp16 (1,1,1,0,0,0,0,0) and zeros
+  for (int i = threadIdx.x; i < ABUFS * kTileM; i += blockDim.x) {
+    const int a = i / kTileM, row = i % kTileM;
+    uint8_t* rowp = s_a + a * A_BYTES + (row / 8) * ASBO + (row % 8) * 16;
+    *reinterpret_cast<uint4*>(rowp + (2 * C8) * ALBO) = make_uint4(0x3C003C00u, 0x00003C00u, 0u, 0u);
+    *reinterpret_cast<uint4*>(rowp + (2 * C8 + 1) * ALBO) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == kProducerWarp) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+      for (int i = 0; i < n_units; ++i, it.next()) {
+        const int tile = it.tile, m = it.m();
+        const int s = i % STAGES;
+        mbar_wait(raw_empty + s, ((i / STAGES) & 1) ^ 1, 10 + s);
+        mbar_expect_tx(raw_full + s, RAW_BYTES);
+        if (!NCHW) {
+          tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, tile * kTileM, raw_full + s);
+        } else {
+          const int b = tile / p.tiles_per_image;
+          const int t = tile - b * p.tiles_per_image;
+          tma_load_3d(s_rawt + s * RAW_BYTES, &tmap, t * kTileM, m * D, b, raw_full + s);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+    // ===================================== MMA issuers ======================================
+    const int h = warp - kMmaWarp;
+    if (h < HALVES) {
+      const uint32_t b_hi = (uint32_t)((SBO >> 4) & 0x3FFF) | (1u << 14);              // SBO, descriptor version 1
+      const uint32_t a_hi = (uint32_t)((ASBO >> 4) & 0x3FFF) | (1u << 14);
+      const uint32_t b_lo0 = ((smem_u32(s_b) + (uint32_t)(h * (NH / 8) * SBO)) >> 4) | ((uint32_t)(128 >> 4) << 16);
+      const uint32_t a_lo0 = (smem_u32(s_a) >> 4) | ((uint32_t)(ALBO >> 4) << 16);
+      int b_loads = 0, cur_slot = -1;
+      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+      for (int i = 0; i < n_units; ++i, it.next()) {
+        const int a = i % ABUFS, t = i & 1;
+        const int tb = t * 2 + h;
+        if (h == 0) EQUSS_TR(7, i);
+        if (it.sslot != cur_slot) {
+          mbar_wait(b_full, b_loads & 1, 20);
+          ++b_loads;
+          cur_slot = it.sslot;
+        }
+        mbar_wait(a_full + a, (i / ABUFS) & 1, 21);
+        mbar_wait(t_empty + tb, ((i >> 1) & 1) ^ 1, 22);
+        tc_fence_after();
+        if (h == 0) EQUSS_TR(3, i);
+        if (lane == 0) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)(a * (A_BYTES >> 4));
+          const uint32_t b_lo = b_lo0 + (uint32_t)(it.g * (B_BYTES >> 4));
+          const uint32_t d_addr = tmem_base + (uint32_t)(t * NC + h * NH);
+          uint32_t acc = 0;
+          // x1.y1, x2.y1, x1.y2 : K-slice kk of a piece starts 2*kk chunks into its region
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            const int a_off = (part == 1) ? C8 : 0;
+            const int b_off = (part == 2) ? C8 : 0;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+              umma_f16(d_addr, desc_from(a_lo + (uint32_t)((a_off + 2 * kk) * (ALBO >> 4)), a_hi),
+                       desc_from(b_lo + (uint32_t)((b_off + 2 * kk) * 8), b_hi), IDESC, acc);
+              acc = 1;
+            }
+          }
+          umma_f16(d_addr, desc_from(a_lo + (uint32_t)(2 * C8 * (ALBO >> 4)), a_hi),
+                   desc_from(b_lo + (uint32_t)(2 * C8 * 8), b_hi), IDESC, 1);
+          umma_commit(t_full + tb);
+          umma_commit(a_empty + a);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kConvWarp0) {
+    // ===================================== convert warps (11-14) ==================================
+    const int ct = threadIdx.x - kConvWarp0 * 32;   // 0..127
+    int b_loads = 0, cur_slot = -1;
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+    for (int i = 0; i < n_units; ++i, it.next()) {
+      const int a = i % ABUFS, s = i % STAGES;
+      mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
+      if (warp == kConvWarp0) EQUSS_TR(0, i);
+      if (it.sslot != cur_slot) {
+        // every earlier MMA must have completed before the operand images are overwritten
+#pragma unroll
+        for (int back = 1; back < ABUFS; ++back)
+          if (i >= back) mbar_wait(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
+        if (ct == 0) {
+          mbar_expect_tx(b_full, (uint32_t)(G * p.img_bytes));
+          bulk_load_1d(s_b, p.images + (size_t)it.sslot * G * p.img_bytes, (uint32_t)(G * p.img_bytes), b_full);
+        }
+        cur_slot = it.sslot;
+        ++b_loads;
+      }
+      mbar_wait(raw_full + s, (i / STAGES) & 1, 33);
+      if (warp == kConvWarp0) EQUSS_TR(1, i);
+      uint8_t* a_tile = s_a + a * A_BYTES;
+      const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
+      if (!NCHW) {
+        // flat: raw[row][D]; LPS lanes per row, one float4 each.  All loads of a batch of passes are issued before
+        // any store (the compiler cannot prove that the A tile and the raw tile do not alias, so a store between
+        // two loads would serialise the passes into one long dependent chain).
+        constexpr int ROWS_PER_PASS = 128 / LPS;
+        constexpr int PASSES = kTileM / ROWS_PER_PASS;
+        constexpr int BATCH = PASSES < 8 ? PASSES : 8;
+        const int l = ct % LPS;
+        const int row0 = ct / LPS;
+#pragma unroll 1
+        for (int pb = 0; pb < PASSES; pb += BATCH) {
+          float4 v[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u)
+            v[u] = *reinterpret_cast<const float4*>(raw + ((pb + u) * ROWS_PER_PASS + row0) * D + l * 4);
+          float ss[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) ss[u] = group_sumsq(v[u].x, v[u].y, v[u].z, v[u].w);
+#pragma unroll
+          for (int sft = 1; sft < LPS; sft <<= 1) {
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], sft);
+          }
+          uint2 hi[BATCH], lo[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const float inv = fminf(rsqrtf(ss[u]), 1e12f);
+            const float zx = v[u].x * inv, zy = v[u].y * inv, zz = v[u].z * inv, zw = v[u].w * inv;
+            const __half2 h01 = __floats2half2_rn(zx, zy), h23 = __floats2half2_rn(zz, zw);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(zx - f01.x, zy - f01.y), l23 = __floats2half2_rn(zz - f23.x, zw - f23.y);
+            hi[u].x = *reinterpret_cast<const uint32_t*>(&h01); hi[u].y = *reinterpret_cast<const uint32_t*>(&h23);
+            lo[u].x = *reinterpret_cast<const uint32_t*>(&l01); lo[u].y = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            const int row = (pb + u) * ROWS_PER_PASS + row0;
+            uint8_t* rowp = a_tile + (row / 8) * ASBO + (row % 8) * 16 + (l >> 1) * ALBO + (l & 1) * 8;
+            *reinterpret_cast<uint2*>(rowp) = hi[u];
+            *reinterpret_cast<uint2*>(rowp + C8 * ALBO) = lo[u];
+          }
+        }
+      } else {
+        // NCHW: raw[channel][128 pixels]; one thread per pixel row
+        const int row = ct;
+        float x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = raw[j * kTileM + row];
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) ss = fmaf(x[j], x[j], ss);
+        const float inv = fminf(rsqrtf(ss), 1e12f);
+        uint8_t* rowp = a_tile + (row / 8) * ASBO + (row % 8) * 16;
+#pragma unroll
+        for (int c = 0; c < C8; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float z0 = x[8 * c + 2 * e] * inv, z1 = x[8 * c + 2 * e + 1] * inv;
+            const __half2 hh = __floats2half2_rn(z0, z1);
+            const float2 ff = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(z0 - ff.x, z1 - ff.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          *reinterpret_cast<uint4*>(rowp + c * ALBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(rowp + (C8 + c) * ALBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async();     // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
+      if (warp == kConvWarp0) EQUSS_TR(2, i);
+    }
+  } else {
+    // ===================================== epilogue warps ===================================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int egroup = (warp - kEpiWarp0) >> 2;  // 0 or 1
+    const int row = q * 32 + lane;
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+    for (int i = 0; i < n_units; ++i, it.next()) {
+      const int t = i & 1;
+      if (t != egroup) continue;     // the other epilogue group's unit
+      const int tile = it.tile, m = it.m(), chunk = it.chunk;
+      // the slot's tolerance: trailer of the operand image (global memory; latency hidden by the barrier wait)
+      const float tol = __ldg(reinterpret_cast<const float*>(p.images + ((size_t)it.sslot * G + it.g) * p.img_bytes +
+                                                               (size_t)(NC / 8) * SBO));
+      float cls[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) cls[r] = -INFINITY;
+      float m1 = -INFINITY, m2 = -INFINITY;
+      int g1 = 0;
+#pragma unroll 1
+      for (int h = 0; h < HALVES; ++h) {
+        const int tb = t * 2 + h;
+        mbar_wait(t_full + tb, (i >> 1) & 1, 41);
+        tc_fence_after();
+        if (q == 0 && h == 0) EQUSS_TR(4, i);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NC + h * NH);
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        if constexpr (NH == 32) {
+          tmem_ld_wait();
+          epi_chunk(va, h * (NH / 16), cls, m1, m2, g1);
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < NH / 32; c += 2) {
+            tmem_ld_wait();
+            tmem_ld32(taddr + (c + 1) * 32, vb);
+            epi_chunk(va, h * (NH / 16) + 2 * c, cls, m1, m2, g1);
+            tmem_ld_wait();
+            if (c + 2 < NH / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+            epi_chunk(vb, h * (NH / 16) + 2 * c + 2, cls, m1, m2, g1);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + tb);
+      }
+
+      if (q == 0) EQUSS_TR(5, i);
+      // winning column = best group * 16 + the class whose running maximum equals the best score
+      int r1 = 0;
+#pragma unroll
+      for (int r = 15; r >= 0; --r) r1 = (cls[r] == m1) ? r : r1;
+      int best_col = g1 * 16 + r1;
+      float runner = m2;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) runner = fmaxf(runner, (r1 == r) ? -INFINITY : cls[r]);
+      long long n;
+      bool live;
+      if (!NCHW) {
+        n = (long long)tile * kTileM + row;
+        live = n < p.n_pixels;
+      } else {
+        const long long b = tile / p.tiles_per_image;
+        const long long sidx = (long long)(tile - (int)b * p.tiles_per_image) * kTileM + row;
+        live = sidx < p.hw;
+        n = b * p.hw + sidx;
+      }
+      const int kvalid = min(NC, p.K - chunk * NC);
+      const bool amb = live && (!(m1 - runner > tol) || best_col >= kvalid);
+      unsigned todo = __ballot_sync(0xffffffffu, amb);
+      if (todo) {
+        // ambiguous rows: exact fp32 re-score of every column whose class maximum is within tolerance, one row
+        // at a time by the whole warp
+        const float thr = m1 - tol;
+        uint32_t cmask = 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) cmask |= (!(cls[r] < thr)) ? (1u << r) : 0u;
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const long long n_s = __shfl_sync(0xffffffffu, n, src);
+          const uint32_t cm_s = __shfl_sync(0xffffffffu, cmask, src);
+          const int res = exact_rescore_warp<D>(p, m, n_s, chunk * NC, kvalid, cm_s, lane);
+          if (lane == src) best_col = res;
+        }
+      }
+      if (live) {
+        if (p.merged == nullptr) {
+          p.idx_out[(long long)m * p.n_pixels + n] = best_col;
+        } else {
+          const long long o = (long long)m * p.n_pixels + n;
+          const unsigned long long mine = ((unsigned long long)sortable(m1) << 32) | (unsigned long long)(uint32_t)(chunk * NC + best_col);
+          const unsigned long long old = atomicMax(p.merged + o, mine);
+          if (old != 0ull) {
+            const float so = unsortable((unsigned int)(old >> 32));
+            if (!(fabsf(so - m1) > 2.f * tol)) p.flag_list[atomicAdd(p.flag_count, 1u)] = (uint32_t)o;
+          }
+        }
+      }
+      if (q == 0) EQUSS_TR(6, i);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW>
+static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st) {
+  constexpr int SMEM = smem_bytes(D, NC, G, STAGES, ABUFS) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, G, STAGES, ABUFS);
+  static_assert(SMEM <= 227 * 1024, "shared-memory plan exceeds 227 KB");
+  EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW><<<grid, kThreads, SMEM, st>>>(tmap, p);
+  EQUSS_LAUNCH_OK("assign_f16x2_kernel");
+  return EQUSS_OK;
+}
+
+// per-d dispatch over (NC, G, layout); one translation unit per d keeps the build parallel.  GV = subspaces
+// per 128-byte line of a flat row (used when M is a multiple of it; NCHW and odd M run with G = 1).
+#define EQUSS_TCH_DISPATCH(DV, GV, STV, ABV)                                                                  \
+  int launch_tch_d##DV(int NC, int G, bool nchw, const CUtensorMap& tmap, const Params& p, int grid,         \
+                       cudaStream_t st) {                                                                    \
+    EQUSS_TCH_ONE(DV, 32, GV, STV, ABV) EQUSS_TCH_ONE(DV, 256, GV, STV, ABV)                                  \
+    set_error("tcgen05 f16x2 assign: no instantiation for d=%d NC=%d", DV, NC);                               \
+    return EQUSS_ERR_UNSUPPORTED;                                                                             \
+  }
+#define EQUSS_TCH_ONE(DV, NCV, GV, STV, ABV)                                                                  \
+  if (NC == NCV) {                                                                                            \
+    if (nchw) return launch_instance<DV, NCV, 1, STV, ABV, true>(tmap, p, grid, st);                          \
+    if (G == GV) return launch_instance<DV, NCV, GV, STV, ABV, false>(tmap, p, grid, st);                     \
+    return launch_instance<DV, NCV, 1, STV, ABV, false>(tmap, p, grid, st);                                   \
+  }
+
+}  // namespace tch
+}  // namespace equss

@@ -196,7 +196,8 @@ using namespace equss;
 
 extern "C" int64_t equss_pq_assign_workspace_bytes(int64_t n_pixels, int M, int K, int d, int algo) {
   if (algo == EQUSS_ASSIGN_SIMT) return 0;
-  return assign_tc_workspace_bytes(n_pixels, M, K, d);
+  const int64_t a = assign_tc_workspace_bytes(n_pixels, M, K, d), b = assign_tch_workspace_bytes(n_pixels, M, K, d);
+  return a > b ? a : b;
 }
 
 extern "C" int equss_pq_assign(const float* z, const equss_zdesc* zd, const float* codebook_norm,
@@ -212,14 +213,18 @@ extern "C" int equss_pq_assign(const float* z, const equss_zdesc* zd, const floa
                 "Unsupported normalize type %d", norm_mode);
   EQUSS_REQUIRE(norm_mode != EQUSS_NORM_AFFINE || (norm_a && norm_b), EQUSS_ERR_INVALID_ARG,
                 "EQUSS_NORM_AFFINE needs norm_a and norm_b");
-  EQUSS_REQUIRE(algo >= EQUSS_ASSIGN_AUTO && algo <= EQUSS_ASSIGN_TCGEN05, EQUSS_ERR_INVALID_ARG, "bad algo %d", algo);
+  EQUSS_REQUIRE(algo >= EQUSS_ASSIGN_AUTO && algo <= EQUSS_ASSIGN_TCGEN05_TF32, EQUSS_ERR_INVALID_ARG, "bad algo %d", algo);
   if (zd->n_pixels == 0) return EQUSS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc_ok = assign_tc_supported(zd, M, K, d, norm_mode, margin_out != nullptr);
-  if (algo == EQUSS_ASSIGN_TCGEN05 && !tc_ok) {
+  const bool tch_ok = assign_tch_supported(zd, M, K, d, norm_mode, margin_out != nullptr);
+  if ((algo == EQUSS_ASSIGN_TCGEN05 || algo == EQUSS_ASSIGN_TCGEN05_TF32) && !tc_ok) {
     set_error("equss_pq_assign: shape (layout=%d M=%d K=%d d=%d norm=%d) is not supported by the tcgen05 kernel",
               zd->layout, M, K, d, norm_mode);
     return EQUSS_ERR_UNSUPPORTED;
+  }
+  if (tch_ok && (algo == EQUSS_ASSIGN_AUTO || algo == EQUSS_ASSIGN_TCGEN05)) {
+    return assign_tch_launch(z, zd, codebook_norm, cnorm2, M, K, d, idx_out, workspace, workspace_bytes, st);
   }
   if (tc_ok && algo != EQUSS_ASSIGN_SIMT) {
     return assign_tc_launch(z, zd, codebook_norm, cnorm2, M, K, d, norm_mode, norm_a, norm_b, idx_out,

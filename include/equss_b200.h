@@ -49,7 +49,9 @@ extern "C" {
  * shape is supported and the exact SIMT kernel otherwise; both are CUDA, neither is a fallback to CPU. */
 #define EQUSS_ASSIGN_AUTO     0
 #define EQUSS_ASSIGN_SIMT     1   /* exact fp32 CUDA-core scan (validator + odd shapes)          */
-#define EQUSS_ASSIGN_TCGEN05  2   /* split-tf32 tcgen05/TMEM GEMM + fused argmin + fp32 re-score */
+#define EQUSS_ASSIGN_TCGEN05  2   /* tcgen05/TMEM GEMM + fused argmin + exact fp32 re-score: the fp16-split kernel
+                                     for l2 rows with d in {16,32,64}, else the split-tf32 kernel            */
+#define EQUSS_ASSIGN_TCGEN05_TF32 3 /* force the split-tf32 tcgen05 kernel (all norm modes, d in {8,16,32,64})  */
 
 typedef struct equss_zdesc {
   int64_t n_pixels;   /* N = B*HW                                  */

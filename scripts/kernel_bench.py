@@ -32,6 +32,8 @@ def run(tag, shape, M, K, d, nbuf=3, only=None):
     res = {}
     if not only or "tc" in only:
         res["assign_tc"] = (timeit(lambda z: ops.pq_assign(z, cbn, cn2, "l2", algo=2), zs), 4 * N * D + 4 * N * M)
+    if only and "tf32" in only:
+        res["assign_tf32"] = (timeit(lambda z: ops.pq_assign(z, cbn, cn2, "l2", algo=3), zs), 4 * N * D + 4 * N * M)
     if not only or "simt" in only:
         res["assign_simt"] = (timeit(lambda z: ops.pq_assign(z, cbn, cn2, "l2", algo=1), zs, iters=5, warm=1), 4 * N * D + 4 * N * M)
     if not only or "rows" in only:

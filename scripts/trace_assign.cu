@@ -1,0 +1,53 @@
+// Pipeline timeline of the fp16-split assign kernel: per-unit clock64 stamps of CTA 0.  Debug tool, not shipped.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DEQUSS_TRACE -lcuda \
+//        -o gpurun_out/trace_assign scripts/trace_assign.cu && gpurun -- gpurun_out/trace_assign
+#include "../expand-and-quantize-for-unsupervised-semantic-segmentation_b200/csrc/equss_core.cu"
+#include "../expand-and-quantize-for-unsupervised-semantic-segmentation_b200/csrc/pq_assign_h.cu"
+#include "../expand-and-quantize-for-unsupervised-semantic-segmentation_b200/csrc/pq_assign_h_d16.cu"
+#include "../expand-and-quantize-for-unsupervised-semantic-segmentation_b200/csrc/pq_assign_h_d32.cu"
+#include "../expand-and-quantize-for-unsupervised-semantic-segmentation_b200/csrc/pq_assign_h_d64.cu"
+#include <vector>
+#include <cstdlib>
+#include <cmath>
+using namespace equss;
+__global__ void cn2_k(const float* cb, int rows, int d, float* o) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) { float s = 0; for (int j = 0; j < d; ++j) s += cb[r * d + j] * cb[r * d + j]; o[r] = s; }
+}
+int main(int argc, char** argv) {
+  int M = 64, K = 256, d = 16; long long N = 51200;
+  if (argc > 1 && atoi(argv[1]) == 64) { M = 16; K = 512; d = 64; N = 50176; }
+  int D = M * d;
+  std::vector<float> hz((size_t)N * D), hc((size_t)M * K * d);
+  srand(1);
+  for (auto& v : hz) v = (rand() / (float)RAND_MAX) * 2 - 1;
+  for (size_t r = 0; r < (size_t)M * K; ++r) { float s = 0; for (int j = 0; j < d; ++j) { float v = (rand() / (float)RAND_MAX) * 2 - 1; hc[r * d + j] = v; s += v * v; } s = 1 / sqrtf(s); for (int j = 0; j < d; ++j) hc[r * d + j] *= s; }
+  float *z, *cb, *cn2; int32_t* idx; void* ws;
+  cudaMalloc(&z, hz.size() * 4); cudaMalloc(&cb, hc.size() * 4); cudaMalloc(&cn2, (size_t)M * K * 4); cudaMalloc(&idx, (size_t)M * N * 4);
+  cudaMemcpy(z, hz.data(), hz.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(cb, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+  cn2_k<<<(M * K + 255) / 256, 256>>>(cb, M * K, d, cn2);
+  equss_zdesc zd; zd.n_pixels = N; zd.hw = N; zd.stride_b = N * D; zd.stride_s = D; zd.stride_c = 1; zd.dim = D; zd.layout = 0;
+  long long wsb = assign_tch_workspace_bytes(N, M, K, d);
+  cudaMalloc(&ws, wsb);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) {
+    cudaEventRecord(e0);
+    int rc = assign_tch_launch(z, &zd, cb, cn2, M, K, d, idx, ws, wsb, 0);
+    cudaEventRecord(e1); cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("rc=%d %s  %.1f us  err=%s\n", rc, equss_last_error_string(), ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+  }
+  static long long tr[256 * 8];
+  cudaMemcpyFromSymbol(tr, tch::g_trace, sizeof(tr));
+  long long t0 = tr[0];
+  printf("unit | conv: a_empty raw_full done | mma: loop_top issue | epi: tfull_h0 halves_done tail_done   (cycles since unit-0 convert start)\n");
+  for (int i = 0; i < 40; ++i) {
+    long long* r = tr + i * 8;
+    printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+  }
+  for (int i = 150; i < 170; ++i) {
+    long long* r = tr + i * 8;
+    printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+  }
+  return 0;
+}

@@ -255,7 +255,8 @@ TC_SHAPES = [
 
 
 @pytest.mark.parametrize("shape,M,K,d,mode", TC_SHAPES)
-def test_tcgen05_assign_equals_exact_kernel(shape, M, K, d, mode):
+@pytest.mark.parametrize("algo", [2, 3])     # 2: fp16-split kernel where it applies (l2, d>=16), 3: split-tf32 kernel
+def test_tcgen05_assign_equals_exact_kernel(shape, M, K, d, mode, algo):
     ops = _ops()
     dev = torch.device("cuda:0")
     torch.manual_seed(99)
@@ -270,8 +271,49 @@ def test_tcgen05_assign_equals_exact_kernel(shape, M, K, d, mode):
     else:
         cbn = cb * 0.5
     idx_simt = ops.pq_assign(z, cbn, normalize=mode, algo=1)
-    idx_tc = ops.pq_assign(z, cbn, normalize=mode, algo=2)
+    idx_tc = ops.pq_assign(z, cbn, normalize=mode, algo=algo)
     torch.cuda.synchronize()
     nbad = int((idx_simt != idx_tc).sum())
     assert nbad == 0, f"{nbad} of {idx_tc.numel()} indices differ between the tcgen05 and the exact kernel"
     assert int(idx_tc.min()) >= 0 and int(idx_tc.max()) < K
+
+
+H_SHAPES = [
+    # (shape, M, K, d, codebook): cases aimed at the fp16-split kernel (l2 rows)
+    (5000, 63, 256, 16, "unit"),              # odd M: no subspace pairing (G = 1)
+    (5000, 64, 40, 16, "unit"),               # padded columns (K < NC)
+    (4099, 16, 1024, 32, "unit"),             # four code chunks, ragged N
+    ((3, 28, 28), 8, 512, 64, "unit"),        # NCHW, hw not a multiple of the 128-pixel tile, two chunks
+    (6000, 8, 256, 64, "scaled"),             # un-normalised codebook (|c| ~ 7): power-of-two operand scaling
+    (6000, 16, 256, 32, "tiny"),              # |c| ~ 1e-3
+    (3000, 8, 512, 16, "duplicates"),         # exact ties inside and across chunks: first index must win
+    (3000, 8, 256, 16, "zero_rows"),          # all-zero pixels (normalised row = 0)
+]
+
+
+@pytest.mark.parametrize("shape,M,K,d,kind", H_SHAPES)
+def test_f16_split_assign_edge_cases(shape, M, K, d, kind):
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    D = M * d
+    z = torch.randn(*((shape[0], D, shape[1], shape[2]) if isinstance(shape, tuple) else (shape, D)), device=dev)
+    cb = torch.randn(M, K, d, device=dev)
+    cbn = F.normalize(cb, dim=2)
+    if kind == "scaled":
+        cbn = cb * 1.7
+    elif kind == "tiny":
+        cbn = cb * 1e-3
+    elif kind == "duplicates":
+        cbn[:, 5] = cbn[:, 3]
+        cbn[:, K // 2:] = cbn[:, :K // 2]          # every code appears twice, NC apart when K = 2*NC
+    elif kind == "zero_rows":
+        z[::7] = 0
+    cbn = cbn.contiguous()
+    idx_simt = ops.pq_assign(z, cbn, normalize="l2", algo=1)
+    idx_h = ops.pq_assign(z, cbn, normalize="l2", algo=2)
+    torch.cuda.synchronize()
+    nbad = int((idx_simt != idx_h).sum())
+    assert nbad == 0, f"{nbad} of {idx_h.numel()} indices differ between the fp16-split and the exact kernel"
+    if kind == "duplicates":
+        assert int(idx_h.max()) < K // 2
