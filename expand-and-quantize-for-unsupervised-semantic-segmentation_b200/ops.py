@@ -187,21 +187,30 @@ def pq_distance_prob(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optio
 
 
 def probe_pack(wmat: torch.Tensor):
-    """Pack probe weights [C_total, D] into the K-major, zero-padded [D, C_pad] layout the kernel reads.
-    Do this once per weight update; pass the result to :func:`probe_logits` instead of the raw matrix."""
+    """Pack probe weights [C_total, D] for :func:`probe_logits`: the K-major, zero-padded [D, C_pad] matrix and,
+    when the shape allows it, the tensor-core operand image.  Do this once per weight update."""
     dev = N.require_cuda(wmat)
+    N.ensure_device(dev)
     wmat = N.f32c(wmat.detach())
     Ct, D = wmat.shape
-    cpad = int(N.lib().equss_probe_cpad(Ct))
+    L = N.lib()
+    cpad = int(L.equss_probe_cpad(Ct))
     wmat_t = torch.zeros((D, cpad), dtype=torch.float32, device=dev)
     wmat_t[:, :Ct] = wmat.t()
-    return wmat_t, Ct
+    image = None
+    nbytes = int(L.equss_probe_image_bytes(D, Ct))
+    if nbytes > 0:
+        image = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        N.check(L.equss_probe_build_image(wmat_t.data_ptr(), D, Ct, image.data_ptr(), N.stream_ptr(dev)),
+                "equss_probe_build_image")
+    return wmat_t, Ct, image
 
 
-def probe_logits(feat: torch.Tensor, wmat, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def probe_logits(feat: torch.Tensor, wmat, bias: Optional[torch.Tensor] = None, algo: int = 0) -> torch.Tensor:
     """Token-resolution probe logits [B*h*w, C_pad] from NCHW features (model/evaluator.py:67,98-100).
-    ``wmat`` is either the [C_total, D] weight matrix or the result of :func:`probe_pack`."""
-    wmat_t, Ct = wmat if isinstance(wmat, tuple) else probe_pack(wmat)
+    ``wmat`` is either the [C_total, D] weight matrix or the result of :func:`probe_pack`.
+    ``algo``: 0 = tcgen05 kernel when the shape is supported, 1 = CUDA-core kernel."""
+    wmat_t, Ct, image = wmat if isinstance(wmat, tuple) else probe_pack(wmat)
     dev = N.require_cuda(feat, wmat_t, bias)
     N.ensure_device(dev)
     feat = N.f32c(feat.detach())
@@ -211,8 +220,14 @@ def probe_logits(feat: torch.Tensor, wmat, bias: Optional[torch.Tensor] = None) 
     b = N.f32c(bias.detach()).reshape(-1) if bias is not None else None
     cpad = wmat_t.shape[1]
     logits = torch.empty((B * h * w, cpad), dtype=torch.float32, device=dev)
-    rc = N.lib().equss_probe_logits(feat.data_ptr(), B, D, h, w, wmat_t.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
-                                    N.stream_ptr(dev))
+    L = N.lib()
+    if algo == 0 and image is not None and L.equss_probe_logits_tc_supported(D, h, w, Ct):
+        rc = L.equss_probe_logits_tc(feat.data_ptr(), B, D, h, w, image.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
+                                     N.stream_ptr(dev))
+        N.check(rc, "equss_probe_logits_tc")
+        return logits
+    rc = L.equss_probe_logits(feat.data_ptr(), B, D, h, w, wmat_t.data_ptr(), N.ptr(b), Ct, logits.data_ptr(),
+                              N.stream_ptr(dev))
     N.check(rc, "equss_probe_logits")
     return logits
 

@@ -177,6 +177,15 @@ int equss_probe_cpad(int c_total);
 int equss_probe_logits(const float* feat, int B, int D, int h, int w,
                        const float* wmat_t, const float* bias, int c_total,
                        float* logits, void* stream);
+/* Tensor-core variant of step 1 (tcgen05 split-tf32 GEMM, fp32-level accuracy): the weights are first packed into
+ * an operand image (equss_probe_image_bytes() bytes, rebuilt whenever the weights change).  Supported when
+ * D % 32 == 0, C_pad <= 64 and h*w % 4 == 0 (equss_probe_logits_tc_supported); equss_probe_logits covers the rest. */
+int64_t equss_probe_image_bytes(int D, int c_total);
+int equss_probe_build_image(const float* wmat_t, int D, int c_total, void* image, void* stream);
+int equss_probe_logits_tc_supported(int D, int h, int w, int c_total);
+int equss_probe_logits_tc(const float* feat, int B, int D, int h, int w,
+                          const void* image, const float* bias, int c_total,
+                          float* logits, void* stream);
 int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
                                  const int64_t* label, int H, int W, int num_classes,
                                  int n_heads, const int32_t* head_off_host, const int32_t* head_cnt_host,

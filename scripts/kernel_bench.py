@@ -50,13 +50,15 @@ if __name__ == "__main__":
     run("C4 flat  N=50176 M16 K512 d64", (50176, 1024), 16, 512, 64, only=only)
     run("C1 flat  N=3136 M8 K256 d64", (3136, 512), 8, 256, 64, nbuf=1, only=only)
     run("d32 flat N=51200 M32 K256", (51200, 1024), 32, 256, 32, only=only)
-    if not only:
+    if not only or "probe" in only:
         B, D, h, w, H, W, C = 32, 1024, 40, 40, 320, 320, 27
         feats = [torch.randn(B, D, h, w, device=dev) for _ in range(3)]
         Cp = 28; wmat = torch.randn(Cp + C, D, device=dev); bias = torch.zeros(Cp + C, device=dev); wpack = ops.probe_pack(wmat)
         label = torch.randint(-1, C, (B, H, W), device=dev)
         ms = timeit(lambda f: ops.probe_logits(f, wpack, bias), feats)
-        print(f"probe_logits {ms*1e3:.1f} us  {4*B*D*h*w/ms/1e6:.1f} GB/s")
+        print(f"probe_logits(tc) {ms*1e3:.1f} us  {4*B*D*h*w/ms/1e6:.1f} GB/s")
+        ms = timeit(lambda f: ops.probe_logits(f, wpack, bias, algo=1), feats)
+        print(f"probe_logits(simt) {ms*1e3:.1f} us  {4*B*D*h*w/ms/1e6:.1f} GB/s")
         logits = ops.probe_logits(feats[0], wpack, bias)
         cc = torch.zeros(C, C, dtype=torch.long, device=dev); lc = torch.zeros(C, C, dtype=torch.long, device=dev)
         ms = timeit(lambda f: ops.probe_argmax_confusion(logits, B, h, w, Cp + C, label, C, [(0, C), (Cp, C)], want_preds=False, confusions=[cc, lc]), feats)
@@ -66,6 +68,7 @@ if __name__ == "__main__":
         preds = torch.randint(0, C, (B, H, W), device=dev)
         ms = timeit(lambda f: ops.confusion_update(preds, label, C, cc), feats)
         print(f"confusion_update {ms*1e3:.1f} us  {16*B*H*W/ms/1e6:.1f} GB/s")
+    if not only:
         db = F.normalize(torch.randn(50000, 768, device=dev), dim=1)
         ms = timeit(lambda f: ops.knn_topk(db[:6250], db, 30), [0], iters=2, warm=1)
         print(f"knn 6250x50000x768 k=30: {ms:.1f} ms  {2*6250*50000*768/ms/1e9:.1f} TFLOP/s")

@@ -81,6 +81,28 @@ def test_probe_vs_oracle(B, D, h, w, H, W):
     assert torch.equal(conf_l, O.confusion_update(torch.zeros(C, C, dtype=torch.long), lp, label, C))
 
 
+@pytest.mark.parametrize("B,D,h,w,Ct", [(32, 1024, 40, 40, 54), (2, 64, 28, 28, 54), (3, 96, 6, 6, 27), (1, 512, 56, 56, 19)])
+def test_probe_logits_tensor_core_accuracy(B, D, h, w, Ct):
+    """tcgen05 split-tf32 logits: fp32-level accuracy against an fp64 contraction, and agreement with the
+    CUDA-core kernel to fp32 summation-order noise."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    feat = torch.randn(B, D, h, w, device=dev)
+    wmat = torch.randn(Ct, D, device=dev)
+    bias = torch.randn(Ct, device=dev)
+    pack = ops.probe_pack(wmat)
+    assert pack[2] is not None, "shape should be supported by the tensor-core kernel"
+    lt = ops.probe_logits(feat, pack, bias, algo=0)
+    ls = ops.probe_logits(feat, pack, bias, algo=1)
+    ref = torch.einsum("bchw,jc->bhwj", feat.double(), wmat.double()).reshape(-1, Ct) + bias.double()
+    scale = float(ref.abs().max())
+    err_t = float((lt[:, :Ct].double() - ref).abs().max()) / scale
+    err_s = float((ls[:, :Ct].double() - ref).abs().max()) / scale
+    assert err_t < 2e-6, f"tensor-core logits off by {err_t:.2e} of the logit scale (CUDA-core kernel: {err_s:.2e})"
+    assert torch.equal(lt[:, Ct:], torch.zeros_like(lt[:, Ct:]))
+
+
 @pytest.mark.parametrize("n,C,extra", [(0, 27, 0), (1, 27, 0), (100003, 27, 0), (50000, 19, 3), (4096, 300, 0)])
 def test_confusion_update_vs_bincount(n, C, extra):
     ops = _ops()
