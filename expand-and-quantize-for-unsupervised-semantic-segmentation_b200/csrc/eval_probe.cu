@@ -317,6 +317,95 @@ probe_argmax_confusion_kernel(const float* __restrict__ logits, int B, int h, in
   }
 }
 
+// step 2, row-block variant (the common case: every head starts at a multiple of four channels and has at most
+// CMAX channels).  One block per (image, RB consecutive label rows), one thread per label column X.  The
+// horizontal interpolation  Hy[c] = w0*L[y][x0][c] + w1*L[y][x1][c]  of the two token rows (y0, y1) depends only
+// on X, so a thread keeps it in registers and reuses it for every label row that maps to the same token-row pair
+// (8 rows at the cocostuff27 shape): per label pixel and channel that leaves  v = h0*H0[c] + h1*H1[c]  and the
+// argmax update -- the association order of PyTorch's upsample_bilinear2d -- instead of four loads and seven
+// multiply-adds.  Confusion bins are per block in shared memory (run-length merged per warp).
+template <int CMAX, int TMAX, int MINB>
+__global__ void __launch_bounds__(TMAX, MINB)
+probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_pad, const long long* __restrict__ label,
+                         int H, int W, int C, ProbeHeads heads, float scale_h, float scale_w, int rows_per_block) {
+  extern __shared__ int s_hist[];   // [hist_per_warp] = all heads' bins, one copy per block
+  for (int i = threadIdx.x; i < heads.hist_per_warp; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int Y0 = blockIdx.x * rows_per_block;
+  const int Y1 = min(H, Y0 + rows_per_block);
+  const float* base = logits + (long long)b * h * w * c_pad;
+  const int Wpad = (W + 31) & ~31;
+  for (int X = threadIdx.x; X < Wpad; X += blockDim.x) {
+    const bool live = X < W;
+    float sx = scale_w * ((float)X + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    int x0 = (int)sx;
+    if (x0 > w - 1) x0 = w - 1;
+    const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+#pragma unroll 1
+    for (int hd = 0; hd < heads.n_heads; ++hd) {
+      const int off = heads.off[hd], cnt = heads.cnt[hd];
+      float H0[CMAX], H1[CMAX];
+      int cy0 = -1;
+#pragma unroll 1
+      for (int Y = Y0; Y < Y1; ++Y) {
+        // PyTorch upsample_bilinear2d, align_corners=False (area_pixel_compute_source_index)
+        float sy = scale_h * ((float)Y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+        int y0 = (int)sy;
+        if (y0 > h - 1) y0 = h - 1;
+        const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+        if (y0 != cy0) {             // block-uniform: a new token-row pair
+          cy0 = y0;
+          const float4* p00 = reinterpret_cast<const float4*>(base + ((long long)y0 * w + x0) * c_pad + off);
+          const float4* p01 = reinterpret_cast<const float4*>(base + ((long long)y0 * w + x1) * c_pad + off);
+          const float4* p10 = reinterpret_cast<const float4*>(base + ((long long)y1 * w + x0) * c_pad + off);
+          const float4* p11 = reinterpret_cast<const float4*>(base + ((long long)y1 * w + x1) * c_pad + off);
+#pragma unroll
+          for (int g = 0; g < CMAX / 4; ++g) {
+            if (4 * g < cnt) {
+              const float4 a = __ldg(p00 + g), bq = __ldg(p01 + g), c = __ldg(p10 + g), dq = __ldg(p11 + g);
+              H0[4 * g + 0] = lx0 * a.x + lx1 * bq.x; H0[4 * g + 1] = lx0 * a.y + lx1 * bq.y;
+              H0[4 * g + 2] = lx0 * a.z + lx1 * bq.z; H0[4 * g + 3] = lx0 * a.w + lx1 * bq.w;
+              H1[4 * g + 0] = lx0 * c.x + lx1 * dq.x; H1[4 * g + 1] = lx0 * c.y + lx1 * dq.y;
+              H1[4 * g + 2] = lx0 * c.z + lx1 * dq.z; H1[4 * g + 3] = lx0 * c.w + lx1 * dq.w;
+            }
+          }
+        }
+        float best = -INFINITY;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j) {
+          if (j < cnt) {
+            const float v = ly0 * H0[j] + ly1 * H1[j];
+            if (v > best) { best = v; bj = j; }       // first maximal index wins (torch.argmax)
+          }
+        }
+        int bin = -1;
+        if (live) {
+          const long long pidx = ((long long)b * H + Y) * W + X;
+          if (heads.preds[hd]) __stcs(heads.preds[hd] + pidx, (long long)bj);
+          if (heads.conf[hd]) {
+            const long long lab = __ldcs(label + pidx);
+            if (lab >= 0 && lab < C && bj < C) bin = bj * C + (int)lab;
+          }
+        }
+        if (heads.conf[hd]) warp_hist_add(s_hist + heads.hist_off[hd], bin);
+      }
+    }
+  }
+  __syncthreads();
+  for (int hd = 0; hd < heads.n_heads; ++hd) {
+    if (!heads.conf[hd]) continue;
+    const int nb = heads.rows[hd] * C;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const int t = s_hist[heads.hist_off[hd] + i];
+      if (t) atomicAdd(heads.conf[hd] + i, (unsigned long long)t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K9 standalone confusion histogram (UnSegMetrics.update)
 // ------------------------------------------------------------------------------------------------
@@ -427,6 +516,31 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
     }
   }
   hd.hist_per_warp = per_warp;
+  const float scale_h = (float)h / (float)H, scale_w = (float)w / (float)W;
+  {
+    // row-block kernel: heads aligned to four channels, at most 28 / 32 channels each
+    bool fast = (size_t)per_warp * sizeof(int) <= 48 * 1024 && getenv("EQUSS_PROBE_ARGMAX_OLD") == nullptr;
+    int cmax = 0;
+    for (int i = 0; i < n_heads; ++i) { fast = fast && (hd.off[i] % 4) == 0; cmax = hd.cnt[i] > cmax ? hd.cnt[i] : cmax; }
+    if (fast && cmax <= 32) {
+      const int rb = 8;
+      int threads = (W + 31) & ~31;
+      if (threads > 512) threads = 256;
+      dim3 grid((unsigned)((H + rb - 1) / rb), (unsigned)B);
+      const size_t smem = (size_t)(per_warp > 0 ? per_warp : 1) * sizeof(int);
+#define EQUSS_ROWS_LAUNCH(CM, TM, MB)                                                                                 \
+      probe_argmax_rows_kernel<CM, TM, MB><<<grid, threads, smem, (cudaStream_t)stream>>>(                            \
+          logits, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w, rb)
+      if (threads <= 320) {
+        if (cmax <= 28) EQUSS_ROWS_LAUNCH(28, 320, 2); else EQUSS_ROWS_LAUNCH(32, 320, 2);
+      } else {
+        if (cmax <= 28) EQUSS_ROWS_LAUNCH(28, 512, 1); else EQUSS_ROWS_LAUNCH(32, 512, 1);
+      }
+#undef EQUSS_ROWS_LAUNCH
+      EQUSS_LAUNCH_OK("probe_argmax_rows_kernel");
+      return EQUSS_OK;
+    }
+  }
   const int threads = 256;
   size_t smem = (size_t)(threads / 32) * per_warp * sizeof(int);
   EQUSS_REQUIRE(smem <= 200 * 1024, EQUSS_ERR_UNSUPPORTED, "confusion bins (%d per warp) do not fit shared memory", per_warp);
@@ -436,7 +550,6 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
   long long blocks = (P + threads - 1) / threads;
   long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  const float scale_h = (float)h / (float)H, scale_w = (float)w / (float)W;
   probe_argmax_confusion_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(
       logits, B, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w);
   EQUSS_LAUNCH_OK("probe_argmax_confusion_kernel");

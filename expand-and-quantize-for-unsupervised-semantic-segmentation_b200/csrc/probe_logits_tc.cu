@@ -4,18 +4,26 @@
 // result carries fp32-level accuracy (the argmax that follows is audited against the fp32 reference).
 //
 // The op is HBM-bound (it reads the feature map once: 4*D bytes per token, 2*D*C flops); the SIMT version was
-// bound by fp32 FMA issue instead.  Structure (persistent CTAs, 10 warps):
-//   warp 4      producer: TMA boxes of the NCHW feature map (32 channels x 128 pixels, pixel-contiguous) into a
-//               ring of raw stages + bulk copies of the matching 32-channel slice of the weight image
-//   warps 6-9   convert: raw[channel][pixel] -> (hi, lo) tf32 pieces in the UMMA K-major core-matrix layout
-//   warp 5      MMA issuer: 12 tcgen05.mma.kind::tf32 (128 x 64 x 8) per 32-channel stage
-//   warps 0-3   epilogue: TMEM -> registers, + bias, 16-byte stores of the token's C_pad logits
+// bound by fp32 FMA issue instead.  Structure (persistent CTAs, 13 warps, stages of 32 channels; the raw ring is 8
+// deep -- 128 KB of loads in flight per SM is what it takes to cover the HBM latency -- while the lo and weight
+// rings, which only decouple convert / L2 from the tensor core, are 2 and 3 deep):
+//   warp 4      producer: per stage one TMA box of the NCHW feature map (32 channels x 4 x 32 pixels, 128-byte
+//               rows, 32-byte-atom swizzle); warp 10: bulk copies of the matching slice of the weight image.
+//               The raw tile IS the hi operand:
+//               it lands in the canonical MN-major SWIZZLE_128B_BASE32B layout and the tensor core ignores the low 13
+//               mantissa bits of an fp32 word (= truncation to tf32)
+//   warps 6-9   convert: lo = x - trunc_tf32(x), element-wise at identical (swizzled) offsets into the lo tile
+//   warps 5-7   MMA issuers, one per product (hi.hi / lo.hi / hi.lo): 4 tcgen05.mma.kind::tf32 (128 x 64 x 8) each
+//               per stage, A MN-major, B K-major.  A 128x64x8 MMA executes in 48 cycles but costs ~130 cycles of
+//               descriptor set-up to issue from one thread, so a single issuer would bound the kernel.
+//   warps 0-3   epilogue: TMEM partial sums -> fp32 registers, + bias, 16-byte stores of the token's C_pad logits
 // Accumulation: the tensor core's fp32 accumulate truncates, which over the D/8 = 128 dependent steps of one
 // output drifts by ~1e-5 of the logit scale.  The dominant hi.hi products are therefore accumulated in TMEM for
 // only kPromote stages (64 channels) at a time; the epilogue warps add each partial to fp32 registers with
 // round-to-nearest adds (ping-pong TMEM buffers, so the tensor core never waits).  The small lo.hi / hi.lo terms
 // (2^-11 of the result) keep their own whole-tile accumulator, where the drift is irrelevant.
 #include <cuda.h>
+#include <cstdlib>
 #include "equss_common.cuh"
 #include "equss_tcgen05.cuh"
 
@@ -27,21 +35,24 @@ using namespace ::equss::ptx;
 constexpr int kTileM = 128;        // pixels per tile
 constexpr int kN = 64;             // accumulator columns (probe channels, zero-padded)
 constexpr int kKC = 32;            // feature channels per pipeline stage
-constexpr int kThreads = 320;
-constexpr int kEpiWarp0 = 0, kProducerWarp = 4, kMmaWarp = 5, kConvWarp0 = 6;
-constexpr int kRawStages = 4, kABufs = 2, kBBufs = 3;
+constexpr int kThreads = 416;
+constexpr int kEpiWarp0 = 0, kProducerWarp = 4, kMmaWarp = 5 /* 5,6,7: one issuer per product */, kConvWarp0 = 8, kBProducerWarp = 12;
+constexpr int kRawStages = 8, kLoBufs = 2, kBBufs = 3;
 constexpr int kPromote = 2;        // stages per TMEM partial of the hi.hi products
-constexpr int kRawBytes = kKC * kTileM * 4;                 // 16 KB
-constexpr int kAPiece = kTileM * kKC * 4;                   // 16 KB: one of (hi, lo)
-constexpr int kABytes = 2 * kAPiece;
+constexpr int kAPiece = kTileM * kKC * 4;                   // 16 KB: raw (= hi) or lo tile
 constexpr int kBPiece = kN * kKC * 4;                       // 8 KB
 constexpr int kBBytes = 2 * kBPiece;                        // per 32-channel slice: hi then lo
-constexpr int kALBO = 128, kASBO = (kKC / 4) * kALBO;       // K-major, no swizzle: 8 chunks of 16 B per row
+// A (MN-major fp32/tf32 operands use the SWIZZLE_128B_BASE32B layout = TMA's 128B_ATOM_32B: 32-byte chunks of a
+// 128-byte row XOR-ed with the row index mod 4): 32 pixels contiguous (128 B), 4 channels per 512-byte swizzle atom
+// (SBO), the four 32-pixel blocks of a tile 4096 B apart (LBO); one MMA (K = 8) spans two atoms = 1024 B.
+// B (K-major, no swizzle): 8 chunks of 16 B per row.
+constexpr int kALBO = kKC * 128, kASBO = 512;
 constexpr int kBLBO = 128, kBSBO = (kKC / 4) * kBLBO;
-constexpr int kSmem = 128 + kRawStages * kRawBytes + kABufs * kABytes + kBBufs * kBBytes + 512;
+constexpr int kSmem = 1024 + (kRawStages + kLoBufs) * kAPiece + kBBufs * kBBytes + 512;
 
+// kind::tf32, fp32 accumulate, A MN-major (bit 15), B K-major, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 struct Params {
@@ -50,6 +61,7 @@ struct Params {
   const uint8_t* image;      // [D/32][hi 8 KB | lo 8 KB]
   const float* bias;
   float* logits;
+  int debug;                 // EQUSS_PROBE_DEBUG: 1 = issue no MMAs, 2 = also skip the lo conversion, 4 = skip promotions (timing experiments)
 };
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -83,21 +95,21 @@ build_probe_image_kernel(const float* __restrict__ wmat_t, int D, int c_pad, uin
 __global__ void __launch_bounds__(kThreads, 1)
 probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  uint8_t* s_raw = smem;
-  uint8_t* s_a = s_raw + kRawStages * kRawBytes;
-  uint8_t* s_b = s_a + kABufs * kABytes;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // swizzle atoms are 1024-byte aligned
+  uint8_t* s_raw = smem;                                  // [kRawStages][16 KB]  raw = hi tiles
+  uint8_t* s_lo = s_raw + kRawStages * kAPiece;           // [kLoBufs][16 KB]
+  uint8_t* s_b = s_lo + kLoBufs * kAPiece;                // [kBBufs][hi 8 KB | lo 8 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kBBufs * kBBytes);
-  uint64_t* raw_full = bars;
-  uint64_t* raw_empty = raw_full + kRawStages;
-  uint64_t* a_full = raw_empty + kRawStages;
-  uint64_t* a_empty = a_full + kABufs;
-  uint64_t* b_full = a_empty + kABufs;
-  uint64_t* b_empty = b_full + kBBufs;
-  uint64_t* m_full = b_empty + kBBufs;      // [2] main (hi.hi) partial ready
-  uint64_t* m_empty = m_full + 2;           // [2]
-  uint64_t* s_full = m_empty + 2;           // [2] small-term accumulator of a tile ready
-  uint64_t* s_empty = s_full + 2;           // [2]
+  uint64_t* raw_full = bars;                    // [kRawStages] TMA box landed
+  uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages] the stage's MMAs completed
+  uint64_t* lo_full = raw_empty + kRawStages;   // [kLoBufs] convert warps wrote the lo tile
+  uint64_t* lo_empty = lo_full + kLoBufs;       // [kLoBufs] MMAs completed
+  uint64_t* b_full = lo_empty + kLoBufs;        // [kBBufs]
+  uint64_t* b_empty = b_full + kBBufs;          // [kBBufs]
+  uint64_t* m_full = b_empty + kBBufs;          // [2] main (hi.hi) partial ready
+  uint64_t* m_empty = m_full + 2;               // [2]
+  uint64_t* s_full = m_empty + 2;               // [2] small-term accumulator of a tile ready
+  uint64_t* s_empty = s_full + 2;               // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,14 +117,14 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   const int n_kc = p.n_kc;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRawStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 4); }
-    for (int i = 0; i < kABufs; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < kBBufs; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < kRawStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 2); }   // issuers 0, 2
+    for (int i = 0; i < kLoBufs; ++i) { mbar_init(lo_full + i, 4); mbar_init(lo_empty + i, 1); }         // issuer 1
+    for (int i = 0; i < kBBufs; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 3); }
     for (int i = 0; i < 2; ++i) { mbar_init(m_full + i, 1); mbar_init(m_empty + i, 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full + i, 2); mbar_init(s_empty + i, 4); }                 // issuers 1, 2
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc<4 * kN>(s_tmem);
+  if (warp == kMmaWarp) tmem_alloc<512>(s_tmem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -124,87 +136,95 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
       for (int it = 0; it < n_my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int b = tile / p.tiles_per_image;
-        const int s0 = (tile - b * p.tiles_per_image) * kTileM;
+        const int blk0 = (tile - b * p.tiles_per_image) * (kTileM / 32);      // first 32-pixel block of the tile
         for (int c = 0; c < n_kc; ++c, ++g) {
-          const int rs = g % kRawStages, bs = g % kBBufs;
-          mbar_wait(b_empty + bs, ((g / kBBufs) & 1) ^ 1, 11);
-          mbar_expect_tx(b_full + bs, kBBytes);
-          bulk_load_1d(s_b + bs * kBBytes, p.image + (size_t)c * kBBytes, kBBytes, b_full + bs);
+          const int rs = g % kRawStages;
           mbar_wait(raw_empty + rs, ((g / kRawStages) & 1) ^ 1, 10);
-          mbar_expect_tx(raw_full + rs, kRawBytes);
-          tma_load_3d(s_raw + rs * kRawBytes, &tmap, s0, c * kKC, b, raw_full + rs);
+          mbar_expect_tx(raw_full + rs, kAPiece);
+          tma_load_4d(s_raw + rs * kAPiece, &tmap, 0, c * kKC, blk0, b, raw_full + rs);
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kBProducerWarp) {
+    if (lane == 0) {
+      int g = 0;
+      for (int it = 0; it < n_my_tiles; ++it) {
+        for (int c = 0; c < n_kc; ++c, ++g) {
+          const int bs = g % kBBufs;
+          mbar_wait(b_empty + bs, ((g / kBBufs) & 1) ^ 1, 11);
+          if (p.debug & 8) { mbar_arrive(b_full + bs); continue; }
+          mbar_expect_tx(b_full + bs, kBBytes);
+          bulk_load_1d(s_b + bs * kBBytes, p.image + (size_t)c * kBBytes, kBBytes, b_full + bs);
+        }
+      }
+    }
+  } else if (warp >= kMmaWarp && warp < kMmaWarp + 3) {
+    // issuer `part`: 0 = x_hi.w_hi -> main partials (promoted), 1 = x_lo.w_hi, 2 = x_hi.w_lo -> small accumulators
+    const int part = warp - kMmaWarp;
     constexpr uint32_t IDESC = make_idesc_tf32(kN);
-    const uint32_t a_hi = (uint32_t)((kASBO >> 4) & 0x3FFF) | (1u << 14);
+    const uint32_t a_hi = (uint32_t)((kASBO >> 4) & 0x3FFF) | (1u << 14) | (1u << 29);     // SBO, version 1, SWIZZLE_128B_BASE32B
     const uint32_t b_hi = (uint32_t)((kBSBO >> 4) & 0x3FFF) | (1u << 14);
-    const uint32_t a_lo0 = (smem_u32(s_a) >> 4) | ((uint32_t)(kALBO >> 4) << 16);
-    const uint32_t b_lo0 = (smem_u32(s_b) >> 4) | ((uint32_t)(kBLBO >> 4) << 16);
+    const uint32_t a_lo0 = (smem_u32(part == 1 ? s_lo : s_raw) >> 4) | ((uint32_t)(kALBO >> 4) << 16);
+    const uint32_t b_lo0 = ((smem_u32(s_b) + (part == 2 ? kBPiece : 0)) >> 4) | ((uint32_t)(kBLBO >> 4) << 16);
     int g = 0, G = 0;                       // global stage / promotion-group counters
     for (int it = 0; it < n_my_tiles; ++it) {
       const int sb = it & 1;
-      mbar_wait(s_empty + sb, ((it >> 1) & 1) ^ 1, 22);
-      const uint32_t d_small = tmem_base + (uint32_t)((2 + sb) * kN);
+      if (part > 0) mbar_wait(s_empty + sb, ((it >> 1) & 1) ^ 1, 22);
+      const uint32_t d_small = tmem_base + (uint32_t)((2 * part + sb) * kN);      // columns 128.. (part 1), 256.. (part 2)
       for (int c = 0; c < n_kc; ++c, ++g) {
-        const int as = g % kABufs, bs = g % kBBufs;
+        const int rs = g % kRawStages, ls = g % kLoBufs, bs = g % kBBufs;
         const int mb = G & 1;
         const bool group_first = (c % kPromote) == 0;
         const bool group_last = (c % kPromote) == kPromote - 1 || c == n_kc - 1;
-        if (group_first) mbar_wait(m_empty + mb, ((G >> 1) & 1) ^ 1, 23);
-        mbar_wait(a_full + as, (g / kABufs) & 1, 20);
+        if (part == 0 && group_first) mbar_wait(m_empty + mb, ((G >> 1) & 1) ^ 1, 23);
+        if (part == 1) mbar_wait(lo_full + ls, (g / kLoBufs) & 1, 20);
+        else mbar_wait(raw_full + rs, (g / kRawStages) & 1, 24);
         mbar_wait(b_full + bs, (g / kBBufs) & 1, 21);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)(as * (kABytes >> 4));
+          const uint32_t a_lo = a_lo0 + (uint32_t)((part == 1 ? ls : rs) * (kAPiece >> 4));
           const uint32_t b_lo = b_lo0 + (uint32_t)(bs * (kBBytes >> 4));
-          const uint32_t d_main = tmem_base + (uint32_t)(mb * kN);
+          const uint32_t d_addr = (part == 0) ? tmem_base + (uint32_t)(mb * kN) : d_small;
 #pragma unroll
-          for (int part = 0; part < 3; ++part) {
-            const uint32_t a_off = (part == 1) ? (kAPiece >> 4) : 0;     // x_lo for the middle product
-            const uint32_t b_off = (part == 2) ? (kBPiece >> 4) : 0;     // w_lo for the last product
-#pragma unroll
-            for (int kk = 0; kk < kKC / 8; ++kk) {
-              const uint32_t acc = (part == 0) ? ((!group_first || kk > 0) ? 1u : 0u)
-                                               : ((c > 0 || part > 1 || kk > 0) ? 1u : 0u);
-              umma_tf32(part == 0 ? d_main : d_small, desc_from(a_lo + a_off + (uint32_t)(2 * kk * (kALBO >> 4)), a_hi),
-                        desc_from(b_lo + b_off + (uint32_t)(2 * kk * (kBLBO >> 4)), b_hi), IDESC, acc);
-            }
+          for (int kk = 0; kk < kKC / 8; ++kk) {
+            if (p.debug & 1) break;
+            const uint32_t acc = (part == 0) ? ((!group_first || kk > 0) ? 1u : 0u) : ((c > 0 || kk > 0) ? 1u : 0u);
+            umma_tf32(d_addr, desc_from(a_lo + (uint32_t)(kk * (1024 >> 4)), a_hi),
+                      desc_from(b_lo + (uint32_t)(2 * kk * (kBLBO >> 4)), b_hi), IDESC, acc);
           }
-          umma_commit(a_empty + as);
+          if (part == 1) umma_commit(lo_empty + ls); else umma_commit(raw_empty + rs);
           umma_commit(b_empty + bs);
-          if (group_last) umma_commit(m_full + mb);
-          if (c == n_kc - 1) umma_commit(s_full + sb);
+          if (part == 0 && group_last) umma_commit(m_full + mb);
+          if (part > 0 && c == n_kc - 1) umma_commit(s_full + sb);
         }
         __syncwarp();
         if (group_last) ++G;
       }
     }
-  } else if (warp >= kConvWarp0) {
-    const int row = threadIdx.x - kConvWarp0 * 32;     // pixel row of the tile
+  } else if (warp >= kConvWarp0 && warp < kConvWarp0 + 4) {
+    const int ct = threadIdx.x - kConvWarp0 * 32;     // 0..127
     int g = 0;
     for (int it = 0; it < n_my_tiles; ++it) {
       for (int c = 0; c < n_kc; ++c, ++g) {
-        const int rs = g % kRawStages, as = g % kABufs;
-        mbar_wait(a_empty + as, ((g / kABufs) & 1) ^ 1, 30);
+        const int rs = g % kRawStages, ls = g % kLoBufs;
+        mbar_wait(lo_empty + ls, ((g / kLoBufs) & 1) ^ 1, 30);
         mbar_wait(raw_full + rs, (g / kRawStages) & 1, 31);
-        const float* raw = reinterpret_cast<const float*>(s_raw + rs * kRawBytes);
-        float x[kKC];
+        const uint8_t* raw = s_raw + rs * kAPiece;
+        uint8_t* lo = s_lo + ls * kAPiece;
+        float4 v[8];
 #pragma unroll
-        for (int j = 0; j < kKC; ++j) x[j] = raw[j * kTileM + row];
-        uint8_t* rowp = s_a + as * kABytes + (row / 8) * kASBO + (row % 8) * 16;
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(raw + (u * 128 + ct) * 16);
 #pragma unroll
-        for (int q = 0; q < kKC / 4; ++q) {
-          float4 hi, lo;
-          hi.x = tf32_trunc(x[4 * q]); hi.y = tf32_trunc(x[4 * q + 1]); hi.z = tf32_trunc(x[4 * q + 2]); hi.w = tf32_trunc(x[4 * q + 3]);
-          lo.x = x[4 * q] - hi.x; lo.y = x[4 * q + 1] - hi.y; lo.z = x[4 * q + 2] - hi.z; lo.w = x[4 * q + 3] - hi.w;
-          *reinterpret_cast<float4*>(rowp + q * kALBO) = hi;
-          *reinterpret_cast<float4*>(rowp + kAPiece + q * kALBO) = lo;
+        for (int u = 0; u < 8; ++u) {
+          if (p.debug & 2) break;
+          float4 l;
+          l.x = v[u].x - tf32_trunc(v[u].x); l.y = v[u].y - tf32_trunc(v[u].y);
+          l.z = v[u].z - tf32_trunc(v[u].z); l.w = v[u].w - tf32_trunc(v[u].w);
+          *reinterpret_cast<float4*>(lo + (u * 128 + ct) * 16) = l;
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(raw_empty + rs); mbar_arrive(a_full + as); }
+        if (lane == 0) mbar_arrive(lo_full + ls);
       }
     }
   } else {
@@ -245,17 +265,19 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
         mbar_wait(s_full + sb, (it >> 1) & 1, 41);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(lane_base + (uint32_t)((2 + sb) * kN), v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
-        tmem_ld32(lane_base + (uint32_t)((2 + sb) * kN + 32), v);
-        tmem_ld_wait();
+        for (int part = 1; part <= 2; ++part) {
+#pragma unroll
+          for (int hcol = 0; hcol < 2; ++hcol) {
+            tmem_ld32(lane_base + (uint32_t)((2 * part + sb) * kN + 32 * hcol), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[32 * hcol + j] += __uint_as_float(v[j]);
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty + sb);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(v[j]);
       }
       if (s < p.hw) {
         float* o = p.logits + ((long long)b * p.hw + s) * p.c_pad;
@@ -279,7 +301,7 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<4 * kN>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -319,7 +341,7 @@ extern "C" int equss_probe_build_image(const float* wmat_t, int D, int c_total, 
 }
 
 extern "C" int equss_probe_logits_tc_supported(int D, int h, int w, int c_total) {
-  return equss_probe_image_bytes(D, c_total) > 0 && ((h * w) % 4) == 0;
+  return equss_probe_image_bytes(D, c_total) > 0 && ((h * w) % 32) == 0;
 }
 
 extern "C" int equss_probe_logits_tc(const float* feat, int B, int D, int h, int w, const void* image, const float* bias,
@@ -329,19 +351,20 @@ extern "C" int equss_probe_logits_tc(const float* feat, int B, int D, int h, int
   EQUSS_REQUIRE(B > 0 && D > 0 && h > 0 && w > 0 && c_total > 0, EQUSS_ERR_INVALID_ARG,
                 "equss_probe_logits_tc: bad shape B=%d D=%d h=%d w=%d C=%d", B, D, h, w, c_total);
   EQUSS_REQUIRE(equss_probe_logits_tc_supported(D, h, w, c_total), EQUSS_ERR_UNSUPPORTED,
-                "equss_probe_logits_tc: needs D %% %d == 0, C_pad <= %d, h*w %% 4 == 0", kKC, kN);
+                "equss_probe_logits_tc: needs D %% %d == 0, C_pad <= %d, h*w %% 32 == 0", kKC, kN);
   EQUSS_REQUIRE(!((uintptr_t)feat & 15) && !((uintptr_t)logits & 15) && !((uintptr_t)image & 15), EQUSS_ERR_INVALID_ARG,
                 "equss_probe_logits_tc: pointers must be 16-byte aligned");
   PFN_encodeTiled encode = get_encode_fn();
   EQUSS_REQUIRE(encode != nullptr, EQUSS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const int hw = h * w;
+  // dims: 32 pixels (one 128-byte swizzle row) | channel | 32-pixel block | image -> smem [block][channel][32 px]
   CUtensorMap tmap;
-  cuuint64_t gdim[3] = {(cuuint64_t)hw, (cuuint64_t)D, (cuuint64_t)B};
-  cuuint64_t gstr[2] = {(cuuint64_t)hw * 4, (cuuint64_t)D * hw * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kKC, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)feat, gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  cuuint64_t gdim[4] = {32, (cuuint64_t)D, (cuuint64_t)(hw / 32), (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)hw * 4, 128, (cuuint64_t)D * hw * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)kKC, (cuuint32_t)(kTileM / 32), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)feat, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EQUSS_REQUIRE(cr == CUDA_SUCCESS, EQUSS_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)cr);
   Params p;
@@ -350,6 +373,7 @@ extern "C" int equss_probe_logits_tc(const float* feat, int B, int D, int h, int
   p.n_tiles = B * p.tiles_per_image;
   p.n_kc = D / kKC;
   p.image = (const uint8_t*)image; p.bias = bias; p.logits = logits;
+  p.debug = getenv("EQUSS_PROBE_DEBUG") ? atoi(getenv("EQUSS_PROBE_DEBUG")) : 0;
   int grid = num_sms();
   if (p.n_tiles < grid) grid = p.n_tiles;
   EQUSS_CUDA_OK(cudaFuncSetAttribute(probe_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));

@@ -179,7 +179,7 @@ int equss_probe_logits(const float* feat, int B, int D, int h, int w,
                        float* logits, void* stream);
 /* Tensor-core variant of step 1 (tcgen05 split-tf32 GEMM, fp32-level accuracy): the weights are first packed into
  * an operand image (equss_probe_image_bytes() bytes, rebuilt whenever the weights change).  Supported when
- * D % 32 == 0, C_pad <= 64 and h*w % 4 == 0 (equss_probe_logits_tc_supported); equss_probe_logits covers the rest. */
+ * D % 32 == 0, C_pad <= 64 and h*w % 32 == 0 (equss_probe_logits_tc_supported); equss_probe_logits covers the rest. */
 int64_t equss_probe_image_bytes(int D, int c_total);
 int equss_probe_build_image(const float* wmat_t, int D, int c_total, void* image, void* stream);
 int equss_probe_logits_tc_supported(int D, int h, int w, int c_total);
