@@ -324,16 +324,21 @@ probe_argmax_confusion_kernel(const float* __restrict__ logits, int B, int h, in
 // (8 rows at the cocostuff27 shape): per label pixel and channel that leaves  v = h0*H0[c] + h1*H1[c]  and the
 // argmax update -- the association order of PyTorch's upsample_bilinear2d -- instead of four loads and seven
 // multiply-adds.  Confusion bins are per block in shared memory (run-length merged per warp).
+constexpr int kRowsPerBlock = 8;
 template <int CMAX, int TMAX, int MINB>
 __global__ void __launch_bounds__(TMAX, MINB)
 probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_pad, const long long* __restrict__ label,
-                         int H, int W, int C, ProbeHeads heads, float scale_h, float scale_w, int rows_per_block) {
+                         int H, int W, int C, ProbeHeads heads, float scale_h, float scale_w, int rows_per_block,
+                         int row_shift) {
   extern __shared__ int s_hist[];   // [hist_per_warp] = all heads' bins, one copy per block
   for (int i = threadIdx.x; i < heads.hist_per_warp; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const int b = blockIdx.y;
-  const int Y0 = blockIdx.x * rows_per_block;
-  const int Y1 = min(H, Y0 + rows_per_block);
+  // block k covers label rows [k*RB - shift, (k+1)*RB - shift): with an integer H/h ratio and shift = RB/2 these
+  // are exactly the rows that interpolate between one pair of token rows
+  const int Ya = (int)blockIdx.x * rows_per_block - row_shift;
+  const int Y0 = max(Ya, 0);
+  const int Y1 = min(H, Ya + rows_per_block);
   const float* base = logits + (long long)b * h * w * c_pad;
   const int Wpad = (W + 31) & ~31;
   for (int X = threadIdx.x; X < Wpad; X += blockDim.x) {
@@ -343,13 +348,28 @@ probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_p
     if (x0 > w - 1) x0 = w - 1;
     const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
     const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    // labels of this column for all rows of the block, loaded up front (one latency, RB loads in flight)
+    unsigned long long labs = 0;         // one byte per row: label, or 255 = ignore (C <= 255 on this path)
+#pragma unroll
+    for (int r = 0; r < kRowsPerBlock; ++r) {
+      const int Y = Ya + r;
+      long long lab = -1;
+      if (live && Y >= Y0 && Y < Y1) lab = __ldcs(label + ((long long)b * H + Y) * W + X);
+      labs |= (unsigned long long)((lab >= 0 && lab < C) ? (unsigned)lab : 255u) << (8 * r);
+    }
 #pragma unroll 1
     for (int hd = 0; hd < heads.n_heads; ++hd) {
       const int off = heads.off[hd], cnt = heads.cnt[hd];
+      long long* preds = heads.preds[hd];
+      const bool want_conf = heads.conf[hd] != nullptr;
+      int* hist = s_hist + heads.hist_off[hd];
       float H0[CMAX], H1[CMAX];
       int cy0 = -1;
 #pragma unroll 1
-      for (int Y = Y0; Y < Y1; ++Y) {
+      for (int r = 0; r < kRowsPerBlock; ++r) {
+        const int Y = Ya + r;
+        if (Y < Y0) continue;        // block-uniform
+        if (Y >= Y1) break;
         // PyTorch upsample_bilinear2d, align_corners=False (area_pixel_compute_source_index)
         float sy = scale_h * ((float)Y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
         int y0 = (int)sy;
@@ -364,34 +384,31 @@ probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_p
           const float4* p11 = reinterpret_cast<const float4*>(base + ((long long)y1 * w + x1) * c_pad + off);
 #pragma unroll
           for (int g = 0; g < CMAX / 4; ++g) {
-            if (4 * g < cnt) {
-              const float4 a = __ldg(p00 + g), bq = __ldg(p01 + g), c = __ldg(p10 + g), dq = __ldg(p11 + g);
-              H0[4 * g + 0] = lx0 * a.x + lx1 * bq.x; H0[4 * g + 1] = lx0 * a.y + lx1 * bq.y;
-              H0[4 * g + 2] = lx0 * a.z + lx1 * bq.z; H0[4 * g + 3] = lx0 * a.w + lx1 * bq.w;
-              H1[4 * g + 0] = lx0 * c.x + lx1 * dq.x; H1[4 * g + 1] = lx0 * c.y + lx1 * dq.y;
-              H1[4 * g + 2] = lx0 * c.z + lx1 * dq.z; H1[4 * g + 3] = lx0 * c.w + lx1 * dq.w;
-            }
+            const float4 a = __ldg(p00 + g), bq = __ldg(p01 + g), c = __ldg(p10 + g), dq = __ldg(p11 + g);
+            H0[4 * g + 0] = lx0 * a.x + lx1 * bq.x; H0[4 * g + 1] = lx0 * a.y + lx1 * bq.y;
+            H0[4 * g + 2] = lx0 * a.z + lx1 * bq.z; H0[4 * g + 3] = lx0 * a.w + lx1 * bq.w;
+            H1[4 * g + 0] = lx0 * c.x + lx1 * dq.x; H1[4 * g + 1] = lx0 * c.y + lx1 * dq.y;
+            H1[4 * g + 2] = lx0 * c.z + lx1 * dq.z; H1[4 * g + 3] = lx0 * c.w + lx1 * dq.w;
           }
+          // CMAX - 4 < cnt <= CMAX (host check): only the last group can hold channels past the head's end; they
+          // are made unable to win here, so the argmax loop needs no per-channel guard
+#pragma unroll
+          for (int j = CMAX - 3; j < CMAX; ++j)
+            if (j >= cnt) { H0[j] = -1e30f; H1[j] = -1e30f; }
         }
         float best = -INFINITY;
         int bj = 0;
 #pragma unroll
         for (int j = 0; j < CMAX; ++j) {
-          if (j < cnt) {
-            const float v = ly0 * H0[j] + ly1 * H1[j];
-            if (v > best) { best = v; bj = j; }       // first maximal index wins (torch.argmax)
-          }
+          const float v = ly0 * H0[j] + ly1 * H1[j];
+          if (v > best) { best = v; bj = j; }       // first maximal index wins (torch.argmax)
         }
-        int bin = -1;
-        if (live) {
-          const long long pidx = ((long long)b * H + Y) * W + X;
-          if (heads.preds[hd]) __stcs(heads.preds[hd] + pidx, (long long)bj);
-          if (heads.conf[hd]) {
-            const long long lab = __ldcs(label + pidx);
-            if (lab >= 0 && lab < C && bj < C) bin = bj * C + (int)lab;
-          }
+        if (live && preds) __stcs(preds + ((long long)b * H + Y) * W + X, (long long)bj);
+        if (want_conf) {
+          const int lab = (int)((labs >> (8 * r)) & 0xFFull);
+          const int bin = (live && lab != 255 && bj < C) ? bj * C + lab : -1;
+          warp_hist_add(hist, bin);
         }
-        if (heads.conf[hd]) warp_hist_add(s_hist + heads.hist_off[hd], bin);
       }
     }
   }
@@ -519,23 +536,32 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
   const float scale_h = (float)h / (float)H, scale_w = (float)w / (float)W;
   {
     // row-block kernel: heads aligned to four channels, at most 28 / 32 channels each
-    bool fast = (size_t)per_warp * sizeof(int) <= 48 * 1024 && getenv("EQUSS_PROBE_ARGMAX_OLD") == nullptr;
+    bool fast = (size_t)per_warp * sizeof(int) <= 48 * 1024 && num_classes <= 255 && getenv("EQUSS_PROBE_ARGMAX_OLD") == nullptr;
     int cmax = 0;
     for (int i = 0; i < n_heads; ++i) { fast = fast && (hd.off[i] % 4) == 0; cmax = hd.cnt[i] > cmax ? hd.cnt[i] : cmax; }
-    if (fast && cmax <= 32) {
-      const int rb = 8;
+    int cmin = cmax;
+    for (int i = 0; i < n_heads; ++i) cmin = hd.cnt[i] < cmin ? hd.cnt[i] : cmin;
+    const int cm = (cmax + 3) & ~3;          // every head must end inside the last group of four
+    if (fast && cm <= 32 && cmin > cm - 4) {
+      // rows per block = label rows per token row when H/h is an integer in [2, 8]; else 8 rows, unaligned
+      int rb = kRowsPerBlock, shift = 0;
+      if (H % h == 0 && H / h >= 2 && H / h <= kRowsPerBlock) { rb = H / h; shift = rb / 2; }
       int threads = (W + 31) & ~31;
       if (threads > 512) threads = 256;
-      dim3 grid((unsigned)((H + rb - 1) / rb), (unsigned)B);
+      dim3 grid((unsigned)((H + shift + rb - 1) / rb), (unsigned)B);
       const size_t smem = (size_t)(per_warp > 0 ? per_warp : 1) * sizeof(int);
 #define EQUSS_ROWS_LAUNCH(CM, TM, MB)                                                                                 \
       probe_argmax_rows_kernel<CM, TM, MB><<<grid, threads, smem, (cudaStream_t)stream>>>(                            \
-          logits, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w, rb)
-      if (threads <= 320) {
-        if (cmax <= 28) EQUSS_ROWS_LAUNCH(28, 320, 2); else EQUSS_ROWS_LAUNCH(32, 320, 2);
-      } else {
-        if (cmax <= 28) EQUSS_ROWS_LAUNCH(28, 512, 1); else EQUSS_ROWS_LAUNCH(32, 512, 1);
+          logits, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w, rb, shift)
+#define EQUSS_ROWS_CM(TM, MB)                                                                                         \
+      switch (cm) {                                                                                                   \
+        case 4: EQUSS_ROWS_LAUNCH(4, TM, MB); break;   case 8: EQUSS_ROWS_LAUNCH(8, TM, MB); break;                   \
+        case 12: EQUSS_ROWS_LAUNCH(12, TM, MB); break; case 16: EQUSS_ROWS_LAUNCH(16, TM, MB); break;                 \
+        case 20: EQUSS_ROWS_LAUNCH(20, TM, MB); break; case 24: EQUSS_ROWS_LAUNCH(24, TM, MB); break;                 \
+        case 28: EQUSS_ROWS_LAUNCH(28, TM, MB); break; default: EQUSS_ROWS_LAUNCH(32, TM, MB); break;                 \
       }
+      if (threads <= 320) { EQUSS_ROWS_CM(320, 2) } else { EQUSS_ROWS_CM(512, 1) }
+#undef EQUSS_ROWS_CM
 #undef EQUSS_ROWS_LAUNCH
       EQUSS_LAUNCH_OK("probe_argmax_rows_kernel");
       return EQUSS_OK;
