@@ -32,18 +32,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` elapse,
+// instead of spinning (a spinning waiter costs issue slots and ALU-pipe cycles of the warps that do the work).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.  The slow path lives
+// in one out-of-line function (inlined at every wait it multiplied the kernels' code size) and polls at most every
+// ~2 us: ~1M polls = ~2 s before the watchdog fires.
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+  for (int polls = 0; polls < (1 << 20); ++polls)
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+  printf("equss tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", blockIdx.x, threadIdx.x, tag, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(32);                         // do not steal issue slots from the working warps of this SMSP
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s
-      printf("equss tc watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", blockIdx.x, threadIdx.x, tag,
-             parity);
-      __trap();
-    }
-  }
+  mbar_wait_slow(bar, parity, tag);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

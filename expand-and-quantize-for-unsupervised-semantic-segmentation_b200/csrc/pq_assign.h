@@ -14,7 +14,10 @@ int assign_tc_launch(const float* z, const equss_zdesc* zd, const float* codeboo
 // fp16-split kernel (pq_assign_h.cu): l2 rows, d in {16, 32, 64}
 bool assign_tch_supported(const equss_zdesc* zd, int M, int K, int d, int norm_mode, bool want_margin);
 int64_t assign_tch_workspace_bytes(int64_t n_pixels, int M, int K, int d);
+bool assign_tch_fusable(const equss_zdesc* zd, int M, int K, int d, int norm_mode);
+// gather_src / out / sqerr non-null: the kernel also runs K3 (gather + straight-through value + squared error)
 int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebook_norm, const float* cnorm2,
                       int M, int K, int d, int32_t* idx_out, void* workspace, int64_t workspace_bytes,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const float* gather_src = nullptr, float* out = nullptr,
+                      double* sqerr = nullptr);
 }  // namespace equss

@@ -5,9 +5,9 @@
 namespace equss {
 namespace tch {
 
-int launch_tch_d16(int NC, int G, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
-int launch_tch_d32(int NC, int G, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
-int launch_tch_d64(int NC, int G, bool nchw, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tch_d16(int NC, int G, bool nchw, bool fuse, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tch_d32(int NC, int G, bool nchw, bool fuse, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
+int launch_tch_d64(int NC, int G, bool nchw, bool fuse, const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st);
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -213,11 +213,22 @@ int64_t assign_tch_workspace_bytes(int64_t n_pixels, int M, int K, int d) {
   return bytes + 256;
 }
 
+bool assign_tch_fusable(const equss_zdesc* zd, int M, int K, int d, int norm_mode) {
+  if (!assign_tch_supported(zd, M, K, d, norm_mode, false)) return false;
+  return (d == 16 || d == 32) && K <= 256;          // single code chunk, raw ring deep enough for the gather lag
+}
+
 int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebook_norm, const float* cnorm2, int M,
-                      int K, int d, int32_t* idx_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                      int K, int d, int32_t* idx_out, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                      const float* gather_src, float* out, double* sqerr) {
   using namespace tch;
   const bool nchw = !is_flat(zd);
+  const bool fuse = out != nullptr;
   Plan pl = make_plan(M, K, d, nchw);
+  EQUSS_REQUIRE(!fuse || (gather_src && sqerr && assign_tch_fusable(zd, M, K, d, EQUSS_NORM_L2)), EQUSS_ERR_UNSUPPORTED,
+                "tcgen05 f16x2 assign: fused gather needs d in {16,32}, K <= 256 (got d=%d K=%d)", d, K);
+  EQUSS_REQUIRE(!fuse || (!((uintptr_t)out & 15) && !((uintptr_t)gather_src & 15)), EQUSS_ERR_INVALID_ARG,
+                "tcgen05 f16x2 assign: out and gather_src must be 16-byte aligned");
   EQUSS_REQUIRE(pl.ok, EQUSS_ERR_UNSUPPORTED, "tcgen05 f16x2 assign: unsupported d=%d", d);
   EQUSS_REQUIRE(workspace && workspace_bytes >= assign_tch_workspace_bytes(zd->n_pixels, M, K, d), EQUSS_ERR_INVALID_ARG,
                 "tcgen05 f16x2 assign: workspace of %lld bytes needed, got %lld",
@@ -272,15 +283,16 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
   p.n_tiles = nchw ? (zd->n_pixels / zd->hw) * p.tiles_per_image : (zd->n_pixels + kTileM - 1) / kTileM;
   p.z = z; p.zv = make_view(zd); p.cb = codebook_norm; p.cn2 = cnorm2;
   p.images = images; p.img_bytes = img_bytes; p.idx_out = idx_out; p.merged = merged; p.flag_list = flag_list; p.flag_count = flag_count;
+  p.gsrc = gather_src; p.out = out; p.sqerr = sqerr;
   const long long total_units = (long long)M * pl.nchunks * p.n_tiles;
   int grid = num_sms();
   if (total_units < grid) grid = (int)total_units;
 
   int rc;
   switch (d) {
-    case 16: rc = launch_tch_d16(pl.NC, pl.G, nchw, tmap, p, grid, st); break;
-    case 32: rc = launch_tch_d32(pl.NC, pl.G, nchw, tmap, p, grid, st); break;
-    default: rc = launch_tch_d64(pl.NC, pl.G, nchw, tmap, p, grid, st); break;
+    case 16: rc = launch_tch_d16(pl.NC, pl.G, nchw, fuse, tmap, p, grid, st); break;
+    case 32: rc = launch_tch_d32(pl.NC, pl.G, nchw, fuse, tmap, p, grid, st); break;
+    default: rc = launch_tch_d64(pl.NC, pl.G, nchw, fuse, tmap, p, grid, st); break;
   }
   if (rc != EQUSS_OK) return rc;
   if (merged) {

@@ -2,6 +2,6 @@
 #include "pq_assign_h_kernel.cuh"
 namespace equss {
 namespace tch {
-EQUSS_TCH_DISPATCH(16, 2, 6, 4)
+EQUSS_TCH_DISPATCH(16, 2, 6, 4, 8, 4)
 }  // namespace tch
 }  // namespace equss

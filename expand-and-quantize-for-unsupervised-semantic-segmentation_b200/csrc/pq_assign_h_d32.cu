@@ -2,6 +2,6 @@
 #include "pq_assign_h_kernel.cuh"
 namespace equss {
 namespace tch {
-EQUSS_TCH_DISPATCH(32, 1, 4, 3)
+EQUSS_TCH_DISPATCH(32, 1, 4, 3, 6, 3)
 }  // namespace tch
 }  // namespace equss

@@ -2,6 +2,6 @@
 #include "pq_assign_h_kernel.cuh"
 namespace equss {
 namespace tch {
-EQUSS_TCH_DISPATCH(64, 1, 2, 2)
+EQUSS_TCH_DISPATCH(64, 1, 2, 2, 0, 1)
 }  // namespace tch
 }  // namespace equss

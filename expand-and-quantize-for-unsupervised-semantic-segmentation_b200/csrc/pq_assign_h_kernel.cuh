@@ -28,6 +28,11 @@
 // and the G operand images stay resident in shared memory.  Codebooks with K > NC are split into chunks whose
 // winners are merged with a 64-bit atomicMax on (score, index); cross-chunk near-ties are appended to a list and
 // resolved by a full exact scan (one warp per listed row) after the main kernel.
+//
+// Fused gather (FUSE, single-chunk codebooks, d <= 32): the epilogue also drops each tile's winning columns into a
+// small shared-memory ring, and the convert warps -- which have slack -- run K3 (gather + straight-through value +
+// squared error, model/quantizer.py:474,514,534-536) for the tile LAG units later from the raw tile that is still
+// in shared memory.  The activation tensor is then read from HBM once for assign + gather instead of twice.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -45,12 +50,12 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 480;
 // The SMSP arbiter prefers the highest warp id among eligible warps: the convert warps (the pipeline's critical
 // stage) get the highest ids, the epilogue warps (ALU-pipe heavy, plenty of slack) the lowest.
-constexpr int kEpiWarp0 = 0, kProducerWarp = 8, kMmaWarp = 9, kConvWarp0 = 11;
+constexpr int kEpiWarp0 = 0, kProducerWarp = 8, kConvWarp0 = 9, kMmaWarp = 13;
 constexpr float kTolRel = 1.52587890625e-5f;     // 2^-16
 
 #ifdef EQUSS_TRACE   // scripts/trace_assign.cu: per-unit clock64 stamps of CTA 0 (pipeline timeline)
-__device__ long long g_trace[256 * 8];
-#define EQUSS_TR(slot, i) do { if (blockIdx.x == 0 && (i) < 256 && lane == 0) g_trace[(i) * 8 + (slot)] = clock64(); } while (0)
+__device__ long long g_trace[256 * 12];
+#define EQUSS_TR(slot, i) do { if (blockIdx.x == 0 && (i) < 256 && lane == 0) g_trace[(i) * 12 + (slot)] = clock64(); } while (0)
 #else
 #define EQUSS_TR(slot, i) do { } while (0)
 #endif
@@ -65,8 +70,10 @@ __host__ __device__ constexpr int a_sbo(int D) { return kch(D) * a_lbo(D); }
 __host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * a_sbo(D); }
 __host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
-__host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs) {
-  return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) + 512;
+constexpr int kIdxBufs = 8;                      // fused gather: ring of per-tile winning columns
+__host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false) {
+  return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) +
+         (fuse ? kIdxBufs * kTileM * 4 : 0) + 512;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, both K-major, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -88,6 +95,10 @@ struct Params {
   unsigned long long* merged; // nchunks > 1: [M][N] (sortable score << 32 | index), zero-initialised
   uint32_t* flag_list;        // nchunks > 1: [M*N] rows (m*N + n) with a cross-chunk near-tie (duplicates allowed)
   unsigned int* flag_count;   // nchunks > 1: number of entries in flag_list, zero-initialised
+  // fused gather (FUSE kernels only)
+  const float* gsrc;          // gather source [M][K][d]
+  float* out;                 // same strides as z
+  double* sqerr;              // [M], caller-zeroed
 };
 
 // Walks the CTA's contiguous unit range (sslot-major, then tile, then subspace-in-group) without divisions.
@@ -216,9 +227,10 @@ __device__ __noinline__ int exact_rescore_warp(const Params& p, int m, long long
   return best_col == 0x7fffffff ? 0 : best_col;
 }
 
-template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW>
+template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW, bool FUSE, int LAG>
 __global__ void __launch_bounds__(kThreads, 1)
 assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  static_assert(!FUSE || (LAG >= 1 && LAG < STAGES && LAG < kIdxBufs), "gather lag must fit the raw and index rings");
   constexpr int SBO = b_sbo(D);
   constexpr int ASBO = a_sbo(D), ALBO = a_lbo(D);
   constexpr int B_BYTES = align_up(b_bytes(D, NC), 128);
@@ -238,7 +250,8 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* s_b = smem;                                   // [G][B_BYTES]
   uint8_t* s_a = s_b + G * B_BYTES;                      // [ABUFS][A_BYTES]
   uint8_t* s_rawt = s_a + ABUFS * A_BYTES;               // [STAGES][RAW_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES);
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_rawt + STAGES * RAW_BYTES);   // FUSE: [kIdxBufs][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES + (FUSE ? kIdxBufs * kTileM * 4 : 0));
   uint64_t* raw_full = bars;                    // [STAGES]
   uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
   uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
@@ -246,7 +259,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* t_full = a_empty + ABUFS;           // [4]  (unit parity, half)
   uint64_t* t_empty = t_full + 4;               // [4]
   uint64_t* b_full = t_empty + 4;               // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* idx_full = b_full + 1;              // [kIdxBufs] FUSE: epilogue wrote the tile's columns
+  uint64_t* idx_empty = idx_full + kIdxBufs;    // [kIdxBufs] FUSE: gather consumed them
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(idx_empty + kIdxBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -260,6 +275,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     for (int i = 0; i < ABUFS; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, HALVES); }
     for (int i = 0; i < 4; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
     mbar_init(b_full, 1);
+    for (int i = 0; i < kIdxBufs; ++i) { mbar_init(idx_full + i, 4); mbar_init(idx_empty + i, 4); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<TMEM_COLS>(s_tmem);
@@ -342,13 +358,129 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         __syncwarp();
       }
     }
-  } else if (warp >= kConvWarp0) {
-    // ===================================== convert warps (11-14) ==================================
+  } else if (warp >= kConvWarp0 && warp < kConvWarp0 + 4) {
+    // ===================================== convert warps (9-12) ===================================
     const int ct = threadIdx.x - kConvWarp0 * 32;   // 0..127
     int b_loads = 0, cur_slot = -1;
     UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+    UnitIter itg; itg.init(u0, (int)p.n_tiles, p.nchunks, G);      // FUSE: the unit whose gather is due next
+
+    // K3 for unit j (its raw tile is still in stage j % STAGES, its winning columns in the index ring), in two
+    // halves: gather_prefetch issues the codeword loads, gather_finish -- called after the next convert, which
+    // hides their latency -- normalises, writes the output and accumulates the squared error.
+    constexpr int QN = NCHW ? LPS : 128 / (128 / LPS);      // float4 codeword pieces per thread (= LPS either way)
+    float4 qpre[QN];
+    float e_acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) e_acc[g] = 0.f;
+    int e_sg = -1;                                          // subspace group the accumulators belong to
+    auto flush_err = [&]() {
+      if (e_sg < 0) return;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float t = warp_sum(e_acc[g]);
+        if (lane == 0 && t != 0.f) atomicAdd(p.sqerr + e_sg * G + g, (double)t);
+        e_acc[g] = 0.f;
+      }
+    };
+    auto gather_prefetch = [&](int j) {
+      const int ib = j % kIdxBufs;
+      if (warp == kConvWarp0) EQUSS_TR(8, j);
+      mbar_wait(idx_full + ib, (j / kIdxBufs) & 1, 50);
+      if (warp == kConvWarp0) EQUSS_TR(9, j);
+      const int32_t* sidx = s_idx + ib * kTileM;
+      const float* srcm = p.gsrc + (size_t)itg.m() * p.K * D;
+      if (!NCHW) {
+        constexpr int ROWS_PER_PASS = 128 / LPS;
+        const int l = ct % LPS, row0 = ct / LPS;
+#pragma unroll
+        for (int u = 0; u < QN; ++u)
+          qpre[u] = __ldg(reinterpret_cast<const float4*>(srcm + (size_t)sidx[u * ROWS_PER_PASS + row0] * D) + l);
+      } else {
+        const float4* q4 = reinterpret_cast<const float4*>(srcm + (size_t)sidx[ct] * D);
+#pragma unroll
+        for (int u = 0; u < QN; ++u) qpre[u] = __ldg(q4 + u);
+      }
+    };
+    auto gather_finish = [&](int j) {
+      const int ib = j % kIdxBufs, s = j % STAGES;
+      const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
+      const int m = itg.m(), tile = itg.tile;
+      if (itg.sg != e_sg) { flush_err(); e_sg = itg.sg; }
+      float e_unit = 0.f;
+      if (!NCHW) {
+        constexpr int ROWS_PER_PASS = 128 / LPS;
+        constexpr int PASSES = kTileM / ROWS_PER_PASS;      // == LPS == QN
+        const int l = ct % LPS;
+        const int row0 = ct / LPS;
+        float4 zn[PASSES];       // canonical z_norm, left in the raw stage by the convert pass
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) zn[u] = *reinterpret_cast<const float4*>(raw + (u * ROWS_PER_PASS + row0) * D + l * 4);
+        float ee[PASSES];
+        float4 o[PASSES];
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) {
+          float4 dq;
+          dq.x = qpre[u].x - zn[u].x; dq.y = qpre[u].y - zn[u].y; dq.z = qpre[u].z - zn[u].z; dq.w = qpre[u].w - zn[u].w;
+          o[u].x = zn[u].x + dq.x; o[u].y = zn[u].y + dq.y; o[u].z = zn[u].z + dq.z; o[u].w = zn[u].w + dq.w;     // STE value (:536)
+          ee[u] = group_sumsq(dq.x, dq.y, dq.z, dq.w);
+        }
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) {
+          const long long n = (long long)tile * kTileM + u * ROWS_PER_PASS + row0;
+          const bool live = n < p.n_pixels;
+          if (live) __stcs(reinterpret_cast<float4*>(p.out + n * p.zv.stride_s + m * D) + l, o[u]);
+          ee[u] = live ? ee[u] : 0.f;
+        }
+#pragma unroll
+        for (int sft = 1; sft < LPS; sft <<= 1) {
+#pragma unroll
+          for (int u = 0; u < PASSES; ++u) ee[u] += __shfl_xor_sync(0xffffffffu, ee[u], sft);
+        }
+        if (l == 0) {
+#pragma unroll
+          for (int u = 0; u < PASSES; ++u) e_unit += ee[u];
+        }
+      } else {
+        const int row = ct;
+        const long long bimg = tile / p.tiles_per_image;
+        const long long spix = (long long)(tile - (int)bimg * p.tiles_per_image) * kTileM + row;
+        const bool live = spix < p.hw;
+        float x[D];
+#pragma unroll
+        for (int jj = 0; jj < D; ++jj) x[jj] = raw[jj * kTileM + row];
+        float* o = p.out + bimg * p.zv.stride_b + spix + (long long)m * D * p.zv.stride_c;
+        float e = 0.f;
+#pragma unroll
+        for (int g4 = 0; g4 < LPS; ++g4) {
+          const float4 qq = qpre[g4];
+          const float4 zn = make_float4(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);   // canonical z_norm (convert pass)
+          const float d0 = qq.x - zn.x, d1 = qq.y - zn.y, d2 = qq.z - zn.z, d3 = qq.w - zn.w;
+          if (live) {
+            __stcs(o + (long long)(4 * g4 + 0) * p.zv.stride_c, zn.x + d0);
+            __stcs(o + (long long)(4 * g4 + 1) * p.zv.stride_c, zn.y + d1);
+            __stcs(o + (long long)(4 * g4 + 2) * p.zv.stride_c, zn.z + d2);
+            __stcs(o + (long long)(4 * g4 + 3) * p.zv.stride_c, zn.w + d3);
+          }
+          e += group_sumsq(d0, d1, d2, d3);
+        }
+        if (live) e_unit = e;
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) e_acc[g] += (itg.g == g) ? e_unit : 0.f;
+      if (warp == kConvWarp0) EQUSS_TR(11, j);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(raw_empty + s);
+        mbar_arrive(idx_empty + ib);
+      }
+      if (warp == kConvWarp0) EQUSS_TR(10, j);
+      itg.next();
+    };
+
     for (int i = 0; i < n_units; ++i, it.next()) {
       const int a = i % ABUFS, s = i % STAGES;
+      if constexpr (FUSE) { if (i >= LAG) gather_prefetch(i - LAG); }
       mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (warp == kConvWarp0) EQUSS_TR(0, i);
       if (it.sslot != cur_slot) {
@@ -391,10 +523,18 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             for (int u = 0; u < BATCH; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], sft);
           }
           uint2 hi[BATCH], lo[BATCH];
+          float4 zn4[FUSE ? BATCH : 1];
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
-            const float inv = fminf(rsqrtf(ss[u]), 1e12f);
-            const float zx = v[u].x * inv, zy = v[u].y * inv, zz = v[u].z * inv, zw = v[u].w * inv;
+            float zx, zy, zz, zw;
+            if constexpr (FUSE) {      // canonical z_norm (the gather needs it bit-exact); kept in the raw stage
+              const float4 zn = div4_fast(v[u], l2_denom_fast(ss[u]));
+              zx = zn.x; zy = zn.y; zz = zn.z; zw = zn.w;
+              zn4[u] = zn;
+            } else {
+              const float inv = fminf(rsqrtf(ss[u]), 1e12f);
+              zx = v[u].x * inv; zy = v[u].y * inv; zz = v[u].z * inv; zw = v[u].w * inv;
+            }
             const __half2 h01 = __floats2half2_rn(zx, zy), h23 = __floats2half2_rn(zz, zw);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(zx - f01.x, zy - f01.y), l23 = __floats2half2_rn(zz - f23.x, zw - f23.y);
@@ -407,6 +547,8 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             uint8_t* rowp = a_tile + (row / 8) * ASBO + (row % 8) * 16 + (l >> 1) * ALBO + (l & 1) * 8;
             *reinterpret_cast<uint2*>(rowp) = hi[u];
             *reinterpret_cast<uint2*>(rowp + C8 * ALBO) = lo[u];
+            if constexpr (FUSE)
+              *reinterpret_cast<float4*>(const_cast<float*>(raw) + row * D + l * 4) = zn4[u];
           }
         }
       } else {
@@ -415,10 +557,26 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         float x[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) x[j] = raw[j * kTileM + row];
-        float ss = 0.f;
+        float inv;
+        if constexpr (FUSE) {        // canonical z_norm, written back into the raw stage for the gather
+          float gsum[LPS];
 #pragma unroll
-        for (int j = 0; j < D; ++j) ss = fmaf(x[j], x[j], ss);
-        const float inv = fminf(rsqrtf(ss), 1e12f);
+          for (int g4 = 0; g4 < LPS; ++g4) gsum[g4] = group_sumsq(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);
+          const float denom = l2_denom_fast(butterfly_array<LPS>(gsum));
+#pragma unroll
+          for (int g4 = 0; g4 < LPS; ++g4) {
+            const float4 zn = div4_fast(make_float4(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]), denom);
+            x[4 * g4] = zn.x; x[4 * g4 + 1] = zn.y; x[4 * g4 + 2] = zn.z; x[4 * g4 + 3] = zn.w;
+          }
+#pragma unroll
+          for (int j = 0; j < D; ++j) const_cast<float*>(raw)[j * kTileM + row] = x[j];
+          inv = 1.f;
+        } else {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) ss = fmaf(x[j], x[j], ss);
+          inv = fminf(rsqrtf(ss), 1e12f);
+        }
         uint8_t* rowp = a_tile + (row / 8) * ASBO + (row % 8) * 16;
 #pragma unroll
         for (int c = 0; c < C8; ++c) {
@@ -438,8 +596,13 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       fence_proxy_async();     // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
+      if (lane == 0) { if (!FUSE) mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
       if (warp == kConvWarp0) EQUSS_TR(2, i);
+      if constexpr (FUSE) { if (i >= LAG) gather_finish(i - LAG); }
+    }
+    if constexpr (FUSE) {
+      for (int j = (n_units > LAG ? n_units - LAG : 0); j < n_units; ++j) { gather_prefetch(j); gather_finish(j); }
+      flush_err();
     }
   } else {
     // ===================================== epilogue warps ===================================
@@ -526,6 +689,13 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           if (lane == src) best_col = res;
         }
       }
+      if constexpr (FUSE) {
+        const int ib = i % kIdxBufs;
+        mbar_wait(idx_empty + ib, ((i / kIdxBufs) & 1) ^ 1, 42);
+        s_idx[ib * kTileM + row] = live ? best_col : 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(idx_full + ib);
+      }
       if (live) {
         if (p.merged == nullptr) {
           p.idx_out[(long long)m * p.n_pixels + n] = best_col;
@@ -551,31 +721,40 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   }
 }
 
-template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW>
+template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW, bool FUSE, int LAG>
 static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = smem_bytes(D, NC, G, STAGES, ABUFS) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, G, STAGES, ABUFS);
+  constexpr int SMEM = smem_bytes(D, NC, G, STAGES, ABUFS, FUSE) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, G, STAGES, ABUFS, FUSE);
   static_assert(SMEM <= 227 * 1024, "shared-memory plan exceeds 227 KB");
-  EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW>,
+  EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW><<<grid, kThreads, SMEM, st>>>(tmap, p);
+  assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG><<<grid, kThreads, SMEM, st>>>(tmap, p);
   EQUSS_LAUNCH_OK("assign_f16x2_kernel");
   return EQUSS_OK;
 }
 
-// per-d dispatch over (NC, G, layout); one translation unit per d keeps the build parallel.  GV = subspaces
-// per 128-byte line of a flat row (used when M is a multiple of it; NCHW and odd M run with G = 1).
-#define EQUSS_TCH_DISPATCH(DV, GV, STV, ABV)                                                                  \
-  int launch_tch_d##DV(int NC, int G, bool nchw, const CUtensorMap& tmap, const Params& p, int grid,         \
+// per-d dispatch over (NC, G, layout, fused gather); one translation unit per d keeps the build parallel.  GV =
+// subspaces per 128-byte line of a flat row (used when M is a multiple of it; NCHW and odd M run with G = 1).
+// STF / LAGV: raw-ring depth and gather lag of the fused kernels (STF = 0: no fused instantiation for this d).
+#define EQUSS_TCH_DISPATCH(DV, GV, STV, ABV, STF, LAGV)                                                       \
+  int launch_tch_d##DV(int NC, int G, bool nchw, bool fuse, const CUtensorMap& tmap, const Params& p, int grid, \
                        cudaStream_t st) {                                                                    \
-    EQUSS_TCH_ONE(DV, 32, GV, STV, ABV) EQUSS_TCH_ONE(DV, 256, GV, STV, ABV)                                  \
+    EQUSS_TCH_ONE(DV, 32, GV, STV, ABV, STF, LAGV) EQUSS_TCH_ONE(DV, 256, GV, STV, ABV, STF, LAGV)            \
     set_error("tcgen05 f16x2 assign: no instantiation for d=%d NC=%d", DV, NC);                               \
     return EQUSS_ERR_UNSUPPORTED;                                                                             \
   }
-#define EQUSS_TCH_ONE(DV, NCV, GV, STV, ABV)                                                                  \
+#define EQUSS_TCH_ONE(DV, NCV, GV, STV, ABV, STF, LAGV)                                                       \
   if (NC == NCV) {                                                                                            \
-    if (nchw) return launch_instance<DV, NCV, 1, STV, ABV, true>(tmap, p, grid, st);                          \
-    if (G == GV) return launch_instance<DV, NCV, GV, STV, ABV, false>(tmap, p, grid, st);                     \
-    return launch_instance<DV, NCV, 1, STV, ABV, false>(tmap, p, grid, st);                                   \
+    if constexpr (STF > 0) {                                                                                  \
+      if (fuse) {                                                                                             \
+        if (nchw) return launch_instance<DV, NCV, 1, (STF > 0 ? STF : 2), ABV, true, true, LAGV>(tmap, p, grid, st);     \
+        if (G == GV) return launch_instance<DV, NCV, GV, (STF > 0 ? STF : 2), ABV, false, true, LAGV>(tmap, p, grid, st); \
+        return launch_instance<DV, NCV, 1, (STF > 0 ? STF : 2), ABV, false, true, LAGV>(tmap, p, grid, st);              \
+      }                                                                                                       \
+    }                                                                                                         \
+    if (fuse) { set_error("tcgen05 f16x2 assign: fused gather is not built for d=%d", DV); return EQUSS_ERR_UNSUPPORTED; } \
+    if (nchw) return launch_instance<DV, NCV, 1, STV, ABV, true, false, 1>(tmap, p, grid, st);                \
+    if (G == GV) return launch_instance<DV, NCV, GV, STV, ABV, false, false, 1>(tmap, p, grid, st);           \
+    return launch_instance<DV, NCV, 1, STV, ABV, false, false, 1>(tmap, p, grid, st);                         \
   }
 
 }  // namespace tch

@@ -234,6 +234,26 @@ extern "C" int equss_pq_assign(const float* z, const equss_zdesc* zd, const floa
                             margin_out, st);
 }
 
+extern "C" int equss_pq_assign_gather_supported(const equss_zdesc* zd, int M, int K, int d, int norm_mode) {
+  return (zd && zd->n_pixels > 0 && validate_zdesc(zd, M, d) == EQUSS_OK && assign_tch_fusable(zd, M, K, d, norm_mode)) ? 1 : 0;
+}
+
+extern "C" int equss_pq_assign_gather(const float* z, const equss_zdesc* zd, const float* codebook_norm,
+                                      const float* cnorm2, const float* gather_src, int M, int K, int d,
+                                      int norm_mode, int32_t* idx_out, float* out, double* sqerr, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+  if (zd && zd->n_pixels == 0) return EQUSS_OK;
+  EQUSS_REQUIRE(z && zd && codebook_norm && cnorm2 && gather_src && idx_out && out && sqerr, EQUSS_ERR_INVALID_ARG,
+                "equss_pq_assign_gather: null pointer");
+  int rc = validate_zdesc(zd, M, d); if (rc) return rc;
+  EQUSS_REQUIRE(equss_pq_assign_gather_supported(zd, M, K, d, norm_mode), EQUSS_ERR_UNSUPPORTED,
+                "equss_pq_assign_gather: needs l2 rows, d in {16,32}, K <= 256, flat or NCHW layout "
+                "(layout=%d M=%d K=%d d=%d norm=%d); call equss_pq_assign + equss_pq_gather_loss instead",
+                zd->layout, M, K, d, norm_mode);
+  return assign_tch_launch(z, zd, codebook_norm, cnorm2, M, K, d, idx_out, workspace, workspace_bytes,
+                           (cudaStream_t)stream, gather_src, out, sqerr);
+}
+
 extern "C" int equss_pq_distance_prob(const float* z, const equss_zdesc* zd, const float* codebook_norm,
                                       const float* cnorm2, int M, int K, int d, int norm_mode,
                                       const float* norm_a, const float* norm_b, float temperature,

@@ -13,7 +13,7 @@ import torch
 from . import _native as N
 
 __all__ = [
-    "pq_cnorm2", "pq_assign", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
+    "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
     "pq_distance_prob", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
     "launch_count",
 ]
@@ -83,6 +83,43 @@ def pq_assign(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optional[tor
                            idx.data_ptr(), N.ptr(margin), N.ptr(ws), wsb, algo, N.stream_ptr(dev))
     N.check(rc, "equss_pq_assign")
     return (idx, margin) if return_margin else idx
+
+
+def pq_assign_gather(z: torch.Tensor, codebook_norm: torch.Tensor, gather_src: Optional[torch.Tensor] = None,
+                     cnorm2: Optional[torch.Tensor] = None, normalize: Optional[str] = "l2", norm_a=None, norm_b=None,
+                     fused: Optional[bool] = None):
+    """Nearest-codeword indices AND the gathered / straight-through output in one call:
+    (idx int32 [M, N], out like z, sqerr float64 [M]).  When the shape allows it (l2 rows, d in {16, 32}, K <= 256)
+    one fused tcgen05 kernel reads the activations once; otherwise :func:`pq_assign` + :func:`pq_gather_loss` run
+    back to back.  ``fused=False`` forces the two-kernel path, ``fused=True`` raises if fusion is unavailable."""
+    cb = N.f32c(codebook_norm.detach())
+    src = cb if gather_src is None else N.f32c(gather_src.detach())
+    M, K, d = cb.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    if dz != d or tuple(src.shape) != (M, K, d):
+        raise ValueError("codebook / gather source shape does not match the activation sub-dim")
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    L = N.lib()
+    can = bool(L.equss_pq_assign_gather_supported(zd, M, K, d, mode))
+    if fused is True and not can:
+        raise ValueError("pq_assign_gather: fused kernel not available for this shape")
+    if not can or fused is False:
+        idx = pq_assign(z, cb, cnorm2, normalize, norm_a, norm_b)
+        out, sqerr, _ = pq_gather_loss(z, src, idx, normalize, norm_a, norm_b)
+        return idx, out, sqerr
+    if cnorm2 is None:
+        cnorm2 = pq_cnorm2(cb)
+    cnorm2 = N.f32c(cnorm2)
+    n = zd.n_pixels
+    idx = torch.empty((M, n), dtype=torch.int32, device=dev)
+    out = torch.empty_like(z)
+    sqerr = torch.zeros((M,), dtype=torch.float64, device=dev)
+    wsb = int(L.equss_pq_assign_workspace_bytes(n, M, K, d, N.ASSIGN_TCGEN05))
+    ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
+    rc = L.equss_pq_assign_gather(z.data_ptr(), zd, cb.data_ptr(), cnorm2.data_ptr(), src.data_ptr(), M, K, d, mode,
+                                  idx.data_ptr(), out.data_ptr(), sqerr.data_ptr(), ws.data_ptr(), wsb, N.stream_ptr(dev))
+    N.check(rc, "equss_pq_assign_gather")
+    return idx, out, sqerr
 
 
 def pq_gather_loss(z: torch.Tensor, gather_src: torch.Tensor, idx: torch.Tensor, normalize: Optional[str] = "l2",

@@ -107,6 +107,17 @@ int equss_pq_gather_loss(const float* z, const equss_zdesc* zd,
                          int norm_mode, const float* norm_a, const float* norm_b,
                          float* out, float* znorm_out, double* sqerr, void* stream);
 
+/* K1 + K3 in one pass over the activations (the tcgen05 assign kernel gathers each tile from shared memory a few
+ * tiles after assigning it): idx as equss_pq_assign, out / sqerr as equss_pq_gather_loss.  Available for l2 rows
+ * with d in {16, 32} and K <= 256 (equss_pq_assign_gather_supported); other shapes: call K1 then K3.
+ * workspace: equss_pq_assign_workspace_bytes(..., EQUSS_ASSIGN_TCGEN05) bytes. */
+int equss_pq_assign_gather_supported(const equss_zdesc* zd, int M, int K, int d, int norm_mode);
+int equss_pq_assign_gather(const float* z, const equss_zdesc* zd,
+                           const float* codebook_norm, const float* cnorm2, const float* gather_src,
+                           int M, int K, int d, int norm_mode,
+                           int32_t* idx_out, float* out, double* sqerr,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* backward of K3 w.r.t. z for the straight-through output and the commitment/codebook MSE terms
  * (SURVEY 8b "Autograd"):  g_znorm = grad_out + coef[m] * (z_norm - q),   grad_z = J_norm(z)^T g_znorm
  *   coef[m] = 2*beta*grad_loss_m/(N*d) is supplied by the caller ([M] fp32 on device).

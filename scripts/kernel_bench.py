@@ -32,6 +32,8 @@ def run(tag, shape, M, K, d, nbuf=3, only=None):
     res = {}
     if not only or "tc" in only:
         res["assign_tc"] = (timeit(lambda z: ops.pq_assign(z, cbn, cn2, "l2", algo=2), zs), 4 * N * D + 4 * N * M)
+    if not only or "fused" in only:
+        res["assign_gather"] = (timeit(lambda z: ops.pq_assign_gather(z, cbn, None, cn2, "l2"), zs), 8 * N * D + 4 * N * M)
     if only and "tf32" in only:
         res["assign_tf32"] = (timeit(lambda z: ops.pq_assign(z, cbn, cn2, "l2", algo=3), zs), 4 * N * D + 4 * N * M)
     if not only or "simt" in only:

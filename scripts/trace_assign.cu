@@ -29,24 +29,27 @@ int main(int argc, char** argv) {
   equss_zdesc zd; zd.n_pixels = N; zd.hw = N; zd.stride_b = N * D; zd.stride_s = D; zd.stride_c = 1; zd.dim = D; zd.layout = 0;
   long long wsb = assign_tch_workspace_bytes(N, M, K, d);
   cudaMalloc(&ws, wsb);
+  const bool fuse = argc > 2 && atoi(argv[2]) == 1;
+  float* outp; double* sq; cudaMalloc(&outp, hz.size() * 4); cudaMalloc(&sq, M * 8); cudaMemset(sq, 0, M * 8);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    int rc = assign_tch_launch(z, &zd, cb, cn2, M, K, d, idx, ws, wsb, 0);
+    int rc = fuse ? assign_tch_launch(z, &zd, cb, cn2, M, K, d, idx, ws, wsb, 0, cb, outp, sq)
+                  : assign_tch_launch(z, &zd, cb, cn2, M, K, d, idx, ws, wsb, 0);
     cudaEventRecord(e1); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("rc=%d %s  %.1f us  err=%s\n", rc, equss_last_error_string(), ms * 1e3, cudaGetErrorString(cudaGetLastError()));
   }
-  static long long tr[256 * 8];
+  static long long tr[256 * 12];
   cudaMemcpyFromSymbol(tr, tch::g_trace, sizeof(tr));
   long long t0 = tr[0];
   printf("unit | conv: a_empty raw_full done | mma: loop_top issue | epi: tfull_h0 halves_done tail_done   (cycles since unit-0 convert start)\n");
   for (int i = 0; i < 40; ++i) {
-    long long* r = tr + i * 8;
-    printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
+    long long* r = tr + i * 12;
+    printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld | g: %7lld %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0, r[8] - t0, r[9] - t0, r[11] - t0, r[10] - t0);
   }
   for (int i = 150; i < 170; ++i) {
-    long long* r = tr + i * 8;
+    long long* r = tr + i * 12;
     printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
   }
   return 0;

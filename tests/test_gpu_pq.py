@@ -317,3 +317,33 @@ def test_f16_split_assign_edge_cases(shape, M, K, d, kind):
     assert nbad == 0, f"{nbad} of {idx_h.numel()} indices differ between the fp16-split and the exact kernel"
     if kind == "duplicates":
         assert int(idx_h.max()) < K // 2
+
+
+FUSED_SHAPES = [
+    (51200, 64, 256, 16),              # config 2, flat, subspace pairs
+    ((32, 40, 40), 64, 256, 16),       # config 2, NCHW
+    (5000, 63, 256, 16),               # odd M (no pairing), ragged N
+    ((3, 28, 28), 16, 200, 32),        # d = 32, NCHW, hw not a multiple of the tile, padded columns
+    (777, 32, 32, 32),                 # small codebook (NC = 32)
+    (100, 64, 256, 16),                # fewer tiles than the gather lag
+]
+
+
+@pytest.mark.parametrize("shape,M,K,d", FUSED_SHAPES)
+def test_fused_assign_gather_equals_two_kernel_path(shape, M, K, d):
+    """equss_pq_assign_gather (K1 + K3 in one pass) must reproduce K1's indices and K3's output bit for bit;
+    the squared error differs only by fp32 summation order."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    D = M * d
+    z = torch.randn(*((shape[0], D, shape[1], shape[2]) if isinstance(shape, tuple) else (shape, D)), device=dev)
+    cbn = F.normalize(torch.randn(M, K, d, device=dev), dim=2).contiguous()
+    src = torch.randn(M, K, d, device=dev)          # gather from a different table (dino_new_vq.py:403)
+    idx_f, out_f, sq_f = ops.pq_assign_gather(z, cbn, src, normalize="l2", fused=True)
+    idx_r = ops.pq_assign(z, cbn, normalize="l2", algo=1)
+    out_r, sq_r, _ = ops.pq_gather_loss(z, src, idx_r, normalize="l2")
+    torch.cuda.synchronize()
+    assert torch.equal(idx_f, idx_r)
+    assert torch.equal(out_f, out_r)
+    torch.testing.assert_close(sq_f, sq_r, rtol=1e-6, atol=1e-9)
