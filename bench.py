@@ -211,24 +211,21 @@ def run_equss(args):
         conf_l = torch.zeros(C, C, dtype=torch.long, device=dev)
         cbn = F.normalize(codebook, dim=2).contiguous()
         cn2 = ops.pq_cnorm2(cbn)
-        stages = ["pq_assign", "pq_gather_loss", "probe_logits", "probe_argmax_confusion"]
+        stages = ["pq_assign_gather", "probe_logits", "probe_argmax_confusion"]
 
         def step(i, ev=None):
             z, lab = zs[i % NBUF], labels[i % NBUF]
             if ev: ev[0].record()
-            idx = ops.pq_assign(z, cbn, cn2, "l2")
+            idx, zq, sqerr = ops.pq_assign_gather(z, cbn, None, cn2, "l2")     # K1 + K3 fused: z is read once
             if ev: ev[1].record()
-            zq, sqerr, _ = ops.pq_gather_loss(z, cbn, idx, "l2")
-            if ev: ev[2].record()
             logits = ops.probe_logits(zq, wpack, bias)
-            if ev: ev[3].record()
+            if ev: ev[2].record()
             ops.probe_argmax_confusion(logits, B, h, w, Cp + C, lab, C, [(0, C), (Cp, C)], want_preds=False,
                                        confusions=[conf_c, conf_l])
-            if ev: ev[4].record()
+            if ev: ev[3].record()
 
         alg_bytes = {
-            "pq_assign": 4 * N * D + 4 * N * M,
-            "pq_gather_loss": 8 * N * D + 4 * N * M,
+            "pq_assign_gather": 8 * N * D + 4 * N * M,        # read z, write z_q, write int32 indices
             "probe_logits": 4 * N * D + 4 * N * 56,
             "probe_argmax_confusion": 8 * P + 4 * N * 56,
         }
@@ -383,7 +380,7 @@ def run_equss(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (split-tf32 tensor-core contraction with exact fp32 re-score)", "data": "synthetic",
+        "dtype": "f32 (fp16-split / split-tf32 tensor-core contractions with exact fp32 re-score)", "data": "synthetic",
         "config": {"workload": ("cocostuff27_eval (BASELINE configs[1]): PQ assign+gather, cluster+linear probe argmax, "
                                 "2x 27x27 confusion" if not train else
                                 "pq_train (BASELINE configs[2]): assign + gather/loss + scatter-add + packed all-reduce + EMA"),

@@ -45,8 +45,12 @@ class PQGatherLoss(torch.autograd.Function):
     commitment -> activations (through the normalisation), codebook -> gathered rows."""
 
     @staticmethod
-    def forward(ctx, z, gather_src, idx, normalize, norm_a, norm_b):
-        out, sqerr, _ = ops.pq_gather_loss(z, gather_src, idx, normalize, norm_a, norm_b)
+    def forward(ctx, z, gather_src, idx, normalize, norm_a, norm_b, pre_out=None, pre_sqerr=None):
+        # pre_out / pre_sqerr: K3 results already produced by the fused assign+gather kernel
+        if pre_out is not None:
+            out, sqerr = pre_out, pre_sqerr
+        else:
+            out, sqerr, _ = ops.pq_gather_loss(z, gather_src, idx, normalize, norm_a, norm_b)
         M, K, d = gather_src.shape
         n = idx.shape[1]
         mse = (sqerr / max(n * d, 1)).to(torch.float32)
@@ -70,7 +74,7 @@ class PQGatherLoss(torch.autograd.Function):
                                           want_grad_z=need_z, cb_coef=cb_coef)
         if gz is not None and gz.dtype != z.dtype:
             gz = gz.to(z.dtype)
-        return gz, gsrc, None, None, None, None
+        return gz, gsrc, None, None, None, None, None, None
 
 
 def pq_quantize(z: torch.Tensor, codebook_norm: torch.Tensor, gather_src: torch.Tensor, normalize: Optional[str],
@@ -81,9 +85,14 @@ def pq_quantize(z: torch.Tensor, codebook_norm: torch.Tensor, gather_src: torch.
     z32 = z if z.dtype == torch.float32 else z.float()
     cbn = codebook_norm.detach()
     cn2 = ops.pq_cnorm2(cbn)
-    idx = ops.pq_assign(z32, cbn, cn2, normalize, norm_a, norm_b, algo=algo)
+    pre_out = pre_sq = None
+    if algo == 0:
+        # one fused kernel (K1 + K3, activations read once) where the shape allows it, else K1 then K3
+        idx, pre_out, pre_sq = ops.pq_assign_gather(z32, cbn, gather_src.detach(), cn2, normalize, norm_a, norm_b)
+    else:
+        idx = ops.pq_assign(z32, cbn, cn2, normalize, norm_a, norm_b, algo=algo)
     prob = ops.pq_distance_prob(z32, cbn, cn2, normalize, norm_a, norm_b, temperature) if want_prob else None
-    out, mse_commit, mse_cb = PQGatherLoss.apply(z32, gather_src, idx, normalize, norm_a, norm_b)
+    out, mse_commit, mse_cb = PQGatherLoss.apply(z32, gather_src, idx, normalize, norm_a, norm_b, pre_out, pre_sq)
     return idx, out, mse_commit, mse_cb, prob
 
 
