@@ -173,6 +173,7 @@ def run_equss(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     c = CFG
     B, D, h, w, H, W, M, K, C = (c[k] for k in ("B", "D", "h", "w", "H", "W", "M", "K", "C"))
