@@ -239,11 +239,44 @@ def run_equss(args):
             for q in pq.quantizers:
                 q.codebook.weight.copy_(torch.randn(K, d, device=dev)); q.codebook.weight_avg.copy_(q.codebook.weight)
         stages = ["pq_train_step"]
+        graphs = None
+        launches_per_graph = 0
+
+        def eager_step(i):
+            with torch.no_grad():
+                return pq(zs[i % NBUF])
+
+        if not args.no_graphs:
+            # The step is ~10 library kernels plus a few dozen tiny torch ops (statistics on [64, 256] tensors): the
+            # launches, not the GPU work, bound an eager loop.  One CUDA graph per rotating input buffer (including
+            # the NCCL all-reduce of the packed EMA statistics) removes that; the module code is unchanged.
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(3):
+                        eager_step(i)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                graphs = []
+                lc0 = ops.launch_count()
+                for k in range(NBUF):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        eager_step(k)
+                    graphs.append(g)
+                launches_per_graph = (ops.launch_count() - lc0) // NBUF     # library kernels each replay launches
+            except Exception as e:      # capture is an optimisation, never a requirement
+                print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing the eager loop", file=sys.stderr)
+                graphs = None
+                torch.cuda.synchronize()
 
         def step(i, ev=None):
             if ev: ev[0].record()
-            with torch.no_grad():
-                pq(zs[i % NBUF])
+            if graphs is not None:
+                graphs[i % NBUF].replay()
+            else:
+                eager_step(i)
             if ev: ev[1].record()
 
         alg_bytes = {"pq_train_step": 3 * 4 * N * D + 3 * 4 * N * M}
@@ -387,9 +420,11 @@ def run_equss(args):
                                 "pq_train (BASELINE configs[2]): assign + gather/loss + scatter-add + packed all-reduce + EMA"),
                    **CFG, "normalize": "l2", "pixels_per_step_per_gpu": N, "parallelism": f"dp{world}",
                    "materialize_distance_prob": False,
+                   **({"launch": "CUDA graph per input buffer" if graphs is not None else "eager"} if train else {}),
                    "l2": f"{NBUF} rotating input sets of {(4 * N * D + 8 * P) / 1e6:.0f} MB each (> 126 MB L2), no flush kernel"},
         "roofline": roof, "kernels": kern, "cpu_baseline": cpu_base, "e2e": e2e,
-        "gpu_launches": int(l1 - l0), "clocks": clocks,
+        "gpu_launches": int(l1 - l0) + (launches_per_graph * args.steps if (train and graphs is not None) else 0),
+        "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
@@ -404,6 +439,7 @@ def main():
     ap.add_argument("--impl", default="equss", choices=["equss", "reference"])
     ap.add_argument("--workload", default="cocostuff27_eval", choices=["cocostuff27_eval", "pq_train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="pq_train: time the eager module loop instead of CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "equss" else args.warmup
     if args.impl == "reference":

@@ -403,6 +403,58 @@ ema_update_kernel(const float* __restrict__ packed, int K, int d, float decay, f
 }
 
 // cnorm2[m][k] = sum_j c^2 (canonical order)
+// ------------------------------------------------------------------------------------------------
+// K7 usage percentiles (get_histogram_count, model/quantizer.py:15-30), one block per subspace:
+// prob = count / (sum + 1), sorted descending (bitonic sort in shared memory), sequential cumulative sum,
+// first rank whose cumulative usage reaches 10 / 50 / 90 %, divided by K; NaN where the reference returns None.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+usage_percentiles_kernel(const float* __restrict__ count, long long row_stride, long long k_stride, int K, int Kp,
+                         float* __restrict__ out) {
+  extern __shared__ float s_p[];     // [Kp]
+  __shared__ float s_tot[8];
+  const int m = blockIdx.x;
+  const float* c = count + (long long)m * row_stride;
+  float part = 0.f;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    const float v = (k < K) ? c[(long long)k * k_stride] : -1.f;      // padding sorts to the end
+    s_p[k] = v;
+    if (k < K) part += v;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = part;
+  __syncthreads();
+  float total = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) total += s_tot[i];
+  for (int size = 2; size <= Kp; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < Kp / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const float a = s_p[lo], b = s_p[hi];
+        if (desc ? (a < b) : (a > b)) { s_p[lo] = b; s_p[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float denom = total + 1.f;
+    // torch.cumsum on the reference's CPU path accumulates fp32 inputs in double and rounds each prefix to fp32
+    double acc = 0.0;
+    float p10 = NAN, p50 = NAN, p90 = NAN;
+    bool f10 = false, f50 = false, f90 = false;
+    for (int i = 0; i < K; ++i) {
+      acc += (double)(s_p[i] / denom);
+      const float cs = (float)acc;
+      if (!f10 && cs >= 0.1f) { f10 = true; p10 = (float)i / (float)K; }
+      if (!f50 && cs >= 0.5f) { f50 = true; p50 = (float)i / (float)K; }
+      if (!f90 && cs >= 0.9f) { f90 = true; p90 = (float)i / (float)K; break; }
+    }
+    out[m * 3 + 0] = p10; out[m * 3 + 1] = p50; out[m * 3 + 2] = p90;
+  }
+}
+
 __global__ void cnorm2_kernel(const float* __restrict__ cb, long long rows, int d, float* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
@@ -578,5 +630,17 @@ extern "C" int equss_ema_update(const float* packed, int M, int K, int d, double
                                                           (float)eps, (float)((double)K * eps), vq_count,
                                                           weight_avg, weight, exact_count, unused_out);
   EQUSS_LAUNCH_OK("ema_update_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_usage_percentiles(const float* count, int64_t row_stride, int64_t k_stride, int M, int K,
+                                       float* out, void* stream) {
+  EQUSS_REQUIRE(M >= 0 && K > 0 && K <= 8192, EQUSS_ERR_INVALID_ARG, "equss_usage_percentiles: bad shape M=%d K=%d", M, K);
+  if (M == 0) return EQUSS_OK;
+  EQUSS_REQUIRE(count && out, EQUSS_ERR_INVALID_ARG, "equss_usage_percentiles: null pointer");
+  int Kp = 2;
+  while (Kp < K) Kp <<= 1;
+  equss::usage_percentiles_kernel<<<M, 256, Kp * sizeof(float), (cudaStream_t)stream>>>(count, row_stride, k_stride, K, Kp, out);
+  EQUSS_LAUNCH_OK("usage_percentiles_kernel");
   return EQUSS_OK;
 }

@@ -14,7 +14,7 @@ from . import _native as N
 
 __all__ = [
     "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
-    "pq_distance_prob", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "pq_distance_prob", "usage_percentiles", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
     "launch_count",
 ]
 
@@ -204,6 +204,21 @@ def ema_update(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.T
                                   N.stream_ptr(dev))
     N.check(rc, "equss_ema_update")
     return unused
+
+
+def usage_percentiles(count: torch.Tensor) -> torch.Tensor:
+    """get_histogram_count (model/quantizer.py:15-30) for counts [M, K] (any strides): float32 [M, 3] with the
+    p10 / p50 / p90 ranks divided by K, NaN where the reference returns None.  One launch, no host sync."""
+    dev = N.require_cuda(count)
+    N.ensure_device(dev)
+    if count.dtype != torch.float32:
+        count = count.float()
+    M, K = count.shape
+    out = torch.empty((M, 3), dtype=torch.float32, device=dev)
+    rc = N.lib().equss_usage_percentiles(count.data_ptr(), count.stride(0), count.stride(1), M, K, out.data_ptr(),
+                                         N.stream_ptr(dev))
+    N.check(rc, "equss_usage_percentiles")
+    return out
 
 
 def pq_distance_prob(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optional[torch.Tensor] = None,

@@ -158,6 +158,14 @@ int equss_ema_update(const float* packed, int M, int K, int d, double decay, dou
                      float* vq_count, float* weight_avg, float* weight,
                      float* exact_count, int32_t* unused_out, void* stream);
 
+/* K7  codebook-usage percentiles      replaces get_histogram_count, model/quantizer.py:15-30 (a Python loop with
+ *   ~6K tensor->bool host syncs per subspace in the reference).  count: M rows of K entries, element (m, k) at
+ *   count[m*row_stride + k*k_stride] (so the count column of the packed K4 buffer can be read in place).
+ *   out: [M][3] = first rank whose descending cumulative usage reaches 10 / 50 / 90 %, divided by K; NaN where the
+ *   reference returns None. */
+int equss_usage_percentiles(const float* count, int64_t row_stride, int64_t k_stride, int M, int K,
+                            float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  soft assignment              replaces model/quantizer.py:468 + :609 (softmax(-distance), concatenated
  *                                  over subspaces on the last dim; dino_pqgo.py:655 divides by jsd_ts)

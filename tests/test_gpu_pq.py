@@ -347,3 +347,25 @@ def test_fused_assign_gather_equals_two_kernel_path(shape, M, K, d):
     assert torch.equal(idx_f, idx_r)
     assert torch.equal(out_f, out_r)
     torch.testing.assert_close(sq_f, sq_r, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("M,K", [(64, 256), (3, 40), (1, 1024), (16, 512)])
+def test_usage_percentiles_vs_oracle(M, K):
+    """equss_usage_percentiles == get_histogram_count (model/quantizer.py:15-30) per subspace, NaN for None."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(M * K)
+    count = torch.randint(0, 50, (M, K)).float() * (torch.rand(M, K) < 0.6).float()
+    count[0] = 0                                   # never reaches any level -> None / NaN
+    if M > 1:
+        count[1] = 0; count[1, K // 3] = 7          # a single used code reaches every level at rank 0
+    packed = torch.zeros(M, K, 5)
+    packed[:, :, 4] = count                        # strided view, as the count column of the K4 buffer
+    got = ops.usage_percentiles(packed.to(dev)[:, :, 4]).cpu()
+    for m in range(M):
+        ref = O.histogram_percentiles(count[m], "x")
+        for j, tag in enumerate(("x-p10", "x-p50", "x-p90")):
+            if ref[tag] is None:
+                assert torch.isnan(got[m, j])
+            else:
+                assert float(got[m, j]) == pytest.approx(float(ref[tag]), abs=1e-7), (m, tag)
