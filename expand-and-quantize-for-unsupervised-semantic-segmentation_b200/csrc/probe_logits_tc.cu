@@ -101,7 +101,7 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   uint8_t* s_b = s_lo + kLoBufs * kAPiece;                // [kBBufs][hi 8 KB | lo 8 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kBBufs * kBBytes);
   uint64_t* raw_full = bars;                    // [kRawStages] TMA box landed
-  uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages] the stage's MMAs completed
+  uint64_t* raw_empty = raw_full + kRawStages;  // [kRawStages] the stage's readers (two MMA issuers, convert) are done
   uint64_t* lo_full = raw_empty + kRawStages;   // [kLoBufs] convert warps wrote the lo tile
   uint64_t* lo_empty = lo_full + kLoBufs;       // [kLoBufs] MMAs completed
   uint64_t* b_full = lo_empty + kLoBufs;        // [kBBufs]
@@ -117,7 +117,9 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   const int n_kc = p.n_kc;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kRawStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 2); }   // issuers 0, 2
+    // a raw stage is free again when the hi.hi / hi.lo issuers (tcgen05.commit) AND the four convert warps (which
+    // read it to build the lo tile) are done with it
+    for (int i = 0; i < kRawStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 2 + 4); }
     for (int i = 0; i < kLoBufs; ++i) { mbar_init(lo_full + i, 4); mbar_init(lo_empty + i, 1); }         // issuer 1
     for (int i = 0; i < kBBufs; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 3); }
     for (int i = 0; i < 2; ++i) { mbar_init(m_full + i, 1); mbar_init(m_empty + i, 4); }
@@ -224,7 +226,7 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(lo_full + ls);
+        if (lane == 0) { mbar_arrive(lo_full + ls); mbar_arrive(raw_empty + rs); }
       }
     }
   } else {
