@@ -7,9 +7,14 @@
 // streaming selection keeps the running top-k in registers (lane i holds the i-th best), so the N x N
 // matrix never exists.  Ordering: larger similarity first, ties broken by the lower database index.
 #include <climits>
+#include <cstdlib>
 #include "equss_common.cuh"
 
 namespace equss {
+
+// knn_tc.cu: tcgen05 split-tf32 similarity GEMM (F % 32 == 0, 16-byte aligned pointers)
+bool knn_gemm_tc_supported(const float* Q, const float* DB, const float* S, long long n, int F);
+int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st);
 
 constexpr int KNN_BM = 128, KNN_BN = 128, KNN_BK = 8;
 
@@ -152,11 +157,18 @@ extern "C" int equss_knn_topk(const float* queries, int64_t nq, const float* db,
                 (long long)workspace_bytes);
   float* S = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  // tensor-core GEMM whenever the shape allows it (EQUSS_KNN_SIMT=1 forces the CUDA-core kernel, for comparisons)
+  const bool use_tc = knn_gemm_tc_supported(queries, db, S, n, F) && ((F * 4) % 16 == 0) && getenv("EQUSS_KNN_SIMT") == nullptr;
   for (long long q0 = 0; q0 < nq; q0 += rc) {
     long long rows = nq - q0 < rc ? nq - q0 : rc;
-    dim3 grid((unsigned)((n + KNN_BN - 1) / KNN_BN), (unsigned)((rows + KNN_BM - 1) / KNN_BM));
-    knn_gemm_kernel<<<grid, 256, 0, st>>>(queries + q0 * F, db, S, rows, n, F);
-    EQUSS_LAUNCH_OK("knn_gemm_kernel");
+    if (use_tc) {
+      int rc2 = knn_gemm_tc_launch(queries + q0 * F, db, S, rows, n, F, st);
+      if (rc2 != EQUSS_OK) return rc2;
+    } else {
+      dim3 grid((unsigned)((n + KNN_BN - 1) / KNN_BN), (unsigned)((rows + KNN_BM - 1) / KNN_BM));
+      knn_gemm_kernel<<<grid, 256, 0, st>>>(queries + q0 * F, db, S, rows, n, F);
+      EQUSS_LAUNCH_OK("knn_gemm_kernel");
+    }
     knn_select_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S, rows, n, k, (long long*)idx_out + q0 * k,
                                                                    sim_out ? sim_out + q0 * k : nullptr);
     EQUSS_LAUNCH_OK("knn_select_kernel");

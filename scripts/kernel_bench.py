@@ -70,7 +70,7 @@ if __name__ == "__main__":
         preds = torch.randint(0, C, (B, H, W), device=dev)
         ms = timeit(lambda f: ops.confusion_update(preds, label, C, cc), feats)
         print(f"confusion_update {ms*1e3:.1f} us  {16*B*H*W/ms/1e6:.1f} GB/s")
-    if not only:
+    if not only or "knn" in only:
         db = F.normalize(torch.randn(50000, 768, device=dev), dim=1)
         ms = timeit(lambda f: ops.knn_topk(db[:6250], db, 30), [0], iters=2, warm=1)
         print(f"knn 6250x50000x768 k=30: {ms:.1f} ms  {2*6250*50000*768/ms/1e9:.1f} TFLOP/s")
