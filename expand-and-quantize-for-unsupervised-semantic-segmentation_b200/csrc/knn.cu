@@ -90,29 +90,41 @@ knn_select_kernel(const float* __restrict__ S, long long rows, long long n, int 
   long long myi = -1;
   float thr = -INFINITY;   // value of the k-th best once the list is full (warp-uniform)
   bool full = false;
-  for (long long base = 0; base < n; base += 32) {
-    long long c = base + lane;
-    float v = (c < n) ? __ldcs(s + c) : -INFINITY;
-    bool cand = (c < n) && (!full || v > thr);
-    unsigned mask = __ballot_sync(0xffffffffu, cand);
-    while (mask) {
-      int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      float cv = __shfl_sync(0xffffffffu, v, src);
-      long long ci = base + src;
-      // entries that rank before the candidate: larger value, or equal value (they have a lower index),
-      // but never an empty slot
-      unsigned ge = __ballot_sync(0xffffffffu, myi >= 0 && myv >= cv);
-      int pos = __popc(ge);
-      if (pos < k) {
-        float upv = __shfl_up_sync(0xffffffffu, myv, 1);
-        long long upi = __shfl_up_sync(0xffffffffu, myi, 1);
-        if (lane > pos) { myv = upv; myi = upi; }
-        else if (lane == pos) { myv = cv; myi = ci; }
-        float tv = __shfl_sync(0xffffffffu, myv, k - 1);
-        long long ti = __shfl_sync(0xffffffffu, myi, k - 1);
-        full = ti >= 0;
-        thr = tv;
+  constexpr int U = 8;          // 8 x 32 similarities in flight per warp: the scan is load-latency bound otherwise
+  for (long long base0 = 0; base0 < n; base0 += 32 * U) {
+    float vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long c = base0 + 32 * u + lane;
+      vv[u] = (c < n) ? __ldcs(s + c) : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long base = base0 + 32 * u;
+      const long long c = base + lane;
+      const float v = vv[u];
+      bool cand = (c < n) && (!full || v > thr);
+      unsigned mask = __ballot_sync(0xffffffffu, cand);
+      while (mask) {
+        int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float cv = __shfl_sync(0xffffffffu, v, src);
+        long long ci = base + src;
+        if (full && !(cv > thr)) continue;       // the threshold may have risen since the ballot (warp-uniform test)
+        // entries that rank before the candidate: larger value, or equal value (they have a lower index),
+        // but never an empty slot
+        unsigned ge = __ballot_sync(0xffffffffu, myi >= 0 && myv >= cv);
+        int pos = __popc(ge);
+        if (pos < k) {
+          float upv = __shfl_up_sync(0xffffffffu, myv, 1);
+          long long upi = __shfl_up_sync(0xffffffffu, myi, 1);
+          if (lane > pos) { myv = upv; myi = upi; }
+          else if (lane == pos) { myv = cv; myi = ci; }
+          float tv = __shfl_sync(0xffffffffu, myv, k - 1);
+          long long ti = __shfl_sync(0xffffffffu, myi, k - 1);
+          full = ti >= 0;
+          thr = tv;
+        }
       }
     }
   }
@@ -123,7 +135,7 @@ knn_select_kernel(const float* __restrict__ S, long long rows, long long n, int 
 }
 
 static long long knn_rows_per_chunk(long long nq, long long n) {
-  const long long budget = 256LL << 20;   // bytes of similarity workspace per chunk
+  const long long budget = 1536LL << 20;  // bytes of similarity workspace per chunk (a 6250 x 50000 shard fits in one)
   long long rc = budget / (n * 4);
   rc = (rc / KNN_BM) * KNN_BM;
   if (rc < KNN_BM) rc = KNN_BM;
