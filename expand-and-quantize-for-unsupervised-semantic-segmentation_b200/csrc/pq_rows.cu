@@ -105,10 +105,14 @@ gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4
     }
     int ch = c4 * 4;
     float4 zn;
-    zn.x = norm_elem(v.x, r, mode, na, nb, ch);
-    zn.y = norm_elem(v.y, r, mode, na, nb, ch + 1);
-    zn.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
-    zn.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
+    if (mode == EQUSS_NORM_L2) {
+      zn = div4_by(v, r.denom);              // correctly rounded, one reciprocal for the four lanes' elements
+    } else {
+      zn.x = norm_elem(v.x, r, mode, na, nb, ch);
+      zn.y = norm_elem(v.y, r, mode, na, nb, ch + 1);
+      zn.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
+      zn.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
+    }
     int code = __ldg(idx + (long long)m * n_pixels + n);
     float4 q = __ldg(src + ((long long)m * K + code) * LPS + l);
     float4 dq, o;
@@ -121,6 +125,73 @@ gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4
     float e = group_sumsq(dq.x, dq.y, dq.z, dq.w);
     e = butterfly_lanes<LPS>(e);
     if (l == 0 && live) atomicAdd(&s_sq[m], e);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float v = s_sq[i];
+    if (v != 0.f) atomicAdd(sqerr + i, (double)v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 flat fast path (l2 rows): as gather_loss_flat_kernel, four independent float4 per thread and iteration and
+// branch-free correctly rounded sqrt / division, so their memory latencies and dependent chains overlap.
+// ------------------------------------------------------------------------------------------------
+template <int LPS>
+__global__ void __launch_bounds__(256)
+gather_loss_flat_l2_kernel(const float4* __restrict__ z, long long n_pixels, int D4, int M, int K,
+                           const float4* __restrict__ src, const int32_t* __restrict__ idx,
+                           float4* __restrict__ out, double* __restrict__ sqerr) {
+  extern __shared__ float s_sq[];  // [M]
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s_sq[i] = 0.f;
+  __syncthreads();
+  constexpr int U = 4;
+  const long long total = n_pixels * D4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // warp-uniform trip count (xor-shuffles inside); the tail is predicated
+  for (long long f0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); f0 < total; f0 += stride * U) {
+    float4 v[U], q[U];
+    long long f[U];
+    int mm[U], ll[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      f[u] = f0 + u * stride + (threadIdx.x & 31);
+      live[u] = f[u] < total;
+      const long long fc = live[u] ? f[u] : total - 1;
+      const long long n = fc / D4;
+      const int c4 = (int)(fc - n * D4);
+      mm[u] = c4 / LPS; ll[u] = c4 - mm[u] * LPS;
+      v[u] = __ldcs(z + fc);
+      const int code = __ldg(idx + (long long)mm[u] * n_pixels + n);
+      q[u] = __ldg(src + ((long long)mm[u] * K + code) * LPS + ll[u]);
+    }
+    float ss[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ss[u] = group_sumsq(v[u].x, v[u].y, v[u].z, v[u].w);
+#pragma unroll
+    for (int sft = 1; sft < LPS; sft <<= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], sft);
+    }
+    float e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 zn = div4_fast(v[u], l2_denom_fast(ss[u]));
+      float4 dq, o;
+      dq.x = q[u].x - zn.x; dq.y = q[u].y - zn.y; dq.z = q[u].z - zn.z; dq.w = q[u].w - zn.w;
+      o.x = zn.x + dq.x; o.y = zn.y + dq.y; o.z = zn.z + dq.z; o.w = zn.w + dq.w;   // STE value (:536)
+      if (live[u]) __stcs(out + f[u], o);
+      e[u] = group_sumsq(dq.x, dq.y, dq.z, dq.w);
+    }
+#pragma unroll
+    for (int sft = 1; sft < LPS; sft <<= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) e[u] += __shfl_xor_sync(0xffffffffu, e[u], sft);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ll[u] == 0 && live[u]) atomicAdd(&s_sq[mm[u]], e[u]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
@@ -180,6 +251,59 @@ gather_loss_scalar_kernel(const float* __restrict__ z, ZView zv, int M, int K, i
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_part[i];
     if (t != 0.f) atomicAdd(sqerr + m, (double)t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 NCHW fast path (l2 rows, d in {16, 32, 64}): one thread per (pixel, subspace), channel accesses coalesced
+// across the warp's 32 consecutive pixels.  Branch-free correctly rounded sqrt / division (l2_denom_fast,
+// div4_fast: bit-identical to sqrtf and `/`) so the compiler interleaves the d/4 channel groups instead of
+// serialising them behind the slow-path calls of the IEEE routines.
+// ------------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(128)
+gather_loss_nchw_l2_kernel(const float* __restrict__ z, long long hw, long long stride_b, int n_images, int M, int K,
+                           const float* __restrict__ src, const int32_t* __restrict__ idx, float* __restrict__ out,
+                           double* __restrict__ sqerr) {
+  constexpr int G = DT / 4;
+  const int m = blockIdx.y;
+  const int tiles_per_image = (int)((hw + 127) / 128);
+  const long long n_tiles = (long long)n_images * tiles_per_image;
+  const long long n_pixels = (long long)n_images * hw;
+  float local = 0.f;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long b = t / tiles_per_image;
+    const long long s = (t - b * tiles_per_image) * 128 + threadIdx.x;
+    if (s >= hw) continue;
+    const long long base = b * stride_b + (long long)m * DT * hw + s;
+    float x[DT];
+#pragma unroll
+    for (int j = 0; j < DT; ++j) x[j] = __ldcs(z + base + (long long)j * hw);
+    const int code = __ldg(idx + (long long)m * n_pixels + b * hw + s);
+    const float4* q4 = reinterpret_cast<const float4*>(src + ((long long)m * K + code) * DT);
+    float g[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) g[i] = group_sumsq(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    const float denom = l2_denom_fast(butterfly_array<G>(g));
+    float e = 0.f;
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const float4 q = __ldg(q4 + i);
+      const float4 zn = div4_fast(make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]), denom);
+      const float d0 = q.x - zn.x, d1 = q.y - zn.y, d2 = q.z - zn.z, d3 = q.w - zn.w;
+      float* o = out + base + (long long)(4 * i) * hw;
+      __stcs(o, zn.x + d0); __stcs(o + hw, zn.y + d1); __stcs(o + 2 * hw, zn.z + d2); __stcs(o + 3 * hw, zn.w + d3);
+      e += group_sumsq(d0, d1, d2, d3);
+    }
+    local += e;
+  }
+  local = warp_sum(local);
+  __shared__ float s_part[4];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float tsum = ((s_part[0] + s_part[1]) + s_part[2]) + s_part[3];
+    if (tsum != 0.f) atomicAdd(sqerr + m, (double)tsum);
   }
 }
 
@@ -534,11 +658,28 @@ extern "C" int equss_pq_gather_loss(const float* z, const equss_zdesc* zd, const
     int blocks = (int)((total + 255) / 256);
     int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
+    if (norm_mode == EQUSS_NORM_L2 && !znorm_out) {
+      EQUSS_DISPATCH_LPS(lps, (gather_loss_flat_l2_kernel<LPS><<<blocks, 256, M * sizeof(float), st>>>(
+          reinterpret_cast<const float4*>(z), zd->n_pixels, zd->dim / 4, M, K,
+          reinterpret_cast<const float4*>(gather_src), idx, reinterpret_cast<float4*>(out), sqerr)));
+      EQUSS_LAUNCH_OK("gather_loss_flat_l2_kernel");
+      return EQUSS_OK;
+    }
     EQUSS_DISPATCH_LPS(lps, (gather_loss_flat_kernel<LPS><<<blocks, 256, M * sizeof(float), st>>>(
         reinterpret_cast<const float4*>(z), zd->n_pixels, zd->dim / 4, M, K,
         reinterpret_cast<const float4*>(gather_src), idx, norm_mode, norm_a, norm_b,
         reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(znorm_out), sqerr)));
     EQUSS_LAUNCH_OK("gather_loss_flat_kernel");
+  } else if (norm_mode == EQUSS_NORM_L2 && !znorm_out && (d == 16 || d == 32 || d == 64) && zd->stride_s == 1 &&
+             zd->stride_c == zd->hw && zd->n_pixels % zd->hw == 0 && !((uintptr_t)gather_src & 15)) {
+    const int n_images = (int)(zd->n_pixels / zd->hw);
+    long long tiles = (long long)n_images * ((zd->hw + 127) / 128);
+    long long cap = (long long)num_sms() * 32 / M + 1;
+    dim3 grid((unsigned)(tiles < cap ? tiles : cap), (unsigned)M);
+    if (d == 16) gather_loss_nchw_l2_kernel<16><<<grid, 128, 0, st>>>(z, zd->hw, zd->stride_b, n_images, M, K, gather_src, idx, out, sqerr);
+    else if (d == 32) gather_loss_nchw_l2_kernel<32><<<grid, 128, 0, st>>>(z, zd->hw, zd->stride_b, n_images, M, K, gather_src, idx, out, sqerr);
+    else gather_loss_nchw_l2_kernel<64><<<grid, 128, 0, st>>>(z, zd->hw, zd->stride_b, n_images, M, K, gather_src, idx, out, sqerr);
+    EQUSS_LAUNCH_OK("gather_loss_nchw_l2_kernel");
   } else {
     ZView zv = make_view(zd);
     long long bx = (zd->n_pixels + 127) / 128;
