@@ -47,10 +47,15 @@ namespace tch {
 using namespace ::equss::ptx;
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 480;
+constexpr int kEpiGroups = 2;                    // epilogue groups of four warps, rotating over the units
+// A parity wait cannot skip a phase, so every accumulator barrier must always be waited on by the same consumer:
+// the t_full / t_empty barriers form a ring of lcm(2 TMEM buffers, kEpiGroups) unit slots (x 2 halves); slot i % R
+// belongs to one TMEM buffer and one epilogue group.
+constexpr int kTSlots = (kEpiGroups % 2 == 0) ? kEpiGroups : 2 * kEpiGroups;
+constexpr int kThreads = 32 * (4 * kEpiGroups + 1 + 4 + 2);
 // The SMSP arbiter prefers the highest warp id among eligible warps: the convert warps (the pipeline's critical
 // stage) get the highest ids, the epilogue warps (ALU-pipe heavy, plenty of slack) the lowest.
-constexpr int kEpiWarp0 = 0, kProducerWarp = 8, kConvWarp0 = 9, kMmaWarp = 13;
+constexpr int kEpiWarp0 = 0, kProducerWarp = 4 * kEpiGroups, kConvWarp0 = kProducerWarp + 1, kMmaWarp = kConvWarp0 + 4;
 constexpr float kTolRel = 1.52587890625e-5f;     // 2^-16
 
 #ifdef EQUSS_TRACE   // scripts/trace_assign.cu: per-unit clock64 stamps of CTA 0 (pipeline timeline)
@@ -73,7 +78,7 @@ __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / 
 constexpr int kIdxBufs = 8;                      // fused gather: ring of per-tile winning columns
 __host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false) {
   return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) +
-         (fuse ? kIdxBufs * kTileM * 4 : 0) + 512;
+         (fuse ? kIdxBufs * kTileM * 4 : 0) + 1024;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, both K-major, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -256,9 +261,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
   uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
   uint64_t* a_empty = a_full + ABUFS;           // [ABUFS]   arrived by tcgen05.commit: the MMAs have read A (and B)
-  uint64_t* t_full = a_empty + ABUFS;           // [4]  (unit parity, half)
-  uint64_t* t_empty = t_full + 4;               // [4]
-  uint64_t* b_full = t_empty + 4;               // [1]
+  uint64_t* t_full = a_empty + ABUFS;           // [kTSlots][2]  (unit slot, half)
+  uint64_t* t_empty = t_full + 2 * kTSlots;     // [kTSlots][2]
+  uint64_t* b_full = t_empty + 2 * kTSlots;     // [1]
   uint64_t* idx_full = b_full + 1;              // [kIdxBufs] FUSE: epilogue wrote the tile's columns
   uint64_t* idx_empty = idx_full + kIdxBufs;    // [kIdxBufs] FUSE: gather consumed them
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(idx_empty + kIdxBufs);
@@ -273,7 +278,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 4); }
     for (int i = 0; i < ABUFS; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, HALVES); }
-    for (int i = 0; i < 4; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < 2 * kTSlots; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
     mbar_init(b_full, 1);
     for (int i = 0; i < kIdxBufs; ++i) { mbar_init(idx_full + i, 4); mbar_init(idx_empty + i, 4); }
     fence_barrier_init();
@@ -322,7 +327,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
       for (int i = 0; i < n_units; ++i, it.next()) {
         const int a = i % ABUFS, t = i & 1;
-        const int tb = t * 2 + h;
+        const int tb = (i % kTSlots) * 2 + h;                      // this unit's accumulator-barrier slot
         if (h == 0) EQUSS_TR(7, i);
         if (it.sslot != cur_slot) {
           mbar_wait(b_full, b_loads & 1, 20);
@@ -330,7 +335,8 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           cur_slot = it.sslot;
         }
         mbar_wait(a_full + a, (i / ABUFS) & 1, 21);
-        mbar_wait(t_empty + tb, ((i >> 1) & 1) ^ 1, 22);
+        // TMEM buffer t was last used by unit i - 2: wait until that unit's epilogue has drained this half
+        if (i >= 2) mbar_wait(t_empty + ((i - 2) % kTSlots) * 2 + h, ((i - 2) / kTSlots) & 1, 22);
         tc_fence_after();
         if (h == 0) EQUSS_TR(3, i);
         if (lane == 0) {
@@ -607,12 +613,12 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   } else {
     // ===================================== epilogue warps ===================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int egroup = (warp - kEpiWarp0) >> 2;  // 0 or 1
+    const int egroup = (warp - kEpiWarp0) >> 2;  // 0 .. kEpiGroups-1
     const int row = q * 32 + lane;
     UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
     for (int i = 0; i < n_units; ++i, it.next()) {
       const int t = i & 1;
-      if (t != egroup) continue;     // the other epilogue group's unit
+      if (i % kEpiGroups != egroup) continue;     // another epilogue group's unit
       const int tile = it.tile, m = it.m(), chunk = it.chunk;
       // the slot's tolerance: trailer of the operand image (global memory; latency hidden by the barrier wait)
       const float tol = __ldg(reinterpret_cast<const float*>(p.images + ((size_t)it.sslot * G + it.g) * p.img_bytes +
@@ -624,8 +630,8 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       int g1 = 0;
 #pragma unroll 1
       for (int h = 0; h < HALVES; ++h) {
-        const int tb = t * 2 + h;
-        mbar_wait(t_full + tb, (i >> 1) & 1, 41);
+        const int tb = (i % kTSlots) * 2 + h;
+        mbar_wait(t_full + tb, (i / kTSlots) & 1, 41);
         tc_fence_after();
         if (q == 0 && h == 0) EQUSS_TR(4, i);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NC + h * NH);
