@@ -4,10 +4,17 @@
 // (pq_assign_tc.cu) bit for bit -- both use the same canonical z_norm, the same sequential fma dot
 // product and the reference's association order (sum z^2 + sum c^2) - 2*dot, first minimal index wins
 // (model/quantizer.py:457-467) -- and it serves the shapes the tensor-core kernel does not cover.
+#include <cstdlib>
 #include "equss_common.cuh"
 #include "pq_assign.h"
 
 namespace equss {
+
+// pq_prob.cu: register-tiled soft assignment (K <= 256, d in {8,16,32,64})
+bool distance_prob_tiled_supported(int K, int d, const float* prob);
+int distance_prob_tiled_launch(const float* z, const equss_zdesc* zd, const float* cb, const float* cn2, int M, int K,
+                               int d, int mode, const float* na, const float* nb, float temperature, float* prob,
+                               cudaStream_t st);
 
 template <int DT>
 struct AssignRow {
@@ -268,6 +275,9 @@ extern "C" int equss_pq_distance_prob(const float* z, const equss_zdesc* zd, con
                 "EQUSS_NORM_AFFINE needs norm_a and norm_b");
   EQUSS_REQUIRE(temperature != 0.f, EQUSS_ERR_INVALID_ARG, "temperature must be non-zero");
   if (zd->n_pixels == 0) return EQUSS_OK;
+  if (distance_prob_tiled_supported(K, d, prob) && getenv("EQUSS_PROB_WARP") == nullptr)
+    return distance_prob_tiled_launch(z, zd, codebook_norm, cnorm2, M, K, d, norm_mode, norm_a, norm_b, temperature, prob,
+                                      (cudaStream_t)stream);
   const int threads = 256, nwarps = threads / 32;
   size_t smem = ((size_t)K * (d + 1) + K + (size_t)nwarps * d) * sizeof(float);
   EQUSS_REQUIRE(smem <= 200 * 1024, EQUSS_ERR_UNSUPPORTED,
