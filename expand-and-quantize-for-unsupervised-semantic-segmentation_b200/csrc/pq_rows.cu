@@ -378,17 +378,50 @@ gather_loss_bwd_kernel(const float* __restrict__ z, ZView zv, int M, int K, int 
 // K4 segmented scatter-add.  grid = (pixel chunks, M).  Shared accumulators [K][d+1] for subspace
 // blockIdx.y (column d = count), flushed with one global atomic per touched entry.
 // ------------------------------------------------------------------------------------------------
-template <int LPS>
-__global__ void __launch_bounds__(256)
+// fp32 atomicAdd on shared memory is a compare-and-swap loop on sm_100 (LDS + ATOMS.CAST.SPIN per element), and the
+// first version of this kernel spent its time there (2.1 TB/s).  The shared accumulators are therefore laid out as
+// [K][d+4] floats (16-byte aligned rows) and updated four elements at a time with the native 128-bit ATOMS.CAS.128;
+// the per-code count is a separate int array with the native integer atomic.
+__device__ __forceinline__ void shared_add4(float* addr, float4 v) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(addr);
+  float4 old = *reinterpret_cast<const float4*>(addr);
+  while (true) {
+    const uint64_t o0 = ((uint64_t)__float_as_uint(old.y) << 32) | __float_as_uint(old.x);
+    const uint64_t o1 = ((uint64_t)__float_as_uint(old.w) << 32) | __float_as_uint(old.z);
+    const uint64_t n0 = ((uint64_t)__float_as_uint(old.y + v.y) << 32) | __float_as_uint(old.x + v.x);
+    const uint64_t n1 = ((uint64_t)__float_as_uint(old.w + v.w) << 32) | __float_as_uint(old.z + v.z);
+    uint64_t r0, r1;
+    asm volatile("{\n .reg .b128 c, n, r;\n mov.b128 c, {%2, %3};\n mov.b128 n, {%4, %5};\n"
+                 " atom.shared.cas.b128 r, [%6], c, n;\n mov.b128 {%0, %1}, r;\n}"
+                 : "=l"(r0), "=l"(r1) : "l"(o0), "l"(o1), "l"(n0), "l"(n1), "r"(a) : "memory");
+    if (r0 == o0 && r1 == o1) break;
+    old.x = __uint_as_float((uint32_t)r0); old.y = __uint_as_float((uint32_t)(r0 >> 32));
+    old.z = __uint_as_float((uint32_t)r1); old.w = __uint_as_float((uint32_t)(r1 >> 32));
+  }
+}
+
+// flush shared [K][d+4] sums + int counts into the packed [K][d+1] statistics of one subspace
+__device__ __forceinline__ void flush_shared_stats(const float* s_sum, const int* s_cnt, int K, int d, float* pm) {
+  const int ld = d + 1, ls = d + 4;
+  for (int i = threadIdx.x; i < K * ld; i += blockDim.x) {
+    const int k = i / ld, j = i - k * ld;
+    const float v = (j < d) ? s_sum[k * ls + j] : (float)s_cnt[k];
+    if (v != 0.f) atomicAdd(pm + i, v);
+  }
+}
+
+template <int LPS, int kU>
+__global__ void __launch_bounds__(1024)
 accumulate_flat_kernel(const float* __restrict__ z, long long n_pixels, int D, int K,
                        const int32_t* __restrict__ idx, int use_norm, int mode,
                        const float* __restrict__ na, const float* __restrict__ nb,
                        float* __restrict__ packed, long long rows_per_block) {
   constexpr int d = LPS * 4;
-  extern __shared__ float s_acc[];  // [K][d+1]
+  constexpr int ls = d + 4;
+  extern __shared__ __align__(16) float s_acc[];  // [K][d+4] sums, then int [K] counts
+  int* s_cnt = reinterpret_cast<int*>(s_acc + K * ls);
   const int m = blockIdx.y;
-  const int ld = d + 1;
-  for (int i = threadIdx.x; i < K * ld; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < K * ls + K; i += blockDim.x) s_acc[i] = 0.f;   // 0.f and 0 share the bit pattern
   __syncthreads();
   const long long n0 = (long long)blockIdx.x * rows_per_block;
   long long n1 = n0 + rows_per_block;
@@ -396,41 +429,106 @@ accumulate_flat_kernel(const float* __restrict__ z, long long n_pixels, int D, i
   const int rows_per_iter = blockDim.x / LPS;
   const int rl = threadIdx.x / LPS, l = threadIdx.x % LPS;
   const int32_t* idxm = idx + (long long)m * n_pixels;
-  for (long long nb0 = n0; nb0 < n1; nb0 += rows_per_iter) {   // block-uniform trip count (shuffles inside)
-    const long long nr = nb0 + rl;
-    const bool live = nr < n1;
-    const long long n = live ? nr : n1 - 1;
-    float4 v = __ldcs(reinterpret_cast<const float4*>(z + n * D + (long long)m * d) + l);
-    if (use_norm && mode != EQUSS_NORM_NONE) {
-      RowNorm r; r.shift = 0.f; r.denom = 1.f;
-      if (mode == EQUSS_NORM_L2) {
-        r = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v.x, v.y, v.z, v.w)));
-      } else if (mode == EQUSS_NORM_ZNORM) {
-        float mean = butterfly_lanes<LPS>(group_sum(v.x, v.y, v.z, v.w)) / (float)d;
-        float ssd = butterfly_lanes<LPS>(group_sumsq(v.x - mean, v.y - mean, v.z - mean, v.w - mean));
-        r.shift = mean; r.denom = sqrtf(ssd / (float)(d - 1)) + kStdEps;
-      }
-      int ch = m * d + l * 4;
-      v.x = norm_elem(v.x, r, mode, na, nb, ch);
-      v.y = norm_elem(v.y, r, mode, na, nb, ch + 1);
-      v.z = norm_elem(v.z, r, mode, na, nb, ch + 2);
-      v.w = norm_elem(v.w, r, mode, na, nb, ch + 3);
+  // software pipeline: the loads of trip t+1 are issued before the shared updates of trip t (the CAS loop is an
+  // asm volatile with a memory clobber, so the compiler will not do this itself)
+  float4 vn[kU];
+  int coden[kU];
+  auto fetch = [&](long long nb0) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long nr = nb0 + (long long)u * rows_per_iter + rl;
+      const long long n = nr < n1 ? nr : n1 - 1;
+      vn[u] = __ldcs(reinterpret_cast<const float4*>(z + n * D + (long long)m * d) + l);
+      coden[u] = __ldg(idxm + n);
     }
-    if (!live) continue;
-    int code = __ldg(idxm + n);
-    float* a = s_acc + code * ld + l * 4;
-    atomicAdd(a + 0, v.x);
-    atomicAdd(a + 1, v.y);
-    atomicAdd(a + 2, v.z);
-    atomicAdd(a + 3, v.w);
-    if (l == 0) atomicAdd(s_acc + code * ld + d, 1.f);
+  };
+  if (n0 < n1) fetch(n0);
+  for (long long nb0 = n0; nb0 < n1; nb0 += (long long)kU * rows_per_iter) {   // block-uniform trip count (shuffles inside)
+    float4 v[kU];
+    int code[kU];
+    bool live[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      v[u] = vn[u]; code[u] = coden[u];
+      live[u] = nb0 + (long long)u * rows_per_iter + rl < n1;
+    }
+    if (nb0 + (long long)kU * rows_per_iter < n1) fetch(nb0 + (long long)kU * rows_per_iter);
+    if (use_norm && mode != EQUSS_NORM_NONE) {
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        RowNorm r; r.shift = 0.f; r.denom = 1.f;
+        if (mode == EQUSS_NORM_L2) {
+          r = l2_from_sumsq(butterfly_lanes<LPS>(group_sumsq(v[u].x, v[u].y, v[u].z, v[u].w)));
+        } else if (mode == EQUSS_NORM_ZNORM) {
+          float mean = butterfly_lanes<LPS>(group_sum(v[u].x, v[u].y, v[u].z, v[u].w)) / (float)d;
+          float ssd = butterfly_lanes<LPS>(group_sumsq(v[u].x - mean, v[u].y - mean, v[u].z - mean, v[u].w - mean));
+          r.shift = mean; r.denom = sqrtf(ssd / (float)(d - 1)) + kStdEps;
+        }
+        int ch = m * d + l * 4;
+        v[u].x = norm_elem(v[u].x, r, mode, na, nb, ch);
+        v[u].y = norm_elem(v[u].y, r, mode, na, nb, ch + 1);
+        v[u].z = norm_elem(v[u].z, r, mode, na, nb, ch + 2);
+        v[u].w = norm_elem(v[u].w, r, mode, na, nb, ch + 3);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (!live[u]) continue;
+      shared_add4(s_acc + code[u] * ls + l * 4, v[u]);
+      if (l == 0) atomicAdd(s_cnt + code[u], 1);
+    }
   }
   __syncthreads();
-  float* pm = packed + (long long)m * K * ld;
-  for (int i = threadIdx.x; i < K * ld; i += blockDim.x) {
-    float v = s_acc[i];
-    if (v != 0.f) atomicAdd(pm + i, v);
+  flush_shared_stats(s_acc, s_cnt, K, d, packed + (long long)m * K * (d + 1));
+}
+
+// Strided (NCHW) rows: one pixel per thread, the d values of the row in registers, d/4 128-bit shared updates.
+template <int DT>
+__global__ void __launch_bounds__(DT >= 32 ? 512 : 1024)
+accumulate_rows_kernel(const float* __restrict__ z, ZView zv, int K,
+                       const int32_t* __restrict__ idx, int use_norm, int mode,
+                       const float* __restrict__ na, const float* __restrict__ nb,
+                       float* __restrict__ packed, long long rows_per_block) {
+  constexpr int d = DT, ls = DT + 4;
+  extern __shared__ __align__(16) float s_acc[];
+  int* s_cnt = reinterpret_cast<int*>(s_acc + K * ls);
+  const int m = blockIdx.y;
+  for (int i = threadIdx.x; i < K * ls + K; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const long long n0 = (long long)blockIdx.x * rows_per_block;
+  long long n1 = n0 + rows_per_block;
+  if (n1 > zv.n_pixels) n1 = zv.n_pixels;
+  const int nm = use_norm ? mode : EQUSS_NORM_NONE;
+  // the next pixel's row is loaded before this pixel's shared updates (see accumulate_flat_kernel)
+  ScalarRow<DT> nxt;
+  int code_n = 0;
+  auto fetch = [&](long long n) {
+    nxt.load(z + pixel_base(zv, n) + (long long)m * d * zv.stride_c, zv.stride_c, d);
+    code_n = __ldg(idx + (long long)m * zv.n_pixels + n);
+  };
+  constexpr bool kPipe = DT <= 32;                  // two rows of 64 floats do not fit the register file
+  if (kPipe && n0 + threadIdx.x < n1) fetch(n0 + threadIdx.x);
+  for (long long n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+    if (!kPipe) fetch(n);
+    ScalarRow<DT> row = nxt;
+    const int code = code_n;
+    if (kPipe && n + blockDim.x < n1) fetch(n + blockDim.x);
+    RowNorm r; r.shift = 0.f; r.denom = 1.f;
+    if (nm != EQUSS_NORM_NONE) r = row.norm(nm);
+    float* a = s_acc + code * ls;
+#pragma unroll
+    for (int q = 0; q < DT / 4; ++q) {
+      float4 v;
+      v.x = norm_elem(row.raw(4 * q + 0), r, nm, na, nb, m * d + 4 * q + 0);
+      v.y = norm_elem(row.raw(4 * q + 1), r, nm, na, nb, m * d + 4 * q + 1);
+      v.z = norm_elem(row.raw(4 * q + 2), r, nm, na, nb, m * d + 4 * q + 2);
+      v.w = norm_elem(row.raw(4 * q + 3), r, nm, na, nb, m * d + 4 * q + 3);
+      shared_add4(a + 4 * q, v);
+    }
+    atomicAdd(s_cnt + code, 1);
   }
+  __syncthreads();
+  flush_shared_stats(s_acc, s_cnt, K, d, packed + (long long)m * K * (d + 1));
 }
 
 template <int DT>
@@ -727,26 +825,43 @@ extern "C" int equss_pq_accumulate(const float* z, const equss_zdesc* zd, const 
   EQUSS_REQUIRE(K > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_accumulate: K=%d", K);
   if (zd->n_pixels == 0) return EQUSS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)K * (d + 1) * sizeof(float);
+  constexpr int bps = 8;     // blocks per SM over the whole grid (sweep on B200: 4 / 8 / 12 -> 75 / 73 / 77 us at C2)
+  const bool quad = (d % 4) == 0 && (d == 4 || d == 8 || d == 16 || d == 32 || d == 64);
+  // 128-bit path: [K][d+4] sums + [K] int counts; scalar path: [K][d+1] floats
+  const size_t smem = quad ? (size_t)K * (d + 5) * sizeof(float) : (size_t)K * (d + 1) * sizeof(float);
   const bool smem_ok = smem <= 200 * 1024;
-  // chunking: about 4 blocks per SM in total
-  long long chunks = ((long long)num_sms() * 4 + M - 1) / M;
-  if (smem > 96 * 1024) chunks = ((long long)num_sms() + M - 1) / M;
+  // chunking: `bps` blocks per SM in total while the accumulators of several blocks fit one SM; one big block otherwise
+  const bool big = smem > 56 * 1024;
+  const int threads = big ? 1024 : 256;
+  long long chunks = ((long long)num_sms() * (big ? 1 : bps) + M - 1) / M;
   if (chunks < 1) chunks = 1;
   long long rows_per_block = (zd->n_pixels + chunks - 1) / chunks;
   if (rows_per_block < 256) rows_per_block = 256;
   chunks = (zd->n_pixels + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)chunks, (unsigned)M);
-  if (flat_vector_ok(zd, d, z, z) && smem_ok) {
+  if (quad && flat_vector_ok(zd, d, z, z) && smem_ok) {
     int lps = d / 4;
     EQUSS_DISPATCH_LPS(lps, {
-      if (smem > 48 * 1024)
-        EQUSS_CUDA_OK(cudaFuncSetAttribute(accumulate_flat_kernel<LPS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      accumulate_flat_kernel<LPS><<<grid, 256, smem, st>>>(z, zd->n_pixels, zd->dim, K, idx, use_norm,
-                                                           norm_mode, norm_a, norm_b, packed, rows_per_block);
+      auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, threads, smem, st>>>(z, zd->n_pixels, zd->dim, K, idx, use_norm, norm_mode, norm_a, norm_b,
+                                          packed, rows_per_block);
+      };
+      launch(accumulate_flat_kernel<LPS, 2>);   // two rows per thread per trip (1 / 2 / 4 measured equal within noise)
     });
     EQUSS_LAUNCH_OK("accumulate_flat_kernel");
+  } else if (quad && smem_ok) {
+    ZView zv = make_view(zd);
+    EQUSS_DISPATCH_DT(d, {
+      if constexpr (DT >= 4) {
+        if (smem > 48 * 1024)
+          EQUSS_CUDA_OK(cudaFuncSetAttribute(accumulate_rows_kernel<DT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        accumulate_rows_kernel<DT><<<grid, (DT >= 32 && threads > 512) ? 512 : threads, smem, st>>>(z, zv, K, idx, use_norm, norm_mode, norm_a, norm_b,
+                                                                packed, rows_per_block);
+      }
+    });
+    EQUSS_LAUNCH_OK("accumulate_rows_kernel");
   } else {
     ZView zv = make_view(zd);
     EQUSS_DISPATCH_DT(d, {
