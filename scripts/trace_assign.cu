@@ -40,6 +40,7 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("rc=%d %s  %.1f us  err=%s\n", rc, equss_last_error_string(), ms * 1e3, cudaGetErrorString(cudaGetLastError()));
   }
+#ifdef EQUSS_TRACE
   static long long tr[256 * 12];
   cudaMemcpyFromSymbol(tr, tch::g_trace, sizeof(tr));
   long long t0 = tr[0];
@@ -52,5 +53,19 @@ int main(int argc, char** argv) {
     long long* r = tr + i * 12;
     printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);
   }
+#endif
+#ifdef EQUSS_TRACE_Q
+  static long long tq[256 * 24];
+  cudaMemcpyFromSymbol(tq, tch::g_traceq, sizeof(tq));
+  printf("unit | per quarter: tfull_h0 rel_h0 tfull_h1 rel_h1 tail\n");
+  for (int i = 150; i < 166; ++i) {
+    printf("%3d |", i);
+    for (int q = 0; q < 4; ++q) {
+      long long* r = tq + i * 24 + q * 6;
+      printf(" %7lld %5lld %5lld %5lld %5lld |", r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3]);
+    }
+    printf("\n");
+  }
+#endif
   return 0;
 }

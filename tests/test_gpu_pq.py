@@ -109,6 +109,13 @@ SHAPES = [
     ((2, 28, 28), 8, 256, 64, "l2"),   # NCHW
     ((3, 9, 7), 64, 256, 16, "l2"),    # NCHW, tiny odd grid
     ((2, 5, 5), 2, 16, 128, "z_norm"),
+    # scatter-add variants: 128-bit shared CAS kernels (d in 4..64, flat and NCHW), one 1024-thread block per SM when
+    # the accumulators of a subspace exceed 56 KB (K = 600, d = 64: 163 KB), scalar fallback otherwise
+    (257, 4, 16, 4, "l2"),
+    (640, 3, 24, 8, "z_norm"),
+    ((2, 6, 5), 4, 32, 32, "z_norm"),
+    (300, 2, 600, 64, "l2"),
+    ((1, 20, 20), 2, 600, 64, "none"),
 ]
 
 
@@ -349,7 +356,7 @@ def test_fused_assign_gather_equals_two_kernel_path(shape, M, K, d):
     torch.testing.assert_close(sq_f, sq_r, rtol=1e-6, atol=1e-9)
 
 
-@pytest.mark.parametrize("M,K", [(64, 256), (3, 40), (1, 1024), (16, 512)])
+@pytest.mark.parametrize("M,K", [(64, 256), (3, 40), (1, 1024), (16, 512), (2, 2048), (2, 1500)])
 def test_usage_percentiles_vs_oracle(M, K):
     """equss_usage_percentiles == get_histogram_count (model/quantizer.py:15-30) per subspace, NaN for None."""
     ops = _ops()
