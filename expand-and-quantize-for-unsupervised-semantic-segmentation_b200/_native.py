@@ -34,6 +34,7 @@ EXPORTS = [
     "equss_usage_percentiles", "equss_pq_assign_gather_supported", "equss_pq_assign_gather",
     "equss_probe_image_bytes", "equss_probe_build_image", "equss_probe_logits_tc_supported", "equss_probe_logits_tc",
     "equss_knn_workspace_bytes", "equss_knn_topk",
+    "equss_head_gemm_supported", "equss_head_gemm",
 ]
 
 
@@ -119,6 +120,10 @@ def _declare(L: C.CDLL) -> None:
     L.equss_probe_logits_tc_supported.argtypes = [i32, i32, i32, i32]
     L.equss_probe_logits_tc.restype = i32
     L.equss_probe_logits_tc.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.equss_head_gemm_supported.restype = i32
+    L.equss_head_gemm_supported.argtypes = [i32, i32, i32, i32]
+    L.equss_head_gemm.restype = i32
+    L.equss_head_gemm.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]
     L.equss_probe_argmax_confusion.restype = i32
     L.equss_probe_argmax_confusion.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32,
                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -186,6 +191,23 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def is_channels_last(z: torch.Tensor) -> bool:
+    """4-D tensor whose memory is NHWC-dense (and not also NCHW-dense)."""
+    return z.dim() == 4 and not z.is_contiguous() and z.is_contiguous(memory_format=torch.channels_last)
+
+
+def f32_dense(t: torch.Tensor, like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 tensor in a layout the kernels take without a copy where possible: NCHW- or NHWC-dense 4-D, dense
+    otherwise.  With ``like`` the result uses the memory format of ``like`` (gradients of a channels-last z)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if like is not None and is_channels_last(like):
+        return t.contiguous(memory_format=torch.channels_last)
+    if like is None and is_channels_last(t):
+        return t
+    return t.contiguous()
+
+
 def zdesc_for(z: torch.Tensor, M: int) -> "tuple[ZDesc, int, str]":
     """Describe an activation tensor without copying it.
 
@@ -204,6 +226,9 @@ def zdesc_for(z: torch.Tensor, M: int) -> "tuple[ZDesc, int, str]":
         if D % M != 0:
             raise ValueError(f"Embed dim {D} should be divisible by #PQ {M}.")
         hw = h * w
+        if is_channels_last(z):        # (B, D, h, w) view of NHWC memory, e.g. the expansion head's output: flat rows
+            zd = ZDesc(B * hw, max(B * hw, 1), max(B * hw, 1) * D, D, 1, D, LAYOUT_FLAT)
+            return zd, D // M, "flat"
         zd = ZDesc(B * hw, max(hw, 1), D * hw, 1, hw, D, LAYOUT_NCHW)
         return zd, D // M, "nchw"
     raise ValueError(f"expected a (n, D) or (B, D, h, w) tensor, got shape {tuple(z.shape)}")

@@ -43,7 +43,7 @@ def _norm_args(normalize, norm_a, norm_b, D, dev):
 def _prep_z(z: torch.Tensor, M: int):
     dev = N.require_cuda(z)
     N.ensure_device(dev)
-    z = N.f32c(z.detach())
+    z = N.f32_dense(z.detach())
     zd, d, layout = N.zdesc_for(z, M)
     return z, zd, d, dev
 
@@ -155,9 +155,9 @@ def pq_gather_loss_bwd(z: torch.Tensor, gather_src: torch.Tensor, idx: torch.Ten
     M, K, d = src.shape
     z, zd, dz, dev = _prep_z(z, M)
     mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
-    go = N.f32c(grad_out.detach()) if grad_out is not None else None
+    go = N.f32_dense(grad_out.detach(), like=z) if grad_out is not None else None
     if go is not None:
-        assert go.shape == z.shape
+        assert go.shape == z.shape and go.stride() == z.stride()
     cf = N.f32c(coef.detach()).reshape(-1) if coef is not None else None
     cbf = N.f32c(cb_coef.detach()).reshape(-1) if cb_coef is not None else None
     gz = torch.empty_like(z) if want_grad_z else None
@@ -332,6 +332,56 @@ def confusion_update(preds: torch.Tensor, label: torch.Tensor, num_classes: int,
     rc = N.lib().equss_confusion_update(p.data_ptr(), l.data_ptr(), p.numel(), num_classes, int(confusion.shape[0]),
                                         confusion.data_ptr(), N.stream_ptr(dev))
     N.check(rc, "equss_confusion_update")
+
+
+def head_gemm(a1: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+              relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One layer of the expansion head (1x1 convolutions of model/dino_pqgo.py:104-112, model/blocks/module.py:27-36):
+    ``out[r, o] = act(sum_k A[r, k] * w[o, k] + bias[o])`` with ``A = [a1 | a2]`` along k, on the tensor cores
+    (split-tf32, fp32-level accuracy).
+
+    a1: NCHW features (B, C1, h, w) -- read in place when h*w % 32 == 0 -- or flat rows (n, C1); a2: flat rows
+    (n, C2) or None; w: (n_out, C1 + C2) (a Conv2d weight reshaped, branches concatenated along the input channels).
+    Returns the flat (n, n_out) matrix, n = B*h*w: the (pixel, channel) layout the PQ ops take directly."""
+    dev = N.require_cuda(a1, w, bias, a2)
+    N.ensure_device(dev)
+    L = N.lib()
+    a1 = N.f32c(a1.detach())
+    if a1.dim() == 4:
+        B, C1, h, wd = a1.shape
+        hw = h * wd
+        nchw = 1
+        if not L.equss_head_gemm_supported(C1, 0, hw, 1):     # token grid not a multiple of 32: one NHWC copy
+            a1 = a1.permute(0, 2, 3, 1).reshape(B * hw, C1).contiguous()
+            B, hw, nchw = 1, B * hw, 0
+    elif a1.dim() == 2:
+        B, hw, C1, nchw = 1, a1.shape[0], a1.shape[1], 0
+    else:
+        raise ValueError(f"head_gemm: a1 must be (B, C, h, w) or (n, C), got {tuple(a1.shape)}")
+    n = B * hw
+    C2 = 0
+    if a2 is not None:
+        a2 = N.f32c(a2.detach())
+        if a2.dim() != 2 or a2.shape[0] != n:
+            raise ValueError(f"head_gemm: a2 must be ({n}, C2), got {tuple(a2.shape)}")
+        C2 = a2.shape[1]
+    w = N.f32c(w.detach()).reshape(w.shape[0], -1)
+    n_out = w.shape[0]
+    if w.shape[1] != C1 + C2:
+        raise ValueError(f"head_gemm: weight has {w.shape[1]} input channels, activations have {C1 + C2}")
+    b = N.f32c(bias.detach()).reshape(-1) if bias is not None else None
+    if b is not None and b.numel() != n_out:
+        raise ValueError(f"head_gemm: bias has {b.numel()} entries for {n_out} output channels")
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    elif out.shape != (n, n_out) or out.dtype != torch.float32 or out.stride(1) != 1:
+        raise ValueError("head_gemm: out must be a float32 (n, n_out) matrix with unit column stride")
+    if n == 0:
+        return out
+    rc = L.equss_head_gemm(a1.data_ptr(), nchw, C1, N.ptr(a2), C2, B, hw, w.data_ptr(), N.ptr(b), n_out, int(relu),
+                           out.data_ptr(), out.stride(0), N.stream_ptr(dev))
+    N.check(rc, "equss_head_gemm")
+    return out
 
 
 def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int, return_sims: bool = False):

@@ -231,6 +231,22 @@ int equss_knn_topk(const float* queries, int64_t nq, const float* db, int64_t n,
                    int64_t* idx_out, float* sim_out,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K12 expansion head  replaces the 1x1 convolutions of model/dino_pqgo.py:104-112,127-128 and
+ *                                   model/blocks/module.py:20-44:  code = cluster1(x) + cluster2(x)
+ *   One tcgen05 split-tf32 GEMM (fp32-level accuracy), called twice by the host mirror:
+ *     out[r][o] = act( sum_{k<C1} A1[r][k] W[o][k] + sum_{k<C2} A2[r][k] W[o][C1+k] + bias[o] ),   r = b*hw + s
+ *   a1: NCHW [B][C1][hw] (a1_nchw = 1, needs hw % 32 == 0; read in place, no permute) or flat [B*hw][C1];
+ *   a2: flat [B*hw][C2] or NULL (C2 = 0);  w: [n_out][C1+C2] row-major (Conv2d weight (o, c, 1, 1), branches
+ *   concatenated along c);  out: flat [B*hw][out_ld] -- the (pixel, channel) layout the PQ entry points take as
+ *   EQUSS layout FLAT.  relu != 0 applies max(., 0) to the output (the hidden layer of cluster2).
+ *   C1 % 32 == 0 and C2 % 32 == 0 (equss_head_gemm_supported).
+ * ------------------------------------------------------------------------------------------- */
+int equss_head_gemm_supported(int C1, int C2, int hw, int a1_nchw);
+int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float* a2, int C2, int B, int hw,
+                    const float* w, const float* bias, int n_out, int relu, float* out, int64_t out_ld,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

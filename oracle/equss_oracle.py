@@ -255,6 +255,20 @@ def knn(normed_feats: torch.Tensor, k: int = 30, queries: Optional[torch.Tensor]
 
 
 # --------------------------------------------------------------------------------------------------
+# Expansion head  (model/dino_pqgo.py:104-112,127-128; model/blocks/module.py:20-44)
+# --------------------------------------------------------------------------------------------------
+
+
+def expansion_head(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor], w2: torch.Tensor,
+                   b2: Optional[torch.Tensor], w3: torch.Tensor, b3: Optional[torch.Tensor]) -> torch.Tensor:
+    """code = cluster1(x) + cluster2(x): Conv1x1(C->D) plus Conv1x1(C->C), ReLU, Conv1x1(C->D), in the dtype of x
+    (module.py:39-43: ``out = self.cluster1(x); out += self.cluster2(x)``).  Weights are Conv2d-shaped (o, c, 1, 1)."""
+    out = F.conv2d(x, w1, b1)
+    out += F.conv2d(F.relu(F.conv2d(x, w2, b2)), w3, b3)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 # near-tie audit helpers (SURVEY 4.6) used by the parity tests
 # --------------------------------------------------------------------------------------------------
 
