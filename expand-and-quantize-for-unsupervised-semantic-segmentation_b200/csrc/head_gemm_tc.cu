@@ -13,11 +13,11 @@
 // operand tiles ARE the hi operands (the tensor core ignores the low 13 mantissa bits of an fp32 word); eight convert
 // warps write lo = x - trunc(x) element-wise at identical (swizzled) offsets, which is layout-agnostic: an NCHW
 // activation tile arrives through a 4-D tensor map (32 pixels | channel | 32-pixel block | image) in the MN-major
-// SWIZZLE_128B_BASE32B layout, a flat activation or weight tile through a 2-D map in the K-major SWIZZLE_128B layout.
+// SWIZZLE_128B_BASE32B layout, a flat activation or weight tile through a 2-D map in the K-major SWIZZLE_64B layout.
 // The hi.hi products and the small lo.hi / hi.lo products have separate TMEM accumulators (the tensor core's fp32
 // accumulate truncates; the 2^-11-sized terms stay out of the main accumulator); the epilogue adds them, the bias and
 // the activation and streams the row.  Structure as in knn_tc.cu: persistent CTAs, producer warp, two issuer warps,
-// eight convert warps, four epilogue warps, two 96 KB stages.
+// eight convert warps, four epilogue warps, four 48 KB stages (16 channels each).
 #include <cuda.h>
 #include "equss_common.cuh"
 #include "equss_tcgen05.cuh"
@@ -27,12 +27,13 @@ namespace headtc {
 
 using namespace ::equss::ptx;
 
-constexpr int kBM = 128, kBN = 256, kKC = 32;        // pixels / output channels per tile, input channels per stage
-constexpr int kStages = 2;
+constexpr int kBM = 128, kBN = 256, kKC = 16;        // pixels / output channels per tile, input channels per stage
+constexpr int kStages = 4;                           // 48 KB each: four loads in flight cover the L2 / TMA latency
 constexpr int kThreads = 32 * (4 + 1 + 2 + 8);       // 4 epilogue, producer, 2 MMA issuers, 8 convert warps
 constexpr int kEpiWarp0 = 0, kProducerWarp = 4, kMmaWarp = 5, kConvWarp0 = 7;
-constexpr int kARaw = kBM * 128, kBRaw = kBN * 128;  // bytes: 16 KB, 32 KB
-constexpr int kStageBytes = 2 * kARaw + 2 * kBRaw;   // raw A | lo A | raw W | lo W = 96 KB
+constexpr int kRowB = kKC * 4;                       // bytes per K-major row of a stage = the swizzle span (64 B)
+constexpr int kARaw = kBM * kRowB, kBRaw = kBN * kRowB;  // bytes: 8 KB, 16 KB
+constexpr int kStageBytes = 2 * kARaw + 2 * kBRaw;   // raw A | lo A | raw W | lo W = 48 KB
 constexpr int kSmem = 1024 + kStages * kStageBytes + 256;
 
 // kind::tf32, fp32 accumulate, B K-major, M = 128, N; bit 15 = A MN-major
@@ -44,8 +45,8 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 
 struct Params {
   int n_images, hw, tiles_per_image;    // row tile (b, t) = pixels [t*128, t*128+128) of image b (flat input: one "image")
-  int n_out, n_tiles_n;                 // output channels, column tiles
-  int kc1, kc2;                         // 32-channel stages taken from source 1 / source 2
+  int n_out, n_tiles_n, bn;             // output channels, column tiles, columns per tile (256, or 192 when that divides n_out better)
+  int kc1, kc2;                         // kKC-channel stages taken from source 1 / source 2
   int a1_nchw;                          // source 1: 1 = NCHW (MN-major tiles), 0 = flat rows (K-major tiles)
   int relu;
   const float* bias;                    // [n_out] or null
@@ -103,25 +104,25 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
           const int st = g % kStages;
           uint8_t* sp = smem + st * kStageBytes;
           mbar_wait(st_empty + st, ((g / kStages) & 1) ^ 1, 10);
-          mbar_expect_tx(raw_full + st, kARaw + kBRaw);
+          mbar_expect_tx(raw_full + st, (uint32_t)(kARaw + p.bn * kRowB));
           if (c < p.kc1) {
             if (p.a1_nchw) tma_load_4d(sp, &tmap_a1, 0, c * kKC, ti * (kBM / 32), b, raw_full + st);
             else tma_load_2d(sp, &tmap_a1, c * kKC, row0, raw_full + st);
           } else {
             tma_load_2d(sp, &tmap_a2, (c - p.kc1) * kKC, row0, raw_full + st);
           }
-          tma_load_2d(sp + 2 * kARaw, &tmap_w, c * kKC, bn * kBN, raw_full + st);
+          tma_load_2d(sp + 2 * kARaw, &tmap_w, c * kKC, bn * p.bn, raw_full + st);
         }
       }
     }
   } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
     // issuer 0: a_hi.w_hi -> main accumulator (columns 0..255); issuer 1: a_lo.w_hi + a_hi.w_lo -> small (256..511)
     const int part = warp - kMmaWarp;
-    constexpr uint32_t IDESC_K = make_idesc_tf32(kBN, false), IDESC_MN = make_idesc_tf32(kBN, true);
-    // K-major SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 8 floats advances 32 B.
+    const uint32_t IDESC_K = make_idesc_tf32(p.bn, false), IDESC_MN = make_idesc_tf32(p.bn, true);
+    // K-major SWIZZLE_64B: rows of 64 B (16 channels), 8-row groups 512 B apart (SBO); a K step of 8 floats advances 32 B.
     // MN-major SWIZZLE_128B_BASE32B (NCHW activations): 32 pixels per 128-byte row, 4 channels per 512-byte atom (SBO),
-    // 32-pixel blocks 4096 B apart (LBO); a K step of 8 channels advances 1024 B.
-    const uint32_t k_hi = (uint32_t)((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+    // 32-pixel blocks kKC * 128 B apart (LBO); a K step of 8 channels advances 1024 B.
+    const uint32_t k_hi = (uint32_t)(((8u * kRowB) >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
     const uint32_t mn_hi = (uint32_t)((512u >> 4) & 0x3FFF) | (1u << 14) | (1u << 29);
     const uint32_t base = smem_u32(smem);
     int g = 0;
@@ -136,7 +137,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
         if (lane == 0) {
           const bool mn = p.a1_nchw && c < p.kc1;
           const uint32_t sa = base + (uint32_t)(st * kStageBytes);
-          const uint32_t a_lbo = mn ? ((4096u >> 4) << 16) : (1u << 16);
+          const uint32_t a_lbo = mn ? (((uint32_t)(kKC * 128) >> 4) << 16) : (1u << 16);
           const uint32_t a_raw = (sa >> 4) | a_lbo, a_lo = ((sa + kARaw) >> 4) | a_lbo;
           const uint32_t a_step = mn ? (1024u >> 4) : 2u, a_hi = mn ? mn_hi : k_hi;
           const uint32_t idesc = mn ? IDESC_MN : IDESC_K;
@@ -167,21 +168,22 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
         const int st = g % kStages;
         mbar_wait(raw_full + st, (g / kStages) & 1, 31);
         uint8_t* sp = smem + st * kStageBytes;
-        // A: 1024 float4 (4 per thread), W: 2048 float4 (8 per thread); lo tile = raw tile + kARaw / + kBRaw
-        float4 va[4], vb[8];
+        // A: kARaw / 16 float4 (NA per thread), W: kBRaw / 16 (NB per thread); lo tile = raw tile + kARaw / + kBRaw
+        constexpr int NA = kARaw / 16 / 256, NB = kBRaw / 16 / 256;
+        float4 va[NA], vb[NB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) va[u] = *reinterpret_cast<const float4*>(sp + (u * 256 + ct) * 16);
+        for (int u = 0; u < NA; ++u) va[u] = *reinterpret_cast<const float4*>(sp + (u * 256 + ct) * 16);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) vb[u] = *reinterpret_cast<const float4*>(sp + 2 * kARaw + (u * 256 + ct) * 16);
+        for (int u = 0; u < NB; ++u) vb[u] = *reinterpret_cast<const float4*>(sp + 2 * kARaw + (u * 256 + ct) * 16);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NA; ++u) {
           float4 l;
           l.x = va[u].x - tf32_trunc(va[u].x); l.y = va[u].y - tf32_trunc(va[u].y);
           l.z = va[u].z - tf32_trunc(va[u].z); l.w = va[u].w - tf32_trunc(va[u].w);
           *reinterpret_cast<float4*>(sp + kARaw + (u * 256 + ct) * 16) = l;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < NB; ++u) {
           float4 l;
           l.x = vb[u].x - tf32_trunc(vb[u].x); l.y = vb[u].y - tf32_trunc(vb[u].y);
           l.z = vb[u].z - tf32_trunc(vb[u].z); l.w = vb[u].w - tf32_trunc(vb[u].w);
@@ -203,12 +205,12 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
       decode(blockIdx.x + (long long)it * gridDim.x, b, ti, bn);
       const int s = ti * kBM + row;
       const bool live = s < p.hw;
-      const int c0 = bn * kBN;
+      const int c0 = bn * p.bn;
       float* orow = p.out + ((long long)b * p.hw + s) * p.out_ld + c0;
       mbar_wait(acc_full, it & 1, 40);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < kBN / 32; ++ch) {
+      for (int ch = 0; ch < p.bn / 32; ++ch) {
         uint32_t vm[32], vs[32];
         tmem_ld32(lane_base + (uint32_t)(ch * 32), vm);
         tmem_ld32(lane_base + (uint32_t)(kBN + ch * 32), vs);
@@ -299,7 +301,7 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
     cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   CUtensorMap ta1, ta2, tw;
   CUresult c1;
@@ -316,12 +318,16 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   }
   CUresult c2 = (C2 > 0) ? make2d(&ta2, a2, rows, C2, kBM) : CUDA_SUCCESS;
   if (C2 == 0) ta2 = ta1;
-  CUresult c3 = make2d(&tw, w, n_out, K, kBN);
+  const int waste256_ = (n_out + 255) / 256 * 256 - n_out, waste192_ = (n_out + 191) / 192 * 192 - n_out;
+  CUresult c3 = make2d(&tw, w, n_out, K, (waste192_ < waste256_) ? 192 : 256);
   EQUSS_REQUIRE(c1 == CUDA_SUCCESS && c2 == CUDA_SUCCESS && c3 == CUDA_SUCCESS, EQUSS_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (%d, %d, %d)", (int)c1, (int)c2, (int)c3);
   Params p;
   p.n_images = B; p.hw = hw; p.tiles_per_image = (hw + kBM - 1) / kBM;
-  p.n_out = n_out; p.n_tiles_n = (n_out + kBN - 1) / kBN;
+  // 192-column tiles when they waste fewer columns than 256-column tiles (e.g. n_out = 384: 2 x 192 instead of 2 x 256)
+  const int waste256 = (n_out + 255) / 256 * 256 - n_out, waste192 = (n_out + 191) / 192 * 192 - n_out;
+  p.bn = (waste192 < waste256) ? 192 : 256;
+  p.n_out = n_out; p.n_tiles_n = (n_out + p.bn - 1) / p.bn;
   p.kc1 = C1 / kKC; p.kc2 = C2 / kKC;
   p.a1_nchw = a1_nchw ? 1 : 0; p.relu = relu ? 1 : 0;
   p.bias = bias; p.out = out; p.out_ld = out_ld;

@@ -240,7 +240,7 @@ int equss_knn_topk(const float* queries, int64_t nq, const float* db, int64_t n,
  *   a2: flat [B*hw][C2] or NULL (C2 = 0);  w: [n_out][C1+C2] row-major (Conv2d weight (o, c, 1, 1), branches
  *   concatenated along c);  out: flat [B*hw][out_ld] -- the (pixel, channel) layout the PQ entry points take as
  *   EQUSS layout FLAT.  relu != 0 applies max(., 0) to the output (the hidden layer of cluster2).
- *   C1 % 32 == 0 and C2 % 32 == 0 (equss_head_gemm_supported).
+ *   C1 % 16 == 0 and C2 % 16 == 0 (equss_head_gemm_supported).
  * ------------------------------------------------------------------------------------------- */
 int equss_head_gemm_supported(int C1, int C2, int hw, int a1_nchw);
 int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float* a2, int C2, int B, int hw,

@@ -70,6 +70,29 @@ if __name__ == "__main__":
         preds = torch.randint(0, C, (B, H, W), device=dev)
         ms = timeit(lambda f: ops.confusion_update(preds, label, C, cc), feats)
         print(f"confusion_update {ms*1e3:.1f} us  {16*B*H*W/ms/1e6:.1f} GB/s")
+    if not only or "head" in only:
+        from equss_b200.head import SegmentationHead
+        for (B, C, h, w, D) in [(32, 384, 40, 40, 1024), (32, 768, 40, 40, 1024), (16, 768, 56, 56, 1024)]:
+            head = SegmentationHead(C, D).to(dev).eval()
+            xs = [torch.randn(B, C, h, w, device=dev) for _ in range(3)]
+            n = B * h * w
+            fl = 2.0 * n * (C * D * 2 + C * C)
+            with torch.no_grad():
+                ms = timeit(lambda x: head(x), xs)
+                ms_h = timeit(lambda x: ops.head_gemm(x, head.cluster2[0].weight, head.cluster2[0].bias, relu=True), xs)
+                out = head(xs[0])
+                ref = (head.cluster1(xs[0].double()) if False else None)
+                h64 = head.double()
+                ref = h64.cluster1(xs[0].double()) + h64.cluster2(xs[0].double())
+                err = float((out.double() - ref).abs().max() / ref.abs().max())
+                head.float()
+                torch.backends.cudnn.allow_tf32 = True
+                ms_t = timeit(lambda x: head.cluster1(x) + head.cluster2(x), xs)
+                torch.backends.cudnn.allow_tf32 = False
+                ms_f = timeit(lambda x: head.cluster1(x) + head.cluster2(x), xs, iters=5, warm=2)
+            print(f"head B={B} C={C} {h}x{w} D={D}: {ms*1e3:8.1f} us (hidden {ms_h*1e3:.1f}) {fl/ms/1e9:7.1f} TFLOP/s useful, "
+                  f"x3 issued = {3*fl/ms/1e9/1405.3*100:.1f}% of bf16-equivalent peak... rel err {err:.2e} | "
+                  f"torch cudnn tf32 {ms_t*1e3:.1f} us, torch fp32 {ms_f*1e3:.1f} us", flush=True)
     if not only or "knn" in only:
         db = F.normalize(torch.randn(50000, 768, device=dev), dim=1)
         ms = timeit(lambda f: ops.knn_topk(db[:6250], db, 30), [0], iters=2, warm=1)
