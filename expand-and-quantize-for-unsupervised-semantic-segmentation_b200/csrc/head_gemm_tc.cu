@@ -19,6 +19,7 @@
 // the activation and streams the row.  Structure as in knn_tc.cu: persistent CTAs, producer warp, two issuer warps,
 // eight convert warps, four epilogue warps, four 48 KB stages (16 channels each).
 #include <cuda.h>
+#include <cstdlib>
 #include "equss_common.cuh"
 #include "equss_tcgen05.cuh"
 
@@ -28,7 +29,11 @@ namespace headtc {
 using namespace ::equss::ptx;
 
 constexpr int kBM = 128, kBN = 256, kKC = 16;        // pixels / output channels per tile, input channels per stage
-constexpr int kStages = 4;                           // 48 KB each: four loads in flight cover the L2 / TMA latency
+// What bounds the kernel is the L2 -> shared-memory stream, not the tensor core: with the MMAs and the conversion
+// switched off (EQUSS_HEAD_DEBUG=7) it still takes 63 % of its time, ~6 TB/s of operand tiles chip-wide, and a deeper
+// raw ring (7 x 24 KB in flight instead of 4) changed nothing -- throughput-, not latency-limited.  The tile shape
+// (128 x 256 at fp32 operand width) sets the bytes per flop; 2-CTA MMAs sharing the weight tile are the next step.
+constexpr int kStages = 4;                           // 48 KB each
 constexpr int kThreads = 32 * (4 + 1 + 2 + 8);       // 4 epilogue, producer, 2 MMA issuers, 8 convert warps
 constexpr int kEpiWarp0 = 0, kProducerWarp = 4, kMmaWarp = 5, kConvWarp0 = 7;
 constexpr int kRowB = kKC * 4;                       // bytes per K-major row of a stage = the swizzle span (64 B)
@@ -52,6 +57,7 @@ struct Params {
   const float* bias;                    // [n_out] or null
   float* out;                           // [n_images*hw][out_ld]
   long long out_ld;
+  int debug;                            // EQUSS_HEAD_DEBUG timing experiments: 1 = no MMAs, 2 = no small-term MMAs, 4 = no conversion
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -142,10 +148,12 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
           const uint32_t a_step = mn ? (1024u >> 4) : 2u, a_hi = mn ? mn_hi : k_hi;
           const uint32_t idesc = mn ? IDESC_MN : IDESC_K;
           const uint32_t b_raw = ((sa + 2 * kARaw) >> 4) | (1u << 16), b_lo = ((sa + 2 * kARaw + kBRaw) >> 4) | (1u << 16);
-          if (part == 0) {
+          if (p.debug & 1) {
+          } else if (part == 0) {
 #pragma unroll
             for (int kk = 0; kk < kKC / 8; ++kk)
               umma_tf32(d_addr, desc_from(a_raw + a_step * kk, a_hi), desc_from(b_raw + 2 * kk, k_hi), idesc, (c > 0 || kk > 0) ? 1u : 0u);
+          } else if (p.debug & 2) {
           } else {
 #pragma unroll
             for (int kk = 0; kk < kKC / 8; ++kk)
@@ -177,6 +185,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
         for (int u = 0; u < NB; ++u) vb[u] = *reinterpret_cast<const float4*>(sp + 2 * kARaw + (u * 256 + ct) * 16);
 #pragma unroll
         for (int u = 0; u < NA; ++u) {
+          if (p.debug & 4) break;
           float4 l;
           l.x = va[u].x - tf32_trunc(va[u].x); l.y = va[u].y - tf32_trunc(va[u].y);
           l.z = va[u].z - tf32_trunc(va[u].z); l.w = va[u].w - tf32_trunc(va[u].w);
@@ -184,6 +193,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
         }
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
+          if (p.debug & 4) break;
           float4 l;
           l.x = vb[u].x - tf32_trunc(vb[u].x); l.y = vb[u].y - tf32_trunc(vb[u].y);
           l.z = vb[u].z - tf32_trunc(vb[u].z); l.w = vb[u].w - tf32_trunc(vb[u].w);
@@ -331,6 +341,7 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   p.kc1 = C1 / kKC; p.kc2 = C2 / kKC;
   p.a1_nchw = a1_nchw ? 1 : 0; p.relu = relu ? 1 : 0;
   p.bias = bias; p.out = out; p.out_ld = out_ld;
+  p.debug = getenv("EQUSS_HEAD_DEBUG") ? atoi(getenv("EQUSS_HEAD_DEBUG")) : 0;
   const long long total = (long long)p.n_images * p.tiles_per_image * p.n_tiles_n;
   int grid = num_sms();
   if (total < grid) grid = (int)total;
