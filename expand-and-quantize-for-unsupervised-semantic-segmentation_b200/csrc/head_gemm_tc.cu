@@ -52,7 +52,8 @@ struct Params {
   int n_images, hw, tiles_per_image;    // row tile (b, t) = pixels [t*128, t*128+128) of image b (flat input: one "image")
   int n_out, n_tiles_n, bn;             // output channels, column tiles, columns per tile (256, or 192 when that divides n_out better)
   int kc1, kc2;                         // kKC-channel stages taken from source 1 / source 2
-  int a1_nchw;                          // source 1: 1 = NCHW (MN-major tiles), 0 = flat rows (K-major tiles)
+  int a1_nchw;                          // source 1: 0 = flat rows (K-major tiles); NCHW (MN-major tiles): 1 = one 4-D box per
+                                        // tile (hw % 32 == 0), 2 = one 3-D box per 32-pixel block (ragged hw, zero-filled)
   int relu;
   const float* bias;                    // [n_out] or null
   float* out;                           // [n_images*hw][out_ld]
@@ -112,8 +113,15 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
           mbar_wait(st_empty + st, ((g / kStages) & 1) ^ 1, 10);
           mbar_expect_tx(raw_full + st, (uint32_t)(kARaw + p.bn * kRowB));
           if (c < p.kc1) {
-            if (p.a1_nchw) tma_load_4d(sp, &tmap_a1, 0, c * kKC, ti * (kBM / 32), b, raw_full + st);
-            else tma_load_2d(sp, &tmap_a1, c * kKC, row0, raw_full + st);
+            if (p.a1_nchw == 1) {
+              tma_load_4d(sp, &tmap_a1, 0, c * kKC, ti * (kBM / 32), b, raw_full + st);
+            } else if (p.a1_nchw == 2) {
+#pragma unroll
+              for (int blk = 0; blk < kBM / 32; ++blk)      // pixels past hw are zero-filled by the TMA unit
+                tma_load_3d(sp + blk * (kKC * 128), &tmap_a1, ti * kBM + blk * 32, c * kKC, b, raw_full + st);
+            } else {
+              tma_load_2d(sp, &tmap_a1, c * kKC, row0, raw_full + st);
+            }
           } else {
             tma_load_2d(sp, &tmap_a2, (c - p.kc1) * kKC, row0, raw_full + st);
           }
@@ -284,7 +292,7 @@ using namespace equss;
 //   w: [n_out][C1+C2] row-major; out: [B*hw][out_ld] with out_ld >= n_out
 extern "C" int equss_head_gemm_supported(int C1, int C2, int hw, int a1_nchw) {
   if (C1 <= 0 || C1 % headtc::kKC != 0 || C2 < 0 || C2 % headtc::kKC != 0) return 0;
-  if (a1_nchw && (hw % 32) != 0) return 0;
+  if (a1_nchw && (hw % 4) != 0) return 0;          // channel stride must be a multiple of 16 bytes
   return 1;
 }
 
@@ -297,7 +305,7 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   EQUSS_REQUIRE(B > 0 && hw > 0 && n_out > 0 && out_ld >= n_out, EQUSS_ERR_INVALID_ARG,
                 "equss_head_gemm: bad shape B=%d hw=%d n_out=%d out_ld=%lld", B, hw, n_out, (long long)out_ld);
   EQUSS_REQUIRE(equss_head_gemm_supported(C1, C2, hw, a1_nchw), EQUSS_ERR_UNSUPPORTED,
-                "equss_head_gemm: needs C1 %% %d == 0, C2 %% %d == 0 and, for NCHW input, h*w %% 32 == 0 (C1=%d C2=%d hw=%d)",
+                "equss_head_gemm: needs C1 %% %d == 0, C2 %% %d == 0 and, for NCHW input, h*w %% 4 == 0 (C1=%d C2=%d hw=%d)",
                 kKC, kKC, C1, C2, hw);
   EQUSS_REQUIRE(!((uintptr_t)a1 & 15) && !((uintptr_t)a2 & 15) && !((uintptr_t)w & 15) && !((uintptr_t)out & 15),
                 EQUSS_ERR_INVALID_ARG, "equss_head_gemm: pointers must be 16-byte aligned");
@@ -315,7 +323,16 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   };
   CUtensorMap ta1, ta2, tw;
   CUresult c1;
-  if (a1_nchw) {
+  int a1_mode = a1_nchw ? ((hw % 32) == 0 ? 1 : 2) : 0;
+  if (a1_mode == 2) {
+    // ragged token grid (e.g. 28 x 28): pixel | channel | image, one box of 32 pixels x 16 channels per block
+    cuuint64_t gdim[3] = {(cuuint64_t)hw, (cuuint64_t)C1, (cuuint64_t)B};
+    cuuint64_t gstr[2] = {(cuuint64_t)hw * 4, (cuuint64_t)C1 * hw * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)kKC, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    c1 = encode(&ta1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a1, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (a1_mode == 1) {
     // dims: 32 pixels (one 128-byte swizzle row) | channel | 32-pixel block | image -> smem [block][channel][32 px]
     cuuint64_t gdim[4] = {32, (cuuint64_t)C1, (cuuint64_t)(hw / 32), (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)hw * 4, 128, (cuuint64_t)C1 * hw * 4};
@@ -339,7 +356,7 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   p.bn = (waste192 < waste256) ? 192 : 256;
   p.n_out = n_out; p.n_tiles_n = (n_out + p.bn - 1) / p.bn;
   p.kc1 = C1 / kKC; p.kc2 = C2 / kKC;
-  p.a1_nchw = a1_nchw ? 1 : 0; p.relu = relu ? 1 : 0;
+  p.a1_nchw = a1_mode; p.relu = relu ? 1 : 0;
   p.bias = bias; p.out = out; p.out_ld = out_ld;
   p.debug = getenv("EQUSS_HEAD_DEBUG") ? atoi(getenv("EQUSS_HEAD_DEBUG")) : 0;
   const long long total = (long long)p.n_images * p.tiles_per_image * p.n_tiles_n;

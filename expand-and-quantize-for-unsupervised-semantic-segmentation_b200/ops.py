@@ -340,7 +340,7 @@ def head_gemm(a1: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
     ``out[r, o] = act(sum_k A[r, k] * w[o, k] + bias[o])`` with ``A = [a1 | a2]`` along k, on the tensor cores
     (split-tf32, fp32-level accuracy).
 
-    a1: NCHW features (B, C1, h, w) -- read in place when h*w % 32 == 0 -- or flat rows (n, C1); a2: flat rows
+    a1: NCHW features (B, C1, h, w) -- read in place when h*w % 4 == 0 -- or flat rows (n, C1); a2: flat rows
     (n, C2) or None; w: (n_out, C1 + C2) (a Conv2d weight reshaped, branches concatenated along the input channels).
     Returns the flat (n, n_out) matrix, n = B*h*w: the (pixel, channel) layout the PQ ops take directly."""
     dev = N.require_cuda(a1, w, bias, a2)
@@ -351,7 +351,7 @@ def head_gemm(a1: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = 
         B, C1, h, wd = a1.shape
         hw = h * wd
         nchw = 1
-        if not L.equss_head_gemm_supported(C1, 0, hw, 1):     # token grid not a multiple of 32: one NHWC copy
+        if not L.equss_head_gemm_supported(C1, 0, hw, 1):     # token count not a multiple of 4: one NHWC copy
             a1 = a1.permute(0, 2, 3, 1).reshape(B * hw, C1).contiguous()
             B, hw, nchw = 1, B * hw, 0
     elif a1.dim() == 2:

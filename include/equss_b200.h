@@ -236,7 +236,7 @@ int equss_knn_topk(const float* queries, int64_t nq, const float* db, int64_t n,
  *                                   model/blocks/module.py:20-44:  code = cluster1(x) + cluster2(x)
  *   One tcgen05 split-tf32 GEMM (fp32-level accuracy), called twice by the host mirror:
  *     out[r][o] = act( sum_{k<C1} A1[r][k] W[o][k] + sum_{k<C2} A2[r][k] W[o][C1+k] + bias[o] ),   r = b*hw + s
- *   a1: NCHW [B][C1][hw] (a1_nchw = 1, needs hw % 32 == 0; read in place, no permute) or flat [B*hw][C1];
+ *   a1: NCHW [B][C1][hw] (a1_nchw = 1, needs hw % 4 == 0; read in place, no permute) or flat [B*hw][C1];
  *   a2: flat [B*hw][C2] or NULL (C2 = 0);  w: [n_out][C1+C2] row-major (Conv2d weight (o, c, 1, 1), branches
  *   concatenated along c);  out: flat [B*hw][out_ld] -- the (pixel, channel) layout the PQ entry points take as
  *   EQUSS layout FLAT.  relu != 0 applies max(., 0) to the output (the hidden layer of cluster2).

@@ -50,9 +50,10 @@ SHAPES = [
     # (B, C, h, w, D)
     (2, 384, 40, 40, 1024),      # ViT-S features at the cocostuff27 eval grid, config-2 expanded dim
     (1, 768, 56, 56, 1024),      # ViT-B features at the cityscapes grid (config 4)
-    (4, 384, 28, 28, 512),       # config 1 (28 x 28 = 784 tokens, not a multiple of 32: flat-row path)
+    (4, 384, 28, 28, 512),       # config 1 (28 x 28 = 784 tokens, not a multiple of 32: one 3-D TMA box per 32-pixel block)
+    (2, 48, 6, 6, 64),           # 36 tokens: ragged block zero-filled by the TMA unit, C = 3 stages of 16
     (3, 64, 8, 4, 72),           # one 32-pixel block per image, D not a multiple of 4 x 32
-    (1, 32, 5, 7, 33),           # odd everything: flat path, scalar stores
+    (1, 32, 5, 7, 33),           # 35 tokens (not a multiple of 4): NHWC copy + flat-row path, scalar stores
     (2, 96, 16, 18, 300),        # 288 tokens: partial 128-pixel tile inside every image, partial column tile
 ]
 
