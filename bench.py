@@ -172,8 +172,14 @@ def run_equss(args):
         raise SystemExit("bench.py needs a CUDA device: equss_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
+        # keep stdout for the one JSON line: NCCL prints its version banner on fd 1 from C code, so everything that
+        # writes to fd 1 during the run is sent to stderr and the JSON line goes to a duplicate of the real stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     c = CFG
     B, D, h, w, H, W, M, K, C = (c[k] for k in ("B", "D", "h", "w", "H", "W", "M", "K", "C"))
@@ -379,9 +385,24 @@ def run_equss(args):
                "h2d_bytes_per_step": 4 * N * D + 8 * P, "d2h_bytes_per_step": 2 * C * C * 8, "steps": n_e2e,
                "api": "PQGOProductQuantizerWrapper.forward + UnSegEvaluator.predict (fused UnSegMetrics buffers); H2D of batch i+1 overlaps compute of batch i on a copy stream"}
 
+    def finish_process():
+        """Multi-rank teardown.  CUDA graphs that captured NCCL collectives keep the communicator busy: destroying the
+        process group then deadlocked at 8 ranks (the JSON line was already out; torchrun never returned).  The train
+        workload therefore drops the graphs, meets at a barrier and leaves without running the NCCL destructor."""
+        if world <= 1:
+            return
+        if train:
+            nonlocal graphs
+            graphs = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_process()
         return
 
     peak, peak_src = _peaks()
@@ -426,9 +447,12 @@ def run_equss(args):
         "gpu_launches": int(l1 - l0) + (launches_per_graph * args.steps if (train and graphs is not None) else 0),
         "clocks": clocks,
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if json_fd is not None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line))
+        sys.stdout.flush()
+    finish_process()
 
 
 def main():
