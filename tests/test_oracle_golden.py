@@ -102,3 +102,55 @@ def test_histogram_percentiles_none_when_unreached():
     assert out == {"x-p10": None, "x-p50": None, "x-p90": None}
     out = O.histogram_percentiles(torch.tensor([100.0, 0, 0, 0]), "x")
     assert out["x-p10"] == 0.0 and out["x-p90"] == 0.0
+
+
+def test_expansion_head(golden_dir):
+    """oracle expansion_head == the reference SegmentationHead output stored by oracle/make_golden_head.py
+    (model/blocks/module.py:20-44), and the fp64 yardstick of the fixture is what the GPU test measures against."""
+    g = np.load(os.path.join(golden_dir, "expansion_head.npz"))
+    t = {k: torch.from_numpy(g[k]) for k in g.files}
+    args = (t["cluster1_0_weight"], t["cluster1_0_bias"], t["cluster2_0_weight"], t["cluster2_0_bias"],
+            t["cluster2_2_weight"], t["cluster2_2_bias"])
+    out = O.expansion_head(t["x"], *args)
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-5, atol=1e-6)
+    out64 = O.expansion_head(t["x"].double(), *[a.double() for a in args])
+    np.testing.assert_allclose(out64.numpy(), g["out_fp64"], rtol=1e-12, atol=1e-12)
+    assert float(np.abs(g["out"] - g["out_fp64"]).max() / np.abs(g["out_fp64"]).max()) < 1e-6
+
+
+def test_head_mirror_host_logic():
+    """Host side of the head mirror that needs no GPU: reference state_dict keys, the autograd path (PyTorch
+    convolutions on the same parameters) equals the oracle, the packed [W1 | W3] operand follows in-place updates,
+    channels-last activations are described as flat rows, and CUDA-only entry points refuse CPU tensors."""
+    from equss_b200 import _native as N
+    from equss_b200.head import SegmentationHead, _PackedHead
+    torch.manual_seed(3)
+    head = SegmentationHead(16, 24)
+    assert list(head.state_dict().keys()) == ["cluster1.0.weight", "cluster1.0.bias", "cluster2.0.weight",
+                                              "cluster2.0.bias", "cluster2.2.weight", "cluster2.2.bias"]
+    x = torch.randn(2, 16, 3, 5)
+    out = head(x)                                   # parameters require grad -> differentiable torch path, any device
+    sd = head.state_dict()
+    ref = O.expansion_head(x, *[sd[k] for k in sd])
+    torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-6)
+    out.sum().backward()
+    assert head.cluster1[0].weight.grad is not None
+    with torch.no_grad(), pytest.raises(N.EqussNativeError):
+        head(x)                                     # kernel path: no CPU fallback
+    pk = _PackedHead()
+    w13, b13 = pk.get(head.cluster1[0], head.cluster2[2])
+    assert w13.shape == (24, 32) and torch.equal(w13[:, :16], head.cluster1[0].weight.reshape(24, 16))
+    torch.testing.assert_close(b13, head.cluster1[0].bias + head.cluster2[2].bias)
+    assert pk.get(head.cluster1[0], head.cluster2[2])[0] is w13            # cached
+    with torch.no_grad():
+        head.cluster2[2].weight.add_(1.0)
+    w13b, _ = pk.get(head.cluster1[0], head.cluster2[2])
+    assert w13b is not w13 and torch.equal(w13b[:, 16:], head.cluster2[2].weight.reshape(24, 16))
+    # (B, D, h, w) view of NHWC memory == flat rows for the PQ kernels; NCHW-dense stays NCHW
+    z = torch.randn(2, 3, 5, 8).permute(0, 3, 1, 2)            # (2, 8, 3, 5), channels-last memory
+    assert N.is_channels_last(z)
+    zd, d, layout = N.zdesc_for(z, 4)
+    assert layout == "flat" and d == 2 and zd.n_pixels == 30 and zd.stride_s == 8 and zd.stride_c == 1
+    zd2, _, layout2 = N.zdesc_for(z.contiguous(), 4)
+    assert layout2 == "nchw" and zd2.stride_c == 15 and zd2.stride_s == 1
+    assert N.f32_dense(z) is z and N.f32_dense(z.contiguous(), like=z).stride() == z.stride()
