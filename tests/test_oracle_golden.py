@@ -154,3 +154,44 @@ def test_head_mirror_host_logic():
     zd2, _, layout2 = N.zdesc_for(z.contiguous(), 4)
     assert layout2 == "nchw" and zd2.stride_c == 15 and zd2.stride_s == 1
     assert N.f32_dense(z) is z and N.f32_dense(z.contiguous(), like=z).stride() == z.stride()
+
+
+def test_unseg_metrics_compute_host_side(tmp_path, monkeypatch):
+    """UnSegMetrics.compute / map_clusters (host side, no GPU): equal to the oracle for extra_classes == 0, and -- where
+    the reference checkout exists (the build container) -- equal to the unmodified model/metric.py on random confusion
+    matrices, with and without extra classes."""
+    import importlib.util
+    from equss_b200.metric import UnSegMetrics
+    monkeypatch.chdir(tmp_path)                       # compute() writes ./class_matrix/... like the reference
+    torch.manual_seed(0)
+    for hung in (True, False):
+        conf = torch.randint(0, 40, (7, 7))
+        m = UnSegMetrics(7, 0, hung, torch.device("cpu"))
+        m.confusion_matrix.copy_(conf)
+        got, ref = m.compute(prefix="t"), O.metrics_compute(conf, hung)
+        assert torch.equal(got["iou"], ref["iou"]) and torch.equal(got["accuracy"], ref["accuracy"])
+    with pytest.raises(ValueError):
+        UnSegMetrics(7, 2, False, torch.device("cpu"))
+    ref_file = os.path.join(os.environ.get("EQUSS_REFERENCE", "/root/reference"), "model", "metric.py")
+    if not os.path.exists(ref_file):
+        return
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(ref_file)))       # the reference imports utils.dist_utils
+    try:
+        spec = importlib.util.spec_from_file_location("ref_metric", ref_file)
+        ref_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_mod)
+    finally:
+        sys.path.pop(0)
+    for trial in range(20):
+        C = int(torch.randint(3, 10, (1,)))
+        extra = int(torch.randint(1, 4, (1,))) if trial % 2 else 0
+        conf = torch.randint(0, 50, (C + extra, C))
+        a = UnSegMetrics(C, extra, True, torch.device("cpu"))
+        b = ref_mod.UnSegMetrics(C, extra, True, torch.device("cpu"))
+        a.confusion_matrix.copy_(conf); b.confusion_matrix.copy_(conf)
+        ra, rb = a.compute(prefix="t"), b.compute(prefix="t")
+        assert torch.equal(ra["iou"], rb["iou"]) and torch.equal(ra["accuracy"], rb["accuracy"])
+        assert torch.equal(a.histogram, b.histogram)
+        ids = torch.randint(0, C + extra, (3, 4))
+        assert torch.equal(a.map_clusters(ids), b.map_clusters(ids))
