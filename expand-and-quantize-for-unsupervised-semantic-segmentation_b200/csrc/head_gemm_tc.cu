@@ -345,15 +345,15 @@ extern "C" int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float
   }
   CUresult c2 = (C2 > 0) ? make2d(&ta2, a2, rows, C2, kBM) : CUDA_SUCCESS;
   if (C2 == 0) ta2 = ta1;
-  const int waste256_ = (n_out + 255) / 256 * 256 - n_out, waste192_ = (n_out + 191) / 192 * 192 - n_out;
-  CUresult c3 = make2d(&tw, w, n_out, K, (waste192_ < waste256_) ? 192 : 256);
+  // 192-column tiles when they waste fewer columns than 256-column tiles (e.g. n_out = 384: 2 x 192 instead of 2 x 256)
+  const int waste256 = (n_out + 255) / 256 * 256 - n_out, waste192 = (n_out + 191) / 192 * 192 - n_out;
+  const int bn = (waste192 < waste256) ? 192 : 256;
+  CUresult c3 = make2d(&tw, w, n_out, K, bn);
   EQUSS_REQUIRE(c1 == CUDA_SUCCESS && c2 == CUDA_SUCCESS && c3 == CUDA_SUCCESS, EQUSS_ERR_CUDA,
                 "cuTensorMapEncodeTiled failed (%d, %d, %d)", (int)c1, (int)c2, (int)c3);
   Params p;
   p.n_images = B; p.hw = hw; p.tiles_per_image = (hw + kBM - 1) / kBM;
-  // 192-column tiles when they waste fewer columns than 256-column tiles (e.g. n_out = 384: 2 x 192 instead of 2 x 256)
-  const int waste256 = (n_out + 255) / 256 * 256 - n_out, waste192 = (n_out + 191) / 192 * 192 - n_out;
-  p.bn = (waste192 < waste256) ? 192 : 256;
+  p.bn = bn;
   p.n_out = n_out; p.n_tiles_n = (n_out + p.bn - 1) / p.bn;
   p.kc1 = C1 / kKC; p.kc2 = C2 / kKC;
   p.a1_nchw = a1_mode; p.relu = relu ? 1 : 0;
