@@ -1,0 +1,60 @@
+"""Rare host-side maintenance paths of the PQ head that depend on the HOST random number generators and therefore
+stay in Python: dead-code restart and most-used-code splitting.
+
+They are written once here and shared by every quantiser flavour (the reference repeats them per class:
+model/quantizer.py:73-103,298-381; dino_pqgo.py:546-577; dino_new_vq.py:293-325,516-535).  The random draws are made
+with the same generators, in the same order and with the same arguments as the reference, so a seeded run
+replaces the same codes by the same rows (tests/test_gpu_variants.py::test_restart_paths).
+"""
+from __future__ import annotations
+
+import random
+from typing import List, Tuple, Union
+
+import torch
+
+__all__ = ["draw_restart", "split_codes"]
+
+
+@torch.no_grad()
+def draw_restart(count: torch.Tensor, rows: torch.Tensor) -> Tuple[Union[torch.Tensor, List[int]], torch.Tensor]:
+    """Pick replacement rows for the codes nobody selected.
+
+    count: (K,) selections of each code in this step;  rows: (n, d) candidate rows (z or z_norm, per variant).
+    Returns (dead code ids, replacement rows).  One ``random.shuffle`` of range(n) decides which rows are used; when
+    there are more dead codes than rows, a second shuffle decides which dead codes are served
+    (model/quantizer.py:298-319)."""
+    n_rows = rows.shape[0]
+    dead = torch.nonzero(count == 0, as_tuple=True)[0]
+    perm = list(range(n_rows))
+    random.shuffle(perm)
+    n_dead = int(dead.numel())
+    if n_dead > n_rows:
+        served = dead.tolist()
+        random.shuffle(served)
+        return served[:n_rows], rows[perm]
+    return dead, rows[perm[:n_dead]]
+
+
+@torch.no_grad()
+def split_codes(count: torch.Tensor, ema_count: torch.Tensor, weight: torch.Tensor, weight_avg: torch.Tensor,
+                sigma: float = 0.02) -> int:
+    """Give every dead code half of a busy code (model/quantizer.py:330-381), in place on the EMA state.
+
+    The j-th dead code (in a random order drawn with ``torch.randperm``) is paired with the j-th most used code
+    (by EMA count).  The pair shares the busy code's EMA count and running sum in halves, and their vectors
+    become ``w + e`` (dead) and ``w - e`` (busy) with ``e ~ N(0, sigma^2)``.  Returns the number of codes replaced."""
+    dead = torch.nonzero(count == 0, as_tuple=True)[0]
+    n = int(dead.numel())
+    if n == 0:
+        return 0
+    dead = dead[torch.randperm(n)]             # CPU generator, like the reference (:340)
+    busy = torch.argsort(ema_count, dim=0, descending=True)[:n]
+    jitter = sigma * torch.randn(n, weight.shape[1], dtype=weight.dtype, device=weight.device)
+    w_busy, half_cnt, half_avg = weight[busy], ema_count[busy] / 2.0, weight_avg[busy] / 2.0
+    # dead codes first, busy codes second: a code that is both (all codes dead) ends up with the busy value
+    for ids, w_new in ((dead, w_busy + jitter), (busy, w_busy - jitter)):
+        weight[ids] = w_new
+        ema_count[ids] = half_cnt
+        weight_avg[ids] = half_avg
+    return n

@@ -35,6 +35,7 @@ EXPORTS = [
     "equss_probe_image_bytes", "equss_probe_build_image", "equss_probe_logits_tc_supported", "equss_probe_logits_tc",
     "equss_knn_workspace_bytes", "equss_knn_topk",
     "equss_head_gemm_supported", "equss_head_gemm",
+    "equss_pq_soft_stats_supported", "equss_pq_soft_stats", "equss_channel_moments",
 ]
 
 
@@ -124,6 +125,12 @@ def _declare(L: C.CDLL) -> None:
     L.equss_head_gemm_supported.argtypes = [i32, i32, i32, i32]
     L.equss_head_gemm.restype = i32
     L.equss_head_gemm.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, i32, i32, vp, i64, vp]
+    L.equss_pq_soft_stats_supported.restype = i32
+    L.equss_pq_soft_stats_supported.argtypes = [i32, i32]
+    L.equss_pq_soft_stats.restype = i32
+    L.equss_pq_soft_stats.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp]
+    L.equss_channel_moments.restype = i32
+    L.equss_channel_moments.argtypes = [vp, zp, vp, vp]
     L.equss_probe_argmax_confusion.restype = i32
     L.equss_probe_argmax_confusion.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32,
                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32),
@@ -162,6 +169,12 @@ def require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
             raise EqussNativeError(f"tensors on different devices: {t.device} vs {dev}")
     if dev is None:
         raise EqussNativeError("no tensor given")
+    # kernels are launched on the CURRENT device's context (stream handle, SM count, function attributes): a tensor
+    # on another device would be launched against the wrong context
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        raise EqussNativeError(
+            f"tensor lives on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; call "
+            "torch.cuda.set_device() (one process per GPU) or wrap the call in `with torch.cuda.device(...)`")
     return dev
 
 

@@ -3,19 +3,25 @@ the inline ``Codebook`` / ``EMACodebook`` / ``ProductQuantizerWrapper`` copies i
 (V5, the ``train.py`` path), ``model/dino_new_vq.py`` (V4, the ``train_vq.py`` path) and
 ``model/dino_pqgo_cls.py`` (V6).  They differ from ``model/quantizer.py`` in: NCHW input, the quantised
 rows come from the RAW codebook, the soft assignment is divided by ``jsd_ts``, the loss keys, and the
-return tuples.  Host-RNG research flags (pq_dropout, gumbel, weighted-sum, k-means / restart init) are
-not part of the accelerated path.
+return tuples.  One ``Codebook`` class serves the three files; ``variant`` selects the file it stands for:
+
+  variant     forward(...)          returns                                  vq-loss                  restart rows
+  "pqgo"      (z, z_pos)            q, out, prob (b,h,w,K), idx (b,h,w)     book*cb + beta*commit    z_norm
+  "new_vq"    (z, i, it)            q, out, prob (n,K)  (+ jsd, entropy)    cb + beta*commit         raw z
+  "pqgo_cls"  (z)                   q, out, prob (b,h,w,K), idx (n,)        cb + beta*commit         z_norm
+
+Host-RNG research flags (pq_dropout, gumbel, weighted-sum, k-means init) are not part of the accelerated path.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F  # noqa
 
 from . import _pq_core as core
 from . import ops
+from ._host_paths import draw_restart
 from .dist_utils import all_reduce_tensor
 from .quantizer import EmbeddingEMA
 
@@ -24,23 +30,31 @@ __all__ = ["Codebook", "EMACodebook", "PQGOProductQuantizerWrapper", "NewVQProdu
 
 
 class EntropyLoss(nn.Module):
-    """model/loss.py:490-505."""
+    """model/loss.py:490-505: the NEGATIVE entropy of the batch-averaged assignment, sum_k a_k log(a_k + 1e-8) with
+    a = mean over rows of ``p``; the second argument is ignored, as in the reference."""
 
-    def forward(self, p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
-        avg_p = p.mean(0)
-        return -torch.sum(-avg_p * torch.log(avg_p + 1e-8), dim=-1)
+    def forward(self, p: torch.Tensor, q: Optional[torch.Tensor] = None) -> torch.Tensor:
+        a = p.mean(dim=0)
+        return torch.sum(a * torch.log(a + 1e-8), dim=-1)
 
 
 class JSDLoss(nn.Module):
-    """model/loss.py:508-525."""
+    """model/loss.py:508-525: Jensen-Shannon divergence of two row-stochastic matrices with the reference's 1e-6
+    smoothing, averaged over rows ("batchmean")."""
 
-    def __init__(self, reduction="batchmean"):
+    def __init__(self, reduction: str = "batchmean"):
         super().__init__()
-        self.kl = nn.KLDivLoss(reduction=reduction, log_target=True)
+        if reduction != "batchmean":
+            raise ValueError("JSDLoss mirrors the reference's batchmean reduction only")
 
-    def forward(self, p: torch.Tensor, q: torch.Tensor):
-        m = (0.5 * (p + q).add(1e-6)).log()
-        return 0.5 * (self.kl(m, p.add(1e-6).log()) + self.kl(m, q.add(1e-6).log()))
+    def forward(self, p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+        lo, hi = torch.aminmax(torch.stack([p.detach().amin(), p.detach().amax(), q.detach().amin(), q.detach().amax()]))
+        if lo < 0.0 or hi > 1.0:
+            raise ValueError(f"min, max of the inputs : {float(lo)}, {float(hi)}")        # loss.py:519-521
+        ps, qs = p + 1e-6, q + 1e-6
+        log_mix = torch.log(0.5 * (p + q + 1e-6))
+        kl = (ps * (torch.log(ps) - log_mix)).sum() + (qs * (torch.log(qs) - log_mix)).sum()
+        return 0.5 * kl / p.shape[0]
 
 
 def _unsupported(**flags) -> None:
@@ -50,21 +64,24 @@ def _unsupported(**flags) -> None:
 
 
 class Codebook(nn.Module):
-    """Learned codebook, model/dino_pqgo.py:460-705 (same class in dino_new_vq.py:462-671 and
-    dino_pqgo_cls.py:191-405 modulo the forward arity).  ``forward(z, z_pos=None)``."""
+    """Learned codebook, model/dino_pqgo.py:460-705, dino_new_vq.py:462-671, dino_pqgo_cls.py:191-405."""
 
     def __init__(self, num_codebook_vectors: int, latent_dim: int, beta=0.25, book=1.0, normalize: str = "none",
                  use_restart: bool = False, use_split: bool = False, use_weighted_sum: bool = False,
                  use_gumbel: bool = False, need_initialized: str = "none", pq_dropout: float = 0.0, jsd_ts: float = 1.0,
-                 num_query: int = 3, num_pos: int = 10):
+                 num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
         _unsupported(use_weighted_sum=use_weighted_sum, use_gumbel=use_gumbel, pq_dropout=pq_dropout > 0.0,
-                     use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal"))
+                     use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand"))
+        if variant not in ("pqgo", "new_vq", "pqgo_cls"):
+            raise ValueError(f"unknown Codebook variant {variant}")
+        self.variant = variant
         self.latent_dim, self.beta, self.book = latent_dim, beta, book
         self.num_codebook_vectors = num_codebook_vectors
         self.embedding = nn.Embedding(num_codebook_vectors, latent_dim)
         self.embedding.weight.data.uniform_(-1.0 / num_codebook_vectors, 1.0 / num_codebook_vectors)
         self.vq_count = torch.zeros(self.num_codebook_vectors)
+        self.update_indices = self.update_candidates = None
         self.normalize = normalize
         if normalize == "z_trainable":
             self.z_mean = nn.Parameter(torch.zeros(self.latent_dim))
@@ -73,33 +90,70 @@ class Codebook(nn.Module):
         self.need_initialized = need_initialized
         self.jsd_ts = jsd_ts
 
-    def forward(self, z: torch.Tensor, z_pos: Optional[torch.Tensor] = None):
-        q, out, prob, idx = _codebook_group_forward([self], z)
-        return q, out, prob[0], idx[0]
+    @torch.no_grad()
+    def prepare_restart(self, vq_current_count: torch.Tensor, z_flat: torch.Tensor) -> None:
+        self.update_indices, self.update_candidates = draw_restart(vq_current_count, z_flat)
+
+    @torch.no_grad()
+    def restart(self) -> None:
+        """dino_pqgo.py:572-577: overwrite the drawn dead codes, clear the exact counter."""
+        if self.update_indices is None or self.update_candidates is None:
+            return
+        self.embedding.weight.data[self.update_indices] = self.update_candidates.float()
+        self.vq_count.fill_(0)
+        self.update_indices = self.update_candidates = None
+
+    def forward(self, z: torch.Tensor, *args, **kwargs):
+        """Arity follows the variant (see module docstring); extra arguments (z_pos / i / it) are not used by the
+        arithmetic -- the reference's second pass over ``z_pos`` (dino_pqgo.py:650-656,700) produces nothing that
+        leaves the function."""
+        q, out, probs, idxs = _codebook_group_forward([self], z)
+        if self.variant == "new_vq":
+            B, D, h, w = z.shape
+            return q, out, probs[0].reshape(B * h * w, -1)
+        if self.variant == "pqgo_cls":
+            return q, out, probs[0], idxs[0].reshape(-1)
+        return q, out, probs[0], idxs[0]
+
+
+def _init_codebooks(mods: List[Codebook], z: torch.Tensor, d: int) -> None:
+    """First-training-call initialisation (dino_pqgo.py:589-609): "rand" draws K rows of z, "uni" / "normal" re-draw
+    the embedding with Xavier; k-means init is not offered (sklearn on the host)."""
+    zf = None
+    for i, q in enumerate(mods):
+        if q.need_initialized == "rand":
+            if zf is None:
+                zf = z.detach().permute(0, 2, 3, 1).reshape(-1, z.shape[1])
+            q.vq_count = q.vq_count.to(z.device)
+            q.prepare_restart(torch.zeros(q.num_codebook_vectors, dtype=torch.long, device=z.device), zf[:, i * d:(i + 1) * d])
+            q.restart()
+        elif q.need_initialized == "uni":
+            nn.init.xavier_uniform_(q.embedding.weight)
+        elif q.need_initialized == "normal":
+            nn.init.xavier_normal_(q.embedding.weight)
+        q.need_initialized = "none"
 
 
 def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bool = True):
-    """dino_pqgo.Codebook.forward for M subspaces at once.  Returns (z_q NCHW, outputs, [prob_i (B,h,w,K)],
-    [idx_i (B,h,w)])."""
+    """Codebook.forward of the three inline variants for M subspaces at once.  Returns (z_q NCHW, outputs,
+    [prob_i (B,h,w,K)] or [None], [idx_i (B,h,w)])."""
     q0 = mods[0]
-    M, K, mode = len(mods), q0.num_codebook_vectors, q0.normalize
+    M, K, mode, variant = len(mods), q0.num_codebook_vectors, q0.normalize, q0.variant
     B, D, h, w = z.shape
     d = D // M
     training = q0.training
     if q0.need_initialized != "none" and training:
-        for q in mods:
-            if q.need_initialized == "uni":
-                nn.init.xavier_uniform_(q.embedding.weight)
-            elif q.need_initialized == "normal":
-                nn.init.xavier_normal_(q.embedding.weight)
-            q.need_initialized = "none"
+        _init_codebooks(mods, z, d)
     codebook = torch.stack([q.embedding.weight for q in mods])
     norm_a = norm_b = None
     if mode == "z_trainable":
         norm_a = torch.cat([q.z_mean for q in mods])
         norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
     cbn = core.normalize_codebook(codebook, mode, ema_style=True)                 # dino_pqgo.py:613-641
-    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, codebook, mode, norm_a, norm_b, want_prob=want_prob,
+    need_soft_stats = variant == "new_vq"
+    grad_path = core._wants_grad(z, codebook, norm_a, norm_b)
+    make_prob = want_prob or (need_soft_stats and grad_path)
+    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, codebook, mode, norm_a, norm_b, want_prob=make_prob,
                                                           temperature=q0.jsd_ts)   # :646-665 (raw embedding gathered)
     output: Dict[str, torch.Tensor] = {}
     if training:
@@ -108,12 +162,30 @@ def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bo
             count = all_reduce_tensor(packed[:, :, d].contiguous(), op="sum")         # :672-673
             for i, q in enumerate(mods):
                 q.vq_count = q.vq_count.to(z.device) + count[i]                       # :675
+            if q0.use_restart:                                                        # :677-679
+                rows = z.detach().float().permute(0, 2, 3, 1).reshape(B * h * w, M, d)
+                if variant != "new_vq":                                               # pqgo / pqgo_cls draw from z_norm
+                    rows = core._normalize_rows(rows, mode, norm_a.detach() if norm_a is not None else None,
+                                                norm_b.detach() if norm_b is not None else None)
+                for i, q in enumerate(mods):
+                    q.prepare_restart(count[i], rows[:, i])
+                    q.restart()
             output["codebook-usage"] = ((K - (count == 0).sum(dim=1).float()) / K).mean()   # :681-682
-    output["vq-loss"] = (q0.book * mse_cb + q0.beta * mse_commit).mean()              # :685-687
-    n = B * h * w
+    book = q0.book if variant == "pqgo" else 1.0
+    output["vq-loss"] = (book * mse_cb + q0.beta * mse_commit).mean()                 # :685-687
+    if need_soft_stats:                                                               # dino_new_vq.py:666-668
+        output["jsd"], output["entropy"] = _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K)
     idx64 = idx.long()
-    probs = [prob.view(B, h, w, M, K)[:, :, :, i, :] for i in range(M)] if prob is not None else [None] * M
+    probs = [prob.view(B, h, w, M, K)[:, :, :, i, :] for i in range(M)] if (prob is not None and want_prob) else [None] * M
     return out, output, probs, [idx64[i].view(B, h, w) for i in range(M)]
+
+
+def _soft_stats(z, cbn, mode, norm_a, norm_b, jsd_ts, prob, M, K):
+    """jsd / entropy of the soft assignment (dino_new_vq.py:447-450): from the materialised differentiable tensor
+    when there is one, else by the fused kernel that never writes the N x K*M probabilities."""
+    if prob is not None:
+        return core.soft_assignment_stats(prob, M, K)
+    return ops.pq_soft_stats(z, cbn.detach(), None, mode, norm_a, norm_b, jsd_ts)
 
 
 class EMACodebook(nn.Module):
@@ -124,23 +196,37 @@ class EMACodebook(nn.Module):
                  use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "none",
                  pq_dropout: float = 0.0, jsd_ts: float = 1.0, **_ignored):
         super().__init__()
-        _unsupported(use_weighted_sum=use_weighted_sum, pq_dropout=pq_dropout > 0.0, use_restart=use_restart,
-                     need_initialized=need_initialized not in ("none",))
+        _unsupported(use_weighted_sum=use_weighted_sum, pq_dropout=pq_dropout > 0.0,
+                     need_initialized=need_initialized not in ("none", "rand", "uni", "normal"))
         self.latent_dim, self.beta = latent_dim, beta
         self.num_codebook_vectors = num_codebook_vectors
         self.codebook = EmbeddingEMA(num_codebook_vectors, latent_dim, decay=0.99, eps=1.0e-5)
         self.register_buffer("vq_count", torch.zeros(num_codebook_vectors), persistent=False)
+        self.update_indices = self.update_candidates = None
         self.normalize = normalize
         if normalize == "z_trainable":
             self.z_mean = nn.Parameter(torch.zeros(self.latent_dim))
             self.z_log_var = nn.Parameter(torch.zeros(self.latent_dim))
+        self.use_restart = use_restart
         self.need_initialized = need_initialized
         self.jsd_loss, self.entropy_loss = JSDLoss(), EntropyLoss()
         self.jsd_ts = jsd_ts
 
+    @torch.no_grad()
+    def prepare_restart(self, vq_current_count: torch.Tensor, z_flat: torch.Tensor) -> None:
+        self.update_indices, self.update_candidates = draw_restart(vq_current_count, z_flat)
+
+    @torch.no_grad()
+    def restart(self) -> None:
+        """dino_new_vq.py:317-325."""
+        if self.update_indices is None or self.update_candidates is None:
+            return
+        self.codebook.weight.data[self.update_indices] = self.update_candidates
+        self.codebook.reset()
+        self.update_indices = self.update_candidates = None
+
     def forward(self, z: torch.Tensor, i: int = 0, it: int = 0):
-        q, out, prob = _ema_codebook_group_forward([self], z)
-        return q, out, prob
+        return _ema_codebook_group_forward([self], z)
 
 
 def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_prob: bool = True):
@@ -148,6 +234,17 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
     M, K, mode = len(mods), q0.num_codebook_vectors, q0.normalize
     B, D, h, w = z.shape
     d = D // M
+    training = q0.training
+    if q0.need_initialized != "none" and training:                                  # :336-364
+        zf = z.detach().permute(0, 2, 3, 1).reshape(-1, D)
+        for i, q in enumerate(mods):
+            if q.need_initialized == "rand":
+                q.prepare_restart(torch.zeros(K, dtype=torch.long, device=z.device), zf[:, i * d:(i + 1) * d])
+                q.restart()
+            elif q.need_initialized in ("uni", "normal"):
+                init = nn.init.xavier_uniform_ if q.need_initialized == "uni" else nn.init.xavier_normal_
+                init(q.codebook.weight); init(q.codebook.weight_avg)
+            q.need_initialized = "none"
     weight = torch.stack([q.codebook.weight for q in mods])
     norm_a = norm_b = None
     if mode == "z_trainable":
@@ -155,11 +252,12 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
         norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
     with torch.no_grad():
         cbn = core.normalize_codebook(weight, mode, ema_style=True)
-        src = weight.clone()                                                        # raw codebook gathered (:403)
-    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=True,
+        src = weight.clone()                             # raw codebook gathered, as it is BEFORE this step's update (:403)
+    grad_path = core._wants_grad(z, norm_a, norm_b)
+    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob or grad_path,
                                                      temperature=q0.jsd_ts)
     output: Dict[str, torch.Tensor] = {}
-    if q0.training:
+    if training:
         with torch.no_grad():
             packed = core.ema_statistics(z, idx, K)                                 # :408-413 (raw z sums)
             exact = torch.stack([q.vq_count.to(z.device) for q in mods]).contiguous()
@@ -170,17 +268,15 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
             for i, q in enumerate(mods):
                 q.vq_count = exact[i]; q.codebook.vq_count.copy_(vqc[i])
                 q.codebook.weight_avg.copy_(wavg[i]); q.codebook.weight.copy_(wnew[i])
+            if q0.use_restart:                                                      # :424-425 (drawn, applied by restart())
+                rows = z.detach().float().permute(0, 2, 3, 1).reshape(B * h * w, M, d)
+                for i, q in enumerate(mods):
+                    q.prepare_restart(packed[i, :, d], rows[:, i])
             output["codebook-usage"] = ((K - unused.float()) / K).mean()            # :431-432
     output["vq-loss"] = q0.beta * mse_commit.mean()                                 # :435-436
     output["codebook-sum"] = torch.sum(torch.abs(torch.stack([q.codebook.weight for q in mods]))) / M
-    # JSD / entropy between the two halves of the batch (:447-450), per subspace then averaged
-    n = B * h * w
-    pv = prob.view(n, M, K)
-    p1, p2 = torch.chunk(pv, chunks=2, dim=0)
-    jsd = torch.stack([q0.jsd_loss(p1[:, i], p2[:, i]) for i in range(M)]).mean()
-    ent = torch.stack([q0.entropy_loss(p1[:, i], p2[:, i]) for i in range(M)]).mean()
-    output["jsd"], output["entropy"] = jsd, ent
-    return out, output, prob
+    output["jsd"], output["entropy"] = _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K)   # :447-450
+    return out, output, (prob if want_prob else None)
 
 
 class _WrapperBase(nn.Module):
@@ -197,16 +293,19 @@ class PQGOProductQuantizerWrapper(_WrapperBase):
     """model/dino_pqgo.py:708-776: ``forward(z, z_pos=None, it=-1)`` ->
     (z_q, (z_split, [z_q_i], [idx_i (B,h,w)]), outputs, distance_prob (B,h,w,K*M))."""
 
+    variant = "pqgo"
+
     def __init__(self, num_pq: int, num_codebook: int, embed_dim: int, beta: float = 0.25, book: float = 1.0,
                  normalize: Optional[str] = None, decay: float = 0.99, eps: float = 1e-5, use_restart: bool = False,
                  use_split: bool = False, use_gumbel: bool = False, use_weighted_sum: bool = False,
                  update_norm: bool = True, need_initialized: str = "none", pq_dropout: float = 0.0,
                  jsd_ts: float = 1.0, num_query: int = 3, num_pos: int = 10, quantizer_cls=Codebook) -> None:
         super().__init__(num_pq, embed_dim)
+        extra = {"variant": self.variant} if quantizer_cls is Codebook else {}
         self.quantizers = nn.ModuleList([
             quantizer_cls(num_codebook, self.pq_dim, beta=beta, book=book, normalize=normalize, use_restart=use_restart,
                           use_split=use_split, use_weighted_sum=use_weighted_sum, need_initialized=need_initialized,
-                          pq_dropout=pq_dropout, jsd_ts=jsd_ts, num_query=num_query, num_pos=num_pos)
+                          pq_dropout=pq_dropout, jsd_ts=jsd_ts, num_query=num_query, num_pos=num_pos, **extra)
             for _ in range(self.num_pq)
         ])
 
@@ -227,31 +326,35 @@ class NewVQProductQuantizerWrapper(_WrapperBase):
                  normalize: Optional[str] = None, decay: float = 0.99, eps: float = 1e-5, use_restart: bool = False,
                  use_gumbel: bool = False, use_split: bool = False, use_weighted_sum: bool = False,
                  update_norm: bool = True, need_initialized: str = "none", pq_dropout: float = 0.0,
-                 jsd_ts: float = 1.0, quantizer_cls=EMACodebook) -> None:
+                 jsd_ts: float = 1.0, quantizer_cls=Codebook) -> None:
         super().__init__(num_pq, embed_dim)
+        extra = {"variant": "new_vq"} if quantizer_cls is Codebook else {}
         self.quantizers = nn.ModuleList([
             quantizer_cls(num_codebook, self.pq_dim, beta=beta, normalize=normalize, use_restart=use_restart,
                           use_weighted_sum=use_weighted_sum, need_initialized=need_initialized, pq_dropout=pq_dropout,
-                          jsd_ts=jsd_ts)
+                          jsd_ts=jsd_ts, **extra)
             for _ in range(self.num_pq)
         ])
 
     def forward(self, z: torch.Tensor, it: int = 0):
         qs = list(self.quantizers)
         if all(isinstance(q, EMACodebook) for q in qs):
-            return _ema_codebook_group_forward(qs, z)
-        z_q, outputs, probs, _ = _codebook_group_forward(qs, z)
+            return _ema_codebook_group_forward(qs, z, want_prob=self.materialize_prob)
+        z_q, outputs, probs, _ = _codebook_group_forward(qs, z, want_prob=self.materialize_prob)
+        if probs[0] is None:
+            return z_q, outputs, None
         B, D, h, w = z.shape
         K = qs[0].num_codebook_vectors
         return z_q, outputs, torch.cat([p.reshape(B * h * w, K) for p in probs], dim=-1)
 
 
 class PQGOClsProductQuantizerWrapper(PQGOProductQuantizerWrapper):
-    """model/dino_pqgo_cls.py:408-471: ``forward(z, it=-1)`` -> (z_q, outputs, distance_prob); the
-    per-subspace quantiser returns flat (n,) pseudo-label indices."""
+    """model/dino_pqgo_cls.py:408-471: ``forward(z, it=-1)`` -> (z_q, outputs, distance_prob (B,h,w,K*M),
+    pseudo_labels = [idx_i (n,)])."""
+
+    variant = "pqgo_cls"
 
     def forward(self, z: torch.Tensor, it: int = -1):
         z_q, outputs, probs, idxs = _codebook_group_forward(list(self.quantizers), z, want_prob=self.materialize_prob)
         prob = torch.cat(probs, dim=-1) if probs[0] is not None else None
-        self.pseudo_labels = [i.reshape(-1) for i in idxs]
-        return z_q, outputs, prob
+        return z_q, outputs, prob, [i.reshape(-1) for i in idxs]

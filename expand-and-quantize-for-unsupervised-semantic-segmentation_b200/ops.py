@@ -14,7 +14,7 @@ from . import _native as N
 
 __all__ = [
     "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
-    "pq_distance_prob", "usage_percentiles", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "pq_distance_prob", "pq_soft_stats", "channel_moments", "usage_percentiles", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
     "launch_count",
 ]
 
@@ -236,6 +236,52 @@ def pq_distance_prob(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optio
                                         N.ptr(na), N.ptr(nb), float(temperature), prob.data_ptr(), N.stream_ptr(dev))
     N.check(rc, "equss_pq_distance_prob")
     return prob
+
+
+def pq_soft_stats(z: torch.Tensor, codebook_norm: torch.Tensor, cnorm2: Optional[torch.Tensor] = None,
+                  normalize: Optional[str] = "l2", norm_a=None, norm_b=None, temperature: float = 1.0
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(jsd, entropy) of model/dino_new_vq.py:447-450 -- JSDLoss between the soft assignments of the two batch halves
+    and EntropyLoss of the first half's mean assignment (model/loss.py:490-525), each averaged over the subspaces --
+    computed by one fused kernel that never writes the N x (K*M) probabilities.  No autograd history."""
+    cb = N.f32c(codebook_norm.detach())
+    M, K, d = cb.shape
+    z, zd, dz, dev = _prep_z(z, M)
+    if dz != d:
+        raise ValueError(f"codebook sub-dim {d} does not match activation sub-dim {dz}")
+    if cnorm2 is None:
+        cnorm2 = pq_cnorm2(cb)
+    mode, na, nb = _norm_args(normalize, norm_a, norm_b, M * d, dev)
+    n = zd.n_pixels
+    if n % 2 != 0:
+        raise ValueError("JSD needs an even number of rows: the batch holds two views (model/dino_new_vq.py:447)")
+    L = N.lib()
+    if not L.equss_pq_soft_stats_supported(K, d):
+        from ._pq_core import soft_assignment_stats
+        return soft_assignment_stats(pq_distance_prob(z, cb, cnorm2, normalize, norm_a, norm_b, temperature), M, K)
+    acc = torch.zeros((M * (K + 1),), dtype=torch.float64, device=dev)
+    kl, ps = acc[:M], acc[M:].view(M, K)
+    rc = L.equss_pq_soft_stats(z.data_ptr(), zd, cb.data_ptr(), N.f32c(cnorm2).data_ptr(), M, K, d, mode, N.ptr(na),
+                               N.ptr(nb), float(temperature), kl.data_ptr(), ps.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_soft_stats")
+    half = n // 2
+    jsd = (0.5 * kl / half).mean().float()
+    avg = (ps / half).float()
+    ent = (avg * torch.log(avg + 1e-8)).sum(dim=-1).mean()
+    return jsd, ent
+
+
+def channel_moments(z: torch.Tensor) -> torch.Tensor:
+    """Per-channel mean and mean of squares of the activations, float32 [2, D], in one pass over z (flat (n, D) or
+    NCHW (B, D, h, w))  (model/quantizer.py:433-434)."""
+    dev = N.require_cuda(z)
+    N.ensure_device(dev)
+    z = N.f32_dense(z.detach())
+    zd, _, _ = N.zdesc_for(z, 1)
+    D = zd.dim
+    sums = torch.zeros((2, D), dtype=torch.float64, device=dev)
+    N.check(N.lib().equss_channel_moments(z.data_ptr(), zd, sums.data_ptr(), N.stream_ptr(dev)), "equss_channel_moments")
+    return (sums / max(zd.n_pixels, 1)).float()
 
 
 def probe_pack(wmat: torch.Tensor):

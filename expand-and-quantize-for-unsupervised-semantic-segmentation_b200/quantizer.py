@@ -15,7 +15,6 @@ visible to a caller are deliberate and small:
 """
 from __future__ import annotations
 
-import random
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -25,6 +24,7 @@ import torch.nn.functional as F  # noqa
 
 from . import _pq_core as core
 from . import ops
+from ._host_paths import draw_restart, split_codes
 from .dist_utils import all_reduce_tensor
 
 __all__ = ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper", "get_histogram_count"]
@@ -43,27 +43,15 @@ def _check_flags(use_gumbel: bool, use_weighted_sum: bool) -> None:
 
 
 class _RestartMixin:
-    """Dead-code restart shared by both quantiser flavours (model/quantizer.py:73-103, 298-328).
-    Rare host-side path: keeps the reference's use of Python's `random` so seeds behave the same."""
+    """Dead-code restart shared by both quantiser flavours (model/quantizer.py:73-103, 298-328); the draw itself
+    lives in _host_paths.draw_restart (Python's `random`, so seeds behave like the reference's)."""
 
     update_indices = None
     update_candidates = None
 
     @torch.no_grad()
     def prepare_restart(self, vq_current_count: torch.Tensor, z_flat: torch.Tensor) -> None:
-        n_data = z_flat.shape[0]
-        update_indices = torch.nonzero(vq_current_count == 0, as_tuple=True)[0]
-        n_update = len(update_indices)
-        z_indices = list(range(n_data))
-        random.shuffle(z_indices)
-        if n_update <= n_data:
-            z_indices = z_indices[:n_update]
-        else:
-            update_indices = update_indices.tolist()
-            random.shuffle(update_indices)
-            update_indices = update_indices[:n_data]
-        self.update_indices = update_indices
-        self.update_candidates = z_flat[z_indices]
+        self.update_indices, self.update_candidates = draw_restart(vq_current_count, z_flat)
 
 
 class VectorQuantizer(nn.Module, _RestartMixin):
@@ -142,17 +130,20 @@ class EmbeddingEMA(nn.Module):
         ops.ema_update(packed, self.decay, self.eps, self.vq_count.view(1, K), self.weight_avg.view(1, K, d),
                        self.weight.view(1, K, d))
 
-    # kept for API parity with the reference (quantizer.py:241-254)
+    # The three pieces of update() as separate calls, for API parity (quantizer.py:241-254); forward() never uses them.
+    def _decay_towards(self, state: torch.Tensor, observed: torch.Tensor) -> None:
+        torch.add(state.data * self.decay, observed, alpha=1 - self.decay, out=state.data)
+
     def vq_count_ema_update(self, vq_current_count) -> None:
-        self.vq_count.data.mul_(self.decay).add_(vq_current_count, alpha=1 - self.decay)
+        self._decay_towards(self.vq_count, vq_current_count)
 
     def weight_avg_ema_update(self, vq_current_sum) -> None:
-        self.weight_avg.data.mul_(self.decay).add_(vq_current_sum, alpha=1 - self.decay)
+        self._decay_towards(self.weight_avg, vq_current_sum)
 
     def weight_update(self) -> None:
-        n = self.vq_count.sum()
-        smoothed = (self.vq_count + self.eps) / (n + self.num_codebook * self.eps) * n
-        self.weight.data.copy_(self.weight_avg / smoothed.unsqueeze(1))
+        total = self.vq_count.sum()
+        laplace = (self.vq_count + self.eps) / (total + self.num_codebook * self.eps) * total
+        self.weight.data.copy_(self.weight_avg / laplace[:, None])
 
 
 class EMAVectorQuantizer(nn.Module, _RestartMixin):
@@ -192,24 +183,10 @@ class EMAVectorQuantizer(nn.Module, _RestartMixin):
     @torch.no_grad()
     def split(self, vq_current_count: torch.Tensor) -> int:
         """Replace unused codes by perturbed copies of the most used ones (quantizer.py:330-381)."""
-        update_indices = torch.nonzero(vq_current_count == 0, as_tuple=True)[0]
-        if len(update_indices) == 0:
-            return 0
-        n_update = len(update_indices)
-        update_indices = update_indices[torch.randperm(n_update, device=update_indices.device)]
-        total, weight, weight_avg = self.codebook.vq_count, self.codebook.weight, self.codebook.weight_avg
-        order = torch.sort(total, dim=0, descending=True)[1][:n_update]
-        total_c, weight_c, avg_c = total.clone(), weight.clone(), weight_avg.clone()
-        noise = torch.randn(n_update, self.embed_dim, dtype=weight.dtype, device=weight.device).mul_(0.02)
-        weight_c[update_indices] = weight[order] + noise
-        weight_c[order] = weight[order] - noise
-        total_c[update_indices] = total[order] / 2.0
-        total_c[order] = total[order] / 2.0
-        avg_c[update_indices] = weight_avg[order] / 2.0
-        avg_c[order] = weight_avg[order] / 2.0
-        total.copy_(total_c); weight.copy_(weight_c); weight_avg.copy_(avg_c)
-        self.vq_count.fill_(0)
-        return n_update
+        n = split_codes(vq_current_count, self.codebook.vq_count, self.codebook.weight, self.codebook.weight_avg)
+        if n:
+            self.vq_count.fill_(0)
+        return n
 
     @torch.no_grad()
     def _maybe_initialize(self, z_flat: torch.Tensor) -> None:
@@ -267,19 +244,27 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
     weight = _stack([q.codebook.weight for q in mods])
     norm_a = norm_b = None
     if mode == "z_trainable":
+        # quantizer.py:429-446: the std is taken BEFORE this step's running-statistics update, the mean is the buffer
+        # itself and already holds the updated value when z is normalised.
+        norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
         if training:
-            with torch.no_grad():     # running statistics of z (quantizer.py:432-444)
-                zm = all_reduce_tensor(z.mean(dim=0), op="mean")
-                zsq = all_reduce_tensor((z * z).mean(dim=0), op="mean")
-                logvar = (zsq - zm * zm).log()
+            with torch.no_grad():
+                # per-channel mean and mean of squares of z in ONE pass (K13) and ONE all-reduce of the [2, D] pair
+                # (the reference: two reductions + two all_reduce_tensor("mean") per subspace, :433-438).  It cannot
+                # ride in the packed EMA buffer: the assignment below depends on the updated mean.
+                mom = all_reduce_tensor(ops.channel_moments(z), op="mean")
+                logvar = (mom[1] - mom[0] * mom[0]).log()
                 for i, q in enumerate(mods):
-                    q.z_mean.data.mul_(q.decay).add_(zm[i * d:(i + 1) * d], alpha=1 - q.decay)
+                    q.z_mean.data.mul_(q.decay).add_(mom[0, i * d:(i + 1) * d], alpha=1 - q.decay)
                     q.z_log_var.data.mul_(q.decay).add_(logvar[i * d:(i + 1) * d], alpha=1 - q.decay)
         norm_a = torch.cat([q.z_mean for q in mods])
-        norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
     with torch.no_grad():
         cbn = core.normalize_codebook(weight, mode, ema_style=True)
-        src = cbn if q0.update_norm else weight.clone()
+        # the gather source must survive the in-place EMA update below until backward() has run: take a snapshot
+        # whenever it would alias the live codebook (mode "none" returns `weight` itself)
+        src = cbn if q0.update_norm else weight
+        if src.data_ptr() == weight.data_ptr():
+            src = src.clone()
     idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob)
     output: Dict[str, torch.Tensor] = {}
     if training:

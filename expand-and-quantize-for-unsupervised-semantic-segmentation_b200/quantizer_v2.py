@@ -71,7 +71,7 @@ def _v2_group_forward(mods, z: torch.Tensor, want_prob: bool = True):
     z_first = z[:, :, :, :].permute(0, 2, 3, 1).reshape(n, D)[:K]               # (K, D) view of the first K pixels
     src = torch.stack([F.normalize(z_first[:, i * d:(i + 1) * d], dim=1) for i in range(M)])   # [M, K, d], differentiable
     out, mse_commit, _ = core.PQGatherLoss.apply(z32.detach(), src.detach(), idx, "l2", None, None)
-    gathered = torch.stack([src[i][idx[i].long()] for i in range(M)], dim=0)    # [M, n, d] keeps the reference's graph
+    gathered = torch.gather(src, 1, idx.long().unsqueeze(-1).expand(M, n, d))   # [M, n, d] keeps the reference's graph
     q = gathered.permute(1, 0, 2).reshape(B, h, w, D).permute(0, 3, 1, 2).contiguous()
     output: Dict[str, torch.Tensor] = {}
     if q0.training:

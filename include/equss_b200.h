@@ -177,6 +177,32 @@ int equss_pq_distance_prob(const float* z, const equss_zdesc* zd,
                            float temperature, float* prob, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K2b fused consumers of the soft assignment   replaces model/dino_new_vq.py:447-450, i.e.
+ *     JSDLoss (model/loss.py:508-525) and EntropyLoss (model/loss.py:490-505) applied to
+ *     torch.chunk(softmax(-distance / T), 2, dim=0), WITHOUT materialising the N x (K*M) probabilities.
+ *   With p = rows [0, N/2) and q = rows [N/2, N) of the soft assignment of subspace m:
+ *     kl_sum[m]      += sum_{n,k} (p+e) log((p+e)/mix) + (q+e) log((q+e)/mix),  mix = (p+q+e)/2, e = 1e-6
+ *                       (jsd_m = 0.5 * kl_sum[m] / (N/2), KLDivLoss "batchmean")
+ *     prob_sum[m][k] += sum_n p[n][k]          (entropy_m = sum_k a log(a + 1e-8), a = prob_sum / (N/2))
+ *   Both outputs are fp64, caller-zeroed.  N must be even; K <= 256, d in {8,16,32,64}
+ *   (equss_pq_soft_stats_supported); other shapes: materialise with equss_pq_distance_prob.
+ * ------------------------------------------------------------------------------------------- */
+int equss_pq_soft_stats_supported(int K, int d);
+int equss_pq_soft_stats(const float* z, const equss_zdesc* zd,
+                        const float* codebook_norm, const float* cnorm2, int M, int K, int d,
+                        int norm_mode, const float* norm_a, const float* norm_b,
+                        float temperature, double* kl_sum, double* prob_sum, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K13 per-channel moments of the activations   replaces model/quantizer.py:433-434 (torch.mean(z, 0) and
+ *     torch.mean(z*z, 0), evaluated per subspace) for the running statistics of the "z_trainable" mode.
+ *   sums[0][c] += sum_n z[n][c],  sums[1][c] += sum_n z[n][c]^2     sums: fp64 [2][D], caller-zeroed.
+ *   One pass over z for all D = M*d channels; the caller divides by N and all-reduces the [2][D] pair once
+ *   (the reference issues two all_reduce_tensor("mean") calls per subspace, :437-438).
+ * ------------------------------------------------------------------------------------------- */
+int equss_channel_moments(const float* z, const equss_zdesc* zd, double* sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K8  cluster / linear probe at label resolution   replaces model/evaluator.py:53-54,67-70,95-106
  *   step 1 (token resolution):  logits[b][s][j] = <feat[b,:,s], w[j,:]> + bias[j]
  *           feat: NCHW (B, D, h, w);  wmat_t: K-major weights [D][C_pad] (column j = probe channel j: columns

@@ -98,14 +98,33 @@ class EmaState:
 
 def ema_vq_forward(z_flat: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: Optional[str],
                    beta: float = 0.25, training: bool = True, update_norm: bool = True,
-                   allreduce=None) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
-    """One subspace of EMAVectorQuantizer.forward (model/quantizer.py:383-542; l2/z_norm/none modes,
-    top-1 assignment, no restart/split/gumbel).  ``allreduce`` stands for all_reduce_tensor(:490-491).
+                   allreduce=None, allreduce_mean=None, z_mean: Optional[torch.Tensor] = None,
+                   z_log_var: Optional[torch.Tensor] = None, temperature: float = 1.0, ema_decay: float = 0.99
+                   ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """One subspace of EMAVectorQuantizer.forward (model/quantizer.py:383-542; all four normalisation modes,
+    top-1 assignment, no restart/split/gumbel).  ``allreduce`` stands for all_reduce_tensor(:490-491),
+    ``allreduce_mean`` for the op="mean" calls of the z_trainable statistics (:437-438); ``z_mean`` /
+    ``z_log_var`` are that mode's buffers, updated in place in training.
     Returns (z_q_ste, outputs, distance_prob, indices)."""
-    z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize)
+    if normalize == "z_trainable":
+        # NB (:429-446): the std is evaluated BEFORE the running statistics are updated, the mean is the
+        # buffer itself and therefore already holds the updated value when z is normalised.
+        std_before = z_log_var.exp().sqrt()                                       # :430
+        if training:                                                              # :432-444 running stats of z
+            m0 = torch.mean(z_flat, dim=0)
+            sq0 = torch.mean(z_flat * z_flat, dim=0)
+            if allreduce_mean is not None:
+                m0, sq0 = allreduce_mean(m0), allreduce_mean(sq0)
+            z_mean.mul_(ema_decay).add_(m0, alpha=1 - ema_decay)
+            z_log_var.mul_(ema_decay).add_((sq0 - m0 * m0).log(), alpha=1 - ema_decay)
+        z_norm = (z_flat - z_mean) / (std_before + 1e-5)                          # :446
+        cs, cm = torch.std_mean(state.weight, dim=0)                              # :449
+        cb_norm = (state.weight - cm) / (cs + 1e-5)
+    else:
+        z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize)
     dist = sq_distance(z_norm, cb_norm)
     idx = torch.argmin(dist, dim=1)                                               # :467
-    prob = F.softmax(-dist * 1.0, dim=1)                                          # :468
+    prob = F.softmax(-dist / temperature, dim=1)                                  # :468 / dino_new_vq.py:398
     src = cb_norm if update_norm else state.weight                                # :473-476
     q = F.embedding(idx, src)
     out: Dict = {}
@@ -183,6 +202,136 @@ def v2_ema_vq_forward(z_nchw: torch.Tensor, embeddings: torch.Tensor, beta: floa
     commitment = F.mse_loss(z_norm, emb)
     out = {"commitment-loss": commitment, "loss": beta * commitment, "codebook-sum": torch.sum(torch.abs(embeddings))}
     return emb.view(b, h, w, -1).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+def v2_ema_vq_train_step(z_nchw: torch.Tensor, embeddings: torch.Tensor, N: torch.Tensor, z_avg: torch.Tensor,
+                         beta: float = 0.25, decay: float = 0.99, eps: float = 1e-5
+                         ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """Training-mode quantizer_v2.EMAVectorQuantizer.forward (model/quantizer_v2.py:253-308): as the eval
+    function above, then the EMA update from sums of **z_norm** (:279-281); the two all_reduce_tensor calls
+    discard their result (:283-284), so the statistics are per rank.  Buffers are updated in place; the
+    returned ``codebook-sum`` is evaluated after the update (:304)."""
+    b, d, h, w = z_nchw.shape
+    K = embeddings.shape[0]
+    flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)
+    z_norm, cb_norm = F.normalize(flat, dim=1), F.normalize(embeddings, dim=1)
+    dist = sq_distance(z_norm, cb_norm)
+    prob = F.softmax(-dist * 1.0, dim=1)
+    idx = torch.argmin(dist, dim=1)
+    emb = F.embedding(idx, z_norm)                                                # :274
+    onehot = F.one_hot(idx, K).to(z_nchw.dtype)
+    N.mul_(decay).add_(onehot.sum(dim=0), alpha=1 - decay)                        # :286
+    z_avg.mul_(decay).add_(torch.matmul(onehot.t(), z_norm), alpha=1 - decay)     # :287
+    n = N.sum()
+    weights = (N + eps) / (n + K * eps) * n                                       # :290
+    embeddings.copy_(z_avg / weights.unsqueeze(1))                                # :291-292
+    commitment = F.mse_loss(z_norm, emb)
+    out = {"commitment-loss": commitment, "loss": beta * commitment, "codebook-sum": torch.sum(torch.abs(embeddings))}
+    return emb.view(b, h, w, -1).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+# --------------------------------------------------------------------------------------------------
+# inline variants V4 / V6  (model/dino_new_vq.py:241-671, model/dino_pqgo_cls.py:191-405) and the two
+# distance_prob consumers they call (model/loss.py:490-525)
+# --------------------------------------------------------------------------------------------------
+
+
+def entropy_loss(p: torch.Tensor) -> torch.Tensor:
+    """EntropyLoss.forward (model/loss.py:490-505): MINUS the entropy of the batch-averaged assignment."""
+    avg_p = p.mean(0)
+    return -torch.sum(-avg_p * torch.log(avg_p + 1e-8), dim=-1)
+
+
+def jsd_loss(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+    """JSDLoss.forward (model/loss.py:508-525): KLDivLoss(batchmean, log_target) of both inputs against the
+    smoothed mixture."""
+    m = (0.5 * (p + q).add(1e-6)).log()
+    lp, lq = p.add(1e-6).log(), q.add(1e-6).log()
+    n = p.shape[0]
+    kl = lambda a, t: (t.exp() * (t - a)).sum() / n     # noqa: E731  F.kl_div(a, t, "batchmean", log_target=True)
+    return 0.5 * (kl(m, lp) + kl(m, lq))
+
+
+def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: str,
+                       beta: float = 0.25, jsd_ts: float = 1.0, training: bool = True,
+                       z_mean: Optional[torch.Tensor] = None, z_log_var: Optional[torch.Tensor] = None,
+                       allreduce=None) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """dino_new_vq.EMACodebook.forward (model/dino_new_vq.py:327-459), top-1 path without pq_dropout / init:
+    NCHW in, the quantised rows come from the RAW codebook as it was before this step's update (:403),
+    EMA sums of raw z (:411), softmax(-d / jsd_ts), JSD / entropy between the two batch halves (:447-450)."""
+    b, d, h, w = z_nchw.shape
+    K = state.weight.shape[0]
+    z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)                  # :333-334
+    z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize, z_mean, z_log_var)   # :366-387
+    dist = sq_distance(z_norm, cb_norm)
+    idx = torch.argmin(dist, dim=1)
+    prob = F.softmax(-dist / jsd_ts, dim=1)                                       # :398
+    q = F.embedding(idx, state.weight)                                            # :403 (a copy: pre-update rows)
+    out: Dict = {}
+    if training:
+        onehot = F.one_hot(idx, K).to(z_flat.dtype)
+        count, total = onehot.sum(dim=0), torch.matmul(onehot.t(), z_flat)        # :410-411
+        if allreduce is not None:
+            count, total = allreduce(count), allreduce(total)
+        exact_count += count                                                      # :415
+        state.update(count, total)                                                # :422
+        out["codebook-usage"] = (K - int((count == 0).sum())) / K                 # :431-432
+    commitment = F.mse_loss(z_norm, q)
+    out["vq-loss"] = beta * commitment                                            # :435-436
+    out["codebook-sum"] = torch.sum(torch.abs(state.weight))                      # :445 (after the update)
+    p1, p2 = torch.chunk(prob, chunks=2, dim=0)
+    out["jsd"] = jsd_loss(p1, p2)                                                 # :449
+    out["entropy"] = entropy_loss(p1)                                             # :450
+    q_ste = z_norm + (q - z_norm)
+    return q_ste.view(b, h, w, d).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_count: torch.Tensor, *,
+                            variant: str, normalize: str, beta: float = 0.25, book: float = 1.0,
+                            jsd_ts: float = 1.0, training: bool = True, z_mean: Optional[torch.Tensor] = None,
+                            z_log_var: Optional[torch.Tensor] = None
+                            ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+    """The learned-codebook ``Codebook.forward`` of dino_new_vq.py:537-671 (variant "new_vq"), dino_pqgo.py:579-705
+    ("pqgo") and dino_pqgo_cls.py:303-405 ("pqgo_cls"): raw embedding gathered, counts in training only,
+    ``vq-loss`` = [book *] codebook + beta * commitment; new_vq adds jsd / entropy.  prob is returned flat (n, K);
+    the callers reshape it (pqgo / pqgo_cls: (b, h, w, K))."""
+    b, d, h, w = z_nchw.shape
+    K = codebook.shape[0]
+    z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)
+    z_norm, cb_norm = normalize_pair(z_flat, codebook, normalize, z_mean, z_log_var)
+    dist = sq_distance(z_norm, cb_norm)
+    idx = torch.argmin(dist, dim=1)
+    prob = F.softmax(-dist / jsd_ts, dim=1)
+    q = F.embedding(idx, codebook)
+    out: Dict = {}
+    if training:
+        count = F.one_hot(idx, K).to(z_flat.dtype).sum(dim=0)
+        exact_count += count
+        out["codebook-usage"] = (K - int((count == 0).sum())) / K
+    cb_loss, commit = F.mse_loss(q, z_norm), F.mse_loss(z_norm, q)
+    out["vq-loss"] = (book if variant == "pqgo" else 1.0) * cb_loss + beta * commit
+    if variant == "new_vq":
+        p1, p2 = torch.chunk(prob, chunks=2, dim=0)
+        out["jsd"] = jsd_loss(p1, p2)
+        out["entropy"] = entropy_loss(p1)
+    q_ste = z_norm + (q - z_norm)
+    return q_ste.view(b, h, w, d).permute(0, 3, 1, 2).contiguous(), out, prob, idx
+
+
+def restart_candidates(count: torch.Tensor, z_rows: torch.Tensor, rng) -> Tuple[torch.Tensor, torch.Tensor]:
+    """prepare_restart (model/quantizer.py:298-319 and its inline twins): dead codes and the rows of z that
+    replace them, drawn with Python's ``random`` (``rng`` is a random.Random or the module)."""
+    n_data = z_rows.shape[0]
+    dead = torch.nonzero(count == 0, as_tuple=True)[0]
+    z_indices = list(range(n_data))
+    rng.shuffle(z_indices)
+    if len(dead) <= n_data:
+        z_indices = z_indices[:len(dead)]
+    else:
+        dead = dead.tolist()
+        rng.shuffle(dead)
+        dead = dead[:n_data]
+    return dead, z_rows[z_indices]
 
 
 # --------------------------------------------------------------------------------------------------

@@ -195,3 +195,94 @@ def test_unseg_metrics_compute_host_side(tmp_path, monkeypatch):
         assert torch.equal(a.histogram, b.histogram)
         ids = torch.randint(0, C + extra, (3, 4))
         assert torch.equal(a.map_clusters(ids), b.map_clusters(ids))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# variants pinned in round 2 (oracle/make_golden_variants.py): V4 EMA, V4/V5/V6 learned, V3 train, z_trainable, restart
+# ----------------------------------------------------------------------------------------------------------------
+def _mean_outs(per_subspace):
+    M = len(per_subspace)
+    keys = per_subspace[0].keys()
+    return {k: sum(o[k] for o in per_subspace) / M for k in keys}
+
+
+def _check_outs(out, g, s):
+    keys = {k[len(f"out{s}/"):] for k in g.files if k.startswith(f"out{s}/")}
+    assert set(out.keys()) == keys
+    for k in keys:
+        assert float(out[k]) == pytest.approx(float(g[f"out{s}/{k}"]), rel=1e-5, abs=1e-7), (s, k)
+
+
+@pytest.mark.parametrize("mode", ["l2", "none"])
+def test_new_vq_ema_trajectory(golden_dir, mode):
+    g = _load(golden_dir, f"pq_newvq_ema_{mode}.npz")
+    M, K, ts = int(g["M"]), int(g["K"]), float(g["jsd_ts"])
+    w0 = torch.from_numpy(g["weight0"])
+    states = [O.EmaState(w0[i]) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    for s in range(4):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        res = [O.new_vq_ema_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize=mode, beta=0.25, jsd_ts=ts,
+                                    training=s < 3) for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"zq{s}"], rtol=1e-6, atol=1e-7)
+        _check_outs(_mean_outs([r[1] for r in res]), g, s)
+        np.testing.assert_allclose(torch.stack([st.weight for st in states]).numpy(), g[f"weight_after{s}"], rtol=1e-5, atol=1e-7)
+        assert np.array_equal(torch.stack(exact).numpy(), g[f"exact_after{s}"])
+
+
+@pytest.mark.parametrize("variant,mode", [("new_vq", "l2"), ("new_vq", "z_norm"), ("pqgo_cls", "l2"),
+                                          ("pqgo_cls", "z_trainable"), ("pqgo", "z_norm")])
+def test_inline_codebooks(golden_dir, variant, mode):
+    g = _load(golden_dir, f"pq_inline_{variant}_{mode}.npz")
+    M, K, ts = int(g["M"]), int(g["K"]), float(g["jsd_ts"])
+    cbs = torch.from_numpy(g["codebook"])
+    zm = torch.from_numpy(g["z_mean"]) if mode == "z_trainable" else None
+    zl = torch.from_numpy(g["z_log_var"]) if mode == "z_trainable" else None
+    exact = [torch.zeros(K) for _ in range(M)]
+    for s, training in ((0, True), (1, False)):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        res = [O.inline_codebook_forward(z[:, i * d:(i + 1) * d], cbs[i], exact[i], variant=variant, normalize=mode,
+                                         beta=0.25, book=0.6, jsd_ts=ts, training=training,
+                                         z_mean=None if zm is None else zm[i], z_log_var=None if zl is None else zl[i])
+               for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"zq{s}"], rtol=1e-6, atol=1e-7)
+        _check_outs(_mean_outs([r[1] for r in res]), g, s)
+        assert np.array_equal(torch.stack(exact).numpy(), g[f"exact_after{s}"])
+
+
+def test_v2_train_and_z_trainable_and_restart(golden_dir):
+    g = _load(golden_dir, "pq_v2_train.npz")
+    M, K, dec = int(g["M"]), int(g["K"]), float(g["decay"])
+    emb = [torch.from_numpy(g["embeddings0"][i]).clone() for i in range(M)]
+    Ns = [torch.zeros(K) for _ in range(M)]
+    zav = [e.clone() for e in emb]
+    for s in range(3):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        res = [O.v2_ema_vq_train_step(z[:, i * d:(i + 1) * d], emb[i], Ns[i], zav[i], beta=0.25, decay=dec) for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"q{s}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(torch.stack(emb).numpy(), g[f"embeddings_after{s}"], rtol=1e-5, atol=1e-7)
+    g = _load(golden_dir, "pq_ztrainable.npz")
+    M, K, dec = int(g["M"]), int(g["K"]), float(g["decay"])
+    w0 = torch.from_numpy(g["weight0"])
+    states = [O.EmaState(w0[i], decay=dec) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    zm = [torch.from_numpy(g["z_mean0"][i]).clone() for i in range(M)]
+    zl = [torch.from_numpy(g["z_log_var0"][i]).clone() for i in range(M)]
+    for s in range(4):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        res = [O.ema_vq_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize="z_trainable", beta=0.25,
+                                training=s < 3, z_mean=zm[i], z_log_var=zl[i], ema_decay=dec) for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(torch.stack(zm).numpy(), g[f"z_mean_after{s}"], rtol=1e-6, atol=1e-7)
+    g = _load(golden_dir, "pq_restart.npz")
+    import random
+    dead, cand = O.restart_candidates(torch.zeros(int(g["K"]), dtype=torch.long), torch.from_numpy(g["a_z"]), random.Random(5))
+    np.testing.assert_array_equal(cand.numpy(), g["a_init_rows"])
+    assert len(dead) == int(g["K"])

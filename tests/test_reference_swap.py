@@ -1,0 +1,76 @@
+"""Import-swap on the build box: the reference's OWN wrapper code constructs and holds the mirror
+modules when ``model.evaluator`` / ``model.quantizer`` / ``model.metric`` are replaced in ``sys.modules``.
+
+Needs /root/reference (skipped on the GPU box, where the kernels run but the reference tree is absent; the forward
+arithmetic of the swapped-in modules is what the ``-m gpu`` tests check).  No kernel runs here: a CPU call must fail
+loudly instead of falling back."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+
+
+@pytest.fixture()
+def swapped():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from make_golden import import_reference
+    import_reference()                                   # stubs torchmetrics / pydensecrf, puts REF on sys.path
+    import equss_b200
+    saved = {k: sys.modules.get(k) for k in ("model.evaluator", "model.quantizer", "model.metric", "wrapper.PQGOWrapper")}
+    ref_eval = importlib.import_module("model.evaluator")
+    ref_quant = importlib.import_module("model.quantizer")
+    sys.modules["model.evaluator"] = equss_b200.evaluator
+    sys.modules["model.quantizer"] = equss_b200.quantizer
+    sys.modules["model.metric"] = equss_b200.metric
+    sys.modules.pop("wrapper.PQGOWrapper", None)
+    try:
+        yield ref_eval, ref_quant, equss_b200
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_reference_wrapper_builds_on_the_mirrors(swapped):
+    ref_eval, ref_quant, eq = swapped
+    wrapper = importlib.import_module("wrapper.PQGOWrapper")
+    cfg = {"num_classes": 27, "eval": {"extra_classes": 0, "output_type": "vq0"}, "dataset_name": "cocostuff27",
+           "model": {"vq": {"num_pq": [4], "embed_dims": [64]}}, "loss": {"stego_weight": 1.0, "vq_weight": 1.0}}
+    w = wrapper.PQGOWrapper(cfg, torch.nn.Identity())
+    assert type(w.evaluator) is eq.evaluator.UnSegEvaluator
+    ref_keys = sorted(ref_eval.UnSegEvaluator(64, 27, 0).state_dict().keys())
+    assert sorted(w.evaluator.state_dict().keys()) == ref_keys
+    w.evaluator.load_state_dict(ref_eval.UnSegEvaluator(64, 27, 0).state_dict(), strict=True)
+    # the mirror never computes on the CPU
+    with pytest.raises(eq._native.EqussNativeError):
+        w.evaluator(torch.randn(1, 64, 4, 4), None, torch.zeros(1, 8, 8, dtype=torch.long))
+
+
+def test_quantizer_state_dicts_and_signatures_match(swapped):
+    import inspect
+    ref_eval, ref_quant, eq = swapped
+    for name in ("VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper"):
+        r, m = getattr(ref_quant, name), getattr(eq.quantizer, name)
+        rp = list(inspect.signature(r.__init__).parameters)
+        mp = [p for p in inspect.signature(m.__init__).parameters if not p.startswith("_")]
+        assert mp[:len(rp)] == rp, (name, rp, mp)
+    ref = ref_quant.ProductQuantizerWrapper(4, 16, 32, normalize="l2")
+    mir = eq.quantizer.ProductQuantizerWrapper(4, 16, 32, normalize="l2")
+    assert sorted(ref.state_dict().keys()) == sorted(mir.state_dict().keys())
+    mir.load_state_dict(ref.state_dict(), strict=True)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(mir.state_dict()[k], v)
+    # build.py:77 sorts parameters by isinstance on these three class names
+    from equss_b200.quantizer import EMAVectorQuantizer, EmbeddingEMA, VectorQuantizer
+    kinds = {type(mod) for mod in mir.modules()}
+    assert EMAVectorQuantizer in kinds and EmbeddingEMA in kinds
+    # (the reference's wrapper cannot build the learned-codebook flavour itself: it passes decay= to a ctor without it)
+    assert sorted(VectorQuantizer(8, 16, normalize="l2").state_dict().keys()) == \
+        sorted(ref_quant.VectorQuantizer(8, 16, normalize="l2").state_dict().keys())
