@@ -73,7 +73,7 @@ def test_learned_codebook_variants_match_reference(golden_dir):
         vq.codebook.weight.copy_(torch.from_numpy(g["v1_codebook"]))
     q, out, prob = vq(z)
     np.testing.assert_allclose(q.detach().cpu().numpy(), g["v1_q"], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(prob.cpu().numpy(), g["v1_prob"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(prob.detach().cpu().numpy(), g["v1_prob"], rtol=2e-5, atol=1e-7)
     assert float(out["loss"]) == pytest.approx(float(g["v1_loss"]), rel=1e-5)
     assert float(out["codebook_loss"]) == pytest.approx(float(g["v1_codebook_loss"]), rel=1e-5)
     cb = Codebook(K, d, beta=0.25, book=1.0, normalize="none").to(DEV).eval()
@@ -82,7 +82,7 @@ def test_learned_codebook_variants_match_reference(golden_dir):
     q5, out5, prob5, idx5 = cb(z, torch.zeros_like(z))
     assert np.array_equal(idx5.cpu().numpy(), g["v5_idx"])
     np.testing.assert_allclose(q5.detach().cpu().numpy(), g["v5_q"], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(prob5.cpu().numpy(), g["v5_prob"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(prob5.detach().cpu().numpy(), g["v5_prob"], rtol=2e-5, atol=1e-7)
     assert float(out5["vq-loss"]) == pytest.approx(float(g["v5_vq_loss"]), rel=1e-5)
     w = PQGOProductQuantizerWrapper(1, K, d, normalize="none").to(DEV).eval()
     with torch.no_grad():
