@@ -36,6 +36,7 @@ EXPORTS = [
     "equss_knn_workspace_bytes", "equss_knn_topk",
     "equss_head_gemm_supported", "equss_head_gemm",
     "equss_pq_soft_stats_supported", "equss_pq_soft_stats", "equss_channel_moments",
+    "equss_pq_train_tail_scratch_floats", "equss_pq_train_tail", "equss_pq_prepare_codebook",
 ]
 
 
@@ -129,6 +130,12 @@ def _declare(L: C.CDLL) -> None:
     L.equss_pq_soft_stats_supported.argtypes = [i32, i32]
     L.equss_pq_soft_stats.restype = i32
     L.equss_pq_soft_stats.argtypes = [vp, zp, vp, vp, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp]
+    L.equss_pq_train_tail_scratch_floats.restype = i32
+    L.equss_pq_train_tail_scratch_floats.argtypes = [i32]
+    L.equss_pq_train_tail.restype = i32
+    L.equss_pq_train_tail.argtypes = [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    L.equss_pq_prepare_codebook.restype = i32
+    L.equss_pq_prepare_codebook.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     L.equss_channel_moments.restype = i32
     L.equss_channel_moments.argtypes = [vp, zp, vp, vp]
     L.equss_probe_argmax_confusion.restype = i32

@@ -682,16 +682,15 @@ usage_percentiles_kernel(const float* __restrict__ count, long long row_stride, 
 // The prefix is summed in double like torch's CPU cumsum; double addition of fp32 quotients in [0, 1] is exact unless a
 // term lies more than 2^29 below the running sum, so the tree order agrees with the sequential one.
 constexpr int kPctThreads = 256, kPctItems = 4;
-__global__ void __launch_bounds__(kPctThreads)
-usage_percentiles_small_kernel(const float* __restrict__ count, long long row_stride, long long k_stride, int K,
-                               float* __restrict__ out) {
+// block-wide (kPctThreads threads); out3 receives p10 / p50 / p90 from threads 0..2
+__device__ __forceinline__ void block_usage_percentiles(const float* __restrict__ c, long long k_stride, int K,
+                                                        float* __restrict__ out3) {
   __shared__ float s_v[kPctThreads * kPctItems];
   __shared__ float s_sorted[kPctThreads * kPctItems];
   __shared__ float s_tot[kPctThreads / 32];
   __shared__ double s_wsum[kPctThreads / 32];
   __shared__ int s_first[3];
-  const int m = blockIdx.x;
-  const float* c = count + (long long)m * row_stride;
+  __syncthreads();                                        // a previous call's readers are done
   float part = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float v = c[(long long)k * k_stride];
@@ -749,8 +748,121 @@ usage_percentiles_small_kernel(const float* __restrict__ count, long long row_st
   __syncthreads();
   if (threadIdx.x < 3) {
     const int f = s_first[threadIdx.x];
-    out[m * 3 + threadIdx.x] = (f < K) ? (float)f / (float)K : NAN;
+    out3[threadIdx.x] = (f < K) ? (float)f / (float)K : NAN;
   }
+}
+
+__global__ void __launch_bounds__(kPctThreads)
+usage_percentiles_small_kernel(const float* __restrict__ count, long long row_stride, long long k_stride, int K,
+                               float* __restrict__ out) {
+  block_usage_percentiles(count + (long long)blockIdx.x * row_stride, k_stride, K, out + blockIdx.x * 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Train-step tail (K6 + K7 + the scalar outputs of EMAVectorQuantizer.forward, model/quantizer.py:493-532) in ONE
+// launch: per subspace (one block) the EMA update, the exact-count accumulation, both usage-percentile triples, the
+// unused-code count, sum |weight| and the commitment MSE; the last block to finish averages them over the subspaces
+// (ProductQuantizerWrapper.forward's mean, :607-608).  Replaces ~15 small launches of the eager path.
+//   scratch: [M][kTailStats] floats + one unsigned counter (zero on entry, zero again on exit)
+//   stats_out: [kTailStats] = total-p10/50/90, current-p10/50/90, codebook-usage, codebook-sum, commitment-loss, loss
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailStats = 10;
+__global__ void __launch_bounds__(kPctThreads)
+ema_train_tail_kernel(const float* __restrict__ packed, int M, int K, int d, float decay, float alpha, float eps,
+                      float k_eps, float* __restrict__ vq_count, float* __restrict__ weight_avg,
+                      float* __restrict__ weight, float* __restrict__ exact_count, const double* __restrict__ sqerr,
+                      double inv_nd, float beta, float* __restrict__ scratch, float* __restrict__ stats_out) {
+  const int m = blockIdx.x;
+  const int ld = d + 1;
+  const float* pm = packed + (long long)m * K * ld;
+  float* cnt = vq_count + (long long)m * K;
+  float* ex = exact_count + (long long)m * K;
+  __shared__ float s_red[kPctThreads / 32];
+  __shared__ int s_unused[kPctThreads / 32];
+  __shared__ float s_n, s_abs;
+  __shared__ int s_unused_total;
+  __shared__ bool s_last;
+  float part = 0.f;
+  int unused = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float c = pm[(long long)k * ld + d];
+    float v = cnt[k] * decay;
+    v = v + alpha * c;
+    cnt[k] = v;
+    part += v;
+    ex[k] += c;
+    unused += (c == 0.f);
+  }
+  part = warp_sum(part);
+  for (int o = 16; o > 0; o >>= 1) unused += __shfl_xor_sync(0xffffffffu, unused, o);
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = part; s_unused[threadIdx.x >> 5] = unused; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f; int u = 0;
+    for (int i = 0; i < kPctThreads / 32; ++i) { t += s_red[i]; u += s_unused[i]; }
+    s_n = t; s_unused_total = u;
+  }
+  __syncthreads();
+  const float n = s_n;
+  const float denom_n = n + k_eps;
+  float asum = 0.f;
+  for (int i = threadIdx.x; i < K * d; i += blockDim.x) {
+    const int k = i / d, j = i - k * d;
+    const long long o = (long long)m * K * d + i;
+    float a = weight_avg[o] * decay;
+    a = a + alpha * pm[(long long)k * ld + j];
+    weight_avg[o] = a;
+    const float smoothed = (cnt[k] + eps) / denom_n * n;
+    const float wv = a / smoothed;
+    weight[o] = wv;
+    asum += fabsf(wv);
+  }
+  asum = warp_sum(asum);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = asum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kPctThreads / 32; ++i) t += s_red[i];
+    s_abs = t;
+  }
+  float* sm = scratch + (long long)m * kTailStats;
+  block_usage_percentiles(ex, 1, K, sm);                          // "total"   (:496)
+  block_usage_percentiles(pm + d, ld, K, sm + 3);                 // "current" (:495)
+  if (threadIdx.x == 0) {
+    sm[6] = (float)(K - s_unused_total) / (float)K;               // :510
+    sm[7] = s_abs;                                                // :532
+    sm[8] = sqerr ? (float)(sqerr[m] * inv_nd) : 0.f;             // :514
+    sm[9] = 0.f;
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + (long long)M * kTailStats);
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)(M - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 9) {
+    float t = 0.f;
+    for (int i = 0; i < M; ++i) t += __ldcg(scratch + (long long)i * kTailStats + threadIdx.x);
+    t /= (float)M;
+    stats_out[threadIdx.x] = t;
+    if (threadIdx.x == 8) stats_out[9] = beta * t;               // :526
+  }
+  if (threadIdx.x == 0) *counter = 0u;
+}
+
+// codebook-side normalisation + |c|^2 in one launch (model/quantizer.py:421,426,459): one thread per code
+__global__ void __launch_bounds__(256)
+codebook_prepare_kernel(const float* __restrict__ cb, long long rows, int d, int mode, float* __restrict__ cbn,
+                        float* __restrict__ cn2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* c = cb + i * d;
+  float* o = cbn + i * d;
+  const RowNorm r = row_norm_generic(mode, d, [&](int j) { return __ldg(c + j); });
+  for (int j = 0; j < d; ++j) o[j] = apply_norm(__ldg(c + j), r, mode);
+  cn2[i] = canonical_sumsq(d, [&](int j) { return o[j]; });
 }
 
 __global__ void cnorm2_kernel(const float* __restrict__ cb, long long rows, int d, float* __restrict__ out) {
@@ -979,5 +1091,37 @@ extern "C" int equss_usage_percentiles(const float* count, int64_t row_stride, i
   while (Kp < K) Kp <<= 1;
   equss::usage_percentiles_kernel<<<M, 256, Kp * sizeof(float), (cudaStream_t)stream>>>(count, row_stride, k_stride, K, Kp, out);
   EQUSS_LAUNCH_OK("usage_percentiles_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_train_tail_scratch_floats(int M) { return M * equss::kTailStats + 4; }
+
+extern "C" int equss_pq_train_tail(const float* packed, int M, int K, int d, double decay, double eps, float* vq_count,
+                                   float* weight_avg, float* weight, float* exact_count, const double* sqerr,
+                                   int64_t n_pixels, double beta, float* scratch, float* stats_out, void* stream) {
+  EQUSS_REQUIRE(packed && vq_count && weight_avg && weight && exact_count && scratch && stats_out, EQUSS_ERR_INVALID_ARG,
+                "equss_pq_train_tail: null pointer");
+  EQUSS_REQUIRE(M > 0 && K > 0 && d > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail: bad shape M=%d K=%d d=%d", M, K, d);
+  EQUSS_REQUIRE(K <= equss::kPctThreads * equss::kPctItems, EQUSS_ERR_UNSUPPORTED,
+                "equss_pq_train_tail: K=%d > %d; use equss_ema_update + equss_usage_percentiles", K,
+                equss::kPctThreads * equss::kPctItems);
+  const double inv_nd = (n_pixels > 0) ? 1.0 / ((double)n_pixels * (double)d) : 0.0;
+  equss::ema_train_tail_kernel<<<M, equss::kPctThreads, 0, (cudaStream_t)stream>>>(
+      packed, M, K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps), vq_count, weight_avg, weight,
+      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out);
+  EQUSS_LAUNCH_OK("ema_train_tail_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_prepare_codebook(const float* codebook, int M, int K, int d, int norm_mode, float* codebook_norm,
+                                         float* cnorm2, void* stream) {
+  EQUSS_REQUIRE(codebook && codebook_norm && cnorm2, EQUSS_ERR_INVALID_ARG, "equss_pq_prepare_codebook: null pointer");
+  EQUSS_REQUIRE(M > 0 && K > 0 && d > 0 && d <= equss::kMaxD, EQUSS_ERR_INVALID_ARG, "equss_pq_prepare_codebook: bad shape");
+  EQUSS_REQUIRE(norm_mode == EQUSS_NORM_NONE || norm_mode == EQUSS_NORM_L2 || norm_mode == EQUSS_NORM_ZNORM, EQUSS_ERR_UNSUPPORTED,
+                "equss_pq_prepare_codebook: per-code modes only (none, l2, z_norm); got %d", norm_mode);
+  const long long rows = (long long)M * K;
+  equss::codebook_prepare_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(codebook, rows, d, norm_mode,
+                                                                                                  codebook_norm, cnorm2);
+  EQUSS_LAUNCH_OK("codebook_prepare_kernel");
   return EQUSS_OK;
 }

@@ -98,6 +98,32 @@ class UnSegEvaluator(nn.Module):
         self.cluster_probe = ClusterLookup(embed_dim, num_classes + extra_classes)
         self.linear_loss = nn.CrossEntropyLoss()
         self.compute_losses = True   # set False to skip the two (training-only) loss scalars
+        self._probe_cache = None
+
+    def _packed_probe_weights(self, dev):
+        """Both probes as ONE operand for K8: rows [0, Cc) the L2-normalised cluster centres, rows [Cp, Cp + C) the linear
+        probe, each head starting at a multiple of four channels (the second kernel reads four logits per 16-byte load;
+        padding rows are zero and never compete in the argmax), packed into the kernels' K-major / tensor-core images.
+        In eval() mode the packed operand is cached and rebuilt when a parameter's storage or version counter changes;
+        in train() mode (the probes are being optimised) it is rebuilt on every call.  In-place updates through ``.data``
+        do not bump version counters: call :meth:`invalidate_cache` after such an update."""
+        ps = (self.cluster_probe.clusters, self.linear_probe.weight, self.linear_probe.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (str(dev),)
+        if not self.training and self._probe_cache is not None and self._probe_cache[0] == key:
+            return self._probe_cache[1], self._probe_cache[2]
+        Cc, C, D = self.cluster_probe.n_classes, self.num_classes, self.cluster_probe.dim
+        Cp = (Cc + 3) // 4 * 4
+        wmat = torch.zeros(Cp + C, D, device=dev)
+        wmat[:Cc] = F.normalize(ps[0].detach().float(), dim=1)
+        wmat[Cp:] = ps[1].detach().float().view(C, D)
+        bias = torch.zeros(Cp + C, device=dev)
+        bias[Cp:] = ps[2].detach().float()
+        pack = ops.probe_pack(wmat)
+        self._probe_cache = (key, pack, bias)
+        return pack, bias
+
+    def invalidate_cache(self) -> None:
+        self._probe_cache = None
 
     # -- K8: predictions (and optionally K9 confusion matrices) -----------------------------------
     @torch.no_grad()
@@ -108,15 +134,8 @@ class UnSegEvaluator(nn.Module):
         B, D, h, w = out.shape
         Cc = self.cluster_probe.n_classes
         C = self.num_classes
-        # both probes share one weight matrix; each head starts at a multiple of four channels so the second
-        # kernel can read four logits per 16-byte load (padding rows are zero and never compete in the argmax)
         Cp = (Cc + 3) // 4 * 4
-        dev = out.device
-        wmat = torch.zeros(Cp + C, D, device=dev)
-        wmat[:Cc] = F.normalize(self.cluster_probe.clusters.detach().float(), dim=1)
-        wmat[Cp:] = self.linear_probe.weight.detach().float().view(C, D)
-        bias = torch.zeros(Cp + C, device=dev)
-        bias[Cp:] = self.linear_probe.bias.detach().float()
+        wmat, bias = self._packed_probe_weights(out.device)
         logits = ops.probe_logits(out, wmat, bias)
         confs = None
         if cluster_confusion is not None or linear_confusion is not None:

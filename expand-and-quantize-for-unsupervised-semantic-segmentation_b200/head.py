@@ -48,10 +48,12 @@ class _PackedHead:
         self.key = None
         self.w13 = self.b13 = None
 
-    def get(self, c1: nn.Conv2d, c3: nn.Conv2d) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    def get(self, c1: nn.Conv2d, c3: nn.Conv2d, reuse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """``reuse=False`` (modules in train() mode: EMA-teacher style ``p.data`` updates do not bump version counters)
+        rebuilds unconditionally -- a D x 2C concatenation, cheap next to the GEMM."""
         ps = [c1.weight, c1.bias, c3.weight, c3.bias]
         key = tuple((p.data_ptr(), p._version, p.device) if p is not None else None for p in ps)
-        if key != self.key:
+        if key != self.key or not reuse:
             with torch.no_grad():
                 D = c1.weight.shape[0]
                 self.w13 = torch.cat([c1.weight.reshape(D, -1), c3.weight.reshape(D, -1)], dim=1).float().contiguous()
@@ -95,7 +97,7 @@ def expansion_head(x: torch.Tensor, cluster1: nn.Sequential, cluster2: nn.Sequen
         return code
     B, C, h, w = x.shape
     D = c1.weight.shape[0]
-    w13, b13 = (packed or _PackedHead()).get(c1, c3)
+    w13, b13 = (packed or _PackedHead()).get(c1, c3, reuse=not (cluster1.training or cluster2.training))
     hidden = ops.head_gemm(x, c2.weight, c2.bias, relu=True)                  # (n, C) flat
     code = ops.head_gemm(x, w13, b13, a2=hidden)                              # (n, D) flat
     return code.view(B, h, w, D).permute(0, 3, 1, 2)
@@ -117,6 +119,10 @@ class SegmentationHead(nn.Module):
 
     def make_nonlinear_clusterer(self) -> nn.Sequential:
         return make_nonlinear_clusterer(self.input_dim, self.hidden_dim)
+
+    def invalidate_cache(self) -> None:
+        """Call after changing the convolution weights through ``.data`` while in eval() mode."""
+        self._packed.key = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return expansion_head(x, self.cluster1, self.cluster2, self._packed)

@@ -14,7 +14,8 @@ from . import _native as N
 
 __all__ = [
     "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
-    "pq_distance_prob", "pq_soft_stats", "channel_moments", "usage_percentiles", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "pq_distance_prob", "pq_soft_stats", "channel_moments", "usage_percentiles", "pq_train_tail", "pq_prepare_codebook",
+    "TAIL_KEYS", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
     "launch_count",
 ]
 
@@ -204,6 +205,57 @@ def ema_update(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.T
                                   N.stream_ptr(dev))
     N.check(rc, "equss_ema_update")
     return unused
+
+
+TAIL_KEYS = ("total-p10", "total-p50", "total-p90", "current-p10", "current-p50", "current-p90", "codebook-usage",
+             "codebook-sum", "commitment-loss", "loss")
+_tail_scratch = {}
+
+
+def pq_train_tail(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.Tensor, weight_avg: torch.Tensor,
+                  weight: torch.Tensor, exact_count: torch.Tensor, sqerr: Optional[torch.Tensor], n_pixels: int,
+                  beta: float) -> Optional[torch.Tensor]:
+    """The tail of the EMA training step in one launch: in-place EMA update of the stacked state (as :func:`ema_update`)
+    plus the ten scalar outputs of ``ProductQuantizerWrapper.forward`` (order: :data:`TAIL_KEYS`), averaged over the
+    subspaces (model/quantizer.py:493-532,607-608).  Returns float32 [10], or None when K > 1024 (then call
+    :func:`ema_update` / :func:`usage_percentiles`)."""
+    dev = N.require_cuda(packed, vq_count, weight_avg, weight, exact_count, sqerr)
+    M, K, d1 = packed.shape
+    d = d1 - 1
+    if K > 1024:
+        return None
+    for t, shp in ((vq_count, (M, K)), (weight_avg, (M, K, d)), (weight, (M, K, d)), (exact_count, (M, K))):
+        assert t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == shp, (t.shape, shp)
+    L = N.lib()
+    key = (dev, M)
+    scratch = _tail_scratch.get(key)
+    if scratch is None:     # persistent per (device, M): the kernel's arrival counter lives in it and resets itself
+        scratch = _tail_scratch[key] = torch.zeros((int(L.equss_pq_train_tail_scratch_floats(M)),), dtype=torch.float32, device=dev)
+    stats = torch.empty((10,), dtype=torch.float32, device=dev)
+    if sqerr is not None:
+        assert sqerr.dtype == torch.float64 and sqerr.numel() == M
+    rc = L.equss_pq_train_tail(packed.contiguous().data_ptr(), M, K, d, float(decay), float(eps), vq_count.data_ptr(),
+                               weight_avg.data_ptr(), weight.data_ptr(), exact_count.data_ptr(), N.ptr(sqerr), int(n_pixels),
+                               float(beta), scratch.data_ptr(), stats.data_ptr(), N.stream_ptr(dev))
+    N.check(rc, "equss_pq_train_tail")
+    return stats
+
+
+def pq_prepare_codebook(codebook: torch.Tensor, normalize: Optional[str]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(codebook_norm [M, K, d], cnorm2 [M, K]) for the per-code normalisation modes "l2", "z_norm", "none"
+    (model/quantizer.py:421,426,459) in one launch.  No autograd history (EMA codebooks are buffers)."""
+    dev = N.require_cuda(codebook)
+    N.ensure_device(dev)
+    if normalize not in ("l2", "z_norm", "none"):
+        raise ValueError(f"pq_prepare_codebook: per-code modes only, got {normalize}")
+    cb = N.f32c(codebook.detach())
+    M, K, d = cb.shape
+    cbn = torch.empty_like(cb)
+    cn2 = torch.empty((M, K), dtype=torch.float32, device=dev)
+    rc = N.lib().equss_pq_prepare_codebook(cb.data_ptr(), M, K, d, N.NORM_MODES[normalize], cbn.data_ptr(), cn2.data_ptr(),
+                                           N.stream_ptr(dev))
+    N.check(rc, "equss_pq_prepare_codebook")
+    return cbn, cn2
 
 
 def usage_percentiles(count: torch.Tensor) -> torch.Tensor:

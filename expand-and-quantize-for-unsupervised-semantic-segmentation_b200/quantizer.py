@@ -258,15 +258,24 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
                     q.z_mean.data.mul_(q.decay).add_(mom[0, i * d:(i + 1) * d], alpha=1 - q.decay)
                     q.z_log_var.data.mul_(q.decay).add_(logvar[i * d:(i + 1) * d], alpha=1 - q.decay)
         norm_a = torch.cat([q.z_mean for q in mods])
+    per_code = mode in ("l2", "z_norm", "none")
     with torch.no_grad():
-        cbn = core.normalize_codebook(weight, mode, ema_style=True)
-        # the gather source must survive the in-place EMA update below until backward() has run: take a snapshot
-        # whenever it would alias the live codebook (mode "none" returns `weight` itself)
-        src = cbn if q0.update_norm else weight
-        if src.data_ptr() == weight.data_ptr():
-            src = src.clone()
-    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob)
+        if per_code:                    # normalised codebook + |c|^2 in one launch; a fresh tensor, never an alias
+            cbn, cn2 = ops.pq_prepare_codebook(weight, mode)
+        else:
+            cbn, cn2 = core.normalize_codebook(weight, mode, ema_style=True), None
+        # the gather source must survive the in-place EMA update below until backward() has run
+        src = cbn if q0.update_norm else weight.clone()
+    n = z.shape[0]
+    sqerr = mse_commit = None
+    if core._wants_grad(z):
+        idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob, cnorm2=cn2)
+    else:                               # no autograd bookkeeping: K1+K3 (one kernel where the shape allows), K2 on demand
+        z32 = z if z.dtype == torch.float32 else z.float()
+        idx, out, sqerr = ops.pq_assign_gather(z32, cbn, src, cn2, mode, norm_a, norm_b)
+        prob = ops.pq_distance_prob(z32, cbn, cn2, mode, norm_a, norm_b) if want_prob else None
     output: Dict[str, torch.Tensor] = {}
+    stats = None
     if training:
         with torch.no_grad():
             packed = core.ema_statistics(z, idx, K)                                    # :485-491
@@ -277,25 +286,39 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
                      [q.codebook.weight_avg for q in mods], [q.codebook.weight for q in mods]]
             stacked = [_stack(ts) for ts in state]
             exact_c, vqc_c, wavg_c, w_c = (t.contiguous() for t in stacked)
-            unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
+            if not q0.use_split:
+                # EMA update + percentiles x2 + usage + codebook-sum + loss scalars: ONE launch (:493-532)
+                stats = ops.pq_train_tail(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c,
+                                          sqerr, n, beta)
+            if stats is None:
+                unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
+                output.update(core.percentile_stats(exact_c, "total"))                      # :496
+                output.update(core.percentile_stats(count, "current"))                      # :495
             for ts, st in zip(state, (exact_c, vqc_c, wavg_c, w_c)):
                 if st.data_ptr() != ts[0].data_ptr():
                     for i, t in enumerate(ts):
                         t.copy_(st[i])
-            output.update(core.percentile_stats(exact_c, "total"))                      # :496
-            output.update(core.percentile_stats(count, "current"))                      # :495
             if q0.use_restart:
                 for i, q in enumerate(mods):
                     q.prepare_restart(count[i], z[:, i * d:(i + 1) * d])                # :500-501
-            if q0.use_split:
-                n_split = torch.tensor([float(q.split(count[i])) for i, q in enumerate(mods)], device=z.device)
+            if stats is not None:
+                output.update(zip(ops.TAIL_KEYS[:7], stats.unbind(0)[:7]))
             else:
-                n_split = unused.float()
-            output["codebook-usage"] = ((K - n_split) / K).mean()                       # :510
+                if q0.use_split:
+                    n_split = torch.tensor([float(q.split(count[i])) for i, q in enumerate(mods)], device=z.device)
+                else:
+                    n_split = unused.float()
+                output["codebook-usage"] = ((K - n_split) / K).mean()                       # :510
+    if stats is not None and sqerr is not None:
+        output["loss"], output["commitment-loss"], output["codebook-sum"] = stats[9], stats[8], stats[7]
+        return out, output, prob
+    if mse_commit is None:
+        mse_commit = (sqerr / max(n * d, 1)).to(torch.float32)
     commitment = mse_commit.mean()
     output["loss"] = beta * commitment                                                  # :526
     output["commitment-loss"] = commitment
-    output["codebook-sum"] = torch.sum(torch.abs(_stack([q.codebook.weight for q in mods]))) / M   # :532
+    output["codebook-sum"] = stats[7] if stats is not None else \
+        torch.sum(torch.abs(_stack([q.codebook.weight for q in mods]))) / M             # :532
     return out, output, prob
 
 

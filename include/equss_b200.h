@@ -158,6 +158,27 @@ int equss_ema_update(const float* packed, int M, int K, int d, double decay, dou
                      float* vq_count, float* weight_avg, float* weight,
                      float* exact_count, int32_t* unused_out, void* stream);
 
+/* K6+K7 fused tail of the EMA training step   replaces model/quantizer.py:493-532 (the EMA update, both
+ *   get_histogram_count calls, codebook-usage, codebook-sum, commitment / loss scalars, and the wrapper's mean over
+ *   subspaces, :607-608) -- about fifteen small launches on the eager path -- by ONE launch.
+ *   State update exactly as equss_ema_update (exact_count is required here).  sqerr: [M] fp64 squared errors from K3
+ *   (or NULL: the caller computes the loss terms itself, e.g. through autograd).
+ *   stats_out[10] = { total-p10, total-p50, total-p90, current-p10, current-p50, current-p90, codebook-usage,
+ *                     codebook-sum, commitment-loss, loss = beta * commitment }, each the mean over the M subspaces.
+ *   scratch: equss_pq_train_tail_scratch_floats(M) floats, zero before the first call (the kernel leaves it reusable).
+ *   K <= 1024. */
+int equss_pq_train_tail_scratch_floats(int M);
+int equss_pq_train_tail(const float* packed, int M, int K, int d, double decay, double eps,
+                        float* vq_count, float* weight_avg, float* weight, float* exact_count,
+                        const double* sqerr, int64_t n_pixels, double beta,
+                        float* scratch, float* stats_out, void* stream);
+
+/* Codebook-side normalisation (model/quantizer.py:421 "l2", :426 "z_norm", "none") and cnorm2 of the result in one
+ * launch: codebook_norm [M][K][d], cnorm2 [M][K].  (The "z_trainable" flavours normalise across codes / with learned
+ * statistics and stay with the caller.) */
+int equss_pq_prepare_codebook(const float* codebook, int M, int K, int d, int norm_mode,
+                              float* codebook_norm, float* cnorm2, void* stream);
+
 /* K7  codebook-usage percentiles      replaces get_histogram_count, model/quantizer.py:15-30 (a Python loop with
  *   ~6K tensor->bool host syncs per subspace in the reference).  count: M rows of K entries, element (m, k) at
  *   count[m*row_stride + k*k_stride] (so the count column of the packed K4 buffer can be read in place).
