@@ -15,6 +15,9 @@ namespace equss {
 // knn_tc.cu: tcgen05 split-tf32 similarity GEMM (F % 32 == 0, 16-byte aligned pointers)
 bool knn_gemm_tc_supported(const float* Q, const float* DB, const float* S, long long n, int F);
 int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st);
+int knn_topk_tc_splits(long long rows, long long n);
+int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long long n, int F, int k, int splits,
+                       float* part_val, int* part_idx, cudaStream_t st);
 
 constexpr int KNN_BM = 128, KNN_BN = 128, KNN_BK = 8;
 
@@ -134,8 +137,46 @@ knn_select_kernel(const float* __restrict__ S, long long rows, long long n, int 
   }
 }
 
-static long long knn_rows_per_chunk(long long nq, long long n) {
-  const long long budget = 1536LL << 20;  // bytes of similarity workspace per chunk (a 6250 x 50000 shard fits in one)
+// Merge of the fused kernel's partial lists: one warp per query row, lane i ends with the i-th best candidate.
+// Order: larger similarity first, equal similarities by increasing database index (candidates arrive unordered).
+__global__ void __launch_bounds__(256)
+knn_merge_kernel(const float* __restrict__ pv, const int* __restrict__ pi, long long rows, int ncand, int k,
+                 long long* __restrict__ idx_out, float* __restrict__ sim_out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* v = pv + r * ncand;
+  const int* ix = pi + r * ncand;
+  float myv = -INFINITY;
+  int myi = -1;
+  for (int base = 0; base < ncand; base += 32) {
+    const int c = base + lane;
+    const float cv0 = (c < ncand) ? v[c] : -INFINITY;
+    const int ci0 = (c < ncand) ? ix[c] : -1;
+    unsigned mask = __ballot_sync(0xffffffffu, ci0 >= 0);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float cv = __shfl_sync(0xffffffffu, cv0, src);
+      const int ci = __shfl_sync(0xffffffffu, ci0, src);
+      const unsigned ahead = __ballot_sync(0xffffffffu, myi >= 0 && (myv > cv || (myv == cv && myi < ci)));
+      const int pos = __popc(ahead);
+      if (pos < k) {
+        const float upv = __shfl_up_sync(0xffffffffu, myv, 1);
+        const int upi = __shfl_up_sync(0xffffffffu, myi, 1);
+        if (lane > pos) { myv = upv; myi = upi; }
+        else if (lane == pos) { myv = cv; myi = ci; }
+      }
+    }
+  }
+  if (lane < k) {
+    idx_out[r * k + lane] = (long long)myi;
+    if (sim_out) sim_out[r * k + lane] = myv;
+  }
+}
+
+static long long knn_rows_per_chunk(long long nq, long long n, long long budget = 1536LL << 20) {
+  // rows of similarity workspace per chunk of the unfused path (CUDA-core GEMM shapes)
   long long rc = budget / (n * 4);
   rc = (rc / KNN_BM) * KNN_BM;
   if (rc < KNN_BM) rc = KNN_BM;
@@ -144,13 +185,16 @@ static long long knn_rows_per_chunk(long long nq, long long n) {
   return rc;
 }
 
+static bool knn_fused_shape(int F) { return F > 0 && F % 32 == 0; }
+
 }  // namespace equss
 
 using namespace equss;
 
 extern "C" int64_t equss_knn_workspace_bytes(int64_t nq, int64_t n, int F, int k) {
-  (void)F; (void)k;
   if (nq <= 0 || n <= 0) return 0;
+  if (knn_fused_shape(F) && getenv("EQUSS_KNN_UNFUSED") == nullptr)            // partial top-k lists only: O(nq * k)
+    return nq * (int64_t)knn_topk_tc_splits(nq, n) * k * 8 + 256;
   return knn_rows_per_chunk(nq, n) * n * 4;
 }
 
@@ -162,14 +206,30 @@ extern "C" int equss_knn_topk(const float* queries, int64_t nq, const float* db,
                 (long long)nq, (long long)n, F);
   EQUSS_REQUIRE(k >= 1 && k <= 32, EQUSS_ERR_UNSUPPORTED, "equss_knn_topk: k=%d outside [1,32]", k);
   EQUSS_REQUIRE(k <= n, EQUSS_ERR_INVALID_ARG, "equss_knn_topk: k=%d > database size %lld", k, (long long)n);
+  EQUSS_REQUIRE(n < (1LL << 31), EQUSS_ERR_UNSUPPORTED, "equss_knn_topk: database of %lld rows", (long long)n);
   if (nq == 0) return EQUSS_OK;
-  const long long rc = knn_rows_per_chunk(nq, n);
-  EQUSS_REQUIRE(workspace && workspace_bytes >= rc * n * 4, EQUSS_ERR_INVALID_ARG,
-                "equss_knn_topk: workspace of %lld bytes needed, got %lld", (long long)(rc * n * 4),
-                (long long)workspace_bytes);
-  float* S = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  // tensor-core GEMM whenever the shape allows it (EQUSS_KNN_SIMT=1 forces the CUDA-core kernel, for comparisons)
+  const bool aligned = !((uintptr_t)queries & 15) && !((uintptr_t)db & 15) && !((uintptr_t)workspace & 15);
+  if (knn_fused_shape(F) && aligned && getenv("EQUSS_KNN_UNFUSED") == nullptr && getenv("EQUSS_KNN_SIMT") == nullptr) {
+    // tcgen05 GEMM with the running top-k in its epilogue, then a merge of the per-split lists
+    const int splits = knn_topk_tc_splits(nq, n);
+    const int64_t need = nq * (int64_t)splits * k * 8;
+    EQUSS_REQUIRE(workspace && workspace_bytes >= need, EQUSS_ERR_INVALID_ARG,
+                  "equss_knn_topk: workspace of %lld bytes needed, got %lld", (long long)need, (long long)workspace_bytes);
+    float* pv = (float*)workspace;
+    int* pi = (int*)(pv + nq * (int64_t)splits * k);
+    int rc2 = knn_topk_tc_launch(queries, db, nq, n, F, k, splits, pv, pi, st);
+    if (rc2 != EQUSS_OK) return rc2;
+    knn_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(pv, pi, nq, splits * k, k, (long long*)idx_out, sim_out);
+    EQUSS_LAUNCH_OK("knn_merge_kernel");
+    return EQUSS_OK;
+  }
+  // unfused path (odd feature counts / forced): chunked similarity workspace + streaming selection
+  EQUSS_REQUIRE(workspace && workspace_bytes >= (int64_t)KNN_BM * n * 4, EQUSS_ERR_INVALID_ARG,
+                "equss_knn_topk: workspace of at least %lld bytes needed, got %lld", (long long)(KNN_BM * n * 4),
+                (long long)workspace_bytes);
+  const long long rc = knn_rows_per_chunk(nq, n, workspace_bytes);
+  float* S = (float*)workspace;
   const bool use_tc = knn_gemm_tc_supported(queries, db, S, n, F) && ((F * 4) % 16 == 0) && getenv("EQUSS_KNN_SIMT") == nullptr;
   for (long long q0 = 0; q0 < nq; q0 += rc) {
     long long rows = nq - q0 < rc ? nq - q0 : rc;

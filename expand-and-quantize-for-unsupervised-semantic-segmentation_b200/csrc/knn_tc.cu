@@ -12,6 +12,7 @@
 // Tiles are walked column-major (all row tiles of one database tile before the next), so at any time the 148 CTAs
 // share ~3 database tiles in L2 and the query chunk stays L2-resident.
 #include <cuda.h>
+#include <cstring>
 #include "equss_common.cuh"
 #include "equss_tcgen05.cuh"
 
@@ -38,8 +39,49 @@ struct Params {
   int F, n_kc;
   int m_tiles, n_tiles;
   float* S;
+  // fused top-k (TOPK kernels): a CTA owns (row tile, column split) items and keeps the k best of every row of the item
+  // in shared memory while it walks the split's column tiles; partial lists go to part_val / part_idx [rows][splits][k]
+  int k, splits;
+  float* part_val;
+  int* part_idx;
 };
 
+// Order in which a CTA visits its output tiles; every warp role walks the same sequence.
+//   !TOPK: tiles column-major over the whole grid (t = bn * m_tiles + bm), round-robin over the CTAs.
+//   TOPK : items (bm, split) round-robin over the CTAs; inside an item the split's column tiles in increasing order.
+template <bool TOPK>
+struct TileWalk {
+  long long t, step, total;       // !TOPK: tile id; TOPK: item id
+  int m_tiles, n_tiles, splits;
+  int bm, bn, bn_end;
+  bool first, last;               // TOPK: first / last tile of the current item
+  __device__ __forceinline__ void set_item() {
+    const int sp = (int)(t / m_tiles);
+    bm = (int)(t - (long long)sp * m_tiles);
+    bn = (int)((long long)n_tiles * sp / splits);
+    bn_end = (int)((long long)n_tiles * (sp + 1) / splits);
+    first = true; last = (bn + 1 >= bn_end);
+  }
+  __device__ __forceinline__ bool init(const Params& p) {
+    m_tiles = p.m_tiles; n_tiles = p.n_tiles; splits = p.splits;
+    t = blockIdx.x; step = gridDim.x;
+    total = TOPK ? (long long)p.m_tiles * p.splits : (long long)p.m_tiles * p.n_tiles;
+    if (t >= total) return false;
+    if (TOPK) set_item();
+    else { bn = (int)(t / m_tiles); bm = (int)(t - (long long)bn * m_tiles); first = last = true; }
+    return true;
+  }
+  __device__ __forceinline__ bool next() {
+    if (TOPK && bn + 1 < bn_end) { ++bn; first = false; last = (bn + 1 >= bn_end); return true; }
+    t += step;
+    if (t >= total) return false;
+    if (TOPK) set_item();
+    else { bn = (int)(t / m_tiles); bm = (int)(t - (long long)bn * m_tiles); }
+    return true;
+  }
+};
+
+template <bool TOPK>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -53,9 +95,10 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total = (long long)p.m_tiles * p.n_tiles;
-  const int n_my = (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const int n_kc = p.n_kc;
+  // TOPK: per-row candidate lists behind the barriers: values [k][128] then indices [k][128] (row-minor: no bank conflicts)
+  float* s_lv = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+  int* s_li = reinterpret_cast<int*>(s_lv + 32 * kBM);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(lo_full + i, 8); mbar_init(st_empty + i, 2); }
@@ -72,9 +115,9 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   if (warp == kProducerWarp) {
     if (lane == 0) {
       int g = 0;
-      for (int it = 0; it < n_my; ++it) {
-        const long long t = blockIdx.x + (long long)it * gridDim.x;
-        const int bn = (int)(t / p.m_tiles), bm = (int)(t - (long long)bn * p.m_tiles);
+      TileWalk<TOPK> tw;
+      for (bool ok = tw.init(p); ok; ok = tw.next()) {
+        const int bn = tw.bn, bm = tw.bm;
         for (int c = 0; c < n_kc; ++c, ++g) {
           const int st = g % kStages;
           uint8_t* sp = smem + st * kStageBytes;
@@ -92,8 +135,9 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // K-major SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart (SBO); a K step of 8 floats advances 32 B
     const uint32_t d_hi = (uint32_t)((1024u >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
     const uint32_t base = smem_u32(smem);
-    int g = 0;
-    for (int it = 0; it < n_my; ++it) {
+    int g = 0, it = 0;
+    TileWalk<TOPK> tw;
+    for (bool ok = tw.init(p); ok; ok = tw.next(), ++it) {
       mbar_wait(acc_empty, (it & 1) ^ 1, 22);
       const uint32_t d_addr = tmem_base + (uint32_t)(part * kBN);
       for (int c = 0; c < n_kc; ++c, ++g) {
@@ -126,7 +170,8 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   } else if (warp >= kConvWarp0) {
     const int ct = threadIdx.x - kConvWarp0 * 32;      // 0..255
     int g = 0;
-    for (int it = 0; it < n_my; ++it) {
+    TileWalk<TOPK> tw;
+    for (bool ok = tw.init(p); ok; ok = tw.next()) {
       for (int c = 0; c < n_kc; ++c, ++g) {
         const int st = g % kStages;
         mbar_wait(raw_full + st, (g / kStages) & 1, 31);
@@ -161,11 +206,19 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int it = 0; it < n_my; ++it) {
-      const long long t = blockIdx.x + (long long)it * gridDim.x;
-      const int bn = (int)(t / p.m_tiles), bm = (int)(t - (long long)bn * p.m_tiles);
+    int it = 0;
+    // TOPK state of this thread's row: entries [0, cnt) of the list are valid, `thr` / `minpos` = the weakest of them
+    // once the list is full (cnt == k).  A candidate enters only if it beats `thr`; columns arrive in increasing order
+    // inside an item, so on equal similarity the earlier (lower) index stays -- torch.topk's order for the final merge.
+    const int k = p.k;
+    int cnt = 0, minpos = 0;
+    float thr = -INFINITY;
+    TileWalk<TOPK> tw;
+    for (bool ok = tw.init(p); ok; ok = tw.next(), ++it) {
+      const int bn = tw.bn, bm = tw.bm;
       const long long r = (long long)bm * kBM + row;
       const long long c0 = (long long)bn * kBN;
+      if (TOPK && tw.first) { cnt = 0; minpos = 0; thr = -INFINITY; }
       mbar_wait(acc_full, it & 1, 40);
       tc_fence_after();
 #pragma unroll 1
@@ -174,6 +227,32 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tmem_ld32(lane_base + (uint32_t)(ch * 32), vm);
         tmem_ld32(lane_base + (uint32_t)(kBN + ch * 32), vs);
         tmem_ld_wait();
+        if constexpr (TOPK) {
+          const long long cb = c0 + ch * 32;
+          if (r < p.rows && cb < p.n) {
+            const int nv = (int)((p.n - cb < 32) ? (p.n - cb) : 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(vm[j]) + __uint_as_float(vs[j]);
+              if (j < nv && (cnt < k || v > thr)) {
+                if (cnt < k) {
+                  s_lv[cnt * kBM + row] = v; s_li[cnt * kBM + row] = (int)(cb + j);
+                  ++cnt;
+                } else {
+                  s_lv[minpos * kBM + row] = v; s_li[minpos * kBM + row] = (int)(cb + j);
+                }
+                if (cnt == k) {               // weakest entry of the full list: lowest value, highest index among equals
+                  float mv = s_lv[row]; int mi = s_li[row], mp = 0;
+                  for (int e = 1; e < k; ++e) {
+                    const float ev = s_lv[e * kBM + row]; const int ei = s_li[e * kBM + row];
+                    if (ev < mv || (ev == mv && ei > mi)) { mv = ev; mi = ei; mp = e; }
+                  }
+                  thr = mv; minpos = mp;
+                }
+              }
+            }
+          }
+        } else {
         if (r < p.rows) {
           float* o = p.S + r * p.n + c0 + ch * 32;
           if (c0 + ch * 32 + 32 <= p.n && (p.n & 3) == 0) {
@@ -188,10 +267,21 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               if (c0 + ch * 32 + j < p.n) o[j] = __uint_as_float(vm[j]) + __uint_as_float(vs[j]);
           }
         }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
+      if (TOPK && tw.last && r < p.rows) {
+        // partial list of (row r, this item's split): unfilled slots carry index -1
+        const int sp = (int)(tw.t / p.m_tiles);
+        float* ov = p.part_val + ((long long)r * p.splits + sp) * k;
+        int* oi = p.part_idx + ((long long)r * p.splits + sp) * k;
+        for (int e = 0; e < k; ++e) {
+          ov[e] = (e < cnt) ? s_lv[e * kBM + row] : -INFINITY;
+          oi[e] = (e < cnt) ? s_li[e * kBM + row] : -1;
+        }
+      }
     }
   }
 
@@ -225,11 +315,10 @@ bool knn_gemm_tc_supported(const float* Q, const float* DB, const float* S, long
   return F > 0 && F % knntc::kKC == 0 && !((uintptr_t)Q & 15) && !((uintptr_t)DB & 15) && !((uintptr_t)S & 15);
 }
 
-int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st) {
+static int make_maps(const float* Q, const float* DB, long long rows, long long n, int F, CUtensorMap* tq, CUtensorMap* td) {
   using namespace knntc;
   PFN_encodeTiled encode = get_encode_fn();
   EQUSS_REQUIRE(encode != nullptr, EQUSS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  CUtensorMap tq, td;
   auto make = [&](CUtensorMap* tm, const float* base, long long nrows, int box_rows) {
     cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)nrows};
     cuuint64_t gstr[1] = {(cuuint64_t)F * 4};
@@ -238,19 +327,68 @@ int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
-  CUresult c1 = make(&tq, Q, rows, kBM), c2 = make(&td, DB, n, kBN);
+  CUresult c1 = make(tq, Q, rows, kBM), c2 = make(td, DB, n, kBN);
   EQUSS_REQUIRE(c1 == CUDA_SUCCESS && c2 == CUDA_SUCCESS, EQUSS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)c1, (int)c2);
+  return EQUSS_OK;
+}
+
+int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st) {
+  using namespace knntc;
+  CUtensorMap tq, td;
+  int rc = make_maps(Q, DB, rows, n, F, &tq, &td);
+  if (rc != EQUSS_OK) return rc;
   Params p;
+  memset(&p, 0, sizeof(p));
   p.rows = rows; p.n = n; p.F = F; p.n_kc = F / kKC;
   p.m_tiles = (int)((rows + kBM - 1) / kBM);
   p.n_tiles = (int)((n + kBN - 1) / kBN);
-  p.S = S;
+  p.S = S; p.splits = 1;
   const long long total = (long long)p.m_tiles * p.n_tiles;
   int grid = num_sms();
   if (total < grid) grid = (int)total;
-  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  knn_gemm_tc_kernel<<<grid, kThreads, kSmem, st>>>(tq, td, p);
+  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  knn_gemm_tc_kernel<false><<<grid, kThreads, kSmem, st>>>(tq, td, p);
   EQUSS_LAUNCH_OK("knn_gemm_tc_kernel");
+  return EQUSS_OK;
+}
+
+// Column splits of the fused top-k kernel: (row tiles x splits) items over the SMs with the least idle tail.
+int knn_topk_tc_splits(long long rows, long long n) {
+  using namespace knntc;
+  const long long m_tiles = (rows + kBM - 1) / kBM, n_tiles = (n + kBN - 1) / kBN;
+  const int sms = num_sms();
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 8 && s <= n_tiles; ++s) {
+    const long long items = m_tiles * s;
+    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+// GEMM with the running top-k fused into the epilogue: partial lists [rows][splits][k] (value, index); the similarity
+// matrix is never written.
+int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long long n, int F, int k, int splits,
+                       float* part_val, int* part_idx, cudaStream_t st) {
+  using namespace knntc;
+  CUtensorMap tq, td;
+  int rc = make_maps(Q, DB, rows, n, F, &tq, &td);
+  if (rc != EQUSS_OK) return rc;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.n = n; p.F = F; p.n_kc = F / kKC;
+  p.m_tiles = (int)((rows + kBM - 1) / kBM);
+  p.n_tiles = (int)((n + kBN - 1) / kBN);
+  p.k = k; p.splits = splits; p.part_val = part_val; p.part_idx = part_idx;
+  const long long items = (long long)p.m_tiles * splits;
+  int grid = num_sms();
+  if (items < grid) grid = (int)items;
+  constexpr int kSmemTopk = kSmem + 2 * 32 * kBM * 4;
+  static_assert(kSmemTopk <= 227 * 1024, "top-k lists do not fit next to the operand stages");
+  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTopk));
+  knn_gemm_tc_kernel<true><<<grid, kThreads, kSmemTopk, st>>>(tq, td, p);
+  EQUSS_LAUNCH_OK("knn_gemm_tc_kernel<topk>");
   return EQUSS_OK;
 }
 

@@ -88,6 +88,41 @@ def _upsampled_feature_norm(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     return n2.clamp_min(0).sqrt()
 
 
+class _ProbeLosses(torch.autograd.Function):
+    """Both evaluator losses with gradients for the probe parameters (through ``wmat`` / ``bias``, which the caller
+    assembles differentiably from the cluster centres and the linear probe)."""
+
+    @staticmethod
+    def forward(ctx, out, wmat, bias, label, Cc, Cp, C):
+        B, D, h, w = out.shape
+        out32 = out.detach().float().contiguous()
+        logits = ops.probe_logits(out32, wmat.detach(), bias.detach())
+        gram = ops.token_gram(out32)
+        need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        sums, n_valid, g = ops.probe_losses(logits, gram, B, h, w, Cp + C, label, C, (0, Cc), (Cp, C), want_grad=need)
+        P = label.numel()
+        nv = n_valid.to(torch.float64)
+        linear_loss = (sums[0] / nv[0]).float()              # 0/0 = nan when no pixel is labelled, like F.cross_entropy
+        cluster_loss = (-sums[1] / P).float()
+        if need:
+            ctx.save_for_backward(out32, g, nv)
+        ctx.meta = (Cc, Cp, C, P, wmat.shape[0])
+        return linear_loss, cluster_loss
+
+    @staticmethod
+    def backward(ctx, g_lin, g_clu):
+        out32, g, nv = ctx.saved_tensors
+        Cc, Cp, C, P, rows = ctx.meta
+        B, D, h, w = out32.shape
+        scale = torch.zeros(g.shape[1], device=g.device)
+        scale[:Cc] = -g_clu.float() / P
+        scale[Cp:Cp + C] = g_lin.float() / nv[0].float()
+        gs = g * scale                                                           # [N, C_pad]
+        grad_w = torch.einsum("bnc,bdn->cd", gs.view(B, h * w, -1), out32.view(B, D, h * w))[:rows]
+        grad_b = gs.sum(dim=0)[:rows]
+        return None, grad_w, grad_b, None, None, None, None
+
+
 class UnSegEvaluator(nn.Module):
     """model/evaluator.py:11-82."""
 
@@ -145,6 +180,24 @@ class UnSegEvaluator(nn.Module):
         return preds[1], preds[0]
 
     def _losses(self, out: torch.Tensor, label: torch.Tensor, cluster_preds: torch.Tensor):
+        """(linear_loss, cluster_loss) of model/evaluator.py:65-80,106.  Kernel path (K8b): token logits -> one pass over
+        the label pixels (interpolation + masked cross-entropy + cosine of the winning cluster, and the transposed
+        interpolation of the logit gradients); the probe-parameter gradients are one [C_pad x N] x [N x D] contraction.
+        Features that require a gradient themselves (no reference caller: the wrappers pass ``out.detach()``) take the
+        differentiable PyTorch formulation below."""
+        B, D, h, w = out.shape
+        H, W = label.shape[-2:]
+        C, Cc = self.num_classes, self.cluster_probe.n_classes
+        Cp = (Cc + 3) // 4 * 4
+        if out.requires_grad or not ops.N.lib().equss_probe_losses_supported(h, w, H, W, Cp + C, Cc, C, 0, Cp):
+            return self._losses_torch(out, label, cluster_preds)
+        dev = out.device
+        wmat = torch.cat([F.normalize(self.cluster_probe.clusters.float(), dim=1), torch.zeros(Cp - Cc, D, device=dev),
+                          self.linear_probe.weight.float().view(C, D)], dim=0)
+        bias = torch.cat([torch.zeros(Cp, device=dev), self.linear_probe.bias.float()])
+        return _ProbeLosses.apply(out, wmat, bias, label, Cc, Cp, C)
+
+    def _losses_torch(self, out: torch.Tensor, label: torch.Tensor, cluster_preds: torch.Tensor):
         B, D, h, w = out.shape
         H, W = label.shape[-2:]
         C = self.num_classes

@@ -15,7 +15,8 @@ from . import _native as N
 __all__ = [
     "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
     "pq_distance_prob", "pq_soft_stats", "channel_moments", "usage_percentiles", "pq_train_tail", "pq_prepare_codebook",
-    "TAIL_KEYS", "probe_pack", "probe_logits", "probe_argmax_confusion", "confusion_update", "knn_topk",
+    "TAIL_KEYS", "probe_pack", "probe_logits", "probe_argmax_confusion", "probe_losses", "token_gram",
+    "confusion_update", "knn_topk",
     "launch_count",
 ]
 
@@ -413,6 +414,42 @@ def probe_argmax_confusion(logits: torch.Tensor, B: int, h: int, w: int, c_total
         N.as_i32_array(rows), N.stream_ptr(dev))
     N.check(rc, "equss_probe_argmax_confusion")
     return preds
+
+
+def token_gram(feat: torch.Tensor) -> torch.Tensor:
+    """2x2 Gram terms of the token grid, float32 [B*h*w, 5]: <x,x>, <x,right>, <x,down>, <x,down-right>, <x,down-left>
+    over the channels of feat (B, D, h, w).  The norm of the bilinearly upsampled feature vector at any label pixel
+    (model/evaluator.py:96 F.normalize of the upsampled map) follows from these without forming the map."""
+    dev = N.require_cuda(feat)
+    N.ensure_device(dev)
+    feat = N.f32c(feat.detach())
+    B, D, h, w = feat.shape
+    gram = torch.empty((B * h * w, 5), dtype=torch.float32, device=dev)
+    N.check(N.lib().equss_token_gram(feat.data_ptr(), B, D, h, w, gram.data_ptr(), N.stream_ptr(dev)), "equss_token_gram")
+    return gram
+
+
+def probe_losses(logits: torch.Tensor, gram: torch.Tensor, B: int, h: int, w: int, c_total: int, label: torch.Tensor,
+                 num_classes: int, cluster_head: Tuple[int, int], linear_head: Tuple[int, int], want_grad: bool = False):
+    """Sums behind the two evaluator losses (model/evaluator.py:65-80,95-106) from token-resolution logits, with the
+    bilinear upsampling fused in.  Returns (sums float64 [2], n_valid int64 [1], grad_logits or None):
+    linear_loss = sums[0] / n_valid, cluster_loss = -sums[1] / label.numel(); grad_logits [B*h*w, C_pad] holds the
+    gradients of the two SUMS w.r.t. the token logits (see include/equss_b200.h)."""
+    dev = N.require_cuda(logits, gram, label)
+    label = label.contiguous()
+    assert label.dtype == torch.int64 and label.dim() == 3 and label.shape[0] == B
+    H, W = int(label.shape[1]), int(label.shape[2])
+    L = N.lib()
+    (oc, cc), (ol, cl) = cluster_head, linear_head
+    if not L.equss_probe_losses_supported(h, w, H, W, c_total, cc, cl, oc, ol):
+        raise ValueError("probe_losses: unsupported head layout / shape")
+    acc = torch.zeros((3,), dtype=torch.float64, device=dev)
+    sums, nv = acc[:2], acc[2:].view(torch.int64)
+    g = torch.zeros_like(logits) if want_grad else None
+    rc = L.equss_probe_losses(logits.data_ptr(), gram.data_ptr(), B, h, w, c_total, label.data_ptr(), H, W, num_classes,
+                              oc, cc, ol, cl, sums.data_ptr(), nv.data_ptr(), N.ptr(g), N.stream_ptr(dev))
+    N.check(rc, "equss_probe_losses")
+    return sums, nv, g
 
 
 def confusion_update(preds: torch.Tensor, label: torch.Tensor, num_classes: int, confusion: torch.Tensor) -> None:

@@ -259,6 +259,29 @@ int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c
                                  const int32_t* conf_rows_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K8b probe losses at label resolution   replaces model/evaluator.py:65-80 (masked cross-entropy of the
+ *     linear probe) and :95-106 (ClusterLookup, alpha=None: minus the mean cosine between the upsampled feature and
+ *     its nearest cluster centre), forward and backward, from the token-resolution logits of K8 step 1.
+ *   equss_token_gram: gram[b][y][x][5] = <x,x>, <x,right>, <x,down>, <x,down-right>, <x,down-left> over the D channels
+ *     of feat (B, D, h, w); the norm of the bilinearly interpolated feature vector follows from these 2x2 terms.
+ *   equss_probe_losses:  sums[0] += sum over valid pixels (0 <= label < C) of  logsumexp(v_lin) - v_lin[label]
+ *                        sums[1] += sum over ALL label pixels of  max_j v_clu[j] / max(|up(x)|, 1e-12)
+ *                        n_valid += number of valid pixels       (linear_loss = sums[0]/n_valid, cluster_loss = -sums[1]/(B*H*W))
+ *     grad_logits (optional, [B*h*w][C_pad], caller-zeroed): the transpose of the interpolation applied to the per-pixel
+ *     gradients of the two SUMS above w.r.t. the interpolated logits (softmax - onehot on the linear channels,
+ *     1/norm at the winning cluster channel); the caller scales by 1/n_valid, -1/(B*H*W) and the upstream gradients and
+ *     contracts with the features (a [C_pad x N] x [N x D] library GEMM) to obtain the probe-parameter gradients.
+ *   Heads as in equss_probe_argmax_confusion: cluster channels [off_cluster, +cnt_cluster), linear [off_linear, +cnt_linear).
+ * ------------------------------------------------------------------------------------------- */
+int equss_token_gram(const float* feat, int B, int D, int h, int w, float* gram, void* stream);
+int equss_probe_losses_supported(int h, int w, int H, int W, int c_total, int cnt_cluster, int cnt_linear,
+                                 int off_cluster, int off_linear);
+int equss_probe_losses(const float* logits, const float* gram, int B, int h, int w, int c_total,
+                       const int64_t* label, int H, int W, int num_classes,
+                       int off_cluster, int cnt_cluster, int off_linear, int cnt_linear,
+                       double* sums, uint64_t* n_valid, float* grad_logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K9  confusion histogram          replaces UnSegMetrics.update, model/metric.py:44-58
  *   confusion[pred][label] += 1 for every position with 0<=label<C and 0<=pred<C.
  *   confusion: [rows][C] int64 with rows = C + extra_classes.

@@ -159,3 +159,45 @@ def test_knn_vs_topk(nq, n, Fd, k):
             assert abs(float(exact[r, j] - kth[r])) < 5e-6, (r, j)
     if nq <= n:
         assert torch.equal(idx[:, 0], torch.arange(nq))     # column 0 is the query itself (dataset_aug.py:520)
+
+
+@pytest.mark.parametrize("B,D,h,w,H,W,extra", [(2, 32, 10, 10, 40, 40, 0), (3, 48, 7, 5, 23, 31, 0), (1, 64, 28, 28, 224, 224, 3),
+                                                (2, 16, 6, 6, 6, 6, 0)])
+def test_probe_losses_and_gradients_vs_reference_formulation(B, D, h, w, H, W, extra):
+    """K8b: linear (masked CE) and cluster (mean cosine of the winning centre) losses of UnSegEvaluator.forward and their
+    gradients w.r.t. the probe parameters, against the oracle's formulation on upsampled features with CPU autograd
+    (model/evaluator.py:46-82,95-106).  Integer and non-integer scale factors, identity size, extra clusters."""
+    from equss_b200.evaluator import UnSegEvaluator
+    torch.manual_seed(B * 100 + D)
+    C = 27
+    ev = UnSegEvaluator(D, C, extra_classes=extra)
+    with torch.no_grad():
+        ev.linear_probe.weight.mul_(3.0)
+    feat = torch.randn(B, D, h, w)
+    label = torch.randint(-1, C, (B, H, W))
+    # oracle on CPU with autograd through its own parameters
+    cl = ev.cluster_probe.clusters.detach().clone().requires_grad_(True)
+    lw = ev.linear_probe.weight.detach().view(C, D).clone().requires_grad_(True)
+    lb = ev.linear_probe.bias.detach().clone().requires_grad_(True)
+    ll_ref, lp_ref, cl_ref, cp_ref = O.evaluator_forward(feat, label, cl, lw, lb, C)
+    (ll_ref + 0.7 * cl_ref).backward()
+    ev = ev.to("cuda:0").train()
+    ll, lp, closs, cp = ev(feat.cuda(), None, label.cuda())
+    assert float(ll) == pytest.approx(float(ll_ref), rel=1e-5)
+    assert float(closs) == pytest.approx(float(cl_ref), rel=1e-5)
+    (ll + 0.7 * closs).backward()
+    for got, ref, name in ((ev.cluster_probe.clusters.grad, cl.grad, "clusters"),
+                           (ev.linear_probe.weight.grad.view(C, D), lw.grad, "linear weight"),
+                           (ev.linear_probe.bias.grad, lb.grad, "linear bias")):
+        scale = float(ref.abs().max())
+        err = float((got.cpu() - ref).abs().max())
+        assert err <= 3e-5 * scale + 1e-9, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+    # no-grad call: forward-only kernel, same values
+    ev.eval()
+    with torch.no_grad():
+        ll2, _, cl2, _ = ev(feat.cuda(), None, label.cuda())
+    assert float(ll2) == pytest.approx(float(ll_ref), rel=1e-5) and float(cl2) == pytest.approx(float(cl_ref), rel=1e-5)
+    # all-ignored labels: the reference's cross-entropy over an empty selection is NaN
+    with torch.no_grad():
+        ll3, _, _, _ = ev(feat.cuda(), None, torch.full((B, H, W), -1, device="cuda:0"))
+    assert torch.isnan(ll3)
