@@ -18,6 +18,6 @@ def _lazy(name):
 
 
 def __getattr__(name):
-    if name in ("quantizer", "quantizer_v2", "codebooks", "evaluator", "metric", "knn", "head", "dist_utils", "build"):
+    if name in ("quantizer", "quantizer_v2", "codebooks", "evaluator", "metric", "knn", "head", "dist_utils", "build", "losses"):
         return _lazy(name)
     raise AttributeError(name)

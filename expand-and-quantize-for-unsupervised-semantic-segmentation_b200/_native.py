@@ -37,7 +37,7 @@ EXPORTS = [
     "equss_head_gemm_supported", "equss_head_gemm",
     "equss_pq_soft_stats_supported", "equss_pq_soft_stats", "equss_channel_moments",
     "equss_pq_train_tail_scratch_floats", "equss_pq_train_tail", "equss_pq_prepare_codebook",
-    "equss_token_gram", "equss_probe_losses_supported", "equss_probe_losses",
+    "equss_token_gram", "equss_probe_losses_supported", "equss_probe_losses", "equss_stego_feature_corr",
 ]
 
 
@@ -143,6 +143,8 @@ def _declare(L: C.CDLL) -> None:
     L.equss_probe_losses_supported.argtypes = [i32] * 9
     L.equss_probe_losses.restype = i32
     L.equss_probe_losses.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.equss_stego_feature_corr.restype = i32
+    L.equss_stego_feature_corr.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.equss_channel_moments.restype = i32
     L.equss_channel_moments.argtypes = [vp, zp, vp, vp]
     L.equss_probe_argmax_confusion.restype = i32

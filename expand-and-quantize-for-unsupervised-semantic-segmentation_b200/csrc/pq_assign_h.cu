@@ -102,12 +102,16 @@ finalize_merge_kernel(const unsigned long long* __restrict__ merged, long long t
   if (i < total) idx_out[i] = (int32_t)(merged[i] & 0xFFFFFFFFull);
 }
 
-// Rows listed as cross-chunk near-ties get a full exact scan over all K codes: one warp per row, the row in
-// registers, lanes stride over the codes, first minimal index wins (the SIMT kernel's arithmetic).
-template <int D>
+// Listed rows (ambiguous inside a chunk, or cross-chunk near-ties; duplicates allowed) get a full exact scan over all K
+// codes: one warp per row, the row in registers, lanes stride over the codes, first minimal index wins (the SIMT
+// kernel's arithmetic).  FIX: the main kernel already wrote the fused gather with the provisional winner; rows whose
+// winner changes get their output row rewritten and the squared-error sum corrected (atomicExch on the index makes
+// the repair happen exactly once per row even when the row is listed twice).
+template <int D, bool FIX>
 __global__ void __launch_bounds__(128)
 rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __restrict__ count, const float* __restrict__ z,
-                      ZView zv, const float* __restrict__ cb, const float* __restrict__ cn2, int K, int32_t* __restrict__ idx_out) {
+                      ZView zv, const float* __restrict__ cb, const float* __restrict__ cn2, int K, int32_t* __restrict__ idx_out,
+                      const float* __restrict__ gsrc, float* __restrict__ out, double* __restrict__ sqerr) {
   constexpr int LPS = D / 4;
   const int lane = threadIdx.x & 31;
   const unsigned int n_list = *count;
@@ -151,7 +155,31 @@ rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __r
       const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
       if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) idx_out[o] = (bi == 0x7fffffff) ? 0 : bi;
+    if (bi == 0x7fffffff) bi = 0;
+    int old = bi;
+    if (lane == 0) old = FIX ? atomicExch(idx_out + o, bi) : (idx_out[o] = bi, bi);
+    if constexpr (FIX) {
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old != bi) {
+        // K3 for this row with the exact winner (model/quantizer.py:474,514,536), lanes 0..D/4-1 one float4 each
+        const float* qn = gsrc + ((long long)m * K + bi) * D;
+        const float* qo = gsrc + ((long long)m * K + old) * D;
+        float e_new = 0.f, e_old = 0.f;
+#pragma unroll
+        for (int q = 0; q < LPS; ++q) {
+          const float4 cn = __ldg(reinterpret_cast<const float4*>(qn) + q), co = __ldg(reinterpret_cast<const float4*>(qo) + q);
+          const float d0 = cn.x - x[4 * q], d1 = cn.y - x[4 * q + 1], d2 = cn.z - x[4 * q + 2], d3 = cn.w - x[4 * q + 3];
+          e_new += group_sumsq(d0, d1, d2, d3);
+          e_old += group_sumsq(co.x - x[4 * q], co.y - x[4 * q + 1], co.z - x[4 * q + 2], co.w - x[4 * q + 3]);
+          if (lane == 0) {
+            float* orow = out + base + (long long)(4 * q) * zv.stride_c;
+            orow[0] = x[4 * q] + d0; orow[zv.stride_c] = x[4 * q + 1] + d1;
+            orow[2 * zv.stride_c] = x[4 * q + 2] + d2; orow[3 * zv.stride_c] = x[4 * q + 3] + d3;
+          }
+        }
+        if (lane == 0) atomicAdd(sqerr + m, (double)e_new - (double)e_old);
+      }
+    }
   }
 }
 
@@ -208,8 +236,9 @@ int64_t assign_tch_workspace_bytes(int64_t n_pixels, int M, int K, int d) {
   tch::Plan pl = tch::make_plan(M, K, d, false);
   if (!pl.ok) return 0;
   const int64_t img = tch::align_up(tch::b_bytes(d, pl.NC), 128);
-  int64_t bytes = (int64_t)M * pl.nchunks * img;
-  if (pl.nchunks > 1) bytes += (int64_t)M * n_pixels * 12 + 64;
+  int64_t bytes = (int64_t)M * pl.nchunks * img + 64;                                   // operand images, list counter
+  if (pl.nchunks > 1) bytes += (int64_t)M * n_pixels * 8;                               // cross-chunk merge buffer
+  bytes += (int64_t)M * n_pixels * 4 * (pl.nchunks > 1 ? 2 * pl.nchunks : 1);           // rows listed for the exact scan
   return bytes + 256;
 }
 
@@ -242,13 +271,15 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
   const int img_bytes = align_up(b_bytes(d, pl.NC), 128);
   uint8_t* images = ws;
   unsigned long long* merged = nullptr;
-  uint32_t* flag_list = nullptr;
-  unsigned int* flag_count = nullptr;
+  unsigned int* flag_count = (unsigned int*)(ws + (size_t)M * pl.nchunks * img_bytes);   // 16 bytes, then merge buffer / list
+  uint32_t* flag_list;
   if (pl.nchunks > 1) {
-    flag_count = (unsigned int*)(ws + (size_t)M * pl.nchunks * img_bytes);       // 16 bytes, then the merge buffer
     merged = (unsigned long long*)(flag_count + 4);
     flag_list = (uint32_t*)(merged + (size_t)M * zd->n_pixels);
     EQUSS_CUDA_OK(cudaMemsetAsync(flag_count, 0, 16 + (size_t)M * zd->n_pixels * 8, st));
+  } else {
+    flag_list = (uint32_t*)(flag_count + 4);
+    EQUSS_CUDA_OK(cudaMemsetAsync(flag_count, 0, 16, st));
   }
   build_image_kernel<<<M * pl.nchunks, 256, 0, st>>>(codebook_norm, cnorm2, K, d, pl.NC, pl.nchunks, pl.G, images, img_bytes);
   EQUSS_LAUNCH_OK("build_image_kernel");
@@ -299,12 +330,15 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
     const long long total = (long long)M * zd->n_pixels;
     finalize_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(merged, total, idx_out);
     EQUSS_LAUNCH_OK("finalize_merge_kernel");
-    const int rgrid = num_sms() * 4;
-    if (d == 16) rescan_flagged_kernel<16><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out);
-    else if (d == 32) rescan_flagged_kernel<32><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out);
-    else rescan_flagged_kernel<64><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out);
-    EQUSS_LAUNCH_OK("rescan_flagged_kernel");
   }
+  // exact scan of the listed rows (a few per ten thousand); repairs the fused gather where the winner changes
+  const int rgrid = num_sms() * 4;
+#define EQUSS_RESCAN(DV)                                                                                                  \
+  if (fuse) rescan_flagged_kernel<DV, true><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, gather_src, out, sqerr); \
+  else rescan_flagged_kernel<DV, false><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, nullptr, nullptr, nullptr);
+  if (d == 16) { EQUSS_RESCAN(16) } else if (d == 32) { EQUSS_RESCAN(32) } else { EQUSS_RESCAN(64) }
+#undef EQUSS_RESCAN
+  EQUSS_LAUNCH_OK("rescan_flagged_kernel");
   return EQUSS_OK;
 }
 

@@ -61,8 +61,11 @@ constexpr float kTolRel = 1.52587890625e-5f;     // 2^-16
 #ifdef EQUSS_TRACE   // scripts/trace_assign.cu: per-unit clock64 stamps of CTA 0 (pipeline timeline)
 __device__ long long g_trace[256 * 12];
 #define EQUSS_TR(slot, i) do { if (blockIdx.x == 0 && (i) < 256 && lane == 0) g_trace[(i) * 12 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long equss_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define EQUSS_TRG(slot, i) do { if (blockIdx.x == 0 && (i) < 256 && lane == 0) g_trace[(i) * 12 + (slot)] = equss_globaltimer(); } while (0)
 #else
 #define EQUSS_TR(slot, i) do { } while (0)
+#define EQUSS_TRG(slot, i) do { } while (0)
 #endif
 
 __host__ __device__ constexpr int kch(int D) { return 2 * (D / 8) + 2; }           // 16-byte K chunks per row
@@ -534,7 +537,12 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           for (int u = 0; u < BATCH; ++u) {
             float zx, zy, zz, zw;
             if constexpr (FUSE) {      // canonical z_norm (the gather needs it bit-exact); kept in the raw stage
+#ifdef EQUSS_FUSE_FASTNORM
+              const float inv_ = 1.f / l2_denom_fast(ss[u]);
+              const float4 zn = make_float4(v[u].x * inv_, v[u].y * inv_, v[u].z * inv_, v[u].w * inv_);
+#else
               const float4 zn = div4_fast(v[u], l2_denom_fast(ss[u]));
+#endif
               zx = zn.x; zy = zn.y; zz = zn.z; zw = zn.w;
               zn4[u] = zn;
             } else {
@@ -678,22 +686,14 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       const int kvalid = min(NC, p.K - chunk * NC);
       const bool amb = live && (!(m1 - runner > tol) || best_col >= kvalid);
-      unsigned todo = __ballot_sync(0xffffffffu, amb);
-      if (todo) {
-        // ambiguous rows: exact fp32 re-score of every column whose class maximum is within tolerance, one row
-        // at a time by the whole warp
-        const float thr = m1 - tol;
-        uint32_t cmask = 0;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) cmask |= (!(cls[r] < thr)) ? (1u << r) : 0u;
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const long long n_s = __shfl_sync(0xffffffffu, n, src);
-          const uint32_t cm_s = __shfl_sync(0xffffffffu, cmask, src);
-          const int res = exact_rescore_warp<D>(p, m, n_s, chunk * NC, kvalid, cm_s, lane);
-          if (lane == src) best_col = res;
-        }
+      if (amb) {
+        // Ambiguous rows (~3e-4 of them) keep a provisional winner here and are listed for an exact fp32 scan by
+        // rescan_flagged_kernel after this kernel (which also repairs the fused gather of rows whose winner changes).
+        // Re-scoring them inline stalled the pipeline: one warp busy with dependent global loads for several
+        // microseconds holds back its TMEM quarter, the accumulator ring is two deep, and the MMA issuers wait
+        // (clock64 traces: ~45 % of the d = 64 kernel's time, scripts/trace_assign.cu).
+        if (best_col >= kvalid) best_col = 0;
+        p.flag_list[atomicAdd(p.flag_count, 1u)] = (uint32_t)((long long)m * p.n_pixels + n);
       }
       if constexpr (FUSE) {
         const int ib = i % kIdxBufs;
@@ -715,7 +715,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           }
         }
       }
-      if (q == 0) EQUSS_TR(6, i);
+      if (q == 0) { EQUSS_TR(6, i); if (!FUSE) EQUSS_TRG(8, i); }
     }
   }
 

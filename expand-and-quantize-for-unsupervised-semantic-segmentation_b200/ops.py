@@ -16,7 +16,7 @@ __all__ = [
     "pq_cnorm2", "pq_assign", "pq_assign_gather", "pq_gather_loss", "pq_gather_loss_bwd", "pq_accumulate", "ema_update",
     "pq_distance_prob", "pq_soft_stats", "channel_moments", "usage_percentiles", "pq_train_tail", "pq_prepare_codebook",
     "TAIL_KEYS", "probe_pack", "probe_logits", "probe_argmax_confusion", "probe_losses", "token_gram",
-    "confusion_update", "knn_topk",
+    "confusion_update", "knn_topk", "stego_feature_corr",
     "launch_count",
 ]
 
@@ -539,3 +539,23 @@ def knn_topk(queries: torch.Tensor, db: torch.Tensor, k: int, return_sims: bool 
                           N.stream_ptr(dev))
     N.check(rc, "equss_knn_topk")
     return (idx, sims) if return_sims else idx
+
+
+def stego_feature_corr(f1: torch.Tensor, f2: torch.Tensor, pointwise: bool = True) -> torch.Tensor:
+    """Feature-correlation tensor of the STEGO loss (model/loss.py:679-687): cosine similarity of every sampled position
+    of ``f1`` (n, C, S, S) with every sampled position of ``f2``, optionally row-centred and re-centred on the original
+    global mean; returns (n, S, S, S, S), no autograd history (the backbone is frozen)."""
+    dev = N.require_cuda(f1, f2)
+    N.ensure_device(dev)
+    a, b = N.f32c(f1.detach()), N.f32c(f2.detach())
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError(f"stego_feature_corr: expected two (n, C, S, S) tensors, got {tuple(a.shape)} and {tuple(b.shape)}")
+    n, C, S1, S2 = a.shape
+    P = S1 * S2
+    fd = torch.empty((n, P, P), dtype=torch.float32, device=dev)
+    sums = torch.zeros((2,), dtype=torch.float64, device=dev)
+    N.check(N.lib().equss_stego_feature_corr(a.data_ptr(), b.data_ptr(), n, C, P, int(bool(pointwise)), fd.data_ptr(),
+                                             sums.data_ptr(), N.stream_ptr(dev)), "equss_stego_feature_corr")
+    if pointwise:
+        fd += ((sums[0] - sums[1]) / fd.numel()).float()       # fd - fd.mean() + old_mean  (:686)
+    return fd.view(n, S1, S2, S1, S2)

@@ -317,6 +317,17 @@ int equss_head_gemm(const float* a1, int a1_nchw, int C1, const float* a2, int C
                     const float* w, const float* bias, int n_out, int relu, float* out, int64_t out_ld,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K14 STEGO feature correlation   replaces the no-grad half of STEGOLoss.helper, model/loss.py:679-687:
+ *     fd[n][p][q] = < f1[n,:,p] / max(|f1[n,:,p]|, 1e-10) , f2[n,:,q] / max(|f2[n,:,q]|, 1e-10) >
+ *     pointwise != 0:  fd[n][p][:] -= mean_q fd[n][p][:]
+ *   f1, f2: [n][C][P] sampled backbone features (P = feature_samples^2 <= 128 positions); fd: [n][P][P].
+ *   sums (fp64 [2], caller-zeroed): += sum of fd before / after the row centring; the reference's final
+ *   "fd - fd.mean() + old_mean" is the scalar (sums[0] - sums[1]) / (n*P*P) added to every element by the caller.
+ * ------------------------------------------------------------------------------------------- */
+int equss_stego_feature_corr(const float* f1, const float* f2, int n, int C, int P, int pointwise,
+                             float* fd, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -418,6 +418,54 @@ def expansion_head(x: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor]
 
 
 # --------------------------------------------------------------------------------------------------
+# STEGO correspondence loss  (model/loss.py:647-739)
+# --------------------------------------------------------------------------------------------------
+
+
+def stego_helper(f1: torch.Tensor, f2: torch.Tensor, c1: torch.Tensor, c2: torch.Tensor, shift: float, cfg: Dict
+                 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """STEGOLoss.helper (model/loss.py:677-700): feature correlation (no grad, optionally row-centred and re-centred on
+    its original mean), code correlation, ``-clamp(cd) * (fd - shift)``."""
+    with torch.no_grad():
+        fd = torch.einsum("nchw,ncij->nhwij", F.normalize(f1, dim=1, eps=1e-10), F.normalize(f2, dim=1, eps=1e-10))
+        if cfg["pointwise"]:
+            old_mean = fd.mean()
+            fd -= fd.mean([3, 4], keepdim=True)
+            fd = fd - fd.mean() + old_mean
+    cd = torch.einsum("nchw,ncij->nhwij", F.normalize(c1, dim=1, eps=1e-10), F.normalize(c2, dim=1, eps=1e-10))
+    min_val = 0.0 if cfg["zero_clamp"] else -9999.0
+    if cfg["stabilize"]:
+        loss = -cd.clamp(min_val, .8) * (fd - shift)
+    else:
+        loss = -cd.clamp(min_val) * (fd - shift)
+    return loss, cd
+
+
+def stego_forward(cfg: Dict, feats: torch.Tensor, feats_pos: torch.Tensor, code: torch.Tensor, code_pos: torch.Tensor
+                  ) -> torch.Tensor:
+    """STEGOLoss.forward (model/loss.py:702-739), drawing its random numbers in the reference's order on the tensors'
+    device (two coordinate sets, then one fixed-point-free permutation per negative sample)."""
+    def samp(t, coords):
+        return F.grid_sample(t, coords.permute(0, 2, 1, 3), padding_mode="border", align_corners=True)
+    n, S, dev = feats.shape[0], cfg["feature_samples"], feats.device
+    coords1 = torch.rand([n, S, S, 2], device=dev) * 2 - 1
+    coords2 = torch.rand([n, S, S, 2], device=dev) * 2 - 1
+    f, c = samp(feats, coords1), samp(code, coords1)
+    fp, cp = samp(feats_pos, coords2), samp(code_pos, coords2)
+    intra, _ = stego_helper(f, f, c, c, cfg["pos_intra_shift"], cfg)
+    inter, _ = stego_helper(f, fp, c, cp, cfg["pos_inter_shift"], cfg)
+    negs = []
+    for _ in range(cfg["neg_samples"]):
+        perm = torch.randperm(n, device=dev, dtype=torch.long)
+        perm[perm == torch.arange(n, device=dev)] += 1
+        perm = perm % n
+        neg, _ = stego_helper(f, samp(feats[perm], coords2), c, samp(code[perm], coords2), cfg["neg_inter_shift"], cfg)
+        negs.append(neg)
+    return (cfg["pos_intra_weight"] * intra.mean() + cfg["pos_inter_weight"] * inter.mean() +
+            cfg["neg_inter_weight"] * torch.cat(negs, dim=0).mean())
+
+
+# --------------------------------------------------------------------------------------------------
 # near-tie audit helpers (SURVEY 4.6) used by the parity tests
 # --------------------------------------------------------------------------------------------------
 

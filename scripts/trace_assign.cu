@@ -49,6 +49,13 @@ int main(int argc, char** argv) {
     long long* r = tr + i * 12;
     printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld | g: %7lld %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0, r[8] - t0, r[9] - t0, r[11] - t0, r[10] - t0);
   }
+  if (!fuse) {
+    int last = 0;
+    for (int i = 0; i < 256; ++i) if (tr[i * 12 + 6] != 0) last = i;
+    printf("units of CTA 0: %d; unit 2 -> unit %d: %lld cycles, %lld ns  => SM clock %.3f GHz\n", last + 1, last,
+           tr[last * 12 + 6] - tr[2 * 12 + 6], tr[last * 12 + 8] - tr[2 * 12 + 8],
+           (double)(tr[last * 12 + 6] - tr[2 * 12 + 6]) / (double)(tr[last * 12 + 8] - tr[2 * 12 + 8]));
+  }
   for (int i = 150; i < 170; ++i) {
     long long* r = tr + i * 12;
     printf("%3d | %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld %7lld\n", i, r[0] - t0, r[1] - t0, r[2] - t0, r[7] - t0, r[3] - t0, r[4] - t0, r[5] - t0, r[6] - t0);

@@ -327,3 +327,39 @@ def test_channel_moments_and_soft_stats_kernels():
         jr, er = core.soft_assignment_stats(prob.double(), M, K)
         assert float(jsd) == pytest.approx(float(jr), rel=1e-5), (M, K, d)
         assert float(ent) == pytest.approx(float(er), rel=1e-5), (M, K, d)
+
+
+def test_stego_loss_matches_reference(golden_dir):
+    """STEGOLoss.helper on the reference's fixture (loss tensor, code correlation, gradients w.r.t. both
+    code maps; pointwise / zero_clamp / stabilize variants), and the full forward against the oracle's formulation run
+    on the same device with the same generator state (coordinate draws + fixed-point-free permutations)."""
+    import equss_oracle as O
+    from equss_b200.losses import STEGOLoss
+    g = np.load(os.path.join(golden_dir, "stego.npz"))
+    cfg = {"pointwise": True, "zero_clamp": True, "stabilize": False, "feature_samples": 11, "neg_samples": 2,
+           "pos_intra_shift": float(g["pos_intra_shift"]), "pos_inter_shift": float(g["pos_inter_shift"]),
+           "neg_inter_shift": float(g["neg_inter_shift"]), "pos_intra_weight": float(g["pos_intra_weight"]),
+           "pos_inter_weight": float(g["pos_inter_weight"]), "neg_inter_weight": float(g["neg_inter_weight"])}
+    f1, f2 = torch.from_numpy(g["f1"]).to(DEV), torch.from_numpy(g["f2"]).to(DEV)
+    for tag, cfgv in (("a", cfg), ("b", dict(cfg, pointwise=False, zero_clamp=False, stabilize=True))):
+        mod = STEGOLoss(cfgv)
+        c1 = torch.from_numpy(g["c1"]).to(DEV).requires_grad_(True)
+        c2 = torch.from_numpy(g["c2"]).to(DEV).requires_grad_(True)
+        loss, cd = mod.helper(f1, f2, c1, c2, 0.2)
+        np.testing.assert_allclose(cd.detach().cpu().numpy(), g[f"{tag}_cd"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"{tag}_loss"], rtol=1e-5, atol=2e-6)
+        loss.mean().backward()
+        _close_grad(c1.grad, g[f"{tag}_g1"], f"stego {tag} d code")
+        _close_grad(c2.grad, g[f"{tag}_g2"], f"stego {tag} d code_pos")
+    torch.manual_seed(5)
+    n, Cf, Cc = 4, 384, 70
+    feats, feats_pos = torch.randn(n, Cf, 28, 28, device=DEV), torch.randn(n, Cf, 28, 28, device=DEV)
+    code = torch.randn(n, Cc, 28, 28, device=DEV, requires_grad=True)
+    code_pos = torch.randn(n, Cc, 28, 28, device=DEV)
+    torch.manual_seed(6)
+    got = STEGOLoss(cfg)(feats, feats_pos, code, code_pos)
+    torch.manual_seed(6)
+    ref = O.stego_forward(cfg, feats, feats_pos, code.detach(), code_pos)
+    assert float(got) == pytest.approx(float(ref), rel=1e-5, abs=1e-7)
+    got.backward()
+    assert code.grad is not None and float(code.grad.abs().sum()) > 0

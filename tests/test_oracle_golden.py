@@ -286,3 +286,13 @@ def test_v2_train_and_z_trainable_and_restart(golden_dir):
     dead, cand = O.restart_candidates(torch.zeros(int(g["K"]), dtype=torch.long), torch.from_numpy(g["a_z"]), random.Random(5))
     np.testing.assert_array_equal(cand.numpy(), g["a_init_rows"])
     assert len(dead) == int(g["K"])
+
+
+def test_stego_helper_fixture(golden_dir):
+    g = _load(golden_dir, "stego.npz")
+    cfg = {"pointwise": True, "zero_clamp": True, "stabilize": False}
+    f1, f2, c1, c2 = (torch.from_numpy(g[k]) for k in ("f1", "f2", "c1", "c2"))
+    for tag, cfgv in (("a", cfg), ("b", {"pointwise": False, "zero_clamp": False, "stabilize": True})):
+        loss, cd = O.stego_helper(f1, f2, c1, c2, 0.2, cfgv)
+        np.testing.assert_allclose(loss.numpy(), g[f"{tag}_loss"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(cd.numpy(), g[f"{tag}_cd"], rtol=1e-6, atol=1e-7)
