@@ -16,8 +16,9 @@ namespace equss {
 bool knn_gemm_tc_supported(const float* Q, const float* DB, const float* S, long long n, int F);
 int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st);
 int knn_topk_tc_splits(long long rows, long long n);
+int64_t knn_topk_tc_scratch_bytes();
 int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long long n, int F, int k, int splits,
-                       float* part_val, int* part_idx, cudaStream_t st);
+                       float* part_val, int* part_idx, void* scratch, cudaStream_t st);
 
 constexpr int KNN_BM = 128, KNN_BN = 128, KNN_BK = 8;
 
@@ -193,8 +194,8 @@ using namespace equss;
 
 extern "C" int64_t equss_knn_workspace_bytes(int64_t nq, int64_t n, int F, int k) {
   if (nq <= 0 || n <= 0) return 0;
-  if (knn_fused_shape(F) && getenv("EQUSS_KNN_UNFUSED") == nullptr)            // partial top-k lists only: O(nq * k)
-    return nq * (int64_t)knn_topk_tc_splits(nq, n) * k * 8 + 256;
+  if (knn_fused_shape(F) && getenv("EQUSS_KNN_UNFUSED") == nullptr)            // partial top-k lists O(nq * k) + per-SM scratch
+    return nq * (int64_t)knn_topk_tc_splits(nq, n) * k * 8 + knn_topk_tc_scratch_bytes() + 256;
   return knn_rows_per_chunk(nq, n) * n * 4;
 }
 
@@ -213,12 +214,13 @@ extern "C" int equss_knn_topk(const float* queries, int64_t nq, const float* db,
   if (knn_fused_shape(F) && aligned && getenv("EQUSS_KNN_UNFUSED") == nullptr && getenv("EQUSS_KNN_SIMT") == nullptr) {
     // tcgen05 GEMM with the running top-k in its epilogue, then a merge of the per-split lists
     const int splits = knn_topk_tc_splits(nq, n);
-    const int64_t need = nq * (int64_t)splits * k * 8;
+    const int64_t lists = (nq * (int64_t)splits * k * 8 + 15) & ~(int64_t)15;
+    const int64_t need = lists + knn_topk_tc_scratch_bytes();
     EQUSS_REQUIRE(workspace && workspace_bytes >= need, EQUSS_ERR_INVALID_ARG,
                   "equss_knn_topk: workspace of %lld bytes needed, got %lld", (long long)need, (long long)workspace_bytes);
     float* pv = (float*)workspace;
     int* pi = (int*)(pv + nq * (int64_t)splits * k);
-    int rc2 = knn_topk_tc_launch(queries, db, nq, n, F, k, splits, pv, pi, st);
+    int rc2 = knn_topk_tc_launch(queries, db, nq, n, F, k, splits, pv, pi, (char*)workspace + lists, st);
     if (rc2 != EQUSS_OK) return rc2;
     knn_merge_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(pv, pi, nq, splits * k, k, (long long*)idx_out, sim_out);
     EQUSS_LAUNCH_OK("knn_merge_kernel");

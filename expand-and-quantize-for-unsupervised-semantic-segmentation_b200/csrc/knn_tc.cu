@@ -13,6 +13,7 @@
 // share ~3 database tiles in L2 and the query chunk stays L2-resident.
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 #include "equss_common.cuh"
 #include "equss_tcgen05.cuh"
 
@@ -23,6 +24,8 @@ using namespace ::equss::ptx;
 
 constexpr int kBM = 128, kBN = 256, kKC = 32;        // tile rows / columns, features per stage
 constexpr int kStages = 2;
+constexpr int kCand = 128;        // fused top-k: candidate slots per row; compacted to the k best when fewer than kCandReserve are free
+constexpr int kCandReserve = 16;  // columns examined between two occupancy checks
 constexpr int kThreads = 32 * (4 + 1 + 2 + 8);       // 4 epilogue, producer, 2 MMA issuers, 8 convert warps
 constexpr int kEpiWarp0 = 0, kProducerWarp = 4, kMmaWarp = 5, kConvWarp0 = 7;
 constexpr int kARaw = kBM * 128, kBRaw = kBN * 128;  // bytes: 16 KB, 32 KB
@@ -44,6 +47,8 @@ struct Params {
   int k, splits;
   float* part_val;
   int* part_idx;
+  int debug;           // EQUSS_KNN_DEBUG (timing experiments): 1 = epilogue reads TMEM only
+  uint2* cand;         // [gridDim.x][kBM][kCand] candidate buffers (value bits, column), L2-resident scratch
 };
 
 // Order in which a CTA visits its output tiles; every warp role walks the same sequence.
@@ -96,9 +101,6 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kc = p.n_kc;
-  // TOPK: per-row candidate lists behind the barriers: values [k][128] then indices [k][128] (row-minor: no bank conflicts)
-  float* s_lv = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
-  int* s_li = reinterpret_cast<int*>(s_lv + 32 * kBM);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(raw_full + i, 1); mbar_init(lo_full + i, 8); mbar_init(st_empty + i, 2); }
@@ -207,18 +209,77 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     int it = 0;
-    // TOPK state of this thread's row: entries [0, cnt) of the list are valid, `thr` / `minpos` = the weakest of them
-    // once the list is full (cnt == k).  A candidate enters only if it beats `thr`; columns arrive in increasing order
-    // inside an item, so on equal similarity the earlier (lower) index stays -- torch.topk's order for the final merge.
+    // TOPK: every row of the tile owns kCand candidate slots in an L2-resident scratch buffer.  The thread that owns a
+    // row (TMEM lane = row) appends every similarity above the row's threshold `thr` -- two stores and a counter, no
+    // list maintenance.  When a row has fewer than kCandReserve free slots, the WARP compacts it: the 128 candidates are
+    // ranked cooperatively (4 per lane, all-pairs through shuffles; larger value first, lower column on ties), the k
+    // best are written back in order and the k-th becomes the new threshold.  Exact: `thr` is always the k-th best of
+    // the columns seen so far or lower, so nothing that belongs to the final top-k is ever dropped.
     const int k = p.k;
-    int cnt = 0, minpos = 0;
+    int cnt = 0;
     float thr = -INFINITY;
+    uint2* my = TOPK ? p.cand + ((size_t)blockIdx.x * kBM + row) * kCand : nullptr;
+    uint2* wbase = TOPK ? p.cand + ((size_t)blockIdx.x * kBM + q * 32) * kCand : nullptr;
+    // compaction of the candidates of row (q*32 + src) by the whole warp; returns the new (cnt, thr) to every lane
+    auto compact = [&](int src, int n_src, float& thr_out) -> int {
+      uint2* buf = wbase + (size_t)src * kCand;
+      // 64-bit sort keys: (order-preserving bits of the value) << 32 | ~column  -- larger key = better candidate, keys
+      // are distinct, and one integer comparison replaces the (value, column) pair logic (no divergent branches)
+      unsigned long long key[4];
+      int rank[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int e = lane + 32 * t;
+        uint2 u = make_uint2(0u, 0u);
+        if (e < n_src) u = __ldcg(buf + e);
+        const uint32_t sv = (u.x & 0x80000000u) ? ~u.x : (u.x | 0x80000000u);
+        key[t] = (e < n_src) ? (((unsigned long long)sv << 32) | (unsigned long long)(~u.y)) : 0ull;
+        rank[t] = 0;
+      }
+#pragma unroll
+      for (int t2 = 0; t2 < 4; ++t2) {
+        if (t2 * 32 >= n_src) break;                                                        // warp-uniform
+#pragma unroll 8
+        for (int l2 = 0; l2 < 32; ++l2) {
+          const unsigned long long ok = __shfl_sync(0xffffffffu, key[t2], l2);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) rank[t] += (ok > key[t]) ? 1 : 0;
+        }
+      }
+      __syncwarp();
+      const int keep = n_src < k ? n_src : k;
+      float kth = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t sv = (uint32_t)(key[t] >> 32);
+        const uint32_t vb = (sv & 0x80000000u) ? (sv & 0x7fffffffu) : ~sv;
+        if (lane + 32 * t < n_src && rank[t] < keep) __stcg(buf + rank[t], make_uint2(vb, ~(uint32_t)key[t]));
+        if (rank[t] == k - 1 && lane + 32 * t < n_src) kth = __uint_as_float(vb);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kth = fmaxf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+      __syncwarp();
+      thr_out = kth;                      // -inf while the row holds fewer than k candidates
+      return keep;
+    };
+    auto compact_rows = [&](bool mine) {
+      unsigned todo = __ballot_sync(0xffffffffu, mine);
+      if (todo) __syncwarp();             // the owners' appends are visible to the lanes that are about to read them
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+        float nthr;
+        const int ncnt = compact(src, n_src, nthr);
+        if (lane == src) { cnt = ncnt; thr = nthr; }
+      }
+    };
     TileWalk<TOPK> tw;
     for (bool ok = tw.init(p); ok; ok = tw.next(), ++it) {
       const int bn = tw.bn, bm = tw.bm;
       const long long r = (long long)bm * kBM + row;
       const long long c0 = (long long)bn * kBN;
-      if (TOPK && tw.first) { cnt = 0; minpos = 0; thr = -INFINITY; }
+      if (TOPK && tw.first) { cnt = 0; thr = -INFINITY; }
       mbar_wait(acc_full, it & 1, 40);
       tc_fence_after();
 #pragma unroll 1
@@ -229,28 +290,16 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tmem_ld_wait();
         if constexpr (TOPK) {
           const long long cb = c0 + ch * 32;
-          if (r < p.rows && cb < p.n) {
-            const int nv = (int)((p.n - cb < 32) ? (p.n - cb) : 32);
+          const int nv = (r < p.rows && cb < p.n && !(p.debug & 1)) ? (int)((p.n - cb < 32) ? (p.n - cb) : 32) : 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+          for (int half = 0; half < 32 / kCandReserve; ++half) {
+#pragma unroll
+            for (int jj = 0; jj < kCandReserve; ++jj) {
+              const int j = half * kCandReserve + jj;
               const float v = __uint_as_float(vm[j]) + __uint_as_float(vs[j]);
-              if (j < nv && (cnt < k || v > thr)) {
-                if (cnt < k) {
-                  s_lv[cnt * kBM + row] = v; s_li[cnt * kBM + row] = (int)(cb + j);
-                  ++cnt;
-                } else {
-                  s_lv[minpos * kBM + row] = v; s_li[minpos * kBM + row] = (int)(cb + j);
-                }
-                if (cnt == k) {               // weakest entry of the full list: lowest value, highest index among equals
-                  float mv = s_lv[row]; int mi = s_li[row], mp = 0;
-                  for (int e = 1; e < k; ++e) {
-                    const float ev = s_lv[e * kBM + row]; const int ei = s_li[e * kBM + row];
-                    if (ev < mv || (ev == mv && ei > mi)) { mv = ev; mi = ei; mp = e; }
-                  }
-                  thr = mv; minpos = mp;
-                }
-              }
+              if (j < nv && v > thr) { __stcg(my + cnt, make_uint2(__float_as_uint(v), (uint32_t)(cb + j))); ++cnt; }
             }
+            compact_rows(cnt > kCand - kCandReserve);
           }
         } else {
         if (r < p.rows) {
@@ -272,14 +321,18 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
-      if (TOPK && tw.last && r < p.rows) {
-        // partial list of (row r, this item's split): unfilled slots carry index -1
-        const int sp = (int)(tw.t / p.m_tiles);
-        float* ov = p.part_val + ((long long)r * p.splits + sp) * k;
-        int* oi = p.part_idx + ((long long)r * p.splits + sp) * k;
-        for (int e = 0; e < k; ++e) {
-          ov[e] = (e < cnt) ? s_lv[e * kBM + row] : -INFINITY;
-          oi[e] = (e < cnt) ? s_li[e * kBM + row] : -1;
+      if (TOPK && tw.last) {
+        // final compaction of every row, then the (at most k, ordered) survivors of (row, split) to the partial lists
+        compact_rows(cnt > 0);
+        if (r < p.rows) {
+          const int sp = (int)(tw.t / p.m_tiles);
+          float* ov = p.part_val + ((long long)r * p.splits + sp) * k;
+          int* oi = p.part_idx + ((long long)r * p.splits + sp) * k;
+          for (int e = 0; e < k; ++e) {
+            const uint2 u = (e < cnt) ? __ldcg(my + e) : make_uint2(0xff800000u, 0xffffffffu);
+            ov[e] = __uint_as_float(u.x);
+            oi[e] = (int)u.y;
+          }
         }
       }
     }
@@ -357,6 +410,7 @@ int knn_topk_tc_splits(long long rows, long long n) {
   using namespace knntc;
   const long long m_tiles = (rows + kBM - 1) / kBM, n_tiles = (n + kBN - 1) / kBN;
   const int sms = num_sms();
+  if (getenv("EQUSS_KNN_SPLITS")) return atoi(getenv("EQUSS_KNN_SPLITS"));
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= 8 && s <= n_tiles; ++s) {
@@ -369,8 +423,10 @@ int knn_topk_tc_splits(long long rows, long long n) {
 
 // GEMM with the running top-k fused into the epilogue: partial lists [rows][splits][k] (value, index); the similarity
 // matrix is never written.
+int64_t knn_topk_tc_scratch_bytes() { return (int64_t)num_sms() * knntc::kBM * knntc::kCand * 8; }
+
 int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long long n, int F, int k, int splits,
-                       float* part_val, int* part_idx, cudaStream_t st) {
+                       float* part_val, int* part_idx, void* scratch, cudaStream_t st) {
   using namespace knntc;
   CUtensorMap tq, td;
   int rc = make_maps(Q, DB, rows, n, F, &tq, &td);
@@ -380,14 +436,13 @@ int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long lon
   p.rows = rows; p.n = n; p.F = F; p.n_kc = F / kKC;
   p.m_tiles = (int)((rows + kBM - 1) / kBM);
   p.n_tiles = (int)((n + kBN - 1) / kBN);
-  p.k = k; p.splits = splits; p.part_val = part_val; p.part_idx = part_idx;
+  p.k = k; p.splits = splits; p.part_val = part_val; p.part_idx = part_idx; p.cand = (uint2*)scratch;
+  p.debug = getenv("EQUSS_KNN_DEBUG") ? atoi(getenv("EQUSS_KNN_DEBUG")) : 0;
   const long long items = (long long)p.m_tiles * splits;
   int grid = num_sms();
   if (items < grid) grid = (int)items;
-  constexpr int kSmemTopk = kSmem + 2 * 32 * kBM * 4;
-  static_assert(kSmemTopk <= 227 * 1024, "top-k lists do not fit next to the operand stages");
-  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTopk));
-  knn_gemm_tc_kernel<true><<<grid, kThreads, kSmemTopk, st>>>(tq, td, p);
+  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+  knn_gemm_tc_kernel<true><<<grid, kThreads, kSmem, st>>>(tq, td, p);
   EQUSS_LAUNCH_OK("knn_gemm_tc_kernel<topk>");
   return EQUSS_OK;
 }

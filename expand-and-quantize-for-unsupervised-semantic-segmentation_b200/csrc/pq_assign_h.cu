@@ -112,11 +112,15 @@ __global__ void __launch_bounds__(128)
 rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __restrict__ count, const float* __restrict__ z,
                       ZView zv, const float* __restrict__ cb, const float* __restrict__ cn2, int K, int32_t* __restrict__ idx_out,
                       const float* __restrict__ gsrc, float* __restrict__ out, double* __restrict__ sqerr) {
+  // one BLOCK per listed row: 128 threads stride over the K codes (a d = 64, K = 512 row is 128 KB of codebook reads;
+  // one warp per row left those loads latency-bound), warp shuffles + a 4-entry shared stage combine the minima
   constexpr int LPS = D / 4;
-  const int lane = threadIdx.x & 31;
+  __shared__ float s_best[4];
+  __shared__ int s_bi[4];
+  __shared__ int s_res[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned int n_list = *count;
-  const unsigned int warps = gridDim.x * (blockDim.x >> 5);
-  for (unsigned int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_list; e += warps) {
+  for (unsigned int e = blockIdx.x; e < n_list; e += gridDim.x) {
     const long long o = list[e];
     const int m = (int)(o / zv.n_pixels);
     const long long n = o - (long long)m * zv.n_pixels;
@@ -135,7 +139,7 @@ rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __r
     const float zn2 = butterfly_array<LPS>(gsum);
     float best = INFINITY;
     int bi = 0x7fffffff;
-    for (int k = lane; k < K; k += 32) {
+    for (int k = threadIdx.x; k < K; k += 128) {
       const float4* c4 = reinterpret_cast<const float4*>(cb + ((long long)m * K + k) * D);
       float dot = 0.f;
 #pragma unroll
@@ -155,29 +159,39 @@ rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __r
       const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
       if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (bi == 0x7fffffff) bi = 0;
-    int old = bi;
-    if (lane == 0) old = FIX ? atomicExch(idx_out + o, bi) : (idx_out[o] = bi, bi);
+    __syncthreads();                       // the previous row's readers of the shared stage are done
+    if (lane == 0) { s_best[warp] = best; s_bi[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w2 = 1; w2 < 4; ++w2)
+        if (s_best[w2] < best || (s_best[w2] == best && s_bi[w2] < bi)) { best = s_best[w2]; bi = s_bi[w2]; }
+      if (bi == 0x7fffffff) bi = 0;
+      s_res[0] = bi;
+      s_res[1] = FIX ? atomicExch(idx_out + o, bi) : (idx_out[o] = bi, bi);
+    }
     if constexpr (FIX) {
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old != bi) {
-        // K3 for this row with the exact winner (model/quantizer.py:474,514,536), lanes 0..D/4-1 one float4 each
-        const float* qn = gsrc + ((long long)m * K + bi) * D;
-        const float* qo = gsrc + ((long long)m * K + old) * D;
+      __syncthreads();
+      bi = s_res[0];
+      const int old = s_res[1];
+      if (old != bi && warp == 0) {
+        // K3 for this row with the exact winner (model/quantizer.py:474,514,536): lane q handles float4 piece q
         float e_new = 0.f, e_old = 0.f;
+        if (lane < LPS) {
+          const float4 cn = __ldg(reinterpret_cast<const float4*>(gsrc + ((long long)m * K + bi) * D) + lane);
+          const float4 co = __ldg(reinterpret_cast<const float4*>(gsrc + ((long long)m * K + old) * D) + lane);
+          float xq[4];
 #pragma unroll
-        for (int q = 0; q < LPS; ++q) {
-          const float4 cn = __ldg(reinterpret_cast<const float4*>(qn) + q), co = __ldg(reinterpret_cast<const float4*>(qo) + q);
-          const float d0 = cn.x - x[4 * q], d1 = cn.y - x[4 * q + 1], d2 = cn.z - x[4 * q + 2], d3 = cn.w - x[4 * q + 3];
-          e_new += group_sumsq(d0, d1, d2, d3);
-          e_old += group_sumsq(co.x - x[4 * q], co.y - x[4 * q + 1], co.z - x[4 * q + 2], co.w - x[4 * q + 3]);
-          if (lane == 0) {
-            float* orow = out + base + (long long)(4 * q) * zv.stride_c;
-            orow[0] = x[4 * q] + d0; orow[zv.stride_c] = x[4 * q + 1] + d1;
-            orow[2 * zv.stride_c] = x[4 * q + 2] + d2; orow[3 * zv.stride_c] = x[4 * q + 3] + d3;
-          }
+          for (int q = 0; q < LPS; ++q)
+            if (q == lane) { xq[0] = x[4 * q]; xq[1] = x[4 * q + 1]; xq[2] = x[4 * q + 2]; xq[3] = x[4 * q + 3]; }
+          const float d0 = cn.x - xq[0], d1 = cn.y - xq[1], d2 = cn.z - xq[2], d3 = cn.w - xq[3];
+          e_new = group_sumsq(d0, d1, d2, d3);
+          e_old = group_sumsq(co.x - xq[0], co.y - xq[1], co.z - xq[2], co.w - xq[3]);
+          float* orow = out + base + (long long)(4 * lane) * zv.stride_c;
+          orow[0] = xq[0] + d0; orow[zv.stride_c] = xq[1] + d1;
+          orow[2 * zv.stride_c] = xq[2] + d2; orow[3 * zv.stride_c] = xq[3] + d3;
         }
-        if (lane == 0) atomicAdd(sqerr + m, (double)e_new - (double)e_old);
+        const float de = warp_sum(e_new) - warp_sum(e_old);
+        if (lane == 0) atomicAdd(sqerr + m, (double)de);
       }
     }
   }
@@ -332,7 +346,7 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
     EQUSS_LAUNCH_OK("finalize_merge_kernel");
   }
   // exact scan of the listed rows (a few per ten thousand); repairs the fused gather where the winner changes
-  const int rgrid = num_sms() * 4;
+  const int rgrid = num_sms() * 8;
 #define EQUSS_RESCAN(DV)                                                                                                  \
   if (fuse) rescan_flagged_kernel<DV, true><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, gather_src, out, sqerr); \
   else rescan_flagged_kernel<DV, false><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, nullptr, nullptr, nullptr);
