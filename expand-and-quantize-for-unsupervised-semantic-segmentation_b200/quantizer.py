@@ -229,9 +229,11 @@ def _stack(ts: List[torch.Tensor]) -> torch.Tensor:
     return torch.stack(ts)
 
 
-def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_prob: bool = True):
+def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_prob: bool = True, stacked=None):
     """EMAVectorQuantizer.forward (quantizer.py:383-542) for M = len(mods) subspaces at once; z is flat
-    (n, M*d)."""
+    (n, M*d).  ``stacked``: the wrapper's cached [M, ...] views of (exact count, EMA count, weight_avg, weight) --
+    verifying on every call that the per-subspace buffers are slices of one storage costs more host time than the
+    whole step's launches at M = 64."""
     q0 = mods[0]
     M, K, mode, beta = len(mods), q0.num_codebook, q0.normalize, q0.beta
     if z.dim() != 2:
@@ -241,7 +243,7 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
     if q0.need_initialized != "none" and training:
         for i, q in enumerate(mods):
             q._maybe_initialize(z[:, i * d:(i + 1) * d])
-    weight = _stack([q.codebook.weight for q in mods])
+    weight = stacked[3] if stacked is not None else _stack([q.codebook.weight for q in mods])
     norm_a = norm_b = None
     if mode == "z_trainable":
         # quantizer.py:429-446: the std is taken BEFORE this step's running-statistics update, the mean is the buffer
@@ -282,9 +284,11 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
             count = packed[:, :, d]
             # in-place EMA update on the stacked state; zero-copy when the buffers are slices of one
             # storage (ProductQuantizerWrapper._restack), otherwise stack -> update -> write back
-            state = [[q.vq_count for q in mods], [q.codebook.vq_count for q in mods],
-                     [q.codebook.weight_avg for q in mods], [q.codebook.weight for q in mods]]
-            stacked = [_stack(ts) for ts in state]
+            state = None
+            if stacked is None:
+                state = [[q.vq_count for q in mods], [q.codebook.vq_count for q in mods],
+                         [q.codebook.weight_avg for q in mods], [q.codebook.weight for q in mods]]
+                stacked = [_stack(ts) for ts in state]
             exact_c, vqc_c, wavg_c, w_c = (t.contiguous() for t in stacked)
             if not q0.use_split:
                 # EMA update + percentiles x2 + usage + codebook-sum + loss scalars: ONE launch (:493-532)
@@ -294,7 +298,7 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
                 unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
                 output.update(core.percentile_stats(exact_c, "total"))                      # :496
                 output.update(core.percentile_stats(count, "current"))                      # :495
-            for ts, st in zip(state, (exact_c, vqc_c, wavg_c, w_c)):
+            for ts, st in zip(state or (), (exact_c, vqc_c, wavg_c, w_c)):
                 if st.data_ptr() != ts[0].data_ptr():
                     for i, t in enumerate(ts):
                         t.copy_(st[i])
@@ -317,8 +321,7 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
     commitment = mse_commit.mean()
     output["loss"] = beta * commitment                                                  # :526
     output["commitment-loss"] = commitment
-    output["codebook-sum"] = stats[7] if stats is not None else \
-        torch.sum(torch.abs(_stack([q.codebook.weight for q in mods]))) / M             # :532
+    output["codebook-sum"] = stats[7] if stats is not None else torch.sum(torch.abs(weight)) / M   # :532 (buffers updated in place)
     return out, output, prob
 
 
@@ -385,14 +388,19 @@ class ProductQuantizerWrapper(nn.Module):
     # dict exposes are views into it, so the kernels update every subspace in place with one launch.
     def _restack(self) -> None:
         qs = list(self.quantizers)
+        self._stacked = None
         if not qs or not all(isinstance(q, EMAVectorQuantizer) for q in qs):
             return
+        cache = {}
         with torch.no_grad():
-            for owner, name in ((lambda q: q.codebook, "weight"), (lambda q: q.codebook, "weight_avg"),
-                                (lambda q: q.codebook, "vq_count"), (lambda q: q, "vq_count")):
+            for key, owner, name in (("weight", lambda q: q.codebook, "weight"), ("weight_avg", lambda q: q.codebook, "weight_avg"),
+                                     ("ema_count", lambda q: q.codebook, "vq_count"), ("exact", lambda q: q, "vq_count")):
                 stacked = torch.stack([owner(q)._buffers[name] for q in qs]).contiguous()
                 for i, q in enumerate(qs):
                     owner(q)._buffers[name] = stacked[i]
+                cache[key] = stacked
+        # order expected by _ema_group_forward; dropped (-> re-derived per call) if a buffer is ever re-assigned
+        self._stacked = (cache["exact"], cache["ema_count"], cache["weight_avg"], cache["weight"])
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -401,6 +409,15 @@ class ProductQuantizerWrapper(nn.Module):
 
     def forward(self, z: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor], torch.Tensor]:
         qs = list(self.quantizers)
+        st = self._stacked
+        if st is not None:
+            # the cached views stay valid as long as nobody re-assigned a buffer (load_state_dict / .to() keep or rebuild them)
+            q0, qm = qs[0], qs[-1]
+            if q0.codebook.weight.data_ptr() == st[3].data_ptr() and qm.codebook.weight.data_ptr() == st[3][-1].data_ptr() \
+                    and q0.vq_count.data_ptr() == st[0].data_ptr():
+                return _ema_group_forward(qs, z, want_prob=self.materialize_prob, stacked=st)
+            self._restack()
+            return _ema_group_forward(qs, z, want_prob=self.materialize_prob, stacked=self._stacked)
         if all(isinstance(q, EMAVectorQuantizer) for q in qs):
             return _ema_group_forward(qs, z, want_prob=self.materialize_prob)
         if all(isinstance(q, VectorQuantizer) for q in qs):
