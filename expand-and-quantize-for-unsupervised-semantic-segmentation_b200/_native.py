@@ -37,7 +37,7 @@ EXPORTS = [
     "equss_head_gemm_supported", "equss_head_gemm",
     "equss_pq_soft_stats_supported", "equss_pq_soft_stats", "equss_channel_moments",
     "equss_pq_train_tail_scratch_floats", "equss_pq_train_tail", "equss_pq_prepare_codebook",
-    "equss_token_gram", "equss_probe_losses_supported", "equss_probe_losses", "equss_stego_feature_corr",
+    "equss_pq_train_tail_peers", "equss_token_gram", "equss_probe_losses_supported", "equss_probe_losses", "equss_stego_feature_corr",
 ]
 
 
@@ -135,6 +135,8 @@ def _declare(L: C.CDLL) -> None:
     L.equss_pq_train_tail_scratch_floats.argtypes = [i32]
     L.equss_pq_train_tail.restype = i32
     L.equss_pq_train_tail.argtypes = [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    L.equss_pq_train_tail_peers.restype = i32
+    L.equss_pq_train_tail_peers.argtypes = [vp, i32, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
     L.equss_pq_prepare_codebook.restype = i32
     L.equss_pq_prepare_codebook.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     L.equss_token_gram.restype = i32

@@ -58,6 +58,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
 }
+// Call-free variant (no printf): a kernel that re-partitions the register file with setmaxnreg must not contain ABI
+// calls -- with a callee shared by regions of different budgets ptxas falls back to the smallest budget everywhere.
+__device__ __forceinline__ void mbar_wait_nc(uint64_t* bar, uint32_t parity, int /*tag*/) {
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (int polls = 0; polls < (1 << 20); ++polls)
+    if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+  __trap();
+}
+// Wait of a warp that has slack (an epilogue group between its units, the TMA producer running ahead): explicit
+// nanosleep back-off between polls.  ncu showed the hint form above returning within ~50 ns however large the hint
+// (NANOSLEEP.SYNCS wakes on any barrier traffic of the CTA), i.e. ~50 polls x 9 instructions per wait: a quarter of
+// all instructions the assign kernel issued were polls.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (int polls = 0; polls < (1 << 24); ++polls) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  __trap();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -114,6 +136,13 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0` the compiler keeps the surrounding values in
+// uniform registers, so tcgen05.mma / tcgen05.commit issue without a per-instruction ELECT + R2UR.BROADCAST loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -74,7 +74,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
   uint64_t* acc_empty = acc_full + 1;         // [1] epilogue drained the accumulators
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const long long total = (long long)p.n_images * p.tiles_per_image * p.n_tiles_n;
   const int n_my = (int)((total - blockIdx.x + gridDim.x - 1) / gridDim.x);
   const int n_kc = p.kc1 + p.kc2;
@@ -89,7 +89,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
   // tile t (row-major: the n_tiles_n column tiles of a pixel tile are adjacent, so concurrent CTAs share its
   // activation tiles in L2 and the weights stay L2-resident)
@@ -101,7 +101,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
   };
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop (uniform values -> uniform registers), one elected lane issues the copies
       int g = 0;
       for (int it = 0; it < n_my; ++it) {
         int b, ti, bn;
@@ -111,6 +111,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
           const int st = g % kStages;
           uint8_t* sp = smem + st * kStageBytes;
           mbar_wait(st_empty + st, ((g / kStages) & 1) ^ 1, 10);
+          if (elect_one()) {
           mbar_expect_tx(raw_full + st, (uint32_t)(kARaw + p.bn * kRowB));
           if (c < p.kc1) {
             if (p.a1_nchw == 1) {
@@ -126,6 +127,8 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
             tma_load_2d(sp, &tmap_a2, (c - p.kc1) * kKC, row0, raw_full + st);
           }
           tma_load_2d(sp + 2 * kARaw, &tmap_w, c * kKC, bn * p.bn, raw_full + st);
+          }
+          __syncwarp();
         }
       }
     }
@@ -148,7 +151,7 @@ head_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a1, const __grid_co
         if (part == 0) mbar_wait(raw_full + st, (g / kStages) & 1, 20);
         else mbar_wait(lo_full + st, (g / kStages) & 1, 21);          // implies raw_full
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {   // elected lane + uniform operands: UTCHMMA issues from uniform registers
           const bool mn = p.a1_nchw && c < p.kc1;
           const uint32_t sa = base + (uint32_t)(st * kStageBytes);
           const uint32_t a_lbo = mn ? (((uint32_t)(kKC * 128) >> 4) << 16) : (1u << 16);

@@ -99,7 +99,7 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* acc_empty = acc_full + 1;         // [1] epilogue drained the accumulators
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int n_kc = p.n_kc;
 
   if (threadIdx.x == 0) {
@@ -112,10 +112,10 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop (uniform values -> uniform registers), one elected lane issues the copies
       int g = 0;
       TileWalk<TOPK> tw;
       for (bool ok = tw.init(p); ok; ok = tw.next()) {
@@ -124,9 +124,12 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const int st = g % kStages;
           uint8_t* sp = smem + st * kStageBytes;
           mbar_wait(st_empty + st, ((g / kStages) & 1) ^ 1, 10);
-          mbar_expect_tx(raw_full + st, kARaw + kBRaw);
-          tma_load_2d(sp, &tmap_q, c * kKC, bm * kBM, raw_full + st);
-          tma_load_2d(sp + 2 * kARaw, &tmap_db, c * kKC, bn * kBN, raw_full + st);
+          if (elect_one()) {
+            mbar_expect_tx(raw_full + st, kARaw + kBRaw);
+            tma_load_2d(sp, &tmap_q, c * kKC, bm * kBM, raw_full + st);
+            tma_load_2d(sp + 2 * kARaw, &tmap_db, c * kKC, bn * kBN, raw_full + st);
+          }
+          __syncwarp();
         }
       }
     }
@@ -147,7 +150,7 @@ knn_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         if (part == 0) mbar_wait(raw_full + st, (g / kStages) & 1, 20);
         else mbar_wait(lo_full + st, (g / kStages) & 1, 21);          // implies raw_full
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {   // elected lane + uniform operands: UTCHMMA issues from uniform registers
           const uint32_t sa = base + (uint32_t)(st * kStageBytes);
           const uint32_t a_raw = (sa >> 4) | (1u << 16), a_lo = ((sa + kARaw) >> 4) | (1u << 16);
           const uint32_t b_raw = ((sa + 2 * kARaw) >> 4) | (1u << 16), b_lo = ((sa + 2 * kARaw + kBRaw) >> 4) | (1u << 16);

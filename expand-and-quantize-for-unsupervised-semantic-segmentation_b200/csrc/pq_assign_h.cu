@@ -25,7 +25,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 build_image_kernel(const float* __restrict__ cb, const float* __restrict__ cn2, int K, int D, int NC, int nchunks, int G,
-                   uint8_t* __restrict__ images, int img_bytes) {
+                   uint8_t* __restrict__ images, int img_bytes, unsigned int* __restrict__ flag_count) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0u;      // list of rows for the exact rescan starts empty
   const int m = blockIdx.x / nchunks, c = blockIdx.x % nchunks;
   uint8_t* img = images + (size_t)(((m / G) * nchunks + c) * G + (m % G)) * img_bytes;
   const int sbo = b_sbo(D);
@@ -292,10 +293,9 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
     flag_list = (uint32_t*)(merged + (size_t)M * zd->n_pixels);
     EQUSS_CUDA_OK(cudaMemsetAsync(flag_count, 0, 16 + (size_t)M * zd->n_pixels * 8, st));
   } else {
-    flag_list = (uint32_t*)(flag_count + 4);
-    EQUSS_CUDA_OK(cudaMemsetAsync(flag_count, 0, 16, st));
+    flag_list = (uint32_t*)(flag_count + 4);          // the counter is reset by build_image_kernel
   }
-  build_image_kernel<<<M * pl.nchunks, 256, 0, st>>>(codebook_norm, cnorm2, K, d, pl.NC, pl.nchunks, pl.G, images, img_bytes);
+  build_image_kernel<<<M * pl.nchunks, 256, 0, st>>>(codebook_norm, cnorm2, K, d, pl.NC, pl.nchunks, pl.G, images, img_bytes, flag_count);
   EQUSS_LAUNCH_OK("build_image_kernel");
 
   CUtensorMap tmap;

@@ -2,6 +2,10 @@
 #include "pq_assign_h_kernel.cuh"
 namespace equss {
 namespace tch {
-EQUSS_TCH_DISPATCH(16, 2, 6, 4, 8, 4)
+#ifndef EQUSS_D16_STF
+#define EQUSS_D16_STF 8
+#define EQUSS_D16_LAG 4
+#endif
+EQUSS_TCH_DISPATCH(16, 2, 6, 4, EQUSS_D16_STF, EQUSS_D16_LAG)
 }  // namespace tch
 }  // namespace equss

@@ -2,6 +2,10 @@
 #include "pq_assign_h_kernel.cuh"
 namespace equss {
 namespace tch {
-EQUSS_TCH_DISPATCH(32, 1, 4, 3, 6, 3)
+#ifndef EQUSS_D32_STF
+#define EQUSS_D32_STF 6
+#define EQUSS_D32_LAG 4
+#endif
+EQUSS_TCH_DISPATCH(32, 1, 4, 3, EQUSS_D32_STF, EQUSS_D32_LAG)
 }  // namespace tch
 }  // namespace equss

@@ -45,18 +45,50 @@ namespace equss {
 namespace tch {
 
 using namespace ::equss::ptx;
+#ifdef EQUSS_DEBUG_WATCHDOG      // debug builds: the printf watchdog names the barrier a warp is stuck on (costs the
+#define mbar_wait_nc mbar_wait   // flow-sensitive register allocation, see mbar_wait_nc)
+#endif
 
 constexpr int kTileM = 128;
-constexpr int kEpiGroups = 2;                    // epilogue groups of four warps, rotating over the units
+#ifndef EQUSS_EPI_GROUPS
+#define EQUSS_EPI_GROUPS 3
+#endif
+// Register file split by warp group (setmaxnreg): 24 warps are launched with 80 registers each (the CTA's pool is what
+// the launch allocated: 24 x 80 = 1920 warp-registers, NOT the SM's 2048 -- asking for more deadlocks in TRY_ALLOC);
+// producer / MMA issuers / idle warp give back 40 each, epilogue and convert groups grow to 88.
+#if !defined(EQUSS_NO_SETMAXNREG) && !defined(EQUSS_SETMAXNREG)
+#define EQUSS_SETMAXNREG
+#endif
+#ifndef EQUSS_REGS_EPI
+#define EQUSS_REGS_EPI 88
+#define EQUSS_REGS_CONV 88
+#define EQUSS_REGS_MISC 40
+#endif
+constexpr int kEpiGroups = EQUSS_EPI_GROUPS;     // epilogue groups of four warps, rotating over the units
 // A parity wait cannot skip a phase, so every accumulator barrier must always be waited on by the same consumer:
 // the t_full / t_empty barriers form a ring of lcm(2 TMEM buffers, kEpiGroups) unit slots (x 2 halves); slot i % R
 // belongs to one TMEM buffer and one epilogue group.
 constexpr int kTSlots = (kEpiGroups % 2 == 0) ? kEpiGroups : 2 * kEpiGroups;
-constexpr int kThreads = 32 * (4 * kEpiGroups + 1 + 4 + 2);
+#ifndef EQUSS_CONV_GROUPS
+#define EQUSS_CONV_GROUPS 2
+#endif
+constexpr int kConvGroups = EQUSS_CONV_GROUPS;   // convert groups of four warps, rotating over the units like the epilogue groups
+#ifdef EQUSS_SETMAXNREG   // register file split by warp group (epilogue / convert / the rest): needs complete warp groups
+constexpr int kThreads = 32 * (4 * kEpiGroups + 4 * kConvGroups + 4);
+#else
+constexpr int kThreads = 32 * (4 * kEpiGroups + 4 * kConvGroups + 1 + 2);
+#endif
 // The SMSP arbiter prefers the highest warp id among eligible warps: the convert warps (the pipeline's critical
-// stage) get the highest ids, the epilogue warps (ALU-pipe heavy, plenty of slack) the lowest.
-constexpr int kEpiWarp0 = 0, kProducerWarp = 4 * kEpiGroups, kConvWarp0 = kProducerWarp + 1, kMmaWarp = kConvWarp0 + 4;
+// stage) sit above the epilogue warps (ALU-pipe heavy, plenty of slack).  Epilogue and convert groups start at a
+// multiple of four, so warp % 4 is the TMEM lane quarter / the SMSP.
+constexpr int kEpiWarp0 = 0, kConvWarp0 = 4 * kEpiGroups, kProducerWarp = kConvWarp0 + 4 * kConvGroups, kMmaWarp = kProducerWarp + 1;
 constexpr float kTolRel = 1.52587890625e-5f;     // 2^-16
+#ifndef EQUSS_EPI_SLEEP_NS
+#define EQUSS_EPI_SLEEP_NS 64
+#endif
+#ifndef EQUSS_PROD_SLEEP_NS
+#define EQUSS_PROD_SLEEP_NS 200
+#endif
 
 #ifdef EQUSS_TRACE   // scripts/trace_assign.cu: per-unit clock64 stamps of CTA 0 (pipeline timeline)
 __device__ long long g_trace[256 * 12];
@@ -78,7 +110,10 @@ __host__ __device__ constexpr int a_sbo(int D) { return kch(D) * a_lbo(D); }
 __host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * a_sbo(D); }
 __host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
-constexpr int kIdxBufs = 8;                      // fused gather: ring of per-tile winning columns
+#ifndef EQUSS_IDX_BUFS
+#define EQUSS_IDX_BUFS 8
+#endif
+constexpr int kIdxBufs = EQUSS_IDX_BUFS;         // fused gather: ring of per-tile winning columns
 __host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false) {
   return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) +
          (fuse ? kIdxBufs * kTileM * 4 : 0) + 1024;
@@ -112,22 +147,30 @@ struct Params {
 // Walks the CTA's contiguous unit range (sslot-major, then tile, then subspace-in-group) without divisions.
 struct UnitIter {
   int sslot, tile, g, sg, chunk, n_tiles, nchunks, G;
-  __device__ __forceinline__ void init(long long u0, int n_tiles_, int nchunks_, int G_) {
+  int img, timg, tpi;          // NCHW: image of the tile, tile within the image, tiles per image (flat: one "image")
+  __device__ __forceinline__ void init(long long u0, int n_tiles_, int nchunks_, int G_, int tpi_ = 0) {
     n_tiles = n_tiles_; nchunks = nchunks_; G = G_;
     const long long per = (long long)n_tiles_ * G_;
     sslot = (int)(u0 / per);
     const int rem = (int)(u0 - (long long)sslot * per);
     tile = rem / G_; g = rem - tile * G_;
     sg = sslot / nchunks_; chunk = sslot - sg * nchunks_;
+    tpi = tpi_ > 0 ? tpi_ : n_tiles_;
+    img = tile / tpi; timg = tile - img * tpi;
   }
   __device__ __forceinline__ void next() {
     if (++g == G) {
       g = 0;
+      if (++timg == tpi) { timg = 0; ++img; }
       if (++tile == n_tiles) {
-        tile = 0; ++sslot;
+        tile = 0; img = 0; timg = 0; ++sslot;
         if (++chunk == nchunks) { chunk = 0; ++sg; }
       }
     }
+  }
+  __device__ __forceinline__ void advance(int k) {
+#pragma unroll
+    for (int j = 0; j < k; ++j) next();
   }
   __device__ __forceinline__ int m() const { return sg * G + g; }
 };
@@ -140,9 +183,9 @@ __device__ __forceinline__ float unsortable(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-// One 32-column chunk of accumulators: class maxima (column mod 16), top-2 of the 16-column group maxima and
-// the id of the best group.  `gid` = index of the chunk's first group.
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int gid, float (&cls)[16], float& m1, float& m2, int& g1) {
+// One 32-column chunk of accumulators: 16 running class maxima (column mod 16) and the maxima of the chunk's two
+// 16-column groups -- 31 FMNMX3/FMNMX for 32 elements, nothing else in the streaming part of the epilogue.
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], float (&cls)[16], float& gm_a, float& gm_b) {
 #pragma unroll
   for (int r = 0; r < 16; ++r) cls[r] = max3f(cls[r], __uint_as_float(v[r]), __uint_as_float(v[r + 16]));
 #pragma unroll
@@ -151,12 +194,44 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], int gid, floa
 #define F(i) __uint_as_float(k[i])
     float t0 = max3f(F(0), F(1), F(2)), t1 = max3f(F(3), F(4), F(5)), t2 = max3f(F(6), F(7), F(8));
     float t3 = max3f(F(9), F(10), F(11)), t4 = max3f(F(12), F(13), F(14));
-    float gm = fmaxf(max3f(t0, t1, t2), max3f(t3, t4, F(15)));
+    const float gm = fmaxf(max3f(t0, t1, t2), max3f(t3, t4, F(15)));
 #undef F
-    m2 = fmaxf(m2, fminf(m1, gm));
-    g1 = (gm > m1) ? (gid + g) : g1;
-    m1 = fmaxf(m1, gm);
+    if (g == 0) gm_a = gm; else gm_b = gm;
   }
+}
+
+// Knock-out tournament over 16 values: index of the maximum (the lower index on exactly equal values), the maximum
+// and the exact runner-up = the best of the four losers on the winner's path (the second best always loses to the
+// best directly).  51 ALU operations; an equality scan plus a masked maximum takes 80.
+__device__ __forceinline__ void tournament16(const float (&v)[16], int& win, float& best, float& runner) {
+  float ta[8], tb[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ta[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tb[j] = fmaxf(ta[2 * j], ta[2 * j + 1]);
+  const float tc0 = fmaxf(tb[0], tb[1]), tc1 = fmaxf(tb[2], tb[3]);
+  const bool p3 = tc1 > tc0;
+  const float l3 = fminf(tc0, tc1);
+  const float sb0 = p3 ? tb[2] : tb[0], sb1 = p3 ? tb[3] : tb[1];
+  const bool p2 = sb1 > sb0;
+  const float l2 = fminf(sb0, sb1);
+  float sa[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sa[j] = p3 ? ta[4 + j] : ta[j];
+  const float sa0 = p2 ? sa[2] : sa[0], sa1 = p2 ? sa[3] : sa[1];
+  const bool p1 = sa1 > sa0;
+  const float l1 = fminf(sa0, sa1);
+  float sc8[8], sc4[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc8[j] = p3 ? v[8 + j] : v[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sc4[j] = p2 ? sc8[4 + j] : sc8[j];
+  const float sc0 = p1 ? sc4[2] : sc4[0], sc1 = p1 ? sc4[3] : sc4[1];
+  const bool p0 = sc1 > sc0;
+  const float l0 = fminf(sc0, sc1);
+  win = (p3 ? 8 : 0) + (p2 ? 4 : 0) + (p1 ? 2 : 0) + (p0 ? 1 : 0);
+  best = fmaxf(tc0, tc1);
+  runner = fmaxf(max3f(l3, l2, l1), l0);
 }
 
 // Exact fp32 re-score of the chunk-local columns {r + 16 j : bit r of cmask set, column < kvalid} of row n,
@@ -271,7 +346,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* idx_empty = idx_full + kIdxBufs;    // [kIdxBufs] FUSE: gather consumed them
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(idx_empty + kIdxBufs);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index goes through a shuffle so that ptxas knows it is warp-uniform: the role branches below are then
+  // uniform branches and what the tcgen05 / TMA instructions consume can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   const long long total_units = (long long)p.M * p.nchunks * p.n_tiles;
   const long long u0 = total_units * blockIdx.x / gridDim.x;
@@ -298,54 +375,66 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
+  if (warp >= kProducerWarp) {
+#ifdef EQUSS_SETMAXNREG      // (each setmaxnreg sits at the top of the branch it governs: after a merge point ptxas assumes the smallest budget)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(EQUSS_REGS_MISC));
+#endif
   if (warp == kProducerWarp) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+    {   // the whole warp walks the loop (uniform values -> uniform registers), one elected lane issues the copy
+      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
       for (int i = 0; i < n_units; ++i, it.next()) {
         const int tile = it.tile, m = it.m();
         const int s = i % STAGES;
-        mbar_wait(raw_empty + s, ((i / STAGES) & 1) ^ 1, 10 + s);
-        mbar_expect_tx(raw_full + s, RAW_BYTES);
-        if (!NCHW) {
-          tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, tile * kTileM, raw_full + s);
-        } else {
-          const int b = tile / p.tiles_per_image;
-          const int t = tile - b * p.tiles_per_image;
-          tma_load_3d(s_rawt + s * RAW_BYTES, &tmap, t * kTileM, m * D, b, raw_full + s);
+        if (EQUSS_PROD_SLEEP_NS > 0) mbar_wait_sleep(raw_empty + s, ((i / STAGES) & 1) ^ 1, EQUSS_PROD_SLEEP_NS);
+        else mbar_wait_nc(raw_empty + s, ((i / STAGES) & 1) ^ 1, 10 + s);
+        if (elect_one()) {
+          mbar_expect_tx(raw_full + s, RAW_BYTES);
+          if (!NCHW) {
+            tma_load_2d(s_rawt + s * RAW_BYTES, &tmap, m * D, tile * kTileM, raw_full + s);
+          } else {
+            tma_load_3d(s_rawt + s * RAW_BYTES, &tmap, it.timg * kTileM, m * D, it.img, raw_full + s);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
     // ===================================== MMA issuers ======================================
+    // Everything the tcgen05 instructions consume is made provably warp-uniform (the warp index and the TMEM base go
+    // through a shuffle): ptxas then keeps the descriptors in uniform registers and issues UTCHMMA / UTCBAR directly.
+    // With per-thread registers it wraps every one of them in an ELECT + 5 x R2UR.BROADCAST loop, ~130 cycles of
+    // dependent latency per instruction -- the issuer warps, not the tensor pipe, then set the pace (clock64 traces:
+    // ~1000 cycles to issue the 4 MMAs and 2 commits of a unit).
     const int h = warp - kMmaWarp;
+    const uint32_t tmem_base_u = tmem_base;
     if (h < HALVES) {
       const uint32_t b_hi = (uint32_t)((SBO >> 4) & 0x3FFF) | (1u << 14);              // SBO, descriptor version 1
       const uint32_t a_hi = (uint32_t)((ASBO >> 4) & 0x3FFF) | (1u << 14);
       const uint32_t b_lo0 = ((smem_u32(s_b) + (uint32_t)(h * (NH / 8) * SBO)) >> 4) | ((uint32_t)(128 >> 4) << 16);
       const uint32_t a_lo0 = (smem_u32(s_a) >> 4) | ((uint32_t)(ALBO >> 4) << 16);
       int b_loads = 0, cur_slot = -1;
-      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
+      UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
       for (int i = 0; i < n_units; ++i, it.next()) {
         const int a = i % ABUFS, t = i & 1;
         const int tb = (i % kTSlots) * 2 + h;                      // this unit's accumulator-barrier slot
         if (h == 0) EQUSS_TR(7, i);
         if (it.sslot != cur_slot) {
-          mbar_wait(b_full, b_loads & 1, 20);
+          mbar_wait_nc(b_full, b_loads & 1, 20);
           ++b_loads;
           cur_slot = it.sslot;
         }
-        mbar_wait(a_full + a, (i / ABUFS) & 1, 21);
+        mbar_wait_nc(a_full + a, (i / ABUFS) & 1, 21);
         // TMEM buffer t was last used by unit i - 2: wait until that unit's epilogue has drained this half
-        if (i >= 2) mbar_wait(t_empty + ((i - 2) % kTSlots) * 2 + h, ((i - 2) / kTSlots) & 1, 22);
+        if (i >= 2) mbar_wait_nc(t_empty + ((i - 2) % kTSlots) * 2 + h, ((i - 2) / kTSlots) & 1, 22);
         tc_fence_after();
         if (h == 0) EQUSS_TR(3, i);
-        if (lane == 0) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)(a * (A_BYTES >> 4));
-          const uint32_t b_lo = b_lo0 + (uint32_t)(it.g * (B_BYTES >> 4));
-          const uint32_t d_addr = tmem_base + (uint32_t)(t * NC + h * NH);
+        const uint32_t a_lo = a_lo0 + (uint32_t)(a * (A_BYTES >> 4));
+        const uint32_t b_lo = b_lo0 + (uint32_t)(it.g * (B_BYTES >> 4));
+        const uint32_t d_addr = tmem_base_u + (uint32_t)(t * NC + h * NH);
+        if (elect_one()) {
           uint32_t acc = 0;
           // x1.y1, x2.y1, x1.y2 : K-slice kk of a piece starts 2*kk chunks into its region
 #pragma unroll
@@ -367,12 +456,22 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         __syncwarp();
       }
     }
-  } else if (warp >= kConvWarp0 && warp < kConvWarp0 + 4) {
-    // ===================================== convert warps (9-12) ===================================
-    const int ct = threadIdx.x - kConvWarp0 * 32;   // 0..127
-    int b_loads = 0, cur_slot = -1;
-    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
-    UnitIter itg; itg.init(u0, (int)p.n_tiles, p.nchunks, G);      // FUSE: the unit whose gather is due next
+  }
+  } else if (warp >= kConvWarp0) {
+    // ===================================== convert warps ===================================
+    // kConvGroups groups of four warps; group c owns the units i with i % kConvGroups == c (conversion AND, fused,
+    // the gather of the same unit), so that two units are in conversion at any time: one warp per SMSP cannot hide
+    // the latency of its own shared-memory / MUFU / conversion chain.
+    static_assert(!FUSE || LAG % kConvGroups == 0, "a unit's gather runs in the group that converted it");
+#ifdef EQUSS_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(EQUSS_REGS_CONV));
+#endif
+    const int cgroup = (warp - kConvWarp0) >> 2;
+    const int ct = (threadIdx.x - kConvWarp0 * 32) & 127;   // 0..127 within the group
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
+    UnitIter itg; itg.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);      // FUSE: the unit whose gather is due next
+    it.advance(cgroup);
+    itg.advance(cgroup);
 
     // K3 for unit j (its raw tile is still in stage j % STAGES, its winning columns in the index ring), in two
     // halves: gather_prefetch issues the codeword loads, gather_finish -- called after the next convert, which
@@ -395,7 +494,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     auto gather_prefetch = [&](int j) {
       const int ib = j % kIdxBufs;
       if (warp == kConvWarp0) EQUSS_TR(8, j);
-      mbar_wait(idx_full + ib, (j / kIdxBufs) & 1, 50);
+      mbar_wait_nc(idx_full + ib, (j / kIdxBufs) & 1, 50);
       if (warp == kConvWarp0) EQUSS_TR(9, j);
       const int32_t* sidx = s_idx + ib * kTileM;
       const float* srcm = p.gsrc + (size_t)itg.m() * p.K * D;
@@ -452,8 +551,8 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         }
       } else {
         const int row = ct;
-        const long long bimg = tile / p.tiles_per_image;
-        const long long spix = (long long)(tile - (int)bimg * p.tiles_per_image) * kTileM + row;
+        const long long bimg = itg.img;
+        const long long spix = (long long)itg.timg * kTileM + row;
         const bool live = spix < p.hw;
         float x[D];
 #pragma unroll
@@ -484,27 +583,27 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         mbar_arrive(idx_empty + ib);
       }
       if (warp == kConvWarp0) EQUSS_TR(10, j);
-      itg.next();
+      itg.advance(kConvGroups);
     };
 
-    for (int i = 0; i < n_units; ++i, it.next()) {
+    for (int i = cgroup; i < n_units; i += kConvGroups, it.advance(kConvGroups)) {    // this group's units only
       const int a = i % ABUFS, s = i % STAGES;
+      // the operand images change with the first unit of a slot: only that unit's owner loads them
+      const bool new_slot = (i == 0) || (it.tile == 0 && it.g == 0);
       if constexpr (FUSE) { if (i >= LAG) gather_prefetch(i - LAG); }
-      mbar_wait(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
+      mbar_wait_nc(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (warp == kConvWarp0) EQUSS_TR(0, i);
-      if (it.sslot != cur_slot) {
+      if (new_slot) {
         // every earlier MMA must have completed before the operand images are overwritten
 #pragma unroll
         for (int back = 1; back < ABUFS; ++back)
-          if (i >= back) mbar_wait(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
+          if (i >= back) mbar_wait_nc(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
         if (ct == 0) {
           mbar_expect_tx(b_full, (uint32_t)(G * p.img_bytes));
           bulk_load_1d(s_b, p.images + (size_t)it.sslot * G * p.img_bytes, (uint32_t)(G * p.img_bytes), b_full);
         }
-        cur_slot = it.sslot;
-        ++b_loads;
       }
-      mbar_wait(raw_full + s, (i / STAGES) & 1, 33);
+      mbar_wait_nc(raw_full + s, (i / STAGES) & 1, 33);
       if (warp == kConvWarp0) EQUSS_TR(1, i);
       uint8_t* a_tile = s_a + a * A_BYTES;
       const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
@@ -615,48 +714,62 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       if constexpr (FUSE) { if (i >= LAG) gather_finish(i - LAG); }
     }
     if constexpr (FUSE) {
-      for (int j = (n_units > LAG ? n_units - LAG : 0); j < n_units; ++j) { gather_prefetch(j); gather_finish(j); }
+      for (int j = (n_units > LAG ? n_units - LAG : 0); j < n_units; ++j) {
+        if (j % kConvGroups != cgroup) continue;
+        gather_prefetch(j); gather_finish(j);
+      }
       flush_err();
     }
-  } else {
+  } else if (warp < 4 * kEpiGroups) {
     // ===================================== epilogue warps ===================================
+#ifdef EQUSS_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(EQUSS_REGS_EPI));
+#endif
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int egroup = (warp - kEpiWarp0) >> 2;  // 0 .. kEpiGroups-1
     const int row = q * 32 + lane;
-    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G);
-    for (int i = 0; i < n_units; ++i, it.next()) {
+    UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
+    it.advance(egroup);
+    for (int i = egroup; i < n_units; i += kEpiGroups, it.advance(kEpiGroups)) {   // this group's units only
       const int t = i & 1;
-      if (i % kEpiGroups != egroup) continue;     // another epilogue group's unit
       const int tile = it.tile, m = it.m(), chunk = it.chunk;
       // the slot's tolerance: trailer of the operand image (global memory; latency hidden by the barrier wait)
       const float tol = __ldg(reinterpret_cast<const float*>(p.images + ((size_t)it.sslot * G + it.g) * p.img_bytes +
                                                                (size_t)(NC / 8) * SBO));
-      float cls[16];
+      // Streaming part: class maxima and one maximum per 16-column group, all in registers (the chunk loops are fully
+      // unrolled so that the group maxima have compile-time indices); the winner and the runner-up come out of two
+      // tournaments below -- no per-group bookkeeping (5 ALU operations per group before) inside the stream.
+      float cls[16], gm[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) cls[r] = -INFINITY;
-      float m1 = -INFINITY, m2 = -INFINITY;
-      int g1 = 0;
-#pragma unroll 1
+      for (int r = 0; r < 16; ++r) { cls[r] = -INFINITY; gm[r] = -INFINITY; }
+#pragma unroll
       for (int h = 0; h < HALVES; ++h) {
         const int tb = (i % kTSlots) * 2 + h;
-        mbar_wait(t_full + tb, (i / kTSlots) & 1, 41);
+        if (EQUSS_EPI_SLEEP_NS > 0 && h == 0) mbar_wait_sleep(t_full + tb, (i / kTSlots) & 1, EQUSS_EPI_SLEEP_NS);
+        else mbar_wait_nc(t_full + tb, (i / kTSlots) & 1, 41);
         tc_fence_after();
         if (q == 0 && h == 0) EQUSS_TR(4, i);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NC + h * NH);
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-        if constexpr (NH == 32) {
-          tmem_ld_wait();
-          epi_chunk(va, h * (NH / 16), cls, m1, m2, g1);
+        if constexpr (kEpiGroups >= 3 || NH == 32) {
+          // three groups: the other groups' warps cover the TMEM load latency, one 32-register buffer is enough
+          uint32_t va[32];
+#pragma unroll
+          for (int c = 0; c < NH / 32; ++c) {
+            tmem_ld32(taddr + c * 32, va);
+            tmem_ld_wait();
+            epi_chunk(va, cls, gm[h * (NH / 16) + 2 * c], gm[h * (NH / 16) + 2 * c + 1]);
+          }
         } else {
-#pragma unroll 1
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr, va);
+#pragma unroll
           for (int c = 0; c < NH / 32; c += 2) {
             tmem_ld_wait();
             tmem_ld32(taddr + (c + 1) * 32, vb);
-            epi_chunk(va, h * (NH / 16) + 2 * c, cls, m1, m2, g1);
+            epi_chunk(va, cls, gm[h * (NH / 16) + 2 * c], gm[h * (NH / 16) + 2 * c + 1]);
             tmem_ld_wait();
             if (c + 2 < NH / 32) tmem_ld32(taddr + (c + 2) * 32, va);
-            epi_chunk(vb, h * (NH / 16) + 2 * c + 2, cls, m1, m2, g1);
+            epi_chunk(vb, cls, gm[h * (NH / 16) + 2 * c + 2], gm[h * (NH / 16) + 2 * c + 3]);
           }
         }
         tc_fence_before();
@@ -665,24 +778,24 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
 
       if (q == 0) EQUSS_TR(5, i);
-      // winning column = best group * 16 + the class whose running maximum equals the best score
-      int r1 = 0;
-#pragma unroll
-      for (int r = 15; r >= 0; --r) r1 = (cls[r] == m1) ? r : r1;
+      // winning column = best group * 16 + best class; the runner-up is the better of the two tournaments' runners-up
+      // (a column other than the winner differs from it in its class or in its group).  On exactly equal maxima the
+      // runner-up equals m1, the gap is zero and the row is ambiguous, as it must be.
+      int r1, g1;
+      float m1, run_c, run_g;
+      tournament16(cls, r1, m1, run_c);
+      tournament16(gm, g1, m1, run_g);
       int best_col = g1 * 16 + r1;
-      float runner = m2;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) runner = fmaxf(runner, (r1 == r) ? -INFINITY : cls[r]);
+      const float runner = fmaxf(run_c, run_g);
       long long n;
       bool live;
       if (!NCHW) {
         n = (long long)tile * kTileM + row;
         live = n < p.n_pixels;
       } else {
-        const long long b = tile / p.tiles_per_image;
-        const long long sidx = (long long)(tile - (int)b * p.tiles_per_image) * kTileM + row;
+        const int sidx = it.timg * kTileM + row;
         live = sidx < p.hw;
-        n = b * p.hw + sidx;
+        n = (long long)it.img * p.hw + sidx;
       }
       const int kvalid = min(NC, p.K - chunk * NC);
       const bool amb = live && (!(m1 - runner > tol) || best_col >= kvalid);
@@ -697,7 +810,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       if constexpr (FUSE) {
         const int ib = i % kIdxBufs;
-        mbar_wait(idx_empty + ib, ((i / kIdxBufs) & 1) ^ 1, 42);
+        mbar_wait_nc(idx_empty + ib, ((i / kIdxBufs) & 1) ^ 1, 42);
         s_idx[ib * kTileM + row] = live ? best_col : 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(idx_full + ib);

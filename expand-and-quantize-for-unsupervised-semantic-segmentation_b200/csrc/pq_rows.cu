@@ -771,9 +771,36 @@ __global__ void __launch_bounds__(kPctThreads)
 ema_train_tail_kernel(const float* __restrict__ packed, int M, int K, int d, float decay, float alpha, float eps,
                       float k_eps, float* __restrict__ vq_count, float* __restrict__ weight_avg,
                       float* __restrict__ weight, float* __restrict__ exact_count, const double* __restrict__ sqerr,
-                      double inv_nd, float beta, float* __restrict__ scratch, float* __restrict__ stats_out) {
+                      double inv_nd, float beta, float* __restrict__ scratch, float* __restrict__ stats_out,
+                      const float* const* __restrict__ peers, int world, float* __restrict__ packed_out) {
   const int m = blockIdx.x;
   const int ld = d + 1;
+  if (peers != nullptr) {
+    // K5 fused in: the data-parallel sum of the packed statistics is taken straight from the peers' symmetric
+    // buffers over NVLink (one pass of P2P loads, ranks added in a fixed order so every replica computes the same
+    // bits) instead of a separate all-reduce; the reduced slice lands in packed_out, which the rest of the kernel
+    // (and the caller, for restart / split) reads.
+    const long long off = (long long)m * K * ld;
+    const int cnt = K * ld;
+    if ((cnt & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < cnt; i += blockDim.x * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < world; ++r) {
+          const float4 v = __ldcv(reinterpret_cast<const float4*>(peers[r] + off + i));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(packed_out + off + i) = acc;
+      }
+    } else {
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        float acc = 0.f;
+        for (int r = 0; r < world; ++r) acc += __ldcv(peers[r] + off + i);
+        packed_out[off + i] = acc;
+      }
+    }
+    __syncthreads();
+    packed = packed_out;
+  }
   const float* pm = packed + (long long)m * K * ld;
   float* cnt = vq_count + (long long)m * K;
   float* ex = exact_count + (long long)m * K;
@@ -1108,8 +1135,26 @@ extern "C" int equss_pq_train_tail(const float* packed, int M, int K, int d, dou
   const double inv_nd = (n_pixels > 0) ? 1.0 / ((double)n_pixels * (double)d) : 0.0;
   equss::ema_train_tail_kernel<<<M, equss::kPctThreads, 0, (cudaStream_t)stream>>>(
       packed, M, K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps), vq_count, weight_avg, weight,
-      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out);
+      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, nullptr, 1, nullptr);
   EQUSS_LAUNCH_OK("ema_train_tail_kernel");
+  return EQUSS_OK;
+}
+
+extern "C" int equss_pq_train_tail_peers(const void* const* peer_packed, int world, float* packed_out, int M, int K, int d,
+                                         double decay, double eps, float* vq_count, float* weight_avg, float* weight,
+                                         float* exact_count, const double* sqerr, int64_t n_pixels, double beta,
+                                         float* scratch, float* stats_out, void* stream) {
+  EQUSS_REQUIRE(peer_packed && packed_out && vq_count && weight_avg && weight && exact_count && scratch && stats_out,
+                EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail_peers: null pointer");
+  EQUSS_REQUIRE(world >= 1 && world <= 64, EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail_peers: world=%d", world);
+  EQUSS_REQUIRE(M > 0 && K > 0 && d > 0, EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail_peers: bad shape M=%d K=%d d=%d", M, K, d);
+  EQUSS_REQUIRE(K <= equss::kPctThreads * equss::kPctItems, EQUSS_ERR_UNSUPPORTED, "equss_pq_train_tail_peers: K=%d > %d", K,
+                equss::kPctThreads * equss::kPctItems);
+  const double inv_nd = (n_pixels > 0) ? 1.0 / ((double)n_pixels * (double)d) : 0.0;
+  equss::ema_train_tail_kernel<<<M, equss::kPctThreads, 0, (cudaStream_t)stream>>>(
+      packed_out, M, K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps), vq_count, weight_avg, weight,
+      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, (const float* const*)peer_packed, world, packed_out);
+  EQUSS_LAUNCH_OK("ema_train_tail_kernel<peers>");
   return EQUSS_OK;
 }
 

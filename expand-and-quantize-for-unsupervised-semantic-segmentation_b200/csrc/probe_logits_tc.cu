@@ -112,7 +112,7 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   uint64_t* s_empty = s_full + 2;               // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int n_my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_kc = p.n_kc;
 
@@ -130,10 +130,10 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    {   // the whole warp walks the loop (uniform values -> uniform registers), one elected lane issues the copy
       int g = 0;
       for (int it = 0; it < n_my_tiles; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
@@ -142,8 +142,11 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
         for (int c = 0; c < n_kc; ++c, ++g) {
           const int rs = g % kRawStages;
           mbar_wait(raw_empty + rs, ((g / kRawStages) & 1) ^ 1, 10);
-          mbar_expect_tx(raw_full + rs, kAPiece);
-          tma_load_4d(s_raw + rs * kAPiece, &tmap, 0, c * kKC, blk0, b, raw_full + rs);
+          if (elect_one()) {
+            mbar_expect_tx(raw_full + rs, kAPiece);
+            tma_load_4d(s_raw + rs * kAPiece, &tmap, 0, c * kKC, blk0, b, raw_full + rs);
+          }
+          __syncwarp();
         }
       }
     }
@@ -183,7 +186,7 @@ probe_logits_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p)
         else mbar_wait(raw_full + rs, (g / kRawStages) & 1, 24);
         mbar_wait(b_full + bs, (g / kBBufs) & 1, 21);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {   // elected lane + uniform operands: UTCHMMA issues from uniform registers
           const uint32_t a_lo = a_lo0 + (uint32_t)((part == 1 ? ls : rs) * (kAPiece >> 4));
           const uint32_t b_lo = b_lo0 + (uint32_t)(bs * (kBBytes >> 4));
           const uint32_t d_addr = (part == 0) ? tmem_base + (uint32_t)(mb * kN) : d_small;

@@ -8,8 +8,11 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+import os
+import warnings
+
 __all__ = ["is_distributed_set", "get_rank", "get_world_size", "all_reduce_tensor", "all_reduce_packed_",
-           "shard_range"]
+           "shard_range", "PackedPeerExchange", "packed_peer_exchange"]
 
 
 def is_distributed_set() -> bool:
@@ -48,6 +51,59 @@ def all_reduce_packed_(packed: torch.Tensor) -> torch.Tensor:
     if is_distributed_set() and get_world_size() > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
     return packed
+
+
+class PackedPeerExchange:
+    """K5 without a collective call: every rank's packed statistics live in *symmetric memory* (one allocation per
+    rank, mapped into all peers over NVLink / NVSwitch), and the kernel that consumes them
+    (``equss_pq_train_tail_peers``) sums the ranks' buffers itself with P2P loads, in rank order, so all replicas obtain
+    the same bits.  Two buffers alternate: a rank may re-zero a buffer only after every peer has read it, and the one
+    device-side barrier per step (after the scatter-add, before the fused reduce + EMA kernel) of step t+1 orders
+    exactly that for the buffer of step t.
+
+    Replaces the single NCCL all-reduce of :func:`all_reduce_packed_` (58 us at 8 ranks for 1.1 MB, latency-bound)
+    by a barrier (~5 us) plus ~world x 17 KB of peer reads per CTA inside a kernel that runs anyway."""
+
+    def __init__(self, shape, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm.empty(*shape, dtype=torch.float32, device=device)
+            self.handles.append(symm.rendezvous(t, group))
+            self.bufs.append(t)
+        self.step = 0
+
+    def acquire(self):
+        """(zeroed local statistics buffer to accumulate into, its symmetric-memory handle) for this step."""
+        i = self.step & 1
+        self.step += 1
+        buf = self.bufs[i]
+        buf.zero_()
+        return buf, self.handles[i]
+
+
+_peer_exchanges = {}
+
+
+def packed_peer_exchange(shape, device):
+    """The cached :class:`PackedPeerExchange` for a statistics shape, or None when the exchange must go through NCCL:
+    no process group / one rank, a non-NCCL backend, ``EQUSS_PEER_REDUCE=0``, or symmetric memory cannot be set up on
+    this machine (no P2P access, handle exchange refused) -- the latter is reported once."""
+    if not is_distributed_set() or get_world_size() < 2 or os.environ.get("EQUSS_PEER_REDUCE", "1") == "0":
+        return None
+    if dist.get_backend() != "nccl" or torch.device(device).type != "cuda":
+        return None
+    key = (tuple(shape), str(device))
+    if key not in _peer_exchanges:
+        try:
+            _peer_exchanges[key] = PackedPeerExchange(tuple(shape), device)
+        except Exception as e:  # noqa: BLE001 -- any failure means "use the NCCL all-reduce", never a silent wrong result
+            warnings.warn(f"equss_b200: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); "
+                          "the EMA statistics go through one NCCL all-reduce instead")
+            _peer_exchanges[key] = None
+    return _peer_exchanges[key]
 
 
 def shard_range(n: int, rank: int = None, world: int = None):

@@ -215,7 +215,7 @@ _tail_scratch = {}
 
 def pq_train_tail(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.Tensor, weight_avg: torch.Tensor,
                   weight: torch.Tensor, exact_count: torch.Tensor, sqerr: Optional[torch.Tensor], n_pixels: int,
-                  beta: float) -> Optional[torch.Tensor]:
+                  beta: float, peers: Optional[Tuple[int, int]] = None) -> Optional[torch.Tensor]:
     """The tail of the EMA training step in one launch: in-place EMA update of the stacked state (as :func:`ema_update`)
     plus the ten scalar outputs of ``ProductQuantizerWrapper.forward`` (order: :data:`TAIL_KEYS`), averaged over the
     subspaces (model/quantizer.py:493-532,607-608).  Returns float32 [10], or None when K > 1024 (then call
@@ -235,6 +235,15 @@ def pq_train_tail(packed: torch.Tensor, decay: float, eps: float, vq_count: torc
     stats = torch.empty((10,), dtype=torch.float32, device=dev)
     if sqerr is not None:
         assert sqerr.dtype == torch.float64 and sqerr.numel() == M
+    if peers is not None:
+        # `peers` = (device pointer to the array of every rank's packed-buffer pointer, world size): the cross-rank sum
+        # happens inside the kernel over NVLink and the reduced statistics are written into `packed`
+        rc = L.equss_pq_train_tail_peers(int(peers[0]), int(peers[1]), packed.data_ptr(), M, K, d, float(decay), float(eps),
+                                         vq_count.data_ptr(), weight_avg.data_ptr(), weight.data_ptr(), exact_count.data_ptr(),
+                                         N.ptr(sqerr), int(n_pixels), float(beta), scratch.data_ptr(), stats.data_ptr(),
+                                         N.stream_ptr(dev))
+        N.check(rc, "equss_pq_train_tail_peers")
+        return stats
     rc = L.equss_pq_train_tail(packed.contiguous().data_ptr(), M, K, d, float(decay), float(eps), vq_count.data_ptr(),
                                weight_avg.data_ptr(), weight.data_ptr(), exact_count.data_ptr(), N.ptr(sqerr), int(n_pixels),
                                float(beta), scratch.data_ptr(), stats.data_ptr(), N.stream_ptr(dev))

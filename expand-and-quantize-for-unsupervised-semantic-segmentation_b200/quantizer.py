@@ -25,7 +25,7 @@ import torch.nn.functional as F  # noqa
 from . import _pq_core as core
 from . import ops
 from ._host_paths import draw_restart, split_codes
-from .dist_utils import all_reduce_tensor
+from .dist_utils import all_reduce_tensor, packed_peer_exchange
 
 __all__ = ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper", "get_histogram_count"]
 
@@ -280,7 +280,18 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
     stats = None
     if training:
         with torch.no_grad():
-            packed = core.ema_statistics(z, idx, K)                                    # :485-491
+            # K4 + K5 (:485-491).  With more than one NCCL rank and the fused tail kernel available the statistics are
+            # accumulated into symmetric memory and summed over the ranks INSIDE the tail kernel (no all-reduce call).
+            peer = None
+            if not q0.use_split and K <= 1024:
+                peer = packed_peer_exchange((M, K, d + 1), z.device)
+            if peer is not None:
+                local, handle = peer.acquire()
+                ops.pq_accumulate(z.detach().float(), idx, K, out=local)
+                handle.barrier(channel=0)          # every rank's scatter-add is complete and visible to its peers
+                packed = torch.empty_like(local)   # receives the reduced statistics
+            else:
+                packed = core.ema_statistics(z, idx, K)
             count = packed[:, :, d]
             # in-place EMA update on the stacked state; zero-copy when the buffers are slices of one
             # storage (ProductQuantizerWrapper._restack), otherwise stack -> update -> write back
@@ -293,7 +304,8 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
             if not q0.use_split:
                 # EMA update + percentiles x2 + usage + codebook-sum + loss scalars: ONE launch (:493-532)
                 stats = ops.pq_train_tail(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c,
-                                          sqerr, n, beta)
+                                          sqerr, n, beta,
+                                          peers=None if peer is None else (handle.buffer_ptrs_dev, peer.world))
             if stats is None:
                 unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
                 output.update(core.percentile_stats(exact_c, "total"))                      # :496

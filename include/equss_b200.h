@@ -173,6 +173,18 @@ int equss_pq_train_tail(const float* packed, int M, int K, int d, double decay, 
                         const double* sqerr, int64_t n_pixels, double beta,
                         float* scratch, float* stats_out, void* stream);
 
+/* K5 + K6 + K7 in one kernel over peer memory: as equss_pq_train_tail, but the data-parallel SUM of the packed statistics
+ * (model/quantizer.py:490-491, 2*M all_reduce_tensor calls in the reference) is taken inside the kernel from the ranks'
+ * buffers over NVLink: peer_packed is a DEVICE array of `world` device pointers to every rank's packed [M][K][d+1]
+ * buffer (symmetric memory, own rank included), summed in rank order so all replicas obtain identical bits.  The
+ * reduced statistics are written to packed_out (local).  The caller orders the ranks: every rank's K4 must be complete
+ * and visible (a device-side barrier over the symmetric-memory signal pads) before the launch, and a buffer may be
+ * re-zeroed only after all peers have read it (the host mirror alternates two buffers). */
+int equss_pq_train_tail_peers(const void* const* peer_packed, int world, float* packed_out, int M, int K, int d,
+                              double decay, double eps, float* vq_count, float* weight_avg, float* weight,
+                              float* exact_count, const double* sqerr, int64_t n_pixels, double beta,
+                              float* scratch, float* stats_out, void* stream);
+
 /* Codebook-side normalisation (model/quantizer.py:421 "l2", :426 "z_norm", "none") and cnorm2 of the result in one
  * launch: codebook_norm [M][K][d], cnorm2 [M][K].  (The "z_trainable" flavours normalise across codes / with learned
  * statistics and stay with the caller.) */

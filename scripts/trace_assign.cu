@@ -27,6 +27,10 @@ int main(int argc, char** argv) {
   cudaMemcpy(z, hz.data(), hz.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(cb, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
   cn2_k<<<(M * K + 255) / 256, 256>>>(cb, M * K, d, cn2);
   equss_zdesc zd; zd.n_pixels = N; zd.hw = N; zd.stride_b = N * D; zd.stride_s = D; zd.stride_c = 1; zd.dim = D; zd.layout = 0;
+  if (argc > 3 && atoi(argv[3]) == 1) {     // NCHW: 32 images of N/32 pixels (C2: 40x40), the same buffer read as (B, D, hw)
+    const long long hw = N / 32;
+    zd.hw = hw; zd.stride_b = hw * D; zd.stride_s = 1; zd.stride_c = hw; zd.layout = 1;
+  }
   long long wsb = assign_tch_workspace_bytes(N, M, K, d);
   cudaMalloc(&ws, wsb);
   const bool fuse = argc > 2 && atoi(argv[2]) == 1;

@@ -74,6 +74,28 @@ def _worker(rank, world, port, ret):
                 assert torch.equal(ex, torch.stack(exact)), f"{mode} step {s}: global counts differ"
                 if mode == "z_trainable":
                     torch.testing.assert_close(torch.stack([q.z_mean for q in pq.quantizers]).cpu(), torch.stack(zm), rtol=1e-5, atol=1e-6)
+        # the in-kernel peer reduction (symmetric memory) and the NCCL all-reduce give the same bits at two ranks
+        # (a two-term sum is order-independent); which path ran is part of the test's result
+        import copy
+        from equss_b200 import dist_utils
+        torch.manual_seed(7)
+        pq_a = ProductQuantizerWrapper(8, 64, 128, normalize="l2", decay=0.9, quantizer_cls=EMAVectorQuantizer).to(dev).train()
+        pq_b = copy.deepcopy(pq_a)
+        pq_b._restack()
+        for s in range(3):
+            zr = torch.randn(world * 2048, 128)[rank * 2048:(rank + 1) * 2048].to(dev)
+            with torch.no_grad():
+                os.environ["EQUSS_PEER_REDUCE"] = "1"
+                _, out_a, _ = pq_a(zr)
+                os.environ["EQUSS_PEER_REDUCE"] = "0"
+                _, out_b, _ = pq_b(zr)
+            os.environ["EQUSS_PEER_REDUCE"] = "1"
+            for qa, qb in zip(pq_a.quantizers, pq_b.quantizers):
+                assert torch.equal(qa.codebook.weight, qb.codebook.weight) and torch.equal(qa.vq_count, qb.vq_count)
+                assert torch.equal(qa.codebook.weight_avg, qb.codebook.weight_avg)
+            for k in out_a:
+                assert torch.equal(out_a[k], out_b[k]), k
+        peer_used = any(v is not None for v in dist_utils._peer_exchanges.values())
         # query-sharded kNN: every rank ends up with the complete table
         torch.manual_seed(1)
         feats = torch.nn.functional.normalize(torch.randn(1001, 96), dim=1)
@@ -81,7 +103,7 @@ def _worker(rank, world, port, ret):
         ridx, _ = O.knn(feats, 8)
         assert nns.shape == (1001, 8) and torch.equal(nns[:, 0].cpu(), torch.arange(1001))
         assert float((nns.cpu() == ridx).float().mean()) > 0.999
-        ret[rank] = "ok"
+        ret[rank] = "ok" if peer_used else "ok (symmetric memory unavailable: NCCL all-reduce path only)"
     except BaseException as e:   # noqa
         import traceback
         ret[rank] = f"{type(e).__name__}: {e}\n{traceback.format_exc()}"
@@ -96,4 +118,5 @@ def test_two_rank_nccl_training_replicas_stay_identical():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
+    print(dict(ret))
+    assert all(str(v).startswith("ok") for v in dict(ret).values()) and len(ret) == world, dict(ret)
