@@ -424,12 +424,17 @@ def run_equss(args):
             t_ar, _ = timed(lambda i, ev: dist.all_reduce(packed_like), 20, 5)
             t_ar /= 20
         tr_bytes = 3 * 4 * N * D + 3 * 4 * N * M
+        from equss_b200 import dist_utils as _du
+        peer_used = any(v is not None for v in _du._peer_exchanges.values())
+        exchange = ("none (one rank)" if world == 1 else
+                    "in-kernel sum of the ranks' symmetric-memory buffers over NVLink inside the EMA tail kernel (one device barrier, no collective call)"
+                    if peer_used else "one NCCL all-reduce of the packed statistics")
         extras["train"] = {
-            "workload": "pq_train (BASELINE configs[2]): assign + gather/loss + scatter-add + ONE packed all-reduce + EMA "
-                        "update + statistics, eager ProductQuantizerWrapper.forward in train() mode, flat (51200, 1024) per rank",
+            "workload": "pq_train (BASELINE configs[2]): assign + gather/loss + scatter-add + exchange of the packed EMA "
+                        "statistics + EMA update + statistics, eager ProductQuantizerWrapper.forward in train() mode, flat (51200, 1024) per rank",
             "ms_per_step": t_tr / n_x, "value": world * N * n_x / (t_tr / 1e3), "unit": UNIT, "scaling": "weak",
             "launch": "eager module API (no CUDA graph)", "library_kernels_per_step": int(tr_launch),
-            "allreduce_payload_bytes": 4 * M * K * (d + 1), "allreduce_ms_alone": round(t_ar, 4),
+            "exchange": exchange, "exchange_payload_bytes": 4 * M * K * (d + 1), "nccl_allreduce_ms_alone": round(t_ar, 4),
             "roofline": {"bound": "hbm", "achieved": round(tr_bytes / (t_tr / n_x * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(tr_bytes / (t_tr / n_x * 1e-3) / 1e9 / peak, 4), "algorithmic_MB": round(tr_bytes / 1e6, 1)}}
         del ztr, pq

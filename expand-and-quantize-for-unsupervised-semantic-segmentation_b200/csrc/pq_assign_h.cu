@@ -244,6 +244,7 @@ bool assign_tch_supported(const equss_zdesc* zd, int M, int K, int d, int norm_m
   if (!tch::make_plan(M, K, d, !flat).ok) return false;
   if ((int64_t)M * zd->n_pixels >= (int64_t)1 << 32) return false;   // near-tie list entries are 32-bit
   if (!flat && (zd->hw % 4) != 0) return false;      // TMA global strides must be multiples of 16 bytes
+  if (!flat && zd->hw >= ((int64_t)1 << 24)) return false;   // 32-bit channel offsets inside one subspace (d * hw elements)
   return zd->n_pixels > 0;
 }
 

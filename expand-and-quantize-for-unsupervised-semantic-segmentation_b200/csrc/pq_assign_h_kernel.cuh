@@ -551,28 +551,31 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         }
       } else {
         const int row = ct;
-        const long long bimg = itg.img;
-        const long long spix = (long long)itg.timg * kTileM + row;
+        const int spix = itg.timg * kTileM + row;
         const bool live = spix < p.hw;
         float x[D];
 #pragma unroll
-        for (int jj = 0; jj < D; ++jj) x[jj] = raw[jj * kTileM + row];
-        float* o = p.out + bimg * p.zv.stride_b + spix + (long long)m * D * p.zv.stride_c;
+        for (int jj = 0; jj < D; ++jj) x[jj] = raw[jj * kTileM + row];    // canonical z_norm (convert pass)
+        // one 64-bit base per unit (warp-uniform part + the pixel), 32-bit channel offsets: the NCHW channel stride of
+        // one subspace (d * hw elements) always fits, and the address arithmetic moves from 2 ALU operations per
+        // store to one IMAD.WIDE on the FMA pipe
+        float* o = p.out + (long long)itg.img * p.zv.stride_b + (long long)m * D * p.zv.stride_c + spix;
+        const uint32_t sc = (uint32_t)p.zv.stride_c;
         float e = 0.f;
+        float ov[D];
 #pragma unroll
         for (int g4 = 0; g4 < LPS; ++g4) {
           const float4 qq = qpre[g4];
-          const float4 zn = make_float4(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);   // canonical z_norm (convert pass)
-          const float d0 = qq.x - zn.x, d1 = qq.y - zn.y, d2 = qq.z - zn.z, d3 = qq.w - zn.w;
-          if (live) {
-            __stcs(o + (long long)(4 * g4 + 0) * p.zv.stride_c, zn.x + d0);
-            __stcs(o + (long long)(4 * g4 + 1) * p.zv.stride_c, zn.y + d1);
-            __stcs(o + (long long)(4 * g4 + 2) * p.zv.stride_c, zn.z + d2);
-            __stcs(o + (long long)(4 * g4 + 3) * p.zv.stride_c, zn.w + d3);
-          }
+          const float d0 = qq.x - x[4 * g4], d1 = qq.y - x[4 * g4 + 1], d2 = qq.z - x[4 * g4 + 2], d3 = qq.w - x[4 * g4 + 3];
+          ov[4 * g4] = x[4 * g4] + d0; ov[4 * g4 + 1] = x[4 * g4 + 1] + d1;          // STE value (:536)
+          ov[4 * g4 + 2] = x[4 * g4 + 2] + d2; ov[4 * g4 + 3] = x[4 * g4 + 3] + d3;
           e += group_sumsq(d0, d1, d2, d3);
         }
-        if (live) e_unit = e;
+        if (live) {
+#pragma unroll
+          for (int jj = 0; jj < D; ++jj) __stcs(o + (size_t)((uint32_t)jj * sc), ov[jj]);
+          e_unit = e;
+        }
       }
 #pragma unroll
       for (int g = 0; g < G; ++g) e_acc[g] += (itg.g == g) ? e_unit : 0.f;

@@ -68,20 +68,28 @@ class PackedPeerExchange:
         import torch.distributed._symmetric_memory as symm
         group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(group)
-        self.bufs, self.handles = [], []
+        self.bufs, self.handles, self.peer_ptrs = [], [], []
         for _ in range(2):
             t = symm.empty(*shape, dtype=torch.float32, device=device)
-            self.handles.append(symm.rendezvous(t, group))
+            h = symm.rendezvous(t, group)
+            self.handles.append(h)
             self.bufs.append(t)
+            # every rank's address of THIS tensor: the allocation bases the handle lists plus the tensor's offset inside
+            # the (symmetric) allocation -- two tensors may share one allocation
+            off = int(getattr(h, "offset", 0))
+            ptrs = [int(b) + off for b in h.buffer_ptrs]
+            assert ptrs[h.rank] == t.data_ptr(), "symmetric-memory handle does not describe the tensor it was made for"
+            self.peer_ptrs.append(torch.tensor(ptrs, dtype=torch.int64, device=device))
         self.step = 0
 
     def acquire(self):
-        """(zeroed local statistics buffer to accumulate into, its symmetric-memory handle) for this step."""
+        """(zeroed local statistics buffer to accumulate into, its symmetric-memory handle, device array of every
+        rank's address of that buffer) for this step."""
         i = self.step & 1
         self.step += 1
         buf = self.bufs[i]
         buf.zero_()
-        return buf, self.handles[i]
+        return buf, self.handles[i], self.peer_ptrs[i]
 
 
 _peer_exchanges = {}

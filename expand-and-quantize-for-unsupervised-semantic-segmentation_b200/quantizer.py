@@ -286,7 +286,7 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
             if not q0.use_split and K <= 1024:
                 peer = packed_peer_exchange((M, K, d + 1), z.device)
             if peer is not None:
-                local, handle = peer.acquire()
+                local, handle, peer_ptrs = peer.acquire()
                 ops.pq_accumulate(z.detach().float(), idx, K, out=local)
                 handle.barrier(channel=0)          # every rank's scatter-add is complete and visible to its peers
                 packed = torch.empty_like(local)   # receives the reduced statistics
@@ -305,7 +305,7 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
                 # EMA update + percentiles x2 + usage + codebook-sum + loss scalars: ONE launch (:493-532)
                 stats = ops.pq_train_tail(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c,
                                           sqerr, n, beta,
-                                          peers=None if peer is None else (handle.buffer_ptrs_dev, peer.world))
+                                          peers=None if peer is None else (peer_ptrs.data_ptr(), peer.world))
             if stats is None:
                 unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
                 output.update(core.percentile_stats(exact_c, "total"))                      # :496

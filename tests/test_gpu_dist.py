@@ -74,8 +74,8 @@ def _worker(rank, world, port, ret):
                 assert torch.equal(ex, torch.stack(exact)), f"{mode} step {s}: global counts differ"
                 if mode == "z_trainable":
                     torch.testing.assert_close(torch.stack([q.z_mean for q in pq.quantizers]).cpu(), torch.stack(zm), rtol=1e-5, atol=1e-6)
-        # the in-kernel peer reduction (symmetric memory) and the NCCL all-reduce give the same bits at two ranks
-        # (a two-term sum is order-independent); which path ran is part of the test's result
+        # the in-kernel peer reduction (symmetric memory) against the NCCL all-reduce; which path ran is part of the
+        # test's result
         import copy
         from equss_b200 import dist_utils
         torch.manual_seed(7)
@@ -90,11 +90,19 @@ def _worker(rank, world, port, ret):
                 os.environ["EQUSS_PEER_REDUCE"] = "0"
                 _, out_b, _ = pq_b(zr)
             os.environ["EQUSS_PEER_REDUCE"] = "1"
-            for qa, qb in zip(pq_a.quantizers, pq_b.quantizers):
-                assert torch.equal(qa.codebook.weight, qb.codebook.weight) and torch.equal(qa.vq_count, qb.vq_count)
-                assert torch.equal(qa.codebook.weight_avg, qb.codebook.weight_avg)
+            # counts are exact; the sums come out of floating-point atomics of two separate scatter-add launches, whose
+            # order is not fixed, so the two paths agree to rounding (1e-6), not bit for bit
+            for j, (qa, qb) in enumerate(zip(pq_a.quantizers, pq_b.quantizers)):
+                assert torch.equal(qa.vq_count, qb.vq_count), f"step {s} subspace {j}: counts differ"
+                torch.testing.assert_close(qa.codebook.weight_avg, qb.codebook.weight_avg, rtol=2e-6, atol=1e-6)
+                torch.testing.assert_close(qa.codebook.weight, qb.codebook.weight, rtol=2e-6, atol=1e-6)
             for k in out_a:
-                assert torch.equal(out_a[k], out_b[k]), k
+                torch.testing.assert_close(out_a[k], out_b[k], rtol=1e-5, atol=1e-6)
+            # ... while the replicas of the peer path stay bit-identical (every rank sums the buffers in rank order)
+            wa = torch.stack([q.codebook.weight for q in pq_a.quantizers])
+            ga = [torch.empty_like(wa) for _ in range(world)]
+            dist.all_gather(ga, wa)
+            assert all(torch.equal(ga[0], g) for g in ga), f"peer path step {s}: replicas diverged"
         peer_used = any(v is not None for v in dist_utils._peer_exchanges.values())
         # query-sharded kNN: every rank ends up with the complete table
         torch.manual_seed(1)
