@@ -136,7 +136,7 @@ def _declare(L: C.CDLL) -> None:
     L.equss_pq_train_tail.restype = i32
     L.equss_pq_train_tail.argtypes = [vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
     L.equss_pq_train_tail_peers.restype = i32
-    L.equss_pq_train_tail_peers.argtypes = [vp, i32, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp]
+    L.equss_pq_train_tail_peers.argtypes = [vp, i32, vp, i32, i32, i32, f64, f64, vp, vp, vp, vp, vp, i64, f64, vp, vp, vp, vp]
     L.equss_pq_prepare_codebook.restype = i32
     L.equss_pq_prepare_codebook.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp]
     L.equss_token_gram.restype = i32

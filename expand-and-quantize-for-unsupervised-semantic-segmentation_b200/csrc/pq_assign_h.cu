@@ -25,8 +25,11 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 build_image_kernel(const float* __restrict__ cb, const float* __restrict__ cn2, int K, int D, int NC, int nchunks, int G,
-                   uint8_t* __restrict__ images, int img_bytes, unsigned int* __restrict__ flag_count) {
+                   uint8_t* __restrict__ images, int img_bytes, unsigned int* __restrict__ flag_count,
+                   double* __restrict__ sqerr, int M) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0u;      // list of rows for the exact rescan starts empty
+  if (sqerr != nullptr && blockIdx.x == 0)                        // fused gather: the error sums start at zero
+    for (int i = threadIdx.x; i < M; i += blockDim.x) sqerr[i] = 0.0;
   const int m = blockIdx.x / nchunks, c = blockIdx.x % nchunks;
   uint8_t* img = images + (size_t)(((m / G) * nchunks + c) * G + (m % G)) * img_bytes;
   const int sbo = b_sbo(D);
@@ -296,7 +299,8 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
   } else {
     flag_list = (uint32_t*)(flag_count + 4);          // the counter is reset by build_image_kernel
   }
-  build_image_kernel<<<M * pl.nchunks, 256, 0, st>>>(codebook_norm, cnorm2, K, d, pl.NC, pl.nchunks, pl.G, images, img_bytes, flag_count);
+  build_image_kernel<<<M * pl.nchunks, 256, 0, st>>>(codebook_norm, cnorm2, K, d, pl.NC, pl.nchunks, pl.G, images, img_bytes, flag_count,
+                                                          fuse ? sqerr : nullptr, M);
   EQUSS_LAUNCH_OK("build_image_kernel");
 
   CUtensorMap tmap;

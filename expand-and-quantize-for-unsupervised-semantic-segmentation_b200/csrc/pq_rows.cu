@@ -772,9 +772,16 @@ ema_train_tail_kernel(const float* __restrict__ packed, int M, int K, int d, flo
                       float k_eps, float* __restrict__ vq_count, float* __restrict__ weight_avg,
                       float* __restrict__ weight, float* __restrict__ exact_count, const double* __restrict__ sqerr,
                       double inv_nd, float beta, float* __restrict__ scratch, float* __restrict__ stats_out,
-                      const float* const* __restrict__ peers, int world, float* __restrict__ packed_out) {
+                      const float* const* __restrict__ peers, int world, float* __restrict__ packed_out,
+                      float* __restrict__ zero_next) {
   const int m = blockIdx.x;
   const int ld = d + 1;
+  if (zero_next != nullptr) {
+    // the OTHER symmetric buffer (next step's accumulation target) is re-zeroed here: every peer finished reading it
+    // before it entered the barrier that precedes this launch
+    float* zn = zero_next + (long long)m * K * ld;
+    for (int i = threadIdx.x; i < K * ld; i += blockDim.x) zn[i] = 0.f;
+  }
   if (peers != nullptr) {
     // K5 fused in: the data-parallel sum of the packed statistics is taken straight from the peers' symmetric
     // buffers over NVLink (one pass of P2P loads, ranks added in a fixed order so every replica computes the same
@@ -1135,7 +1142,7 @@ extern "C" int equss_pq_train_tail(const float* packed, int M, int K, int d, dou
   const double inv_nd = (n_pixels > 0) ? 1.0 / ((double)n_pixels * (double)d) : 0.0;
   equss::ema_train_tail_kernel<<<M, equss::kPctThreads, 0, (cudaStream_t)stream>>>(
       packed, M, K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps), vq_count, weight_avg, weight,
-      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, nullptr, 1, nullptr);
+      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, nullptr, 1, nullptr, nullptr);
   EQUSS_LAUNCH_OK("ema_train_tail_kernel");
   return EQUSS_OK;
 }
@@ -1143,7 +1150,7 @@ extern "C" int equss_pq_train_tail(const float* packed, int M, int K, int d, dou
 extern "C" int equss_pq_train_tail_peers(const void* const* peer_packed, int world, float* packed_out, int M, int K, int d,
                                          double decay, double eps, float* vq_count, float* weight_avg, float* weight,
                                          float* exact_count, const double* sqerr, int64_t n_pixels, double beta,
-                                         float* scratch, float* stats_out, void* stream) {
+                                         float* scratch, float* stats_out, float* zero_next, void* stream) {
   EQUSS_REQUIRE(peer_packed && packed_out && vq_count && weight_avg && weight && exact_count && scratch && stats_out,
                 EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail_peers: null pointer");
   EQUSS_REQUIRE(world >= 1 && world <= 64, EQUSS_ERR_INVALID_ARG, "equss_pq_train_tail_peers: world=%d", world);
@@ -1153,7 +1160,7 @@ extern "C" int equss_pq_train_tail_peers(const void* const* peer_packed, int wor
   const double inv_nd = (n_pixels > 0) ? 1.0 / ((double)n_pixels * (double)d) : 0.0;
   equss::ema_train_tail_kernel<<<M, equss::kPctThreads, 0, (cudaStream_t)stream>>>(
       packed_out, M, K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps), vq_count, weight_avg, weight,
-      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, (const float* const*)peer_packed, world, packed_out);
+      exact_count, sqerr, inv_nd, (float)beta, scratch, stats_out, (const float* const*)peer_packed, world, packed_out, zero_next);
   EQUSS_LAUNCH_OK("ema_train_tail_kernel<peers>");
   return EQUSS_OK;
 }

@@ -80,16 +80,18 @@ class PackedPeerExchange:
             ptrs = [int(b) + off for b in h.buffer_ptrs]
             assert ptrs[h.rank] == t.data_ptr(), "symmetric-memory handle does not describe the tensor it was made for"
             self.peer_ptrs.append(torch.tensor(ptrs, dtype=torch.int64, device=device))
+        for t in self.bufs:
+            t.zero_()
+        self.reduced = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
         self.step = 0
 
     def acquire(self):
         """(zeroed local statistics buffer to accumulate into, its symmetric-memory handle, device array of every
-        rank's address of that buffer) for this step."""
+        rank's address of that buffer, the OTHER local buffer -- which the consuming kernel must clear for the next
+        step --, a buffer for the reduced statistics) for this step."""
         i = self.step & 1
         self.step += 1
-        buf = self.bufs[i]
-        buf.zero_()
-        return buf, self.handles[i], self.peer_ptrs[i]
+        return self.bufs[i], self.handles[i], self.peer_ptrs[i], self.bufs[i ^ 1], self.reduced[i]
 
 
 _peer_exchanges = {}

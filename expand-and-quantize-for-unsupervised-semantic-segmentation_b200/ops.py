@@ -115,7 +115,7 @@ def pq_assign_gather(z: torch.Tensor, codebook_norm: torch.Tensor, gather_src: O
     n = zd.n_pixels
     idx = torch.empty((M, n), dtype=torch.int32, device=dev)
     out = torch.empty_like(z)
-    sqerr = torch.zeros((M,), dtype=torch.float64, device=dev)
+    sqerr = torch.empty((M,), dtype=torch.float64, device=dev)      # zeroed by the call (with the operand images)
     wsb = int(L.equss_pq_assign_workspace_bytes(n, M, K, d, N.ASSIGN_TCGEN05))
     ws = torch.empty((max(wsb, 1),), dtype=torch.uint8, device=dev)
     rc = L.equss_pq_assign_gather(z.data_ptr(), zd, cb.data_ptr(), cnorm2.data_ptr(), src.data_ptr(), M, K, d, mode,
@@ -215,7 +215,8 @@ _tail_scratch = {}
 
 def pq_train_tail(packed: torch.Tensor, decay: float, eps: float, vq_count: torch.Tensor, weight_avg: torch.Tensor,
                   weight: torch.Tensor, exact_count: torch.Tensor, sqerr: Optional[torch.Tensor], n_pixels: int,
-                  beta: float, peers: Optional[Tuple[int, int]] = None) -> Optional[torch.Tensor]:
+                  beta: float, peers: Optional[Tuple[int, int]] = None,
+                  zero_next: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """The tail of the EMA training step in one launch: in-place EMA update of the stacked state (as :func:`ema_update`)
     plus the ten scalar outputs of ``ProductQuantizerWrapper.forward`` (order: :data:`TAIL_KEYS`), averaged over the
     subspaces (model/quantizer.py:493-532,607-608).  Returns float32 [10], or None when K > 1024 (then call
@@ -241,7 +242,7 @@ def pq_train_tail(packed: torch.Tensor, decay: float, eps: float, vq_count: torc
         rc = L.equss_pq_train_tail_peers(int(peers[0]), int(peers[1]), packed.data_ptr(), M, K, d, float(decay), float(eps),
                                          vq_count.data_ptr(), weight_avg.data_ptr(), weight.data_ptr(), exact_count.data_ptr(),
                                          N.ptr(sqerr), int(n_pixels), float(beta), scratch.data_ptr(), stats.data_ptr(),
-                                         N.stream_ptr(dev))
+                                         N.ptr(zero_next), N.stream_ptr(dev))
         N.check(rc, "equss_pq_train_tail_peers")
         return stats
     rc = L.equss_pq_train_tail(packed.contiguous().data_ptr(), M, K, d, float(decay), float(eps), vq_count.data_ptr(),

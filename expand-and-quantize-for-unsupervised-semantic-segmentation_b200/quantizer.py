@@ -286,10 +286,9 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
             if not q0.use_split and K <= 1024:
                 peer = packed_peer_exchange((M, K, d + 1), z.device)
             if peer is not None:
-                local, handle, peer_ptrs = peer.acquire()
+                local, handle, peer_ptrs, zero_next, packed = peer.acquire()   # `packed` receives the reduced statistics
                 ops.pq_accumulate(z.detach().float(), idx, K, out=local)
                 handle.barrier(channel=0)          # every rank's scatter-add is complete and visible to its peers
-                packed = torch.empty_like(local)   # receives the reduced statistics
             else:
                 packed = core.ema_statistics(z, idx, K)
             count = packed[:, :, d]
@@ -305,7 +304,8 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
                 # EMA update + percentiles x2 + usage + codebook-sum + loss scalars: ONE launch (:493-532)
                 stats = ops.pq_train_tail(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c,
                                           sqerr, n, beta,
-                                          peers=None if peer is None else (peer_ptrs.data_ptr(), peer.world))
+                                          peers=None if peer is None else (peer_ptrs.data_ptr(), peer.world),
+                                          zero_next=None if peer is None else zero_next)
             if stats is None:
                 unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
                 output.update(core.percentile_stats(exact_c, "total"))                      # :496

@@ -110,6 +110,7 @@ int equss_pq_gather_loss(const float* z, const equss_zdesc* zd,
 /* K1 + K3 in one pass over the activations (the tcgen05 assign kernel gathers each tile from shared memory a few
  * tiles after assigning it): idx as equss_pq_assign, out / sqerr as equss_pq_gather_loss.  Available for l2 rows
  * with d in {16, 32} and K <= 256 (equss_pq_assign_gather_supported); other shapes: call K1 then K3.
+ * Unlike equss_pq_gather_loss this entry point OVERWRITES sqerr (it is zeroed by the call's first kernel).
  * workspace: equss_pq_assign_workspace_bytes(..., EQUSS_ASSIGN_TCGEN05) bytes. */
 int equss_pq_assign_gather_supported(const equss_zdesc* zd, int M, int K, int d, int norm_mode);
 int equss_pq_assign_gather(const float* z, const equss_zdesc* zd,
@@ -179,11 +180,13 @@ int equss_pq_train_tail(const float* packed, int M, int K, int d, double decay, 
  * buffer (symmetric memory, own rank included), summed in rank order so all replicas obtain identical bits.  The
  * reduced statistics are written to packed_out (local).  The caller orders the ranks: every rank's K4 must be complete
  * and visible (a device-side barrier over the symmetric-memory signal pads) before the launch, and a buffer may be
- * re-zeroed only after all peers have read it (the host mirror alternates two buffers). */
+ * re-zeroed only after all peers have read it: the host mirror alternates two buffers and passes the OTHER one as
+ * zero_next (optional, [M][K][d+1]), which this launch clears for the next step -- by the barrier above every peer is
+ * past its reads of it. */
 int equss_pq_train_tail_peers(const void* const* peer_packed, int world, float* packed_out, int M, int K, int d,
                               double decay, double eps, float* vq_count, float* weight_avg, float* weight,
                               float* exact_count, const double* sqerr, int64_t n_pixels, double beta,
-                              float* scratch, float* stats_out, void* stream);
+                              float* scratch, float* stats_out, float* zero_next, void* stream);
 
 /* Codebook-side normalisation (model/quantizer.py:421 "l2", :426 "z_norm", "none") and cnorm2 of the result in one
  * launch: codebook_norm [M][K][d], cnorm2 [M][K].  (The "z_trainable" flavours normalise across codes / with learned
