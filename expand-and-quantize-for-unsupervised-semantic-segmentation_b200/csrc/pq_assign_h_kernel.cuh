@@ -110,6 +110,13 @@ __host__ __device__ constexpr int a_sbo(int D) { return kch(D) * a_lbo(D); }
 __host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * a_sbo(D); }
 __host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
+// Fused gather in the EPILOGUE warps (default) instead of the convert warps: the thread that found a row's winner
+// gathers it right away from the raw stage (which still holds the canonical z_norm) -- no index ring, no gather lag,
+// and the ALU-bound epilogue warps get FMA / LSU work of their own to overlap with.
+#ifndef EQUSS_EPI_GATHER
+#define EQUSS_EPI_GATHER 1
+#endif
+constexpr bool kEpiGather = EQUSS_EPI_GATHER != 0;
 #ifndef EQUSS_IDX_BUFS
 #define EQUSS_IDX_BUFS 8
 #endif
@@ -323,6 +330,11 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   constexpr int LPS = D / 4;                   // lanes per pixel row in the flat convert
   constexpr int C8 = D / 8;                    // 16-byte chunks per operand piece
   constexpr int HALVES = (NC >= 64) ? 2 : 1;   // accumulator halves with their own barriers / issuer warps
+#ifdef EQUSS_DBG_CONV_UNFUSED          // timing experiment: the convert pass of the unfused kernel inside the fused one
+  constexpr bool CFUSE = false;
+#else
+  constexpr bool CFUSE = FUSE;
+#endif
   constexpr int NH = NC / HALVES;
   constexpr uint32_t IDESC = make_idesc(NH);
   static_assert(NC % 32 == 0 && NC <= 256, "NC must be a multiple of 32, at most 256");
@@ -593,7 +605,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const int a = i % ABUFS, s = i % STAGES;
       // the operand images change with the first unit of a slot: only that unit's owner loads them
       const bool new_slot = (i == 0) || (it.tile == 0 && it.g == 0);
-      if constexpr (FUSE) { if (i >= LAG) gather_prefetch(i - LAG); }
+      if constexpr (FUSE && !kEpiGather) { if (i >= LAG) gather_prefetch(i - LAG); }
       mbar_wait_nc(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (warp == kConvWarp0) EQUSS_TR(0, i);
       if (new_slot) {
@@ -634,11 +646,11 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             for (int u = 0; u < BATCH; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], sft);
           }
           uint2 hi[BATCH], lo[BATCH];
-          float4 zn4[FUSE ? BATCH : 1];
+          float4 zn4[CFUSE ? BATCH : 1];
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
             float zx, zy, zz, zw;
-            if constexpr (FUSE) {      // canonical z_norm (the gather needs it bit-exact); kept in the raw stage
+            if constexpr (CFUSE) {      // canonical z_norm (the gather needs it bit-exact); kept in the raw stage
 #ifdef EQUSS_FUSE_FASTNORM
               const float inv_ = 1.f / l2_denom_fast(ss[u]);
               const float4 zn = make_float4(v[u].x * inv_, v[u].y * inv_, v[u].z * inv_, v[u].w * inv_);
@@ -663,7 +675,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             uint8_t* rowp = a_tile + (row / 8) * ASBO + (row % 8) * 16 + (l >> 1) * ALBO + (l & 1) * 8;
             *reinterpret_cast<uint2*>(rowp) = hi[u];
             *reinterpret_cast<uint2*>(rowp + C8 * ALBO) = lo[u];
-            if constexpr (FUSE)
+            if constexpr (CFUSE)
               *reinterpret_cast<float4*>(const_cast<float*>(raw) + row * D + l * 4) = zn4[u];
           }
         }
@@ -674,7 +686,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
         for (int j = 0; j < D; ++j) x[j] = raw[j * kTileM + row];
         float inv;
-        if constexpr (FUSE) {        // canonical z_norm, written back into the raw stage for the gather
+        if constexpr (CFUSE) {        // canonical z_norm, written back into the raw stage for the gather
           float gsum[LPS];
 #pragma unroll
           for (int g4 = 0; g4 < LPS; ++g4) gsum[g4] = group_sumsq(x[4 * g4], x[4 * g4 + 1], x[4 * g4 + 2], x[4 * g4 + 3]);
@@ -714,9 +726,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       __syncwarp();
       if (lane == 0) { if (!FUSE) mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
       if (warp == kConvWarp0) EQUSS_TR(2, i);
-      if constexpr (FUSE) { if (i >= LAG) gather_finish(i - LAG); }
+      if constexpr (FUSE && !kEpiGather) { if (i >= LAG) gather_finish(i - LAG); }
     }
-    if constexpr (FUSE) {
+    if constexpr (FUSE && !kEpiGather) {
       for (int j = (n_units > LAG ? n_units - LAG : 0); j < n_units; ++j) {
         if (j % kConvGroups != cgroup) continue;
         gather_prefetch(j); gather_finish(j);
@@ -733,6 +745,19 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int row = q * 32 + lane;
     UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
     it.advance(egroup);
+    float ge_acc[G];                              // FUSE (epilogue gather): this thread's squared error per subspace of the group
+#pragma unroll
+    for (int g = 0; g < G; ++g) ge_acc[g] = 0.f;
+    int ge_sg = -1;
+    auto ge_flush = [&]() {
+      if (ge_sg < 0) return;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float t = warp_sum(ge_acc[g]);
+        if (lane == 0 && t != 0.f) atomicAdd(p.sqerr + ge_sg * G + g, (double)t);
+        ge_acc[g] = 0.f;
+      }
+    };
     for (int i = egroup; i < n_units; i += kEpiGroups, it.advance(kEpiGroups)) {   // this group's units only
       const int t = i & 1;
       const int tile = it.tile, m = it.m(), chunk = it.chunk;
@@ -811,12 +836,67 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         if (best_col >= kvalid) best_col = 0;
         p.flag_list[atomicAdd(p.flag_count, 1u)] = (uint32_t)((long long)m * p.n_pixels + n);
       }
-      if constexpr (FUSE) {
+      if constexpr (FUSE && !kEpiGather) {
         const int ib = i % kIdxBufs;
         mbar_wait_nc(idx_empty + ib, ((i / kIdxBufs) & 1) ^ 1, 42);
         s_idx[ib * kTileM + row] = live ? best_col : 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(idx_full + ib);
+      }
+      if constexpr (FUSE && kEpiGather) {
+        // K3 for this row (model/quantizer.py:474,514,534-536): the raw stage still holds the canonical z_norm the convert
+        // pass left there; 16 channels at a time (the stream's registers are free now)
+        const int s = i % STAGES;
+        const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
+        const float* qrow = p.gsrc + ((size_t)m * p.K + (size_t)(live ? best_col : 0)) * D;
+        if (it.sg != ge_sg) { ge_flush(); ge_sg = it.sg; }
+        float e = 0.f;
+#ifdef EQUSS_DBG_NOGATHER
+#pragma unroll
+        for (int c0 = 0; c0 < 0; c0 += 16) {
+#else
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 16) {
+#endif
+          float4 qv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) qv[u] = __ldg(reinterpret_cast<const float4*>(qrow + c0) + u);
+          float x[16];
+          if constexpr (NCHW) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = raw[(c0 + j) * kTileM + row];
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 t4 = *reinterpret_cast<const float4*>(raw + row * D + c0 + 4 * u);
+              x[4 * u] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+            }
+          }
+          float ov[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float d0 = qv[u].x - x[4 * u], d1 = qv[u].y - x[4 * u + 1], d2 = qv[u].z - x[4 * u + 2], d3 = qv[u].w - x[4 * u + 3];
+            ov[4 * u] = x[4 * u] + d0; ov[4 * u + 1] = x[4 * u + 1] + d1;             // STE value (:536)
+            ov[4 * u + 2] = x[4 * u + 2] + d2; ov[4 * u + 3] = x[4 * u + 3] + d3;
+            e += group_sumsq(d0, d1, d2, d3);
+          }
+          if (live) {
+            if constexpr (NCHW) {
+              float* o = p.out + (long long)it.img * p.zv.stride_b + (long long)(m * D + c0) * p.zv.stride_c + (it.timg * kTileM + row);
+              const uint32_t sc = (uint32_t)p.zv.stride_c;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) __stcs(o + (size_t)((uint32_t)j * sc), ov[j]);
+            } else {
+              float4* o4 = reinterpret_cast<float4*>(p.out + n * p.zv.stride_s + m * D + c0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) __stcs(o4 + u, make_float4(ov[4 * u], ov[4 * u + 1], ov[4 * u + 2], ov[4 * u + 3]));
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) ge_acc[g] += (live && it.g == g) ? e : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_empty + s);      // the stage's last reader is done
       }
       if (live) {
         if (p.merged == nullptr) {
@@ -833,6 +913,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       if (q == 0) { EQUSS_TR(6, i); if (!FUSE) EQUSS_TRG(8, i); }
     }
+    if constexpr (FUSE && kEpiGather) ge_flush();
   }
 
   tc_fence_before();
