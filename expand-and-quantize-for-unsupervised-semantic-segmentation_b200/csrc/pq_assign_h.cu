@@ -334,6 +334,7 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
   p.z = z; p.zv = make_view(zd); p.cb = codebook_norm; p.cn2 = cnorm2;
   p.images = images; p.img_bytes = img_bytes; p.idx_out = idx_out; p.merged = merged; p.flag_list = flag_list; p.flag_count = flag_count;
   p.gsrc = gather_src; p.out = out; p.sqerr = sqerr;
+  p.use_gtab = (fuse && (long long)p.n_tiles * pl.G >= 32 && getenv("EQUSS_NO_GTAB") == nullptr) ? 1 : 0;   // slots much longer than the raw ring
   const long long total_units = (long long)M * pl.nchunks * p.n_tiles;
   int grid = num_sms();
   if (total_units < grid) grid = (int)total_units;

@@ -59,10 +59,15 @@ constexpr int kTileM = 128;
 #if !defined(EQUSS_NO_SETMAXNREG) && !defined(EQUSS_SETMAXNREG)
 #define EQUSS_SETMAXNREG
 #endif
-#ifndef EQUSS_REGS_EPI
-#define EQUSS_REGS_EPI 88
-#define EQUSS_REGS_CONV 88
+// Budgets (warp-registers: 12 x epilogue + 8 x convert + 4 x misc <= 1920).  d = 16: the convert pass needs < 50 registers,
+// which gives the epilogue (stream + tournaments + fused gather) 96 and no spills; wider subspaces keep 88 / 88.
+#ifndef EQUSS_REGS_MISC
 #define EQUSS_REGS_MISC 40
+#endif
+#ifdef EQUSS_REGS_EPI
+template <int D> struct RegPlan { static constexpr int epi = EQUSS_REGS_EPI, conv = EQUSS_REGS_CONV; };
+#else
+template <int D> struct RegPlan { static constexpr int epi = (D == 16) ? 96 : 88, conv = (D == 16) ? 72 : 88; };
 #endif
 constexpr int kEpiGroups = EQUSS_EPI_GROUPS;     // epilogue groups of four warps, rotating over the units
 // A parity wait cannot skip a phase, so every accumulator barrier must always be waited on by the same consumer:
@@ -121,9 +126,14 @@ constexpr bool kEpiGather = EQUSS_EPI_GATHER != 0;
 #define EQUSS_IDX_BUFS 8
 #endif
 constexpr int kIdxBufs = EQUSS_IDX_BUFS;         // fused gather: ring of per-tile winning columns
-__host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false) {
+// Epilogue gather: for d = 16 the gather source of the slot's G subspaces ([NC][D] fp32 each) is kept in shared memory,
+// double-buffered by slot parity, so a row's codeword is one shared-memory read away -- for the row-major layout only
+// (192 -> 175 us at C2): the channel-major path reads whole 64-byte rows per thread, which lands every quarter-warp on
+// two bank groups (4-way conflicts) and loses to the L2 loads (195 vs 189 us)
+__host__ __device__ constexpr int gtab_bytes(int D, int NC, int G, bool nchw) { return (kEpiGather && D == 16 && !nchw) ? 2 * G * NC * D * 4 : 0; }
+__host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false, bool nchw = false) {
   return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) +
-         (fuse ? kIdxBufs * kTileM * 4 : 0) + 1024;
+         (fuse ? (kEpiGather ? gtab_bytes(D, NC, G, nchw) : kIdxBufs * kTileM * 4) : 0) + 1024;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, both K-major, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -148,7 +158,8 @@ struct Params {
   // fused gather (FUSE kernels only)
   const float* gsrc;          // gather source [M][K][d]
   float* out;                 // same strides as z
-  double* sqerr;              // [M], caller-zeroed
+  double* sqerr;              // [M], zeroed by build_image_kernel
+  int use_gtab;               // epilogue gather reads the codewords from the shared-memory table (slots long enough)
 };
 
 // Walks the CTA's contiguous unit range (sslot-major, then tile, then subspace-in-group) without divisions.
@@ -345,8 +356,11 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* s_b = smem;                                   // [G][B_BYTES]
   uint8_t* s_a = s_b + G * B_BYTES;                      // [ABUFS][A_BYTES]
   uint8_t* s_rawt = s_a + ABUFS * A_BYTES;               // [STAGES][RAW_BYTES]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_rawt + STAGES * RAW_BYTES);   // FUSE: [kIdxBufs][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES + (FUSE ? kIdxBufs * kTileM * 4 : 0));
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_rawt + STAGES * RAW_BYTES);   // FUSE, gather in the convert warps: [kIdxBufs][128]
+  float* s_gt = reinterpret_cast<float*>(s_rawt + STAGES * RAW_BYTES);        // FUSE, gather in the epilogue: [2][G][NC][D]
+  constexpr int GTAB = FUSE ? gtab_bytes(D, NC, G, NCHW) : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES +
+                                               (FUSE ? (kEpiGather ? GTAB : kIdxBufs * kTileM * 4) : 0));
   uint64_t* raw_full = bars;                    // [STAGES]
   uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
   uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
@@ -476,7 +490,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     // the latency of its own shared-memory / MUFU / conversion chain.
     static_assert(!FUSE || LAG % kConvGroups == 0, "a unit's gather runs in the group that converted it");
 #ifdef EQUSS_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(EQUSS_REGS_CONV));
+    // (24 warps are launched with 80 registers: below that the limit is lowered, above it raised)
+    if constexpr (RegPlan<D>::conv < 80) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(RegPlan<D>::conv));
+    else if constexpr (RegPlan<D>::conv > 80) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(RegPlan<D>::conv));
 #endif
     const int cgroup = (warp - kConvWarp0) >> 2;
     const int ct = (threadIdx.x - kConvWarp0 * 32) & 127;   // 0..127 within the group
@@ -614,8 +630,15 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         for (int back = 1; back < ABUFS; ++back)
           if (i >= back) mbar_wait_nc(a_empty + ((i - back) % ABUFS), ((i - back) / ABUFS) & 1, 31);
         if (ct == 0) {
-          mbar_expect_tx(b_full, (uint32_t)(G * p.img_bytes));
+          const bool tab = FUSE && GTAB > 0 && p.use_gtab;
+          const uint32_t tab_bytes = (uint32_t)p.K * D * 4;       // per subspace; K <= NC
+          mbar_expect_tx(b_full, (uint32_t)(G * p.img_bytes) + (tab ? (uint32_t)G * tab_bytes : 0u));
           bulk_load_1d(s_b, p.images + (size_t)it.sslot * G * p.img_bytes, (uint32_t)(G * p.img_bytes), b_full);
+          if (tab) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              bulk_load_1d(s_gt + ((it.sslot & 1) * G + g) * (NC * D), p.gsrc + (size_t)(it.sg * G + g) * p.K * D, tab_bytes, b_full);
+          }
         }
       }
       mbar_wait_nc(raw_full + s, (i / STAGES) & 1, 33);
@@ -738,7 +761,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   } else if (warp < 4 * kEpiGroups) {
     // ===================================== epilogue warps ===================================
 #ifdef EQUSS_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(EQUSS_REGS_EPI));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(RegPlan<D>::epi));
 #endif
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int egroup = (warp - kEpiWarp0) >> 2;  // 0 .. kEpiGroups-1
@@ -844,57 +867,69 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         if (lane == 0) mbar_arrive(idx_full + ib);
       }
       if constexpr (FUSE && kEpiGather) {
-        // K3 for this row (model/quantizer.py:474,514,534-536): the raw stage still holds the canonical z_norm the convert
-        // pass left there; 16 channels at a time (the stream's registers are free now)
+        // K3 for this unit (model/quantizer.py:474,514,534-536): the raw stage still holds the canonical z_norm the
+        // convert pass left there.  The codeword comes from the slot's shared-memory table (d = 16, long slots) or from
+        // global memory.  The table was filled by the bulk copies that completed b_full before this unit's MMAs were
+        // issued, i.e. long before t_full.
         const int s = i % STAGES;
         const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
-        const float* qrow = p.gsrc + ((size_t)m * p.K + (size_t)(live ? best_col : 0)) * D;
+        const bool tab = GTAB > 0 && p.use_gtab;
+        const float* tbl = s_gt + ((it.sslot & 1) * G + it.g) * (NC * D);
+        const float* gsrc_m = p.gsrc + (size_t)m * p.K * D;
+        const int col = live ? best_col : 0;
         if (it.sg != ge_sg) { ge_flush(); ge_sg = it.sg; }
         float e = 0.f;
-#ifdef EQUSS_DBG_NOGATHER
+        if constexpr (NCHW) {
+          // one thread per pixel row (channel-major tile: lanes read / write consecutive pixels), 16 channels at a time
 #pragma unroll
-        for (int c0 = 0; c0 < 0; c0 += 16) {
-#else
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            float4 qv[4];
 #pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 16) {
-#endif
-          float4 qv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) qv[u] = __ldg(reinterpret_cast<const float4*>(qrow + c0) + u);
-          float x[16];
-          if constexpr (NCHW) {
+            for (int u = 0; u < 4; ++u)
+              qv[u] = tab ? *reinterpret_cast<const float4*>(tbl + col * D + c0 + 4 * u)
+                          : __ldg(reinterpret_cast<const float4*>(gsrc_m + (size_t)col * D + c0) + u);
+            float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = raw[(c0 + j) * kTileM + row];
-          } else {
+            float ov[16];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float4 t4 = *reinterpret_cast<const float4*>(raw + row * D + c0 + 4 * u);
-              x[4 * u] = t4.x; x[4 * u + 1] = t4.y; x[4 * u + 2] = t4.z; x[4 * u + 3] = t4.w;
+              const float d0 = qv[u].x - x[4 * u], d1 = qv[u].y - x[4 * u + 1], d2 = qv[u].z - x[4 * u + 2], d3 = qv[u].w - x[4 * u + 3];
+              ov[4 * u] = x[4 * u] + d0; ov[4 * u + 1] = x[4 * u + 1] + d1;             // STE value (:536)
+              ov[4 * u + 2] = x[4 * u + 2] + d2; ov[4 * u + 3] = x[4 * u + 3] + d3;
+              e += group_sumsq(d0, d1, d2, d3);
             }
-          }
-          float ov[16];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float d0 = qv[u].x - x[4 * u], d1 = qv[u].y - x[4 * u + 1], d2 = qv[u].z - x[4 * u + 2], d3 = qv[u].w - x[4 * u + 3];
-            ov[4 * u] = x[4 * u] + d0; ov[4 * u + 1] = x[4 * u + 1] + d1;             // STE value (:536)
-            ov[4 * u + 2] = x[4 * u + 2] + d2; ov[4 * u + 3] = x[4 * u + 3] + d3;
-            e += group_sumsq(d0, d1, d2, d3);
-          }
-          if (live) {
-            if constexpr (NCHW) {
+            if (live) {
               float* o = p.out + (long long)it.img * p.zv.stride_b + (long long)(m * D + c0) * p.zv.stride_c + (it.timg * kTileM + row);
               const uint32_t sc = (uint32_t)p.zv.stride_c;
 #pragma unroll
               for (int j = 0; j < 16; ++j) __stcs(o + (size_t)((uint32_t)j * sc), ov[j]);
-            } else {
-              float4* o4 = reinterpret_cast<float4*>(p.out + n * p.zv.stride_s + m * D + c0);
+            }
+          }
+          e = live ? e : 0.f;
+        } else {
+          // row-major tile: LPS lanes share a row (one float4 each), 32 / LPS rows per pass -- shared-memory reads
+          // without bank conflicts and 16-byte stores that fill whole sectors; the rows' winners travel by shuffle
+          constexpr int RPP = 32 / LPS;
+          const int qd = lane % LPS, rsub = lane / LPS;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) __stcs(o4 + u, make_float4(ov[4 * u], ov[4 * u + 1], ov[4 * u + 2], ov[4 * u + 3]));
+          for (int pass = 0; pass < LPS; ++pass) {
+            const int rr = pass * RPP + rsub;                          // row within the warp's 32
+            const int col_r = __shfl_sync(0xffffffffu, col, rr);
+            const long long n_r = (long long)tile * kTileM + q * 32 + rr;
+            const float4 zn = *reinterpret_cast<const float4*>(raw + (q * 32 + rr) * D + qd * 4);
+            const float4 qq = tab ? *reinterpret_cast<const float4*>(tbl + col_r * D + qd * 4)
+                                  : __ldg(reinterpret_cast<const float4*>(gsrc_m + (size_t)col_r * D) + qd);
+            const float d0 = qq.x - zn.x, d1 = qq.y - zn.y, d2 = qq.z - zn.z, d3 = qq.w - zn.w;
+            if (n_r < p.n_pixels) {
+              __stcs(reinterpret_cast<float4*>(p.out + n_r * p.zv.stride_s + m * D) + qd,
+                     make_float4(zn.x + d0, zn.y + d1, zn.z + d2, zn.w + d3));              // STE value (:536)
+              e += group_sumsq(d0, d1, d2, d3);
             }
           }
         }
 #pragma unroll
-        for (int g = 0; g < G; ++g) ge_acc[g] += (live && it.g == g) ? e : 0.f;
+        for (int g = 0; g < G; ++g) ge_acc[g] += (it.g == g) ? e : 0.f;
         __syncwarp();
         if (lane == 0) mbar_arrive(raw_empty + s);      // the stage's last reader is done
       }
@@ -926,7 +961,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 
 template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW, bool FUSE, int LAG>
 static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, cudaStream_t st) {
-  constexpr int SMEM = smem_bytes(D, NC, G, STAGES, ABUFS, FUSE) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, G, STAGES, ABUFS, FUSE);
+  constexpr int SMEM = smem_bytes(D, NC, G, STAGES, ABUFS, FUSE, NCHW) < 120 * 1024 ? 120 * 1024 : smem_bytes(D, NC, G, STAGES, ABUFS, FUSE, NCHW);
   static_assert(SMEM <= 227 * 1024, "shared-memory plan exceeds 227 KB");
   EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
