@@ -29,10 +29,10 @@
 // winners are merged with a 64-bit atomicMax on (score, index); cross-chunk near-ties are appended to a list and
 // resolved by a full exact scan (one warp per listed row) after the main kernel.
 //
-// Fused gather (FUSE, single-chunk codebooks, d <= 32): the epilogue also drops each tile's winning columns into a
-// small shared-memory ring, and the convert warps -- which have slack -- run K3 (gather + straight-through value +
-// squared error, model/quantizer.py:474,514,534-536) for the tile LAG units later from the raw tile that is still
-// in shared memory.  The activation tensor is then read from HBM once for assign + gather instead of twice.
+// Fused gather (FUSE, single-chunk codebooks, d <= 32): the convert pass leaves the canonical z_norm in the raw stage and
+// the epilogue thread that found a row's winner runs K3 for it right away (gather + straight-through value + squared
+// error, model/quantizer.py:474,514,534-536), then releases the stage.  The activation tensor is read from HBM once for
+// assign + gather instead of twice.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -115,25 +115,14 @@ __host__ __device__ constexpr int a_sbo(int D) { return kch(D) * a_lbo(D); }
 __host__ __device__ constexpr int a_bytes(int D) { return (kTileM / 8) * a_sbo(D); }
 __host__ __device__ constexpr int raw_bytes(int D) { return kTileM * D * 4; }
 __host__ __device__ constexpr int align_up(int x, int a) { return (x + a - 1) / a * a; }
-// Fused gather in the EPILOGUE warps (default) instead of the convert warps: the thread that found a row's winner
-// gathers it right away from the raw stage (which still holds the canonical z_norm) -- no index ring, no gather lag,
-// and the ALU-bound epilogue warps get FMA / LSU work of their own to overlap with.
-#ifndef EQUSS_EPI_GATHER
-#define EQUSS_EPI_GATHER 1
-#endif
-constexpr bool kEpiGather = EQUSS_EPI_GATHER != 0;
-#ifndef EQUSS_IDX_BUFS
-#define EQUSS_IDX_BUFS 8
-#endif
-constexpr int kIdxBufs = EQUSS_IDX_BUFS;         // fused gather: ring of per-tile winning columns
 // Epilogue gather: for d = 16 the gather source of the slot's G subspaces ([NC][D] fp32 each) is kept in shared memory,
 // double-buffered by slot parity, so a row's codeword is one shared-memory read away -- for the row-major layout only
 // (192 -> 175 us at C2): the channel-major path reads whole 64-byte rows per thread, which lands every quarter-warp on
 // two bank groups (4-way conflicts) and loses to the L2 loads (195 vs 189 us)
-__host__ __device__ constexpr int gtab_bytes(int D, int NC, int G, bool nchw) { return (kEpiGather && D == 16 && !nchw) ? 2 * G * NC * D * 4 : 0; }
+__host__ __device__ constexpr int gtab_bytes(int D, int NC, int G, bool nchw) { return (D == 16 && !nchw) ? 2 * G * NC * D * 4 : 0; }
 __host__ __device__ constexpr int smem_bytes(int D, int NC, int G, int stages, int a_bufs, bool fuse = false, bool nchw = false) {
   return 128 + G * align_up(b_bytes(D, NC), 128) + a_bufs * align_up(a_bytes(D), 128) + stages * raw_bytes(D) +
-         (fuse ? (kEpiGather ? gtab_bytes(D, NC, G, nchw) : kIdxBufs * kTileM * 4) : 0) + 1024;
+         (fuse ? gtab_bytes(D, NC, G, nchw) : 0) + 1024;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B, both K-major, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -331,7 +320,6 @@ __device__ __noinline__ int exact_rescore_warp(const Params& p, int m, long long
 template <int D, int NC, int G, int STAGES, int ABUFS, bool NCHW, bool FUSE, int LAG>
 __global__ void __launch_bounds__(kThreads, 1)
 assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
-  static_assert(!FUSE || (LAG >= 1 && LAG < STAGES && LAG < kIdxBufs), "gather lag must fit the raw and index rings");
   constexpr int SBO = b_sbo(D);
   constexpr int ASBO = a_sbo(D), ALBO = a_lbo(D);
   constexpr int B_BYTES = align_up(b_bytes(D, NC), 128);
@@ -356,11 +344,9 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* s_b = smem;                                   // [G][B_BYTES]
   uint8_t* s_a = s_b + G * B_BYTES;                      // [ABUFS][A_BYTES]
   uint8_t* s_rawt = s_a + ABUFS * A_BYTES;               // [STAGES][RAW_BYTES]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_rawt + STAGES * RAW_BYTES);   // FUSE, gather in the convert warps: [kIdxBufs][128]
-  float* s_gt = reinterpret_cast<float*>(s_rawt + STAGES * RAW_BYTES);        // FUSE, gather in the epilogue: [2][G][NC][D]
+  float* s_gt = reinterpret_cast<float*>(s_rawt + STAGES * RAW_BYTES);        // FUSE, row-major d = 16: gather table [2][G][NC][D]
   constexpr int GTAB = FUSE ? gtab_bytes(D, NC, G, NCHW) : 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES +
-                                               (FUSE ? (kEpiGather ? GTAB : kIdxBufs * kTileM * 4) : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rawt + STAGES * RAW_BYTES + GTAB);
   uint64_t* raw_full = bars;                    // [STAGES]
   uint64_t* raw_empty = raw_full + STAGES;      // [STAGES]
   uint64_t* a_full = raw_empty + STAGES;        // [ABUFS]
@@ -368,9 +354,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* t_full = a_empty + ABUFS;           // [kTSlots][2]  (unit slot, half)
   uint64_t* t_empty = t_full + 2 * kTSlots;     // [kTSlots][2]
   uint64_t* b_full = t_empty + 2 * kTSlots;     // [1]
-  uint64_t* idx_full = b_full + 1;              // [kIdxBufs] FUSE: epilogue wrote the tile's columns
-  uint64_t* idx_empty = idx_full + kIdxBufs;    // [kIdxBufs] FUSE: gather consumed them
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(idx_empty + kIdxBufs);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(b_full + 1);
 
   // the warp index goes through a shuffle so that ptxas knows it is warp-uniform: the role branches below are then
   // uniform branches and what the tcgen05 / TMA instructions consume can live in uniform registers
@@ -386,7 +370,6 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     for (int i = 0; i < ABUFS; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, HALVES); }
     for (int i = 0; i < 2 * kTSlots; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
     mbar_init(b_full, 1);
-    for (int i = 0; i < kIdxBufs; ++i) { mbar_init(idx_full + i, 4); mbar_init(idx_empty + i, 4); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<TMEM_COLS>(s_tmem);
@@ -488,7 +471,6 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     // kConvGroups groups of four warps; group c owns the units i with i % kConvGroups == c (conversion AND, fused,
     // the gather of the same unit), so that two units are in conversion at any time: one warp per SMSP cannot hide
     // the latency of its own shared-memory / MUFU / conversion chain.
-    static_assert(!FUSE || LAG % kConvGroups == 0, "a unit's gather runs in the group that converted it");
 #ifdef EQUSS_SETMAXNREG
     // (24 warps are launched with 80 registers: below that the limit is lowered, above it raised)
     if constexpr (RegPlan<D>::conv < 80) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(RegPlan<D>::conv));
@@ -497,131 +479,11 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int cgroup = (warp - kConvWarp0) >> 2;
     const int ct = (threadIdx.x - kConvWarp0 * 32) & 127;   // 0..127 within the group
     UnitIter it; it.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);
-    UnitIter itg; itg.init(u0, (int)p.n_tiles, p.nchunks, G, NCHW ? p.tiles_per_image : 0);      // FUSE: the unit whose gather is due next
     it.advance(cgroup);
-    itg.advance(cgroup);
-
-    // K3 for unit j (its raw tile is still in stage j % STAGES, its winning columns in the index ring), in two
-    // halves: gather_prefetch issues the codeword loads, gather_finish -- called after the next convert, which
-    // hides their latency -- normalises, writes the output and accumulates the squared error.
-    constexpr int QN = NCHW ? LPS : 128 / (128 / LPS);      // float4 codeword pieces per thread (= LPS either way)
-    float4 qpre[QN];
-    float e_acc[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) e_acc[g] = 0.f;
-    int e_sg = -1;                                          // subspace group the accumulators belong to
-    auto flush_err = [&]() {
-      if (e_sg < 0) return;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float t = warp_sum(e_acc[g]);
-        if (lane == 0 && t != 0.f) atomicAdd(p.sqerr + e_sg * G + g, (double)t);
-        e_acc[g] = 0.f;
-      }
-    };
-    auto gather_prefetch = [&](int j) {
-      const int ib = j % kIdxBufs;
-      if (warp == kConvWarp0) EQUSS_TR(8, j);
-      mbar_wait_nc(idx_full + ib, (j / kIdxBufs) & 1, 50);
-      if (warp == kConvWarp0) EQUSS_TR(9, j);
-      const int32_t* sidx = s_idx + ib * kTileM;
-      const float* srcm = p.gsrc + (size_t)itg.m() * p.K * D;
-      if (!NCHW) {
-        constexpr int ROWS_PER_PASS = 128 / LPS;
-        const int l = ct % LPS, row0 = ct / LPS;
-#pragma unroll
-        for (int u = 0; u < QN; ++u)
-          qpre[u] = __ldg(reinterpret_cast<const float4*>(srcm + (size_t)sidx[u * ROWS_PER_PASS + row0] * D) + l);
-      } else {
-        const float4* q4 = reinterpret_cast<const float4*>(srcm + (size_t)sidx[ct] * D);
-#pragma unroll
-        for (int u = 0; u < QN; ++u) qpre[u] = __ldg(q4 + u);
-      }
-    };
-    auto gather_finish = [&](int j) {
-      const int ib = j % kIdxBufs, s = j % STAGES;
-      const float* raw = reinterpret_cast<const float*>(s_rawt + s * RAW_BYTES);
-      const int m = itg.m(), tile = itg.tile;
-      if (itg.sg != e_sg) { flush_err(); e_sg = itg.sg; }
-      float e_unit = 0.f;
-      if (!NCHW) {
-        constexpr int ROWS_PER_PASS = 128 / LPS;
-        constexpr int PASSES = kTileM / ROWS_PER_PASS;      // == LPS == QN
-        const int l = ct % LPS;
-        const int row0 = ct / LPS;
-        float4 zn[PASSES];       // canonical z_norm, left in the raw stage by the convert pass
-#pragma unroll
-        for (int u = 0; u < PASSES; ++u) zn[u] = *reinterpret_cast<const float4*>(raw + (u * ROWS_PER_PASS + row0) * D + l * 4);
-        float ee[PASSES];
-        float4 o[PASSES];
-#pragma unroll
-        for (int u = 0; u < PASSES; ++u) {
-          float4 dq;
-          dq.x = qpre[u].x - zn[u].x; dq.y = qpre[u].y - zn[u].y; dq.z = qpre[u].z - zn[u].z; dq.w = qpre[u].w - zn[u].w;
-          o[u].x = zn[u].x + dq.x; o[u].y = zn[u].y + dq.y; o[u].z = zn[u].z + dq.z; o[u].w = zn[u].w + dq.w;     // STE value (:536)
-          ee[u] = group_sumsq(dq.x, dq.y, dq.z, dq.w);
-        }
-#pragma unroll
-        for (int u = 0; u < PASSES; ++u) {
-          const long long n = (long long)tile * kTileM + u * ROWS_PER_PASS + row0;
-          const bool live = n < p.n_pixels;
-          if (live) __stcs(reinterpret_cast<float4*>(p.out + n * p.zv.stride_s + m * D) + l, o[u]);
-          ee[u] = live ? ee[u] : 0.f;
-        }
-#pragma unroll
-        for (int sft = 1; sft < LPS; sft <<= 1) {
-#pragma unroll
-          for (int u = 0; u < PASSES; ++u) ee[u] += __shfl_xor_sync(0xffffffffu, ee[u], sft);
-        }
-        if (l == 0) {
-#pragma unroll
-          for (int u = 0; u < PASSES; ++u) e_unit += ee[u];
-        }
-      } else {
-        const int row = ct;
-        const int spix = itg.timg * kTileM + row;
-        const bool live = spix < p.hw;
-        float x[D];
-#pragma unroll
-        for (int jj = 0; jj < D; ++jj) x[jj] = raw[jj * kTileM + row];    // canonical z_norm (convert pass)
-        // one 64-bit base per unit (warp-uniform part + the pixel), 32-bit channel offsets: the NCHW channel stride of
-        // one subspace (d * hw elements) always fits, and the address arithmetic moves from 2 ALU operations per
-        // store to one IMAD.WIDE on the FMA pipe
-        float* o = p.out + (long long)itg.img * p.zv.stride_b + (long long)m * D * p.zv.stride_c + spix;
-        const uint32_t sc = (uint32_t)p.zv.stride_c;
-        float e = 0.f;
-        float ov[D];
-#pragma unroll
-        for (int g4 = 0; g4 < LPS; ++g4) {
-          const float4 qq = qpre[g4];
-          const float d0 = qq.x - x[4 * g4], d1 = qq.y - x[4 * g4 + 1], d2 = qq.z - x[4 * g4 + 2], d3 = qq.w - x[4 * g4 + 3];
-          ov[4 * g4] = x[4 * g4] + d0; ov[4 * g4 + 1] = x[4 * g4 + 1] + d1;          // STE value (:536)
-          ov[4 * g4 + 2] = x[4 * g4 + 2] + d2; ov[4 * g4 + 3] = x[4 * g4 + 3] + d3;
-          e += group_sumsq(d0, d1, d2, d3);
-        }
-        if (live) {
-#pragma unroll
-          for (int jj = 0; jj < D; ++jj) __stcs(o + (size_t)((uint32_t)jj * sc), ov[jj]);
-          e_unit = e;
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) e_acc[g] += (itg.g == g) ? e_unit : 0.f;
-      if (warp == kConvWarp0) EQUSS_TR(11, j);
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(raw_empty + s);
-        mbar_arrive(idx_empty + ib);
-      }
-      if (warp == kConvWarp0) EQUSS_TR(10, j);
-      itg.advance(kConvGroups);
-    };
-
     for (int i = cgroup; i < n_units; i += kConvGroups, it.advance(kConvGroups)) {    // this group's units only
       const int a = i % ABUFS, s = i % STAGES;
       // the operand images change with the first unit of a slot: only that unit's owner loads them
       const bool new_slot = (i == 0) || (it.tile == 0 && it.g == 0);
-      if constexpr (FUSE && !kEpiGather) { if (i >= LAG) gather_prefetch(i - LAG); }
       mbar_wait_nc(a_empty + a, ((i / ABUFS) & 1) ^ 1, 30);
       if (warp == kConvWarp0) EQUSS_TR(0, i);
       if (new_slot) {
@@ -749,14 +611,6 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       __syncwarp();
       if (lane == 0) { if (!FUSE) mbar_arrive(raw_empty + s); mbar_arrive(a_full + a); }
       if (warp == kConvWarp0) EQUSS_TR(2, i);
-      if constexpr (FUSE && !kEpiGather) { if (i >= LAG) gather_finish(i - LAG); }
-    }
-    if constexpr (FUSE && !kEpiGather) {
-      for (int j = (n_units > LAG ? n_units - LAG : 0); j < n_units; ++j) {
-        if (j % kConvGroups != cgroup) continue;
-        gather_prefetch(j); gather_finish(j);
-      }
-      flush_err();
     }
   } else if (warp < 4 * kEpiGroups) {
     // ===================================== epilogue warps ===================================
@@ -859,14 +713,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         if (best_col >= kvalid) best_col = 0;
         p.flag_list[atomicAdd(p.flag_count, 1u)] = (uint32_t)((long long)m * p.n_pixels + n);
       }
-      if constexpr (FUSE && !kEpiGather) {
-        const int ib = i % kIdxBufs;
-        mbar_wait_nc(idx_empty + ib, ((i / kIdxBufs) & 1) ^ 1, 42);
-        s_idx[ib * kTileM + row] = live ? best_col : 0;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(idx_full + ib);
-      }
-      if constexpr (FUSE && kEpiGather) {
+      if constexpr (FUSE) {
         // K3 for this unit (model/quantizer.py:474,514,534-536): the raw stage still holds the canonical z_norm the
         // convert pass left there.  The codeword comes from the slot's shared-memory table (d = 16, long slots) or from
         // global memory.  The table was filled by the bulk copies that completed b_full before this unit's MMAs were
@@ -948,7 +795,7 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       }
       if (q == 0) { EQUSS_TR(6, i); if (!FUSE) EQUSS_TRG(8, i); }
     }
-    if constexpr (FUSE && kEpiGather) ge_flush();
+    if constexpr (FUSE) ge_flush();
   }
 
   tc_fence_before();
@@ -972,7 +819,8 @@ static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, c
 
 // per-d dispatch over (NC, G, layout, fused gather); one translation unit per d keeps the build parallel.  GV =
 // subspaces per 128-byte line of a flat row (used when M is a multiple of it; NCHW and odd M run with G = 1).
-// STF / LAGV: raw-ring depth and gather lag of the fused kernels (STF = 0: no fused instantiation for this d).
+// STF: raw-ring depth of the fused kernels (STF = 0: no fused instantiation for this d); LAGV: unused (kept in the
+// instantiation names the profiles refer to).
 #define EQUSS_TCH_DISPATCH(DV, GV, STV, ABV, STF, LAGV)                                                       \
   int launch_tch_d##DV(int NC, int G, bool nchw, bool fuse, const CUtensorMap& tmap, const Params& p, int grid, \
                        cudaStream_t st) {                                                                    \
