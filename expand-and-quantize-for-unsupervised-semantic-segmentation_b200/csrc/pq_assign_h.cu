@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256)
 build_image_kernel(const float* __restrict__ cb, const float* __restrict__ cn2, int K, int D, int NC, int nchunks, int G,
                    uint8_t* __restrict__ images, int img_bytes, unsigned int* __restrict__ flag_count,
                    double* __restrict__ sqerr, int M) {
+  asm volatile("griddepcontrol.launch_dependents;");              // the assign kernel's prologue overlaps this kernel
   if (blockIdx.x == 0 && threadIdx.x == 0) *flag_count = 0u;      // list of rows for the exact rescan starts empty
   if (sqerr != nullptr && blockIdx.x == 0)                        // fused gather: the error sums start at zero
     for (int i = threadIdx.x; i < M; i += blockDim.x) sqerr[i] = 0.0;
@@ -123,6 +124,7 @@ rescan_flagged_kernel(const uint32_t* __restrict__ list, const unsigned int* __r
   __shared__ int s_bi[4];
   __shared__ int s_res[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // launched programmatically behind the assign kernel
   const unsigned int n_list = *count;
   for (unsigned int e = blockIdx.x; e < n_list; e += gridDim.x) {
     const long long o = list[e];
@@ -353,9 +355,17 @@ int assign_tch_launch(const float* z, const equss_zdesc* zd, const float* codebo
   }
   // exact scan of the listed rows (a few per ten thousand); repairs the fused gather where the winner changes
   const int rgrid = num_sms() * 8;
+  cudaLaunchConfig_t rcfg = {};
+  rcfg.gridDim = dim3((unsigned)rgrid); rcfg.blockDim = dim3(128); rcfg.dynamicSmemBytes = 0; rcfg.stream = st;
+  cudaLaunchAttribute rattr[1];
+  rattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  rattr[0].val.programmaticStreamSerializationAllowed = (merged == nullptr) ? 1 : 0;   // behind finalize_merge: plain launch
+  rcfg.attrs = rattr; rcfg.numAttrs = 1;
+  const float* no_src = nullptr; float* no_out = nullptr; double* no_err = nullptr;
+  const uint32_t* flag_list_c = flag_list; const unsigned int* flag_count_c = flag_count;
 #define EQUSS_RESCAN(DV)                                                                                                  \
-  if (fuse) rescan_flagged_kernel<DV, true><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, gather_src, out, sqerr); \
-  else rescan_flagged_kernel<DV, false><<<rgrid, 128, 0, st>>>(flag_list, flag_count, z, p.zv, codebook_norm, cnorm2, K, idx_out, nullptr, nullptr, nullptr);
+  if (fuse) { EQUSS_CUDA_OK(cudaLaunchKernelEx(&rcfg, rescan_flagged_kernel<DV, true>, flag_list_c, flag_count_c, z, p.zv, codebook_norm, cnorm2, K, idx_out, gather_src, out, sqerr)); } \
+  else { EQUSS_CUDA_OK(cudaLaunchKernelEx(&rcfg, rescan_flagged_kernel<DV, false>, flag_list_c, flag_count_c, z, p.zv, codebook_norm, cnorm2, K, idx_out, no_src, no_out, no_err)); }
   if (d == 16) { EQUSS_RESCAN(16) } else if (d == 32) { EQUSS_RESCAN(32) } else { EQUSS_RESCAN(64) }
 #undef EQUSS_RESCAN
   EQUSS_LAUNCH_OK("rescan_flagged_kernel");

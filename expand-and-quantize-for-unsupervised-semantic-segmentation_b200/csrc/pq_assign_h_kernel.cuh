@@ -385,6 +385,11 @@ assign_f16x2_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
+  // Programmatic dependent launch: everything above (barriers, TMEM allocation, constant operand rows) ran while
+  // build_image_kernel was still writing the operand images; from here on its results (images, cleared counters) are used
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ... and the exact-rescan kernel behind this one may be scheduled as soon as SMs free up (it waits the same way)
+  asm volatile("griddepcontrol.launch_dependents;");
 
   if (warp >= kProducerWarp) {
 #ifdef EQUSS_SETMAXNREG      // (each setmaxnreg sits at the top of the branch it governs: after a merge point ptxas assumes the smallest budget)
@@ -812,7 +817,13 @@ static int launch_instance(const CUtensorMap& tmap, const Params& p, int grid, c
   static_assert(SMEM <= 227 * 1024, "shared-memory plan exceeds 227 KB");
   EQUSS_CUDA_OK(cudaFuncSetAttribute(assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG><<<grid, kThreads, SMEM, st>>>(tmap, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  EQUSS_CUDA_OK(cudaLaunchKernelEx(&cfg, assign_f16x2_kernel<D, NC, G, STAGES, ABUFS, NCHW, FUSE, LAG>, tmap, p));
   EQUSS_LAUNCH_OK("assign_f16x2_kernel");
   return EQUSS_OK;
 }
