@@ -17,6 +17,10 @@ bool knn_gemm_tc_supported(const float* Q, const float* DB, const float* S, long
 int knn_gemm_tc_launch(const float* Q, const float* DB, float* S, long long rows, long long n, int F, cudaStream_t st);
 int knn_topk_tc_splits(long long rows, long long n);
 int64_t knn_topk_tc_scratch_bytes();
+bool knn_screen_supported(const float* Q, const float* DB, int F, int k);
+int64_t knn_screen_workspace_bytes(int64_t nq, int64_t n, int F);
+int knn_screen_topk_launch(const float* Q, long long nq, const float* DB, long long n, int F, int k, long long* idx_out,
+                           float* sim_out, void* workspace, cudaStream_t st);
 int knn_topk_tc_launch(const float* Q, const float* DB, long long rows, long long n, int F, int k, int splits,
                        float* part_val, int* part_idx, void* scratch, cudaStream_t st);
 
@@ -194,6 +198,8 @@ using namespace equss;
 
 extern "C" int64_t equss_knn_workspace_bytes(int64_t nq, int64_t n, int F, int k) {
   if (nq <= 0 || n <= 0) return 0;
+  if (F > 0 && F % 64 == 0 && F <= 1024 && k <= 32 && getenv("EQUSS_KNN_TF32") == nullptr && getenv("EQUSS_KNN_UNFUSED") == nullptr)
+    return knn_screen_workspace_bytes(nq, n, F);                               // fp16 copies + survivor lists
   if (knn_fused_shape(F) && getenv("EQUSS_KNN_UNFUSED") == nullptr)            // partial top-k lists O(nq * k) + per-SM scratch
     return nq * (int64_t)knn_topk_tc_splits(nq, n) * k * 8 + knn_topk_tc_scratch_bytes() + 256;
   return knn_rows_per_chunk(nq, n) * n * 4;
@@ -211,6 +217,14 @@ extern "C" int equss_knn_topk(const float* queries, int64_t nq, const float* db,
   if (nq == 0) return EQUSS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool aligned = !((uintptr_t)queries & 15) && !((uintptr_t)db & 15) && !((uintptr_t)workspace & 15);
+  if (knn_screen_supported(queries, db, F, k) && getenv("EQUSS_KNN_TF32") == nullptr && getenv("EQUSS_KNN_UNFUSED") == nullptr &&
+      getenv("EQUSS_KNN_SIMT") == nullptr) {
+    // screen on the tensor cores in fp16 (one product), decide in exact fp32 on the survivors (knn_h.cu)
+    const int64_t need = knn_screen_workspace_bytes(nq, n, F);
+    EQUSS_REQUIRE(workspace && workspace_bytes >= need, EQUSS_ERR_INVALID_ARG,
+                  "equss_knn_topk: workspace of %lld bytes needed, got %lld", (long long)need, (long long)workspace_bytes);
+    return knn_screen_topk_launch(queries, nq, db, n, F, k, (long long*)idx_out, sim_out, workspace, st);
+  }
   if (knn_fused_shape(F) && aligned && getenv("EQUSS_KNN_UNFUSED") == nullptr && getenv("EQUSS_KNN_SIMT") == nullptr) {
     // tcgen05 GEMM with the running top-k in its epilogue, then a merge of the per-split lists
     const int splits = knn_topk_tc_splits(nq, n);
