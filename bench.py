@@ -493,7 +493,8 @@ def run_equss(args):
             "queries_per_rank": -(-n5 // world), "ms_per_step": ms5, "value": n5 / (ms5 / 1e3), "unit": "queries/s", "scaling": "strong",
             "roofline": {"bound": "tensor", "achieved": round(flops5 / (ms5 * 1e-3) / 1e12, 1), "peak": tens_pk, "unit": "TFLOP/s",
                          "frac": round(flops5 / (ms5 * 1e-3) / 1e12 / tens_pk, 4),
-                         "note": "useful flops 2*nq*n*F per rank over the whole call (GEMM + top-k + all_gather)"}}
+                         "note": "useful flops 2*nq*n*F per rank over the whole call (fp16 screening GEMM with the top-k in its "
+                                 "epilogue + exact fp32 decision on the survivors + all_gather); peak = measured fp16 dense"}}
         del db
 
         # ---- config 1: pq_baseline ProductQuantizer forward (the reference's own CPU-runnable case) ----------------

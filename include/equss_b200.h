@@ -309,7 +309,8 @@ int equss_confusion_update(const int64_t* preds, const int64_t* label, int64_t n
  *   For each query row, the k database rows with the largest inner product, sorted by decreasing
  *   similarity (ties: lower index first).  queries: [nq][F], db: [n][F] fp32 (caller normalises,
  *   precompute_knns.py:169).  idx_out: [nq][k] int64 (the `nns` array), sim_out: [nq][k] fp32 or NULL.
- *   1 <= k <= 32.
+ *   1 <= k <= 32.  The result is an exact fp32 top-k on every path; for F % 64 == 0 the candidates are screened by an
+ *   fp16 tensor-core GEMM inside a proven error margin and only the survivors are re-scored (no similarity matrix).
  * ------------------------------------------------------------------------------------------- */
 int64_t equss_knn_workspace_bytes(int64_t nq, int64_t n, int F, int k);
 int equss_knn_topk(const float* queries, int64_t nq, const float* db, int64_t n, int F, int k,
