@@ -28,14 +28,11 @@ namespace knnh {
 using namespace ::equss::ptx;
 
 constexpr int kBM = 128, kBN = 256, kKC = 64;          // tile rows / columns, features (fp16, 128 bytes) per stage
-constexpr int kStages = 4;
 constexpr int kCand = 128;                             // candidate slots per row and split
 constexpr int kCandReserve = 16;                       // columns examined between two occupancy checks
 constexpr int kThreads = 32 * 6;                       // 4 epilogue warps, TMA producer, MMA issuer
 constexpr int kProducerWarp = 4, kMmaWarp = 5;
 constexpr int kABytes = kBM * 128, kBBytes = kBN * 128;                 // 16 KB, 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmem = 1024 + kStages * kStageBytes + 256;
 
 // kind::f16: fp16 A / B (K-major), fp32 accumulate, M = 128, N
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -96,21 +93,22 @@ knn_to_half_kernel(const float* __restrict__ x, long long n4, const unsigned int
   }
 }
 
-// (row tile, column split) items round-robin over the CTAs; inside an item the split's column tiles in increasing order
+// (group of RT row tiles, column split) items round-robin over the CTAs; inside an item the split's column tiles in
+// increasing order
 struct TileWalk {
   long long t, step, total;
-  int m_tiles, n_tiles, splits, bm, bn, bn_end;
+  int m_items, n_tiles, splits, bmi, bn, bn_end;
   bool first, last;
   __device__ __forceinline__ void set_item() {
-    const int sp = (int)(t / m_tiles);
-    bm = (int)(t - (long long)sp * m_tiles);
+    const int sp = (int)(t / m_items);
+    bmi = (int)(t - (long long)sp * m_items);
     bn = (int)((long long)n_tiles * sp / splits);
     bn_end = (int)((long long)n_tiles * (sp + 1) / splits);
     first = true; last = (bn + 1 >= bn_end);
   }
-  __device__ __forceinline__ bool init(const Params& p) {
-    m_tiles = p.m_tiles; n_tiles = p.n_tiles; splits = p.splits;
-    t = blockIdx.x; step = gridDim.x; total = (long long)p.m_tiles * p.splits;
+  __device__ __forceinline__ bool init(const Params& p, int rt) {
+    m_items = (p.m_tiles + rt - 1) / rt; n_tiles = p.n_tiles; splits = p.splits;
+    t = blockIdx.x; step = gridDim.x; total = (long long)m_items * p.splits;
     if (t >= total) return false;
     set_item();
     return true;
@@ -122,25 +120,34 @@ struct TileWalk {
     set_item();
     return true;
   }
-  __device__ __forceinline__ int split() const { return (int)(t / m_tiles); }
+  __device__ __forceinline__ int split() const { return (int)(t / m_items); }
 };
 
+// RT = query tiles of 128 rows that share one database tile per stage: RT = 1 keeps two accumulator buffers (MMAs of the
+// next tile under the epilogue of this one); RT = 2 uses both 256-column accumulators for ONE stage's two products and
+// moves 64 KB instead of 96 KB of operands per pair of output tiles -- the screen is bound by that stream.
+template <int RT> __host__ __device__ constexpr int stage_bytes() { return RT * kABytes + kBBytes; }
+template <int RT> __host__ __device__ constexpr int n_stages() { return RT == 1 ? 4 : 3; }
+template <int RT> __host__ __device__ constexpr int smem_bytes() { return 1024 + n_stages<RT>() * stage_bytes<RT>() + 256; }
+
+template <int RT>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_db, const Params p) {
+  constexpr int STAGES = n_stages<RT>(), SB = stage_bytes<RT>(), NB = 2 / RT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle atoms are 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* st_full = bars;                   // [kStages] both TMA boxes landed
-  uint64_t* st_empty = st_full + kStages;     // [kStages] the stage's MMAs completed
-  uint64_t* acc_full = st_empty + kStages;    // [2] tile finished in TMEM buffer b
-  uint64_t* acc_empty = acc_full + 2;         // [2] the epilogue drained buffer b
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SB);
+  uint64_t* st_full = bars;                   // [STAGES] all TMA boxes of the stage landed
+  uint64_t* st_empty = st_full + STAGES;      // [STAGES] the stage's MMAs completed
+  uint64_t* acc_full = st_empty + STAGES;     // [NB] tile (group) finished in TMEM buffer b
+  uint64_t* acc_empty = acc_full + 2;         // [NB] the epilogue drained buffer b
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_kc = p.n_kc;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(st_full + i, 1); mbar_init(st_empty + i, 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(st_full + i, 1); mbar_init(st_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
     fence_barrier_init();
   }
@@ -153,15 +160,17 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   if (warp == kProducerWarp) {
     int g = 0;
     TileWalk tw;
-    for (bool ok = tw.init(p); ok; ok = tw.next()) {
+    for (bool ok = tw.init(p, RT); ok; ok = tw.next()) {
       for (int c = 0; c < n_kc; ++c, ++g) {
-        const int st = g % kStages;
-        uint8_t* sp = smem + st * kStageBytes;
-        mbar_wait(st_empty + st, ((g / kStages) & 1) ^ 1, 10);
+        const int st = g % STAGES;
+        uint8_t* sp = smem + st * SB;
+        mbar_wait(st_empty + st, ((g / STAGES) & 1) ^ 1, 10);
         if (elect_one()) {
-          mbar_expect_tx(st_full + st, kStageBytes);
-          tma_load_2d(sp, &tmap_q, c * kKC, tw.bm * kBM, st_full + st);
-          tma_load_2d(sp + kABytes, &tmap_db, c * kKC, tw.bn * kBN, st_full + st);
+          mbar_expect_tx(st_full + st, SB);
+#pragma unroll
+          for (int rt = 0; rt < RT; ++rt)      // a row tile past the end is zero-filled by the TMA unit
+            tma_load_2d(sp + rt * kABytes, &tmap_q, c * kKC, (tw.bmi * RT + rt) * kBM, st_full + st);
+          tma_load_2d(sp + RT * kABytes, &tmap_db, c * kKC, tw.bn * kBN, st_full + st);
         }
         __syncwarp();
       }
@@ -173,21 +182,25 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t base = smem_u32(smem);
     int g = 0, it = 0;
     TileWalk tw;
-    for (bool ok = tw.init(p); ok; ok = tw.next(), ++it) {
-      const int b = it & 1;
-      mbar_wait(acc_empty + b, ((it >> 1) & 1) ^ 1, 22);
+    for (bool ok = tw.init(p, RT); ok; ok = tw.next(), ++it) {
+      const int b = it % NB;
+      mbar_wait(acc_empty + b, ((it / NB) & 1) ^ 1, 22);
       tc_fence_after();
-      const uint32_t d_addr = tmem_base + (uint32_t)(b * kBN);
       for (int c = 0; c < n_kc; ++c, ++g) {
-        const int st = g % kStages;
-        mbar_wait(st_full + st, (g / kStages) & 1, 20);
+        const int st = g % STAGES;
+        mbar_wait(st_full + st, (g / STAGES) & 1, 20);
         tc_fence_after();
-        const uint32_t sa = base + (uint32_t)(st * kStageBytes);
-        const uint32_t a_lo = (sa >> 4) | (1u << 16), b_lo = ((sa + kABytes) >> 4) | (1u << 16);
+        const uint32_t sa = base + (uint32_t)(st * SB);
+        const uint32_t b_lo = ((sa + RT * kABytes) >> 4) | (1u << 16);
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kKC / 16; ++kk)
-            umma_f16(d_addr, desc_from(a_lo + 2 * kk, d_hi), desc_from(b_lo + 2 * kk, d_hi), IDESC, (c > 0 || kk > 0) ? 1u : 0u);
+          for (int rt = 0; rt < RT; ++rt) {
+            const uint32_t a_lo = ((sa + rt * kABytes) >> 4) | (1u << 16);
+            const uint32_t d_addr = tmem_base + (uint32_t)((b * RT + rt) * kBN);
+#pragma unroll
+            for (int kk = 0; kk < kKC / 16; ++kk)
+              umma_f16(d_addr, desc_from(a_lo + 2 * kk, d_hi), desc_from(b_lo + 2 * kk, d_hi), IDESC, (c > 0 || kk > 0) ? 1u : 0u);
+          }
           umma_commit(st_empty + st);
           if (c == n_kc - 1) umma_commit(acc_full + b);
         }
@@ -204,15 +217,14 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const float sq = pow2_scale(__uint_as_float(p.stats->q_absmax)), sd = pow2_scale(__uint_as_float(p.stats->d_absmax));
     const float nrm = sqrtf(__uint_as_float(p.stats->q_sumsq)) * sq * sqrtf(__uint_as_float(p.stats->d_sumsq)) * sd;
     const float eps = nrm * (2.f * 9.765625e-4f + 1e-5f) + 1e-30f;
-    int cnt = 0;
-    bool overflow = false;
-    float thr = -INFINITY;                 // append threshold = (running approximate k-th best) - eps
-    uint2* my = p.cand + ((size_t)blockIdx.x * kBM + row) * kCand;
-    uint2* wbase = p.cand + ((size_t)blockIdx.x * kBM + q * 32) * kCand;
-    // Compaction of the candidates of row (q*32 + src) by the whole warp: all-pairs rank on 64-bit keys (order-preserving
-    // value bits << 32 | ~column), survivors = everything within eps of the k-th best, written back in rank order.
-    auto compact = [&](int src, int n_src, float& thr_out, bool& ovf_out) -> int {
-      uint2* buf = wbase + (size_t)src * kCand;
+    int cnt[RT];
+    bool overflow[RT];
+    float thr[RT];                         // append threshold = (running approximate k-th best) - eps
+#pragma unroll
+    for (int rt = 0; rt < RT; ++rt) { cnt[rt] = 0; overflow[rt] = false; thr[rt] = -INFINITY; }
+    // Compaction of the candidates of one row by the whole warp: all-pairs rank on 64-bit keys (order-preserving value
+    // bits << 32 | ~column), survivors = everything within eps of the k-th best, written back in rank order.
+    auto compact = [&](uint2* buf, int n_src, float& thr_out, bool& ovf_out) -> int {
       unsigned long long key[4];
       int rank[4];
 #pragma unroll
@@ -235,8 +247,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
       __syncwarp();
-      // approximate k-th best of the row (-inf while it holds fewer than k candidates)
-      float kth = -INFINITY;
+      float kth = -INFINITY;                           // approximate k-th best (-inf while fewer than k candidates)
       float val[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -260,57 +271,65 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       thr_out = cut;
       return keep;
     };
-    auto compact_rows = [&](bool mine) {
-      unsigned todo = __ballot_sync(0xffffffffu, mine);
-      if (todo) __syncwarp();
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-        float nthr; bool novf;
-        const int ncnt = compact(src, n_src, nthr, novf);
-        if (lane == src) { cnt = ncnt; thr = nthr; overflow = overflow || novf; }
-      }
-    };
     int it = 0;
     TileWalk tw;
-    for (bool ok = tw.init(p); ok; ok = tw.next(), ++it) {
-      const int b = it & 1;
-      const long long r = (long long)tw.bm * kBM + row;
+    for (bool ok = tw.init(p, RT); ok; ok = tw.next(), ++it) {
+      const int b = it % NB;
       const long long c0 = (long long)tw.bn * kBN;
-      if (tw.first) { cnt = 0; thr = -INFINITY; overflow = false; }
-      mbar_wait(acc_full + b, (it >> 1) & 1, 40);
+      if (tw.first) {
+#pragma unroll
+        for (int rt = 0; rt < RT; ++rt) { cnt[rt] = 0; thr[rt] = -INFINITY; overflow[rt] = false; }
+      }
+      mbar_wait(acc_full + b, (it / NB) & 1, 40);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < kBN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + (uint32_t)(b * kBN + ch * 32), v);
-        tmem_ld_wait();
-        const long long cb = c0 + ch * 32;
-        const int nv = (r < p.rows && cb < p.n) ? (int)((p.n - cb < 32) ? (p.n - cb) : 32) : 0;
 #pragma unroll
-        for (int half = 0; half < 32 / kCandReserve; ++half) {
-#pragma unroll
-          for (int jj = 0; jj < kCandReserve; ++jj) {
-            const int j = half * kCandReserve + jj;
-            const float s = __uint_as_float(v[j]);
-            if (j < nv && s >= thr) { __stcg(my + cnt, make_uint2(v[j], (uint32_t)(cb + j))); ++cnt; }
+      for (int rt = 0; rt < RT; ++rt) {
+        const long long r = (long long)(tw.bmi * RT + rt) * kBM + row;
+        uint2* my = p.cand + (((size_t)blockIdx.x * RT + rt) * kBM + row) * kCand;
+        uint2* wbase = p.cand + (((size_t)blockIdx.x * RT + rt) * kBM + q * 32) * kCand;
+        auto compact_rows = [&](bool mine) {
+          unsigned todo = __ballot_sync(0xffffffffu, mine);
+          if (todo) __syncwarp();
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int n_src = __shfl_sync(0xffffffffu, cnt[rt], src);
+            float nthr; bool novf;
+            const int ncnt = compact(wbase + (size_t)src * kCand, n_src, nthr, novf);
+            if (lane == src) { cnt[rt] = ncnt; thr[rt] = nthr; overflow[rt] = overflow[rt] || novf; }
           }
-          compact_rows(cnt > kCand - kCandReserve);
+        };
+#pragma unroll 1
+        for (int ch = 0; ch < kBN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + (uint32_t)((b * RT + rt) * kBN + ch * 32), v);
+          tmem_ld_wait();
+          const long long cb = c0 + ch * 32;
+          const int nv = (r < p.rows && cb < p.n) ? (int)((p.n - cb < 32) ? (p.n - cb) : 32) : 0;
+#pragma unroll
+          for (int half = 0; half < 32 / kCandReserve; ++half) {
+#pragma unroll
+            for (int jj = 0; jj < kCandReserve; ++jj) {
+              const int j = half * kCandReserve + jj;
+              const float sv = __uint_as_float(v[j]);
+              if (j < nv && sv >= thr[rt]) { __stcg(my + cnt[rt], make_uint2(v[j], (uint32_t)(cb + j))); ++cnt[rt]; }
+            }
+            compact_rows(cnt[rt] > kCand - kCandReserve);
+          }
+        }
+        if (tw.last) {
+          compact_rows(cnt[rt] > 0);                   // final cut at (k-th best - eps)
+          if (r < p.rows) {
+            const int sp = tw.split();
+            uint2* out = p.lists + ((size_t)r * p.splits + sp) * kCand;
+            for (int e = 0; e < cnt[rt]; ++e) out[e] = __ldcg(my + e);
+            p.counts[r * p.splits + sp] = overflow[rt] ? -1 : cnt[rt];
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + b);
-      if (tw.last) {
-        compact_rows(cnt > 0);                   // final cut at (k-th best - eps)
-        if (r < p.rows) {
-          const int sp = tw.split();
-          uint2* out = p.lists + ((size_t)r * p.splits + sp) * kCand;
-          for (int e = 0; e < cnt; ++e) out[e] = __ldcg(my + e);
-          p.counts[r * p.splits + sp] = overflow ? -1 : cnt;
-        }
-      }
     }
   }
 
@@ -432,18 +451,28 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-static int splits_for(long long rows, long long n) {
+// Column splits (and, for experiments, query tiles per CTA): (row-tile groups x splits) items over the SMs with the least
+// idle tail.
+static void plan_for(long long rows, long long n, int* splits_out, int* rt_out) {
   const long long m_tiles = (rows + kBM - 1) / kBM, n_tiles = (n + kBN - 1) / kBN;
   const int sms = num_sms();
-  if (getenv("EQUSS_KNN_SPLITS")) return atoi(getenv("EQUSS_KNN_SPLITS"));
-  int best = 1;
-  double best_eff = 0.0;
-  for (int s = 1; s <= 8 && s <= n_tiles; ++s) {
-    const long long items = m_tiles * s;
-    const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  double eff_rt[3] = {0.0, 0.0, 0.0};
+  int split_rt[3] = {1, 1, 1};
+  for (int rt = 1; rt <= 2; ++rt) {
+    const long long m_items = (m_tiles + rt - 1) / rt;
+    for (int s = 1; s <= 8 && s <= n_tiles; ++s) {
+      const long long items = m_items * s;
+      const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms) * (double)m_tiles / (double)(m_items * rt);
+      if (eff > eff_rt[rt] + 1e-9) { eff_rt[rt] = eff; split_rt[rt] = s; }
+    }
   }
-  return best;
+  // measured at 50 000 x 50 000 x 768: RT = 2 is SLOWER (8.95 vs 6.69 ms): it trades the second accumulator buffer for 33 %
+  // less operand traffic, and the serialised epilogue + three-stage ring cost more than the traffic saves.  Kept for study.
+  int rt = 1;
+  if (getenv("EQUSS_KNN_RT")) rt = (atoi(getenv("EQUSS_KNN_RT")) == 2 && m_tiles >= 2) ? 2 : 1;
+  int splits = split_rt[rt];
+  if (getenv("EQUSS_KNN_SPLITS")) splits = atoi(getenv("EQUSS_KNN_SPLITS"));
+  *splits_out = splits; *rt_out = rt;
 }
 
 }  // namespace knnh
@@ -456,20 +485,22 @@ static int64_t al256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
 int64_t knn_screen_workspace_bytes(int64_t nq, int64_t n, int F) {
   using namespace knnh;
-  const int splits = splits_for(nq, n);
-  return al256(nq * (int64_t)F * 2) + al256(n * (int64_t)F * 2) + 256 + al256((int64_t)num_sms() * kBM * kCand * 8) +
+  int splits, rt;
+  plan_for(nq, n, &splits, &rt);
+  return al256(nq * (int64_t)F * 2) + al256(n * (int64_t)F * 2) + 256 + al256((int64_t)num_sms() * 2 * kBM * kCand * 8) +
          al256(nq * (int64_t)splits * kCand * 8) + al256(nq * (int64_t)splits * 4) + 1024;
 }
 
 int knn_screen_topk_launch(const float* Q, long long nq, const float* DB, long long n, int F, int k, long long* idx_out,
                            float* sim_out, void* workspace, cudaStream_t st) {
   using namespace knnh;
-  const int splits = splits_for(nq, n);
+  int splits, rt;
+  plan_for(nq, n, &splits, &rt);
   uint8_t* w = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   __half* Qh = (__half*)w;                      w += al256(nq * (int64_t)F * 2);
   __half* Dh = (__half*)w;                      w += al256(n * (int64_t)F * 2);
   Stats* stats = (Stats*)w;                     w += 256;
-  uint2* cand = (uint2*)w;                      w += al256((int64_t)num_sms() * kBM * kCand * 8);
+  uint2* cand = (uint2*)w;                      w += al256((int64_t)num_sms() * 2 * kBM * kCand * 8);
   uint2* lists = (uint2*)w;                     w += al256(nq * (int64_t)splits * kCand * 8);
   int* counts = (int*)w;
 
@@ -502,11 +533,16 @@ int knn_screen_topk_launch(const float* Q, long long nq, const float* DB, long l
   p.m_tiles = (int)((nq + kBM - 1) / kBM);
   p.n_tiles = (int)((n + kBN - 1) / kBN);
   p.k = k; p.splits = splits; p.stats = stats; p.cand = cand; p.lists = lists; p.counts = counts;
-  const long long items = (long long)p.m_tiles * splits;
+  const long long items = (long long)((p.m_tiles + rt - 1) / rt) * splits;
   int grid = num_sms();
   if (items < grid) grid = (int)items;
-  EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  knn_screen_kernel<<<grid, kThreads, kSmem, st>>>(tq, td, p);
+  if (rt == 2) {
+    EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_screen_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
+    knn_screen_kernel<2><<<grid, kThreads, smem_bytes<2>(), st>>>(tq, td, p);
+  } else {
+    EQUSS_CUDA_OK(cudaFuncSetAttribute(knn_screen_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<1>()));
+    knn_screen_kernel<1><<<grid, kThreads, smem_bytes<1>(), st>>>(tq, td, p);
+  }
   EQUSS_LAUNCH_OK("knn_screen_kernel");
 
   const unsigned rgrid = (unsigned)((nq + 7) / 8);
