@@ -161,6 +161,46 @@ def test_knn_vs_topk(nq, n, Fd, k):
         assert torch.equal(idx[:, 0], torch.arange(nq))     # column 0 is the query itself (dataset_aug.py:520)
 
 
+@pytest.mark.parametrize("scale_q,scale_db", [(1.0, 1.0), (1000.0, 3e-4), (1e-3, 250.0)])
+def test_knn_screen_path_is_exact_for_any_scale(scale_q, scale_db):
+    """F % 64 == 0 takes the fp16 screen + exact fp32 decision (csrc/knn_h.cu): un-normalised rows of very different
+    magnitudes (the fp16 copies are rescaled by a power of two, the margin follows the measured norms) must give the
+    same neighbours as an exact top-k."""
+    ops = _ops()
+    torch.manual_seed(11)
+    n, nq, Fd, k = 4000, 300, 128, 12
+    db = torch.randn(n, Fd) * scale_db * (0.2 + torch.rand(n, 1))          # row norms spread over 5x
+    q = torch.randn(nq, Fd) * scale_q
+    idx, sims = ops.knn_topk(q.cuda(), db.cuda(), k, return_sims=True)
+    exact = torch.einsum("nf,mf->nm", q.double(), db.double())
+    rvals, ridx = exact.topk(k, dim=1)
+    idx, sims = idx.cpu(), sims.cpu()
+    torch.testing.assert_close(sims.double(), rvals, rtol=2e-5, atol=1e-6 * scale_q * scale_db)
+    for r in range(nq):
+        for j in set(idx[r].tolist()) ^ set(ridx[r].tolist()):          # only fp32-level ties of the k-th value may differ
+            assert abs(float(exact[r, j] - rvals[r, -1])) <= 2e-5 * abs(float(rvals[r, -1])), (r, j)
+
+
+def test_knn_screen_path_with_duplicate_rows():
+    """Hundreds of identical database rows tie within the screen's margin: the survivor lists overflow and those queries
+    are scanned exhaustively -- the result is still the exact top-k with the lowest indices among equal similarities."""
+    ops = _ops()
+    torch.manual_seed(12)
+    n, Fd, k = 3000, 64, 8
+    db = F.normalize(torch.randn(n, Fd), dim=1)
+    db[500:900] = db[100]                                   # 401 copies of row 100
+    q = torch.cat([db[100:101], db[:40]])
+    idx, sims = ops.knn_topk(q.cuda(), db.cuda(), k, return_sims=True)
+    idx = idx.cpu()
+    want0 = [100] + list(range(500, 500 + k - 1))             # the duplicated row itself: ties broken by the lower index
+    assert idx[0].tolist() == want0, idx[0].tolist()
+    exact = torch.einsum("nf,mf->nm", q.double(), db.double())
+    rvals, ridx = exact.topk(k, dim=1)
+    for r in range(1, q.shape[0]):
+        for j in set(idx[r].tolist()) ^ set(ridx[r].tolist()):
+            assert abs(float(exact[r, j] - rvals[r, -1])) < 5e-6, (r, j)
+
+
 @pytest.mark.parametrize("B,D,h,w,H,W,extra", [(2, 32, 10, 10, 40, 40, 0), (3, 48, 7, 5, 23, 31, 0), (1, 64, 28, 28, 224, 224, 3),
                                                 (2, 16, 6, 6, 6, 6, 0)])
 def test_probe_losses_and_gradients_vs_reference_formulation(B, D, h, w, H, W, extra):
