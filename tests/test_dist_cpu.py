@@ -46,6 +46,10 @@ def _worker(rank, world, port, ret):
         assert torch.equal(DU.all_reduce_tensor(t, op="mean"), torch.full((4,), 1.5))
         with pytest.raises(RuntimeError):
             DU.all_reduce_tensor(t, op="max")
+        # the in-kernel peer exchange needs NCCL + CUDA symmetric memory: with gloo / CPU tensors the step falls back to ONE
+        # all-reduce of the packed buffer, silently (no warning: nothing failed, the backend simply has no peer memory)
+        assert DU.packed_peer_exchange((M, K, d + 1), torch.device("cpu")) is None
+        assert DU.packed_peer_exchange((M, K, d + 1), torch.device("cuda", 0)) is None      # backend is gloo
         # per-rank packed statistics on the shard (oracle arithmetic stands in for K4), one all-reduce (K5)
         packed = torch.zeros(M, K, d + 1)
         idx_full = []
@@ -89,4 +93,5 @@ def test_single_process_helpers_are_identity():
     assert DU.all_reduce_tensor(t) is t                    # reference returns the input itself (dist_utils.py:99-100)
     assert DU.all_reduce_packed_(t) is t
     assert DU.get_world_size() == 1 and DU.get_rank() == 0
+    assert DU.packed_peer_exchange((2, 4, 5), torch.device("cpu")) is None      # no process group: no exchange at all
     assert DU.shard_range(10, 1, 4) == (3, 6) and DU.shard_range(10, 3, 4) == (9, 10)
