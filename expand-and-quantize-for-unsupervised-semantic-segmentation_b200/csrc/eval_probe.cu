@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "equss_common.cuh"
+#include "probe_argmax_core.cuh"
 
 namespace equss {
 
@@ -325,6 +326,7 @@ probe_argmax_confusion_kernel(const float* __restrict__ logits, int B, int h, in
 // argmax update -- the association order of PyTorch's upsample_bilinear2d -- instead of four loads and seven
 // multiply-adds.  Confusion bins are per block in shared memory (run-length merged per warp).
 constexpr int kRowsPerBlock = 8;
+constexpr int kProbeArgmaxDefaultMode = 1;   // see equss_probe_argmax_confusion
 template <int CMAX, int TMAX, int MINB>
 __global__ void __launch_bounds__(TMAX, MINB)
 probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_pad, const long long* __restrict__ label,
@@ -408,6 +410,135 @@ probe_argmax_rows_kernel(const float* __restrict__ logits, int h, int w, int c_p
           const int lab = (int)((labs >> (8 * r)) & 0xFFull);
           const int bin = (live && lab != 255 && bj < C) ? bj * C + lab : -1;
           warp_hist_add(hist, bin);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int hd = 0; hd < heads.n_heads; ++hd) {
+    if (!heads.conf[hd]) continue;
+    const int nb = heads.rows[hd] * C;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const int t = s_hist[heads.hist_off[hd] + i];
+      if (t) atomicAdd(heads.conf[hd] + i, (unsigned long long)t);
+    }
+  }
+}
+
+// step 2, row-block variant with the tournament argmax of probe_argmax_core.cuh (same interpolation arithmetic as
+// probe_argmax_rows_kernel; the horizontal interpolants live in f32x2 register pairs).
+//
+// Work item = (image, RB consecutive label rows that share one token-row pair, slice of blockDim.x label columns).
+// The grid is persistent (blocks x SMs resident CTAs): a CTA zeroes its confusion bins once, walks items
+// blockIdx.x, blockIdx.x + gridDim.x, ... and flushes the bins once.  1312 items on 296 CTAs would take five rounds for
+// 4.43 rounds of work, so the schedule (ProbeSchedule, built on the host) splits the items of the last, partial round
+// into `parts` row ranges each: four full rounds and one half-length round at the cocostuff27 shape.
+// The item's labels wait in shared memory as bytes (written and read by the same thread: no barrier inside the loop).
+// RECOMP: the tournament's second pass recomputes the winning group's values instead of keeping all of them.
+struct ProbeSchedule {
+  int n_full;            // items [0, n_full) are processed whole
+  int n_sched;           // n_full + (n_items - n_full) * parts schedule slots
+  int parts;             // row ranges per item of the remainder (divides rows_per_block)
+  int rowblocks;         // row blocks per image
+  int slices;            // column slices per row block
+};
+
+template <int CMAX, int TMAX, int MINB, bool RECOMP>
+__global__ void __launch_bounds__(TMAX, MINB)
+probe_argmax_rows_t_kernel(const float* __restrict__ logits, int h, int w, int c_pad, const long long* __restrict__ label,
+                           int H, int W, int C, ProbeHeads heads, float scale_h, float scale_w, int rows_per_block,
+                           int row_shift, ProbeSchedule sch) {
+  using pa::f32x2;
+  extern __shared__ int s_hist[];   // [hist_per_warp] = all heads' bins, one copy per block; then the label bytes
+  uint8_t* s_lab = reinterpret_cast<uint8_t*>(s_hist + heads.hist_per_warp);     // [kRowsPerBlock][blockDim.x]
+  for (int i = threadIdx.x; i < heads.hist_per_warp; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (int slot = blockIdx.x; slot < sch.n_sched; slot += gridDim.x) {
+    int item = slot, r_lo = 0, r_hi = rows_per_block;
+    if (slot >= sch.n_full) {
+      const int t = slot - sch.n_full;
+      item = sch.n_full + t / sch.parts;
+      const int rows = rows_per_block / sch.parts;
+      r_lo = (t % sch.parts) * rows;
+      r_hi = r_lo + rows;
+    }
+    const int slice = item % sch.slices;
+    const int rbk = (item / sch.slices) % sch.rowblocks;
+    const int b = item / (sch.slices * sch.rowblocks);
+    const int Ya = rbk * rows_per_block - row_shift;
+    const int Y0 = max(Ya + r_lo, 0);
+    const int Y1 = min(H, Ya + r_hi);
+    const int X = (int)(slice * blockDim.x + threadIdx.x);
+    const bool live = X < W;
+    // labels of this column for all rows of the item, loaded up front (one latency, RB loads in flight); one byte per
+    // row: label, or 255 = ignore (C <= 255 on this path)
+    {
+      long long lab[kRowsPerBlock];
+#pragma unroll
+      for (int r = 0; r < kRowsPerBlock; ++r) {
+        const int Y = Y0 + r;
+        lab[r] = (live && Y < Y1) ? __ldcs(label + ((long long)b * H + Y) * W + X) : -1;
+      }
+#pragma unroll
+      for (int r = 0; r < kRowsPerBlock; ++r)
+        s_lab[r * blockDim.x + threadIdx.x] = (uint8_t)((lab[r] >= 0 && lab[r] < C) ? (unsigned)lab[r] : 255u);
+    }
+    const float* base = logits + (long long)b * h * w * c_pad;
+    float sx = scale_w * ((float)X + 0.5f) - 0.5f; if (sx < 0.f) sx = 0.f;
+    int x0 = (int)sx;
+    if (x0 > w - 1) x0 = w - 1;
+    const int x1 = x0 + ((x0 < w - 1) ? 1 : 0);
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+#pragma unroll 1
+    for (int hd = 0; hd < heads.n_heads; ++hd) {
+      const int off = heads.off[hd], cnt = heads.cnt[hd];
+      f32x2 H0p[CMAX / 2], H1p[CMAX / 2];
+      int cy0 = -1;
+#pragma unroll 1
+      for (int Y = Y0; Y < Y1; ++Y) {
+        // PyTorch upsample_bilinear2d, align_corners=False (area_pixel_compute_source_index)
+        float sy = scale_h * ((float)Y + 0.5f) - 0.5f; if (sy < 0.f) sy = 0.f;
+        int y0 = (int)sy;
+        if (y0 > h - 1) y0 = h - 1;
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+        if (y0 != cy0) {             // block-uniform: a new token-row pair
+          cy0 = y0;
+          const int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+          const f32x2 lx0p = pa::pk(lx0, lx0), lx1p = pa::pk(lx1, lx1);
+          const float4* p00 = reinterpret_cast<const float4*>(base + ((long long)y0 * w + x0) * c_pad + off);
+          const float4* p01 = reinterpret_cast<const float4*>(base + ((long long)y0 * w + x1) * c_pad + off);
+          const float4* p10 = reinterpret_cast<const float4*>(base + ((long long)y1 * w + x0) * c_pad + off);
+          const float4* p11 = reinterpret_cast<const float4*>(base + ((long long)y1 * w + x1) * c_pad + off);
+#pragma unroll
+          for (int g = 0; g < CMAX / 4; ++g) {
+            const float4 a = __ldg(p00 + g), bq = __ldg(p01 + g), c = __ldg(p10 + g), dq = __ldg(p11 + g);
+            // H = fma(lx0, left, lx1 * right): the association of the row kernel
+            H0p[2 * g] = pa::interp2(pa::pk(a.x, a.y), pa::pk(bq.x, bq.y), lx0p, lx1p);
+            H0p[2 * g + 1] = pa::interp2(pa::pk(a.z, a.w), pa::pk(bq.z, bq.w), lx0p, lx1p);
+            H1p[2 * g] = pa::interp2(pa::pk(c.x, c.y), pa::pk(dq.x, dq.y), lx0p, lx1p);
+            H1p[2 * g + 1] = pa::interp2(pa::pk(c.z, c.w), pa::pk(dq.z, dq.w), lx0p, lx1p);
+          }
+          // CMAX - 4 < cnt <= CMAX (host check): only the last group can hold channels past the head's end; they
+          // are made unable to win here, so the argmax needs no per-channel guard
+          {
+            float e0, e1, e2, e3, f0, f1, f2, f3;
+            pa::upk(H0p[CMAX / 2 - 2], e0, e1); pa::upk(H0p[CMAX / 2 - 1], e2, e3);
+            pa::upk(H1p[CMAX / 2 - 2], f0, f1); pa::upk(H1p[CMAX / 2 - 1], f2, f3);
+            if (CMAX - 3 >= cnt) { e1 = -1e30f; f1 = -1e30f; }
+            if (CMAX - 2 >= cnt) { e2 = -1e30f; f2 = -1e30f; }
+            if (CMAX - 1 >= cnt) { e3 = -1e30f; f3 = -1e30f; }
+            H0p[CMAX / 2 - 2] = pa::pk(e0, e1); H0p[CMAX / 2 - 1] = pa::pk(e2, e3);
+            H1p[CMAX / 2 - 2] = pa::pk(f0, f1); H1p[CMAX / 2 - 1] = pa::pk(f2, f3);
+          }
+        }
+        const int lab = s_lab[(Y - Y0) * blockDim.x + threadIdx.x];
+        const int bj = pa::argmax_interp<CMAX, RECOMP>(H0p, H1p, ly0, ly1);
+        long long* preds = heads.preds[hd];
+        if (live && preds) __stcs(preds + ((long long)b * H + Y) * W + X, (long long)bj);
+        if (heads.conf[hd] != nullptr) {
+          const int bin = (live && lab != 255 && bj < C) ? bj * C + lab : -1;
+          warp_hist_add(s_hist + heads.hist_off[hd], bin);
         }
       }
     }
@@ -560,7 +691,45 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
         case 20: EQUSS_ROWS_LAUNCH(20, TM, MB); break; case 24: EQUSS_ROWS_LAUNCH(24, TM, MB); break;                 \
         case 28: EQUSS_ROWS_LAUNCH(28, TM, MB); break; default: EQUSS_ROWS_LAUNCH(32, TM, MB); break;                 \
       }
-      if (threads <= 320) { EQUSS_ROWS_CM(320, 2) } else { EQUSS_ROWS_CM(512, 1) }
+      // EQUSS_PROBE_ARGMAX_T = 0 selects the sequential-argmax kernel (one CTA per item); the default is the
+      // persistent tournament kernel.  Both return identical predictions (tests/test_gpu_eval.py).  Measured on B200 at
+      // the cocostuff27 shape: 80 us sequential, 70.5 us tournament (scripts/bench_probe_argmax.py; variants that were
+      // slower: 160 threads x 3 CTAs with 128 registers 74-78 us, scalar FMUL / FFMA instead of f32x2 74 us, one CTA
+      // per item 73 us).
+      const int tmode = getenv("EQUSS_PROBE_ARGMAX_T") ? atoi(getenv("EQUSS_PROBE_ARGMAX_T")) : kProbeArgmaxDefaultMode;
+#define EQUSS_ROWS_T_LAUNCH(CM, TM, MB)                                                                               \
+      probe_argmax_rows_t_kernel<CM, TM, MB, true><<<tgrid, tthreads, tsmem, (cudaStream_t)stream>>>(                 \
+          logits, h, w, equss_probe_cpad(c_total), (const long long*)label, H, W, num_classes, hd, scale_h, scale_w, rb, shift, sch)
+#define EQUSS_ROWS_T_CM(TM, MB)                                                                                       \
+      {                                                                                                               \
+        const int wpad = (W + 31) & ~31;                                                                              \
+        const int tthreads = wpad < TM ? wpad : TM;                                                                   \
+        ProbeSchedule sch;                                                                                            \
+        sch.rowblocks = (int)grid.x; sch.slices = (wpad + tthreads - 1) / tthreads;                                   \
+        const long long n_items = (long long)B * sch.rowblocks * sch.slices;                                          \
+        EQUSS_REQUIRE(n_items < (1ll << 28), EQUSS_ERR_UNSUPPORTED, "probe argmax: %lld work items", n_items);        \
+        long long ctas = (long long)num_sms() * MB;                                                                   \
+        if (ctas > n_items) ctas = n_items;                                                                           \
+        const int rem = (int)(n_items % ctas);                                                                        \
+        sch.parts = 1;      /* the last, partial round is split into row ranges so that it keeps every CTA busy */    \
+        while (rem > 0 && (long long)rem * sch.parts * 2 <= ctas && rb % (sch.parts * 2) == 0) sch.parts *= 2;        \
+        sch.n_full = (int)(n_items - rem);                                                                            \
+        sch.n_sched = sch.n_full + rem * sch.parts;                                                                   \
+        const dim3 tgrid((unsigned)ctas);                                                                             \
+        const size_t tsmem = smem + (size_t)kRowsPerBlock * tthreads;                                                 \
+        switch (cm) {                                                                                                 \
+          case 4: EQUSS_ROWS_T_LAUNCH(4, TM, MB); break;   case 8: EQUSS_ROWS_T_LAUNCH(8, TM, MB); break;             \
+          case 12: EQUSS_ROWS_T_LAUNCH(12, TM, MB); break; case 16: EQUSS_ROWS_T_LAUNCH(16, TM, MB); break;           \
+          case 20: EQUSS_ROWS_T_LAUNCH(20, TM, MB); break; case 24: EQUSS_ROWS_T_LAUNCH(24, TM, MB); break;           \
+          case 28: EQUSS_ROWS_T_LAUNCH(28, TM, MB); break; default: EQUSS_ROWS_T_LAUNCH(32, TM, MB); break;           \
+        }                                                                                                             \
+      }
+      if (tmode != 0) EQUSS_ROWS_T_CM(320, 2)
+      else {
+        if (threads <= 320) { EQUSS_ROWS_CM(320, 2) } else { EQUSS_ROWS_CM(512, 1) }
+      }
+#undef EQUSS_ROWS_T_CM
+#undef EQUSS_ROWS_T_LAUNCH
 #undef EQUSS_ROWS_CM
 #undef EQUSS_ROWS_LAUNCH
       EQUSS_LAUNCH_OK("probe_argmax_rows_kernel");

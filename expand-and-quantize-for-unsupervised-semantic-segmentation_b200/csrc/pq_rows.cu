@@ -136,9 +136,13 @@ gather_loss_flat_kernel(const float4* __restrict__ z, long long n_pixels, int D4
 // ------------------------------------------------------------------------------------------------
 // K3 flat fast path (l2 rows): as gather_loss_flat_kernel, four independent float4 per thread and iteration and
 // branch-free correctly rounded sqrt / division, so their memory latencies and dependent chains overlap.
+// The codeword load depends on the index load; to keep that second memory latency off the iteration's critical
+// path the indices of iteration i+1 are fetched while iteration i is in flight (software pipeline: z, codeword and
+// the next indices are all issued before the first use), and the (pixel, chunk) position of every element advances
+// incrementally -- no division inside the loop.
 // ------------------------------------------------------------------------------------------------
 template <int LPS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gather_loss_flat_l2_kernel(const float4* __restrict__ z, long long n_pixels, int D4, int M, int K,
                            const float4* __restrict__ src, const int32_t* __restrict__ idx,
                            float4* __restrict__ out, double* __restrict__ sqerr) {
@@ -148,23 +152,44 @@ gather_loss_flat_l2_kernel(const float4* __restrict__ z, long long n_pixels, int
   constexpr int U = 4;
   const long long total = n_pixels * D4;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  // warp-uniform trip count (xor-shuffles inside); the tail is predicated
-  for (long long f0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); f0 < total; f0 += stride * U) {
+  const long long f00 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // element u of an iteration sits at f0 + u * stride; from one iteration to the next it moves by stride * U
+  const long long step = stride * U;
+  const long long dn = step / D4;
+  const int dc = (int)(step - dn * D4);
+  long long n[U];
+  int c4[U], code[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long f = f00 + u * stride;
+    n[u] = f / D4;
+    c4[u] = (int)(f - n[u] * D4);
+    code[u] = (f < total) ? __ldg(idx + (long long)(c4[u] / LPS) * n_pixels + n[u]) : 0;
+  }
+  // warp-uniform trip count (xor-shuffles inside); the tail is predicated.  A group of LPS lanes (one subspace of one
+  // pixel) is live or dead as a whole: total and every warp's first element are multiples of LPS.
+  for (long long f0 = f00; f0 - (threadIdx.x & 31) < total; f0 += step) {
     float4 v[U], q[U];
-    long long f[U];
-    int mm[U], ll[U];
-    bool live[U];
+    int mm[U];
+    bool live[U], first[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      f[u] = f0 + u * stride + (threadIdx.x & 31);
-      live[u] = f[u] < total;
-      const long long fc = live[u] ? f[u] : total - 1;
-      const long long n = fc / D4;
-      const int c4 = (int)(fc - n * D4);
-      mm[u] = c4 / LPS; ll[u] = c4 - mm[u] * LPS;
-      v[u] = __ldcs(z + fc);
-      const int code = __ldg(idx + (long long)mm[u] * n_pixels + n);
-      q[u] = __ldg(src + ((long long)mm[u] * K + code) * LPS + ll[u]);
+      const long long f = f0 + u * stride;
+      live[u] = f < total;
+      mm[u] = c4[u] / LPS;
+      const int ll = c4[u] - mm[u] * LPS;
+      first[u] = ll == 0;
+      v[u] = __ldcs(z + (live[u] ? f : 0));                                       // dead lanes read valid memory
+      q[u] = __ldg(src + ((long long)mm[u] * K + code[u]) * LPS + ll);
+    }
+    // indices of the next iteration
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int c = c4[u] + dc;
+      long long nn = n[u] + dn;
+      if (c >= D4) { c -= D4; ++nn; }
+      c4[u] = c; n[u] = nn;
+      code[u] = (f0 + u * stride + step < total) ? __ldg(idx + (long long)(c / LPS) * n_pixels + nn) : 0;
     }
     float ss[U];
 #pragma unroll
@@ -181,7 +206,7 @@ gather_loss_flat_l2_kernel(const float4* __restrict__ z, long long n_pixels, int
       float4 dq, o;
       dq.x = q[u].x - zn.x; dq.y = q[u].y - zn.y; dq.z = q[u].z - zn.z; dq.w = q[u].w - zn.w;
       o.x = zn.x + dq.x; o.y = zn.y + dq.y; o.z = zn.z + dq.z; o.w = zn.w + dq.w;   // STE value (:536)
-      if (live[u]) __stcs(out + f[u], o);
+      if (live[u]) __stcs(out + (f0 + u * stride), o);
       e[u] = group_sumsq(dq.x, dq.y, dq.z, dq.w);
     }
 #pragma unroll
@@ -191,7 +216,7 @@ gather_loss_flat_l2_kernel(const float4* __restrict__ z, long long n_pixels, int
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (ll[u] == 0 && live[u]) atomicAdd(&s_sq[mm[u]], e[u]);
+      if (first[u] && live[u]) atomicAdd(&s_sq[mm[u]], e[u]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) {

@@ -241,3 +241,36 @@ def test_probe_losses_and_gradients_vs_reference_formulation(B, D, h, w, H, W, e
     with torch.no_grad():
         ll3, _, _, _ = ev(feat.cuda(), None, torch.full((B, H, W), -1, device="cuda:0"))
     assert torch.isnan(ll3)
+
+
+@pytest.mark.parametrize("cnt", [3, 4, 7, 10, 16, 19, 21, 27, 30, 32])
+def test_probe_argmax_tournament_equals_sequential_kernel(cnt, monkeypatch):
+    """The default probe kernel finds the argmax with a max3 tournament (csrc/probe_argmax_core.cuh) and walks a
+    persistent schedule whose last round is split into row ranges; EQUSS_PROBE_ARGMAX_T=0 selects the sequential
+    kernel.  Predictions and confusion matrices must be bit-identical on random, heavily tied and NaN / inf logits,
+    for every channel count the kernel is instantiated for, ragged shapes and shapes with a split remainder."""
+    ops = _ops()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(100 + cnt)
+    cm = (cnt + 3) & ~3
+    ct = 2 * cm
+    heads = [(0, cnt), (cm, cnt)]
+    for (B, h, w, H, W) in [(3, 9, 11, 70, 83), (40, 6, 5, 48, 40), (2, 4, 80, 9, 640)]:
+        lab = torch.randint(-1, cnt, (B, H, W), generator=g).to(dev)
+        rnd = torch.randn(B * h * w, ct, generator=g)
+        tied = torch.randint(-2, 3, (B * h * w, ct), generator=g).float()
+        bad = rnd.clone()
+        bad.view(-1)[torch.randint(0, bad.numel(), (bad.numel() // 20,), generator=g)] = float("nan")
+        bad[::7] = float("nan")
+        bad[3::11] = float("-inf")
+        bad[5::13, : ct // 2] = float("inf")
+        for logits in (rnd, tied, bad):
+            out = {}
+            for mode in ("0", "1"):
+                monkeypatch.setenv("EQUSS_PROBE_ARGMAX_T", mode)
+                confs = [torch.zeros(cnt, cnt, dtype=torch.long, device=dev) for _ in heads]
+                preds = ops.probe_argmax_confusion(logits.to(dev), B, h, w, ct, lab, cnt, heads, confusions=confs)
+                torch.cuda.synchronize()
+                out[mode] = (preds, confs)
+            for a, b in zip(out["0"][0] + out["0"][1], out["1"][0] + out["1"][1]):
+                assert torch.equal(a, b)
