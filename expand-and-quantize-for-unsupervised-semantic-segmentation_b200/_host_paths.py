@@ -1,5 +1,5 @@
-"""Rare host-side maintenance paths of the PQ head that depend on the HOST random number generators and therefore
-stay in Python: dead-code restart and most-used-code splitting.
+"""Rare host-side paths of the PQ head that depend on random number generators and therefore stay in Python
+(SURVEY.md 7.5 / 8a row a6): dead-code restart, most-used-code splitting, and the Gumbel index draw.
 
 They are written once here and shared by every quantiser flavour (the reference repeats them per class:
 model/quantizer.py:73-103,298-381; dino_pqgo.py:546-577; dino_new_vq.py:293-325,516-535).  The random draws are made
@@ -9,11 +9,12 @@ replaces the same codes by the same rows (tests/test_gpu_variants.py::test_resta
 from __future__ import annotations
 
 import random
-from typing import List, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
 import torch
+import torch.nn.functional as F
 
-__all__ = ["draw_restart", "split_codes"]
+__all__ = ["draw_restart", "split_codes", "gumbel_indices"]
 
 
 @torch.no_grad()
@@ -58,3 +59,25 @@ def split_codes(count: torch.Tensor, ema_count: torch.Tensor, weight: torch.Tens
         ema_count[ids] = half_cnt
         weight_avg[ids] = half_avg
     return n
+
+
+@torch.no_grad()
+def gumbel_indices(z_norm: torch.Tensor, codebook_norm: torch.Tensor, divisor: Optional[float]) -> torch.Tensor:
+    """Stochastic assignment of the ``use_gumbel`` research flag (training only).
+
+    z_norm: (n, M, d) normalised rows;  codebook_norm: (M, K, d).  Returns int32 (M, n) indices.
+    Per subspace, in subspace order like the reference's loop (model/quantizer.py:595-604), the reference's distance
+    (:457-461), then ``argmax(F.gumbel_softmax(-distance / divisor, tau=1.0, hard=True, dim=1))`` (:463-465;
+    ``divisor`` = 0.01 for EMAVectorQuantizer, None = plain ``-distance`` for VectorQuantizer :145-147).  The noise
+    comes from torch's generator of the device inside ``F.gumbel_softmax`` -- one call per subspace with an (n, K)
+    argument, so a seeded run consumes the generator exactly like the reference does on the same device."""
+    n, M, _ = z_norm.shape
+    idx = torch.empty((M, n), dtype=torch.int32, device=z_norm.device)
+    for i in range(M):
+        zi, ci = z_norm[:, i, :], codebook_norm[i]
+        distance = (torch.sum(zi ** 2, dim=1, keepdim=True) + torch.sum(ci ** 2, dim=1)
+                    - 2 * torch.matmul(zi, ci.t()))
+        logits = -distance if divisor is None else -distance / divisor
+        hard = F.gumbel_softmax(logits, tau=1.0, hard=True, dim=1)
+        idx[i] = torch.argmax(hard, dim=1).to(torch.int32)
+    return idx

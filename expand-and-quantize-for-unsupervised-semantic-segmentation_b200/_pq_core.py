@@ -169,14 +169,17 @@ def _wants_grad(*ts) -> bool:
 
 def pq_quantize(z: torch.Tensor, codebook_norm: torch.Tensor, gather_src: torch.Tensor, normalize: Optional[str],
                 norm_a=None, norm_b=None, *, want_prob: bool = True, temperature: float = 1.0, algo: int = 0,
-                cnorm2: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+                cnorm2: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """assign -> (soft assignment) -> gather/loss for all M subspaces at once.
+    ``idx``: externally chosen indices (the Gumbel draw of the use_gumbel flag) -- the assignment kernel is skipped.
     Returns (idx int32 [M,N], out like z, mse_commit [M], mse_codebook [M], prob [N, M*K] or None)."""
     z32 = z if z.dtype == torch.float32 else z.float()
     cbn = codebook_norm.detach()
     cn2 = cnorm2 if cnorm2 is not None else ops.pq_cnorm2(cbn)
     pre_out = pre_sq = None
-    if algo == 0:
+    if idx is not None:
+        idx = idx.to(torch.int32).contiguous()
+    elif algo == 0:
         # one fused kernel (K1 + K3, activations read once) where the shape allows it, else K1 then K3
         idx, pre_out, pre_sq = ops.pq_assign_gather(z32, cbn, gather_src.detach(), cn2, normalize, norm_a, norm_b)
     else:

@@ -10,7 +10,10 @@ return tuples.  One ``Codebook`` class serves the three files; ``variant`` selec
   "new_vq"    (z, i, it)            q, out, prob (n,K)  (+ jsd, entropy)    cb + beta*commit         raw z
   "pqgo_cls"  (z)                   q, out, prob (b,h,w,K), idx (n,)        cb + beta*commit         z_norm
 
-Host-RNG research flags (pq_dropout, gumbel, weighted-sum, k-means init) are not part of the accelerated path.
+``use_weighted_sum`` runs as host PyTorch on the kernel's soft assignment (``_weighted_sum``).  ``pq_dropout`` (the
+reference masks the codebook with ``torch.cuda.FloatTensor`` noise and then indexes the FULL codebook with indices
+into the masked one), and the k-means init are not offered; the inline classes' ``use_gumbel`` is only admitted next to the weighted sum,
+whose branch takes precedence (dino_pqgo.py:502-503,658-663), exactly as in the reference.
 """
 from __future__ import annotations
 
@@ -71,8 +74,13 @@ class Codebook(nn.Module):
                  use_gumbel: bool = False, need_initialized: str = "none", pq_dropout: float = 0.0, jsd_ts: float = 1.0,
                  num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
-        _unsupported(use_weighted_sum=use_weighted_sum, use_gumbel=use_gumbel, pq_dropout=pq_dropout > 0.0,
+        _unsupported(pq_dropout=pq_dropout > 0.0,
                      use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand"))
+        self.use_weighted_sum = use_weighted_sum
+        if use_weighted_sum:
+            assert normalize == "none", "Weight_sum should be unnormalized"          # dino_pqgo.py:499-500
+        if use_gumbel:      # :502-503 -- the reference only admits it next to the weighted sum, whose branch then wins (:658-663)
+            assert use_weighted_sum, "Weight_sum and Gumbel should not be both true"
         if variant not in ("pqgo", "new_vq", "pqgo_cls"):
             raise ValueError(f"unknown Codebook variant {variant}")
         self.variant = variant
@@ -152,9 +160,11 @@ def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bo
     cbn = core.normalize_codebook(codebook, mode, ema_style=True)                 # dino_pqgo.py:613-641
     need_soft_stats = variant == "new_vq"
     grad_path = core._wants_grad(z, codebook, norm_a, norm_b)
-    make_prob = want_prob or (need_soft_stats and grad_path)
+    make_prob = want_prob or (need_soft_stats and grad_path) or q0.use_weighted_sum
     idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, codebook, mode, norm_a, norm_b, want_prob=make_prob,
                                                           temperature=q0.jsd_ts)   # :646-665 (raw embedding gathered)
+    if q0.use_weighted_sum:                                                          # dino_pqgo.py:661-662,691
+        out, mse_commit, mse_cb = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
     output: Dict[str, torch.Tensor] = {}
     if training:
         with torch.no_grad():
@@ -180,6 +190,21 @@ def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bo
     return out, output, probs, [idx64[i].view(B, h, w) for i in range(M)]
 
 
+def _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M: int, K: int):
+    """``use_weighted_sum`` (dino_new_vq.py:400-401,616-617; dino_pqgo.py:406-407,661-662): the quantised row is the
+    soft-assignment-weighted sum of the codes, ``softmax(-d / T) @ codebook_norm``, returned WITHOUT the straight-through
+    estimator -- gradients reach z (and a learned codebook) through the soft assignment.  Host PyTorch on the
+    materialised probabilities.  Returns (z_q NCHW, mse(z_norm, z_q.detach()) [M],
+    mse(z_q, z_norm.detach()) [M])."""
+    B, D, h, w = z.shape
+    n = B * h * w
+    zr = core._normalize_rows(core._rows(z.float(), M), mode, norm_a, norm_b)         # (n, M, d), differentiable
+    zq = torch.einsum("nmk,mkd->nmd", prob.view(n, M, K), cbn)
+    commit = ((zr - zq.detach()) ** 2).mean(dim=(0, 2))
+    cb_loss = ((zq - zr.detach()) ** 2).mean(dim=(0, 2))
+    return zq.reshape(B, h, w, D).permute(0, 3, 1, 2).contiguous(), commit, cb_loss
+
+
 def _soft_stats(z, cbn, mode, norm_a, norm_b, jsd_ts, prob, M, K):
     """jsd / entropy of the soft assignment (dino_new_vq.py:447-450): from the materialised differentiable tensor
     when there is one, else by the fused kernel that never writes the N x K*M probabilities."""
@@ -196,8 +221,11 @@ class EMACodebook(nn.Module):
                  use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "none",
                  pq_dropout: float = 0.0, jsd_ts: float = 1.0, **_ignored):
         super().__init__()
-        _unsupported(use_weighted_sum=use_weighted_sum, pq_dropout=pq_dropout > 0.0,
+        _unsupported(pq_dropout=pq_dropout > 0.0,
                      need_initialized=need_initialized not in ("none", "rand", "uni", "normal"))
+        self.use_weighted_sum = use_weighted_sum
+        if use_weighted_sum:
+            assert normalize == "none", "Weight_sum should be unnormalized"          # dino_new_vq.py:276-277
         self.latent_dim, self.beta = latent_dim, beta
         self.num_codebook_vectors = num_codebook_vectors
         self.codebook = EmbeddingEMA(num_codebook_vectors, latent_dim, decay=0.99, eps=1.0e-5)
@@ -254,8 +282,11 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
         cbn = core.normalize_codebook(weight, mode, ema_style=True)
         src = weight.clone()                             # raw codebook gathered, as it is BEFORE this step's update (:403)
     grad_path = core._wants_grad(z, norm_a, norm_b)
-    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b, want_prob=want_prob or grad_path,
+    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b,
+                                                     want_prob=want_prob or grad_path or q0.use_weighted_sum,
                                                      temperature=q0.jsd_ts)
+    if q0.use_weighted_sum:                                                          # dino_new_vq.py:400-401,438
+        out, mse_commit, _ = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
     output: Dict[str, torch.Tensor] = {}
     if training:
         with torch.no_grad():

@@ -10,8 +10,10 @@ visible to a caller are deliberate and small:
 * logging statistics (usage percentiles, ``codebook-usage``) come back as 0-dim tensors instead of
   Python floats, which removes ~6K host synchronisations per subspace per step (quantizer.py:23-29);
 * the arithmetic always runs in fp32, also under autocast (SURVEY 7.6);
-* ``use_gumbel`` / ``use_weighted_sum`` (stochastic / soft assignment research flags) are not part of
-  the accelerated path and raise NotImplementedError.
+* ``use_gumbel`` / ``use_weighted_sum`` (stochastic / soft assignment research flags, quantizer.py:149-151,463-476)
+  keep their sampling / soft sum in host PyTorch (``_host_paths.gumbel_indices``,
+  ``_ema_group_forward_flags``) and use the kernels for everything else; ``F.gumbel_softmax`` is called once per
+  subspace, in subspace order, on the reference's logits, so a seeded run draws the same noise.
 """
 from __future__ import annotations
 
@@ -24,8 +26,8 @@ import torch.nn.functional as F  # noqa
 
 from . import _pq_core as core
 from . import ops
-from ._host_paths import draw_restart, split_codes
-from .dist_utils import all_reduce_tensor, packed_peer_exchange
+from ._host_paths import draw_restart, gumbel_indices, split_codes
+from .dist_utils import all_reduce_packed_, all_reduce_tensor, packed_peer_exchange
 
 __all__ = ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper", "get_histogram_count"]
 
@@ -34,12 +36,6 @@ __all__ = ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuan
 def get_histogram_count(count: torch.Tensor, prefix: str = "") -> Dict:
     """model/quantizer.py:15-30 for a single (K,) count vector (values are 0-dim tensors)."""
     return core.percentile_stats(count.reshape(1, -1), prefix)
-
-
-def _check_flags(use_gumbel: bool, use_weighted_sum: bool) -> None:
-    if use_gumbel or use_weighted_sum:
-        raise NotImplementedError("use_gumbel / use_weighted_sum are outside the accelerated PQ path "
-                                  "(SURVEY.md 7.5); use the reference module for those experiments.")
 
 
 class _RestartMixin:
@@ -80,7 +76,6 @@ class VectorQuantizer(nn.Module, _RestartMixin):
         self.need_initialized = need_initialized
         if use_split:
             raise NotImplementedError("NOT YET implemented. Currently only for EMA.")
-        _check_flags(use_gumbel, use_weighted_sum)
 
     @torch.no_grad()
     def restart(self) -> None:
@@ -170,7 +165,6 @@ class EMAVectorQuantizer(nn.Module, _RestartMixin):
         self.need_initialized = need_initialized
         self.use_weighted_sum = use_weighted_sum
         self.update_norm = update_norm
-        _check_flags(use_gumbel, use_weighted_sum)
 
     @torch.no_grad()
     def restart(self) -> None:
@@ -229,6 +223,102 @@ def _stack(ts: List[torch.Tensor]) -> torch.Tensor:
     return torch.stack(ts)
 
 
+def _z_trainable_prelude(mods, z: torch.Tensor, d: int, training: bool):
+    """Running statistics of z for normalize == "z_trainable" (quantizer.py:429-446): returns the per-channel
+    (shift, scale) the kernels normalise with.  The std is taken BEFORE this step's running-statistics update, the
+    mean is the buffer itself and already holds the updated value when z is normalised."""
+    norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
+    if training:
+        with torch.no_grad():
+            # per-channel mean and mean of squares of z in ONE pass (K13) and ONE all-reduce of the [2, D] pair
+            # (the reference: two reductions + two all_reduce_tensor("mean") per subspace, :433-438).  It cannot
+            # ride in the packed EMA buffer: the assignment below depends on the updated mean.
+            mom = all_reduce_tensor(ops.channel_moments(z), op="mean")
+            logvar = (mom[1] - mom[0] * mom[0]).log()
+            for i, q in enumerate(mods):
+                q.z_mean.data.mul_(q.decay).add_(mom[0, i * d:(i + 1) * d], alpha=1 - q.decay)
+                q.z_log_var.data.mul_(q.decay).add_(logvar[i * d:(i + 1) * d], alpha=1 - q.decay)
+    return torch.cat([q.z_mean for q in mods]), norm_b
+
+
+def _ema_group_forward_flags(mods: List["EMAVectorQuantizer"], z: torch.Tensor, want_prob: bool = True):
+    """EMAVectorQuantizer.forward with ``use_gumbel`` (training) and / or ``use_weighted_sum`` (quantizer.py:463-476,
+    483-486,534-536).  The stochastic index draw and the soft sum are host PyTorch on device tensors (SURVEY.md 7.5);
+    normalisation, distances / soft assignment, gather + loss, scatter-add, EMA update and the usage statistics are
+    the same kernels as the top-1 path (one launch each for all M subspaces, no fused tail)."""
+    q0 = mods[0]
+    M, K, mode, beta = len(mods), q0.num_codebook, q0.normalize, q0.beta
+    d = z.shape[1] // M
+    n = z.shape[0]
+    training = q0.training
+    weight = _stack([q.codebook.weight for q in mods])
+    norm_a, norm_b = _z_trainable_prelude(mods, z, d, training) if mode == "z_trainable" else (None, None)
+    with torch.no_grad():
+        if mode in ("l2", "z_norm", "none"):
+            cbn, cn2 = ops.pq_prepare_codebook(weight, mode)
+        else:
+            cbn = core.normalize_codebook(weight, mode, ema_style=True)
+            cn2 = ops.pq_cnorm2(cbn)
+        src = cbn if q0.update_norm else weight.clone()
+    z32 = z if z.dtype == torch.float32 else z.float()
+    grad = core._wants_grad(z)
+    wsum = q0.use_weighted_sum
+    prob = None
+    if want_prob or wsum:                                                               # :468
+        prob = (core.DistanceProb.apply(z32, cbn, cn2, mode, norm_a, norm_b, 1.0) if grad
+                else ops.pq_distance_prob(z32, cbn, cn2, mode, norm_a, norm_b))
+    with torch.no_grad():
+        if training and q0.use_gumbel:                                                  # :463-465
+            z_norm = core._normalize_rows(core._rows(z32.detach(), M), mode, norm_a, norm_b)
+            idx = gumbel_indices(z_norm, cbn, 0.01)
+        else:
+            idx = ops.pq_assign(z32.detach(), cbn, cn2, mode, norm_a, norm_b)            # :467
+    if wsum:                                                                            # :470-471
+        zr = core._normalize_rows(core._rows(z32, M), mode, norm_a, norm_b)             # (n, M, d), differentiable
+        zq = torch.einsum("nmk,mkd->nmd", prob.view(n, M, K), cbn)
+        mse_commit = ((zr - zq.detach()) ** 2).mean(dim=(0, 2))                         # :514, per subspace
+        out = zq.reshape(n, M * d)                                                      # no straight-through (:534)
+    elif grad:
+        out, mse_commit, _ = core.PQGatherLoss.apply(z32, src, idx, mode, norm_a, norm_b)
+    else:
+        out, sqerr, _ = ops.pq_gather_loss(z32, src, idx, mode, norm_a, norm_b)
+        mse_commit = (sqerr / max(n * d, 1)).to(torch.float32)
+    output: Dict[str, torch.Tensor] = {}
+    if training:
+        with torch.no_grad():
+            if wsum:                                                                    # soft counts / sums (:483-488)
+                p = prob.detach().view(n, M, K)
+                packed = torch.cat([torch.einsum("nmk,nmd->mkd", p, core._rows(z32.detach(), M)),
+                                    p.sum(dim=0).unsqueeze(-1)], dim=-1).contiguous()
+                packed = all_reduce_packed_(packed)
+            else:
+                packed = core.ema_statistics(z, idx, K)
+            count = packed[:, :, d]
+            state = [[q.vq_count for q in mods], [q.codebook.vq_count for q in mods],
+                     [q.codebook.weight_avg for q in mods], [q.codebook.weight for q in mods]]
+            exact_c, vqc_c, wavg_c, w_c = (_stack(ts).contiguous() for ts in state)
+            if q0.use_restart:                                                          # :500-501, before the update
+                for i, q in enumerate(mods):
+                    q.prepare_restart(count[i], z[:, i * d:(i + 1) * d])
+            unused = ops.ema_update(packed, q0.codebook.decay, q0.codebook.eps, vqc_c, wavg_c, w_c, exact_c)  # :493,504
+            output.update(core.percentile_stats(exact_c, "total"))
+            output.update(core.percentile_stats(count, "current"))
+            for ts, st in zip(state, (exact_c, vqc_c, wavg_c, w_c)):
+                if st.data_ptr() != ts[0].data_ptr():
+                    for i, t in enumerate(ts):
+                        t.copy_(st[i])
+            if q0.use_split:
+                n_split = torch.tensor([float(q.split(count[i])) for i, q in enumerate(mods)], device=z.device)
+            else:
+                n_split = unused.float()
+            output["codebook-usage"] = ((K - n_split) / K).mean()                       # :510
+    commitment = mse_commit.mean()
+    output["loss"] = beta * commitment                                                  # :526
+    output["commitment-loss"] = commitment
+    output["codebook-sum"] = torch.sum(torch.abs(_stack([q.codebook.weight for q in mods]))) / M   # :532
+    return out, output, (prob if want_prob else None)
+
+
 def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_prob: bool = True, stacked=None):
     """EMAVectorQuantizer.forward (quantizer.py:383-542) for M = len(mods) subspaces at once; z is flat
     (n, M*d).  ``stacked``: the wrapper's cached [M, ...] views of (exact count, EMA count, weight_avg, weight) --
@@ -243,23 +333,10 @@ def _ema_group_forward(mods: List[EMAVectorQuantizer], z: torch.Tensor, want_pro
     if q0.need_initialized != "none" and training:
         for i, q in enumerate(mods):
             q._maybe_initialize(z[:, i * d:(i + 1) * d])
+    if q0.use_weighted_sum or (training and q0.use_gumbel):
+        return _ema_group_forward_flags(mods, z, want_prob)
     weight = stacked[3] if stacked is not None else _stack([q.codebook.weight for q in mods])
-    norm_a = norm_b = None
-    if mode == "z_trainable":
-        # quantizer.py:429-446: the std is taken BEFORE this step's running-statistics update, the mean is the buffer
-        # itself and already holds the updated value when z is normalised.
-        norm_b = torch.cat([q.z_log_var for q in mods]).exp().sqrt() + 1e-5
-        if training:
-            with torch.no_grad():
-                # per-channel mean and mean of squares of z in ONE pass (K13) and ONE all-reduce of the [2, D] pair
-                # (the reference: two reductions + two all_reduce_tensor("mean") per subspace, :433-438).  It cannot
-                # ride in the packed EMA buffer: the assignment below depends on the updated mean.
-                mom = all_reduce_tensor(ops.channel_moments(z), op="mean")
-                logvar = (mom[1] - mom[0] * mom[0]).log()
-                for i, q in enumerate(mods):
-                    q.z_mean.data.mul_(q.decay).add_(mom[0, i * d:(i + 1) * d], alpha=1 - q.decay)
-                    q.z_log_var.data.mul_(q.decay).add_(logvar[i * d:(i + 1) * d], alpha=1 - q.decay)
-        norm_a = torch.cat([q.z_mean for q in mods])
+    norm_a, norm_b = _z_trainable_prelude(mods, z, d, training) if mode == "z_trainable" else (None, None)
     per_code = mode in ("l2", "z_norm", "none")
     with torch.no_grad():
         if per_code:                    # normalised codebook + |c|^2 in one launch; a fresh tensor, never an alias
@@ -353,7 +430,13 @@ def _param_group_forward(mods: List[VectorQuantizer], z: torch.Tensor, want_prob
     cbn = core.normalize_codebook(codebook, mode, ema_style=False,
                                   z_mean=torch.stack([q.z_mean for q in mods]) if mode == "z_trainable" else None,
                                   z_std=z_std)
-    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, cbn, mode, norm_a, norm_b, want_prob=want_prob)
+    idx_drawn = None
+    if q0.training and q0.use_gumbel:                                         # :145-147 (plain -distance, no 0.01)
+        with torch.no_grad():
+            z_norm = core._normalize_rows(core._rows(z.detach().float(), M), mode, norm_a, norm_b)
+            idx_drawn = gumbel_indices(z_norm, cbn.detach().float(), None)
+    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, cbn, mode, norm_a, norm_b, want_prob=want_prob,
+                                                          idx=idx_drawn)
     output: Dict[str, torch.Tensor] = {}
     with torch.no_grad():                                                     # counts are updated in eval too (:158)
         packed = ops.pq_accumulate(z.detach().float(), idx, K)

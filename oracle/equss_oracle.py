@@ -99,10 +99,13 @@ class EmaState:
 def ema_vq_forward(z_flat: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: Optional[str],
                    beta: float = 0.25, training: bool = True, update_norm: bool = True,
                    allreduce=None, allreduce_mean=None, z_mean: Optional[torch.Tensor] = None,
-                   z_log_var: Optional[torch.Tensor] = None, temperature: float = 1.0, ema_decay: float = 0.99
+                   z_log_var: Optional[torch.Tensor] = None, temperature: float = 1.0, ema_decay: float = 0.99,
+                   use_weighted_sum: bool = False, gumbel_noise: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
-    """One subspace of EMAVectorQuantizer.forward (model/quantizer.py:383-542; all four normalisation modes,
-    top-1 assignment, no restart/split/gumbel).  ``allreduce`` stands for all_reduce_tensor(:490-491),
+    """One subspace of EMAVectorQuantizer.forward (model/quantizer.py:383-542; all four normalisation modes, no
+    restart/split).  ``use_weighted_sum`` (:470-471,483-484,534): soft-assignment-weighted sum of the codes, soft
+    statistics, no straight-through.  ``gumbel_noise`` (n, K), training only: the use_gumbel draw (:463-465) with the
+    noise given -- F.gumbel_softmax(l, tau=1, hard=True) is one_hot(argmax(l + g)) with g = -log(Exp(1)).  ``allreduce`` stands for all_reduce_tensor(:490-491),
     ``allreduce_mean`` for the op="mean" calls of the z_trainable statistics (:437-438); ``z_mean`` /
     ``z_log_var`` are that mode's buffers, updated in place in training.
     Returns (z_q_ste, outputs, distance_prob, indices)."""
@@ -123,14 +126,17 @@ def ema_vq_forward(z_flat: torch.Tensor, state: EmaState, exact_count: torch.Ten
     else:
         z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize)
     dist = sq_distance(z_norm, cb_norm)
-    idx = torch.argmin(dist, dim=1)                                               # :467
+    if training and gumbel_noise is not None:
+        idx = torch.argmax(-dist / 0.01 + gumbel_noise, dim=1)                    # :463-465
+    else:
+        idx = torch.argmin(dist, dim=1)                                           # :467
     prob = F.softmax(-dist / temperature, dim=1)                                  # :468 / dino_new_vq.py:398
     src = cb_norm if update_norm else state.weight                                # :473-476
-    q = F.embedding(idx, src)
+    q = torch.matmul(prob, cb_norm) if use_weighted_sum else F.embedding(idx, src)   # :470-476
     out: Dict = {}
     if training:
         K = state.weight.shape[0]
-        onehot = F.one_hot(idx, K).to(z_flat.dtype)                               # :485
+        onehot = prob if use_weighted_sum else F.one_hot(idx, K).to(z_flat.dtype)   # :483-485
         count = onehot.sum(dim=0)                                                 # :487
         total = torch.matmul(onehot.t(), z_flat)                                  # :488 (raw z, not z_norm)
         if allreduce is not None:
@@ -145,7 +151,7 @@ def ema_vq_forward(z_flat: torch.Tensor, state: EmaState, exact_count: torch.Ten
     out["loss"] = beta * commitment                                               # :526
     out["commitment-loss"] = commitment
     out["codebook-sum"] = torch.sum(torch.abs(state.weight))                      # :532
-    q_ste = z_norm + (q - z_norm)                                                 # :536 (value of the STE)
+    q_ste = q if use_weighted_sum else z_norm + (q - z_norm)                      # :534-536 (value of the STE)
     return q_ste, out, prob, idx
 
 
@@ -168,7 +174,8 @@ def pq_forward_ema(z: torch.Tensor, states: Sequence[EmaState], exact_counts: Se
 
 
 def param_vq_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, *, normalize: Optional[str], beta: float = 0.25,
-                     book: float = 1.0, gather_raw: bool = False, temperature: float = 1.0
+                     book: float = 1.0, gather_raw: bool = False, temperature: float = 1.0,
+                     gumbel_noise: Optional[torch.Tensor] = None
                      ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
     """One subspace of the learned-codebook quantiser on NCHW input: VectorQuantizer.forward
     (model/quantizer.py:105-189) when ``gather_raw`` is False, dino_pqgo.Codebook.forward
@@ -177,7 +184,10 @@ def param_vq_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, *, normalize:
     z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)                  # :112-115
     z_norm, cb_norm = normalize_pair(z_flat, codebook, normalize, ema_style=False)
     dist = sq_distance(z_norm, cb_norm)
-    idx = torch.argmin(dist, dim=1)                                               # :150
+    if gumbel_noise is not None:
+        idx = torch.argmax(-dist + gumbel_noise, dim=1)                           # :145-147 (training, use_gumbel)
+    else:
+        idx = torch.argmin(dist, dim=1)                                           # :150
     prob = F.softmax(-dist / temperature, dim=1)                                  # :151 / dino_pqgo.py:655
     q = F.embedding(idx, codebook if gather_raw else cb_norm)                     # :153 / dino_pqgo.py:665
     codebook_loss = F.mse_loss(q, z_norm)                                         # :175
@@ -255,7 +265,8 @@ def jsd_loss(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
 def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: str,
                        beta: float = 0.25, jsd_ts: float = 1.0, training: bool = True,
                        z_mean: Optional[torch.Tensor] = None, z_log_var: Optional[torch.Tensor] = None,
-                       allreduce=None) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
+                       allreduce=None, use_weighted_sum: bool = False
+                       ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
     """dino_new_vq.EMACodebook.forward (model/dino_new_vq.py:327-459), top-1 path without pq_dropout / init:
     NCHW in, the quantised rows come from the RAW codebook as it was before this step's update (:403),
     EMA sums of raw z (:411), softmax(-d / jsd_ts), JSD / entropy between the two batch halves (:447-450)."""
@@ -266,7 +277,10 @@ def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch
     dist = sq_distance(z_norm, cb_norm)
     idx = torch.argmin(dist, dim=1)
     prob = F.softmax(-dist / jsd_ts, dim=1)                                       # :398
-    q = F.embedding(idx, state.weight)                                            # :403 (a copy: pre-update rows)
+    if use_weighted_sum:
+        q = torch.matmul(prob, cb_norm)                                           # :400-401 (hard statistics below)
+    else:
+        q = F.embedding(idx, state.weight)                                        # :403 (a copy: pre-update rows)
     out: Dict = {}
     if training:
         onehot = F.one_hot(idx, K).to(z_flat.dtype)
@@ -282,14 +296,14 @@ def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch
     p1, p2 = torch.chunk(prob, chunks=2, dim=0)
     out["jsd"] = jsd_loss(p1, p2)                                                 # :449
     out["entropy"] = entropy_loss(p1)                                             # :450
-    q_ste = z_norm + (q - z_norm)
+    q_ste = q if use_weighted_sum else z_norm + (q - z_norm)                      # :438-439
     return q_ste.view(b, h, w, d).permute(0, 3, 1, 2).contiguous(), out, prob, idx
 
 
 def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_count: torch.Tensor, *,
                             variant: str, normalize: str, beta: float = 0.25, book: float = 1.0,
                             jsd_ts: float = 1.0, training: bool = True, z_mean: Optional[torch.Tensor] = None,
-                            z_log_var: Optional[torch.Tensor] = None
+                            z_log_var: Optional[torch.Tensor] = None, use_weighted_sum: bool = False
                             ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
     """The learned-codebook ``Codebook.forward`` of dino_new_vq.py:537-671 (variant "new_vq"), dino_pqgo.py:579-705
     ("pqgo") and dino_pqgo_cls.py:303-405 ("pqgo_cls"): raw embedding gathered, counts in training only,
@@ -302,7 +316,7 @@ def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_
     dist = sq_distance(z_norm, cb_norm)
     idx = torch.argmin(dist, dim=1)
     prob = F.softmax(-dist / jsd_ts, dim=1)
-    q = F.embedding(idx, codebook)
+    q = torch.matmul(prob, cb_norm) if use_weighted_sum else F.embedding(idx, codebook)   # dino_pqgo.py:658-665
     out: Dict = {}
     if training:
         count = F.one_hot(idx, K).to(z_flat.dtype).sum(dim=0)
@@ -314,7 +328,7 @@ def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_
         p1, p2 = torch.chunk(prob, chunks=2, dim=0)
         out["jsd"] = jsd_loss(p1, p2)
         out["entropy"] = entropy_loss(p1)
-    q_ste = z_norm + (q - z_norm)
+    q_ste = q if use_weighted_sum else z_norm + (q - z_norm)                      # dino_pqgo.py:690-691
     return q_ste.view(b, h, w, d).permute(0, 3, 1, 2).contiguous(), out, prob, idx
 
 

@@ -296,3 +296,57 @@ def test_stego_helper_fixture(golden_dir):
         loss, cd = O.stego_helper(f1, f2, c1, c2, 0.2, cfgv)
         np.testing.assert_allclose(loss.numpy(), g[f"{tag}_loss"], rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(cd.numpy(), g[f"{tag}_cd"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,mode,weighted", [("pq_flag_ema_weighted_none", "none", True),
+                                                ("pq_flag_ema_weighted_l2", "l2", True),
+                                                ("pq_flag_ema_gumbel_l2", "l2", False)])
+def test_research_flags_ema(golden_dir, name, mode, weighted):
+    """use_weighted_sum / use_gumbel of model/quantizer.py (fixtures: oracle/make_golden_flags.py, the unmodified
+    reference with the Gumbel noise pinned)."""
+    g = _load(golden_dir, name + ".npz")
+    M, K = int(g["M"]), int(g["K"])
+    steps = int(g["steps"])
+    w0 = torch.from_numpy(g["weight0"])
+    states = [O.EmaState(w0[i]) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    for s in range(steps + 1):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        noise = torch.from_numpy(g[f"noise{s}"]) if f"noise{s}" in g.files else None
+        res = [O.ema_vq_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize=mode, beta=0.25, training=s < steps,
+                                use_weighted_sum=weighted, gumbel_noise=None if noise is None else noise[i]) for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"zq{s}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(torch.stack([st.weight for st in states]).numpy(), g[f"weight_after{s}"], rtol=1e-5, atol=1e-7)
+        loss = sum(float(r[1]["loss"]) for r in res) / M
+        assert loss == pytest.approx(float(g[f"out{s}/loss"]), rel=1e-5)
+    if not weighted:
+        assert int(g["flips"]) > 0 and float(g["min_gumbel_gap"]) > 2e-3
+
+
+def test_research_flags_inline(golden_dir):
+    g = _load(golden_dir, "pq_flag_param_gumbel.npz")
+    q, out, prob, idx = O.param_vq_forward(torch.from_numpy(g["z"]), torch.from_numpy(g["weight"]), normalize="l2", beta=0.25,
+                                           gumbel_noise=torch.from_numpy(g["noise"]))
+    assert np.array_equal(idx.numpy().astype(np.int32), g["idx"]) and int(g["flips"]) > 0
+    np.testing.assert_allclose(q.numpy(), g["zq"], rtol=1e-6, atol=1e-7)
+    g = _load(golden_dir, "pq_flag_newvq_ema_weighted.npz")
+    M, K, ts = int(g["M"]), int(g["K"]), float(g["jsd_ts"])
+    w0 = torch.from_numpy(g["weight0"])
+    states = [O.EmaState(w0[i]) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    for s in range(3):
+        z = torch.from_numpy(g[f"z{s}"])
+        d = z.shape[1] // M
+        res = [O.new_vq_ema_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize="none", beta=0.25, jsd_ts=ts,
+                                    training=s < 2, use_weighted_sum=True) for i in range(M)]
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"zq{s}"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(torch.stack([st.weight for st in states]).numpy(), g[f"weight_after{s}"], rtol=1e-5, atol=1e-8)
+    for variant in ("new_vq", "pqgo"):
+        g = _load(golden_dir, f"pq_flag_inline_{variant}_weighted.npz")
+        q, out, _, _ = O.inline_codebook_forward(torch.from_numpy(g["z"]), torch.from_numpy(g["weight"]), torch.zeros(int(g["K"])),
+                                                 variant=variant, normalize="none", beta=0.25, jsd_ts=float(g["jsd_ts"]),
+                                                 training=True, use_weighted_sum=True)
+        np.testing.assert_allclose(q.numpy(), g["zq"], rtol=1e-6, atol=1e-8)
+        assert float(out["vq-loss"]) == pytest.approx(float(g["out/vq-loss"]), rel=1e-5)
