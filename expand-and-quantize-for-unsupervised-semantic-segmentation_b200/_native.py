@@ -30,7 +30,7 @@ EXPORTS = [
     "equss_last_error_string", "equss_version", "equss_device_check", "equss_launch_count",
     "equss_pq_assign_workspace_bytes", "equss_pq_assign", "equss_pq_cnorm2", "equss_pq_gather_loss",
     "equss_pq_gather_loss_bwd", "equss_pq_accumulate", "equss_ema_update", "equss_pq_distance_prob",
-    "equss_probe_cpad", "equss_probe_logits", "equss_probe_argmax_confusion", "equss_confusion_update",
+    "equss_probe_cpad", "equss_probe_logits", "equss_probe_argmax_schedule", "equss_probe_argmax_confusion", "equss_confusion_update",
     "equss_usage_percentiles", "equss_pq_assign_gather_supported", "equss_pq_assign_gather",
     "equss_probe_image_bytes", "equss_probe_build_image", "equss_probe_logits_tc_supported", "equss_probe_logits_tc",
     "equss_knn_workspace_bytes", "equss_knn_topk",
@@ -109,6 +109,8 @@ def _declare(L: C.CDLL) -> None:
     L.equss_probe_cpad.argtypes = [i32]
     L.equss_probe_logits.restype = i32
     L.equss_probe_logits.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+    L.equss_probe_argmax_schedule.restype = i32
+    L.equss_probe_argmax_schedule.argtypes = [i32, i32, i32, C.POINTER(C.c_int32)]
     L.equss_usage_percentiles.restype = i32
     L.equss_usage_percentiles.argtypes = [vp, i64, i64, i32, i32, vp, vp]
     L.equss_pq_assign_gather_supported.restype = i32

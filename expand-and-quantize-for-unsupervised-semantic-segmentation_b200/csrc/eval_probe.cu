@@ -443,6 +443,17 @@ struct ProbeSchedule {
   int slices;            // column slices per row block
 };
 
+// Items [0, n_full) fill whole rounds of the `ctas` persistent CTAs; the remainder (fewer items than CTAs) is split
+// into `parts` row ranges per item -- the largest power of two that divides the rows of an item and still leaves at
+// most one slot per CTA -- so the last round is 1 / parts as long and keeps parts x as many CTAs busy.
+static void probe_schedule_fill(int n_items, int ctas, int rows_per_block, ProbeSchedule* sch) {
+  const int rem = n_items % ctas;
+  sch->parts = 1;
+  while (rem > 0 && (long long)rem * sch->parts * 2 <= ctas && rows_per_block % (sch->parts * 2) == 0) sch->parts *= 2;
+  sch->n_full = n_items - rem;
+  sch->n_sched = sch->n_full + rem * sch->parts;
+}
+
 template <int CMAX, int TMAX, int MINB, bool RECOMP>
 __global__ void __launch_bounds__(TMAX, MINB)
 probe_argmax_rows_t_kernel(const float* __restrict__ logits, int h, int w, int c_pad, const long long* __restrict__ label,
@@ -633,6 +644,16 @@ extern "C" int equss_probe_logits(const float* feat, int B, int D, int h, int w,
   return EQUSS_OK;
 }
 
+extern "C" int equss_probe_argmax_schedule(int n_items, int ctas, int rows_per_block, int32_t* out3) {
+  EQUSS_REQUIRE(n_items > 0 && ctas > 0 && ctas <= n_items && rows_per_block > 0 && out3, EQUSS_ERR_INVALID_ARG,
+                "equss_probe_argmax_schedule: n_items=%d ctas=%d rows_per_block=%d", n_items, ctas, rows_per_block);
+  ProbeSchedule sch;
+  memset(&sch, 0, sizeof(sch));
+  probe_schedule_fill(n_items, ctas, rows_per_block, &sch);
+  out3[0] = sch.n_full; out3[1] = sch.n_sched; out3[2] = sch.parts;
+  return EQUSS_OK;
+}
+
 extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
                                             const int64_t* label, int H, int W, int num_classes, int n_heads,
                                             const int32_t* head_off_host, const int32_t* head_cnt_host,
@@ -710,11 +731,7 @@ extern "C" int equss_probe_argmax_confusion(const float* logits, int B, int h, i
         EQUSS_REQUIRE(n_items < (1ll << 28), EQUSS_ERR_UNSUPPORTED, "probe argmax: %lld work items", n_items);        \
         long long ctas = (long long)num_sms() * MB;                                                                   \
         if (ctas > n_items) ctas = n_items;                                                                           \
-        const int rem = (int)(n_items % ctas);                                                                        \
-        sch.parts = 1;      /* the last, partial round is split into row ranges so that it keeps every CTA busy */    \
-        while (rem > 0 && (long long)rem * sch.parts * 2 <= ctas && rb % (sch.parts * 2) == 0) sch.parts *= 2;        \
-        sch.n_full = (int)(n_items - rem);                                                                            \
-        sch.n_sched = sch.n_full + rem * sch.parts;                                                                   \
+        probe_schedule_fill((int)n_items, (int)ctas, rb, &sch);                                                       \
         const dim3 tgrid((unsigned)ctas);                                                                             \
         const size_t tsmem = smem + (size_t)kRowsPerBlock * tthreads;                                                 \
         switch (cm) {                                                                                                 \

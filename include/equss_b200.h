@@ -267,6 +267,12 @@ int equss_probe_logits_tc_supported(int D, int h, int w, int c_total);
 int equss_probe_logits_tc(const float* feat, int B, int D, int h, int w,
                           const void* image, const float* bias, int c_total,
                           float* logits, void* stream);
+/* Host-only helper (no GPU work): the persistent schedule equss_probe_argmax_confusion walks.  n_items work items
+ * (image x row block x column slice) on `ctas` persistent CTAs (ctas <= n_items): out3 = { n_full, n_sched, parts } --
+ * items [0, n_full) are processed whole, each of the remaining n_items - n_full items as `parts` row ranges of
+ * rows_per_block / parts rows, n_sched = n_full + (n_items - n_full) * parts slots in total; CTA c handles slots
+ * c, c + ctas, ...  Exposed so that the host logic is testable without a device (tests/test_probe_argmax_core.py). */
+int equss_probe_argmax_schedule(int n_items, int ctas, int rows_per_block, int32_t* out3);
 int equss_probe_argmax_confusion(const float* logits, int B, int h, int w, int c_total,
                                  const int64_t* label, int H, int W, int num_classes,
                                  int n_heads, const int32_t* head_off_host, const int32_t* head_cnt_host,
