@@ -17,6 +17,8 @@ The same JSON line carries one block per remaining BASELINE config, measured the
   c4    : configs[3], cityscapes high-res, 50 176 pixels sharded over the ranks (strong scaling)
   c5    : configs[4], 50k x 768 kNN, queries sharded over the ranks + all_gather (strong scaling)
   c1    : configs[0], pq_baseline forward at 3 136 pixels (latency)
+torch_eager_gpu (N = 1): the oracle port with its tensors on the GPU (PyTorch eager, library kernels) -- the "same-box
+PyTorch" comparator of SURVEY 8d, a reported baseline like cpu_baseline.
 `--impl reference` times the CPU oracle port of the reference path (oracle/equss_oracle.py, torch CPU ops
 with all host threads) on a bounded sample of the same workload; the reference itself is Python and
 /root/reference does not exist on the GPU box.
@@ -52,18 +54,21 @@ def _peaks():
 # ------------------------------------------------------------------------------------------------------
 # CPU oracle pipeline (reference arm + cpu_baseline)
 # ------------------------------------------------------------------------------------------------------
-def cpu_pipeline_factory(n_images):
+def cpu_pipeline_factory(n_images, device="cpu"):
+    """The oracle port of the reference path on `n_images` images of the headline workload.  device="cpu" is the
+    cpu_baseline / reference arm; a CUDA device runs the SAME torch code with library kernels (ATen / cuBLAS) as the
+    "same-box PyTorch eager" comparator of SURVEY 8d -- a reported baseline, never the product path."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import equss_oracle as O
     c = CFG
     g = torch.Generator().manual_seed(0)
     d = c["D"] // c["M"]
-    feat = torch.randn(n_images, c["D"], c["h"], c["w"], generator=g)
-    label = torch.randint(-1, c["C"], (n_images, c["H"], c["W"]), generator=g)
-    cb = torch.randn(c["M"], c["K"], d, generator=g)
-    clusters = torch.randn(c["C"], c["D"], generator=g)
-    lin_w = torch.randn(c["C"], c["D"], generator=g) * 0.03
-    lin_b = torch.zeros(c["C"])
+    feat = torch.randn(n_images, c["D"], c["h"], c["w"], generator=g).to(device)
+    label = torch.randint(-1, c["C"], (n_images, c["H"], c["W"]), generator=g).to(device)
+    cb = torch.randn(c["M"], c["K"], d, generator=g).to(device)
+    clusters = torch.randn(c["C"], c["D"], generator=g).to(device)
+    lin_w = (torch.randn(c["C"], c["D"], generator=g) * 0.03).to(device)
+    lin_b = torch.zeros(c["C"], device=device)
 
     def step():
         qs = []
@@ -72,8 +77,8 @@ def cpu_pipeline_factory(n_images):
             qs.append(q)
         zq = torch.cat(qs, dim=1)
         _, lp, _, cp = O.evaluator_forward(zq, label, clusters, lin_w, lin_b, c["C"])
-        conf_c = O.confusion_update(torch.zeros(c["C"], c["C"], dtype=torch.long), cp, label, c["C"])
-        conf_l = O.confusion_update(torch.zeros(c["C"], c["C"], dtype=torch.long), lp, label, c["C"])
+        conf_c = O.confusion_update(torch.zeros(c["C"], c["C"], dtype=torch.long, device=device), cp, label, c["C"])
+        conf_l = O.confusion_update(torch.zeros(c["C"], c["C"], dtype=torch.long, device=device), lp, label, c["C"])
         return conf_c, conf_l
 
     return step, n_images * c["h"] * c["w"]
@@ -554,6 +559,35 @@ def run_equss(args):
                     "sample": f"{n_img} of {B} images ({px} pixels) x {len(ts)} timed runs of the oracle port "
                               f"(PQ loop + evaluator + 2 confusion updates), {sum(ts):.1f} s of CPU work"}
 
+    # The same oracle code with its tensors on the GPU (library kernels, the reference's op sequence): what a user gets
+    # from `.cuda()` on the reference today.  Reported next to cpu_baseline, one rank only, after every measurement of
+    # the product path; a failure here (e.g. out of memory) is recorded and does not touch the rest of the line.
+    eager_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            n_img = 8
+            gstep, px = cpu_pipeline_factory(n_img, device=dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    gstep()
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_g = 5
+                g0.record()
+                for _ in range(n_g):
+                    gstep()
+                g1.record()
+                torch.cuda.synchronize()
+            ms_g = g0.elapsed_time(g1) / n_g
+            eager_gpu = {"value": px / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": round(ms_g, 3), "kind": "port",
+                         "sample": f"{n_img} of {B} images ({px} pixels) x {n_g} timed runs of the oracle port with its tensors on "
+                                   "cuda:0 (PyTorch eager, ATen / cuBLAS kernels, the reference's per-subspace loop and "
+                                   "label-resolution evaluator), device-resident inputs"}
+            del gstep
+        except Exception as e:                                   # noqa: BLE001 -- a comparator must never cost the line
+            eager_gpu = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -562,7 +596,7 @@ def run_equss(args):
                    **CFG, "normalize": "l2", "pixels_per_step_per_gpu": N, "parallelism": f"dp{world}",
                    "materialize_distance_prob": False,
                    "l2": f"{NBUF} rotating input sets of {(4 * N * D + 8 * P) / 1e6:.0f} MB each (> 126 MB L2), no flush kernel"},
-        "roofline": roof, "kernels": kern, "cpu_baseline": cpu_base, "e2e": e2e,
+        "roofline": roof, "kernels": kern, "cpu_baseline": cpu_base, "torch_eager_gpu": eager_gpu, "e2e": e2e,
         "gpu_launches": int(gpu_launches), "clocks": clocks, **extras,
     }
     if json_fd is not None:
