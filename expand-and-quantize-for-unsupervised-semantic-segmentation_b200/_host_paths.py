@@ -1,5 +1,5 @@
 """Rare host-side paths of the PQ head that depend on random number generators and therefore stay in Python
-(SURVEY.md 7.5 / 8a row a6): dead-code restart, most-used-code splitting, and the Gumbel index draw.
+(SURVEY.md 7.5 / 8a row a6): dead-code restart, most-used-code splitting, the Gumbel index draw and ``pq_dropout``.
 
 They are written once here and shared by every quantiser flavour (the reference repeats them per class:
 model/quantizer.py:73-103,298-381; dino_pqgo.py:546-577; dino_new_vq.py:293-325,516-535).  The random draws are made
@@ -14,7 +14,7 @@ from typing import List, Optional, Tuple, Union
 import torch
 import torch.nn.functional as F
 
-__all__ = ["draw_restart", "split_codes", "gumbel_indices"]
+__all__ = ["draw_restart", "split_codes", "gumbel_indices", "dropout_keep_mask", "dropout_assign"]
 
 
 @torch.no_grad()
@@ -81,3 +81,36 @@ def gumbel_indices(z_norm: torch.Tensor, codebook_norm: torch.Tensor, divisor: O
         hard = F.gumbel_softmax(logits, tau=1.0, hard=True, dim=1)
         idx[i] = torch.argmax(hard, dim=1).to(torch.int32)
     return idx
+
+
+def dropout_keep_mask(num_codes: int, p: float, device) -> torch.Tensor:
+    """The keep mask of ``pq_dropout``: ``uniform(0, 1) > p`` per code (model/dino_new_vq.py:388-389).  The reference
+    draws with ``torch.cuda.FloatTensor(K).uniform_()``, i.e. K floats from the default generator of the current CUDA
+    device; an fp32 ``uniform_`` on a fresh K-element tensor of the activations' device consumes that generator in the
+    same way.  Tests replace this function to inject the reference's draws."""
+    return torch.empty(num_codes, dtype=torch.float32, device=device).uniform_() > p
+
+
+def dropout_assign(z_norm: torch.Tensor, codebook_norm: torch.Tensor, p: float, temperature: float
+                   ) -> Tuple[torch.Tensor, List[torch.Tensor], List[torch.Tensor]]:
+    """Assignment under the ``pq_dropout`` research flag (model/dino_new_vq.py:387-399,599-609; dino_pqgo.py:640-657).
+
+    z_norm: (n, M, d) normalised rows (may carry a graph);  codebook_norm: (M, K, d) (may carry a graph).
+    Per subspace, in subspace order like the reference's loop, one keep mask is drawn, the reference's distance is
+    taken to the kept codes only, and ``argmin`` / ``softmax(-distance / temperature)`` follow.  Returns
+    (int32 (M, n) indices -- positions in the KEPT list, which is how the reference then addresses the full
+    codebook --, [prob_i (n, kept_i)], [keep_i (K,) bool]).  The width of the soft assignment differs per subspace,
+    so this stays a host loop over library matmuls."""
+    n, M, _ = z_norm.shape
+    K = codebook_norm.shape[1]
+    idx = torch.empty((M, n), dtype=torch.int32, device=z_norm.device)
+    probs, keeps = [], []
+    for i in range(M):
+        keep = dropout_keep_mask(K, p, z_norm.device)
+        zi, ci = z_norm[:, i, :], codebook_norm[i][keep]
+        distance = (torch.sum(zi ** 2, dim=1, keepdim=True) + torch.sum(ci ** 2, dim=1)
+                    - 2 * torch.matmul(zi, ci.t()))
+        idx[i] = torch.argmin(distance.detach(), dim=1).to(torch.int32)
+        probs.append(F.softmax(-distance / temperature, dim=1))
+        keeps.append(keep)
+    return idx, probs, keeps

@@ -10,9 +10,11 @@ return tuples.  One ``Codebook`` class serves the three files; ``variant`` selec
   "new_vq"    (z, i, it)            q, out, prob (n,K)  (+ jsd, entropy)    cb + beta*commit         raw z
   "pqgo_cls"  (z)                   q, out, prob (b,h,w,K), idx (n,)        cb + beta*commit         z_norm
 
-``use_weighted_sum`` runs as host PyTorch on the kernel's soft assignment (``_weighted_sum``).  ``pq_dropout`` (the
-reference masks the codebook with ``torch.cuda.FloatTensor`` noise and then indexes the FULL codebook with indices
-into the masked one), and the k-means init are not offered; the inline classes' ``use_gumbel`` is only admitted next to the weighted sum,
+``use_weighted_sum`` runs as host PyTorch on the kernel's soft assignment (``_weighted_sum``).  ``pq_dropout`` (pqgo /
+new_vq; the reference masks the codebook with ``torch.cuda.FloatTensor`` noise on every call and then indexes the FULL
+codebook with indices into the masked one) draws and assigns in host PyTorch (``_host_paths.dropout_assign``: the soft
+assignment has a different width per subspace) and feeds the drawn indices to the gather / scatter-add / EMA kernels.
+The k-means init is not offered; the inline classes' ``use_gumbel`` is only admitted next to the weighted sum,
 whose branch takes precedence (dino_pqgo.py:502-503,658-663), exactly as in the reference.
 """
 from __future__ import annotations
@@ -22,6 +24,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from . import _host_paths as hp
 from . import _pq_core as core
 from . import ops
 from ._host_paths import draw_restart
@@ -74,8 +77,9 @@ class Codebook(nn.Module):
                  use_gumbel: bool = False, need_initialized: str = "none", pq_dropout: float = 0.0, jsd_ts: float = 1.0,
                  num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
-        _unsupported(pq_dropout=pq_dropout > 0.0,
+        _unsupported(pq_dropout=pq_dropout > 0.0 and variant == "pqgo_cls",       # dino_pqgo_cls.py has no such flag
                      use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand"))
+        self.pq_dropout = pq_dropout
         self.use_weighted_sum = use_weighted_sum
         if use_weighted_sum:
             assert normalize == "none", "Weight_sum should be unnormalized"          # dino_pqgo.py:499-500
@@ -161,10 +165,15 @@ def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bo
     need_soft_stats = variant == "new_vq"
     grad_path = core._wants_grad(z, codebook, norm_a, norm_b)
     make_prob = want_prob or (need_soft_stats and grad_path) or q0.use_weighted_sum
-    idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, codebook, mode, norm_a, norm_b, want_prob=make_prob,
-                                                          temperature=q0.jsd_ts)   # :646-665 (raw embedding gathered)
-    if q0.use_weighted_sum:                                                          # dino_pqgo.py:661-662,691
-        out, mse_commit, mse_cb = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
+    drop = None
+    if q0.pq_dropout > 0.0:                                                          # dino_pqgo.py:641-644, every call
+        idx, out, mse_commit, mse_cb, drop = _dropout_quantize(z, cbn, codebook, mode, norm_a, norm_b, M, q0)
+        prob = None
+    else:
+        idx, out, mse_commit, mse_cb, prob = core.pq_quantize(z, cbn, codebook, mode, norm_a, norm_b, want_prob=make_prob,
+                                                              temperature=q0.jsd_ts)   # :646-665 (raw embedding gathered)
+        if q0.use_weighted_sum:                                                      # dino_pqgo.py:661-662,691
+            out, mse_commit, mse_cb = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
     output: Dict[str, torch.Tensor] = {}
     if training:
         with torch.no_grad():
@@ -180,12 +189,17 @@ def _codebook_group_forward(mods: List[Codebook], z: torch.Tensor, want_prob: bo
                 for i, q in enumerate(mods):
                     q.prepare_restart(count[i], rows[:, i])
                     q.restart()
-            output["codebook-usage"] = ((K - (count == 0).sum(dim=1).float()) / K).mean()   # :681-682
+            kept = drop.kept if drop is not None else K                               # codes the argmin could see
+            output["codebook-usage"] = ((kept - (count == 0).sum(dim=1).float()) / kept).mean()   # :681-682
     book = q0.book if variant == "pqgo" else 1.0
     output["vq-loss"] = (book * mse_cb + q0.beta * mse_commit).mean()                 # :685-687
     if need_soft_stats:                                                               # dino_new_vq.py:666-668
-        output["jsd"], output["entropy"] = _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K)
+        output["jsd"], output["entropy"] = (drop.soft_stats() if drop is not None else
+                                            _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K))
     idx64 = idx.long()
+    if drop is not None:
+        probs = [p.view(B, h, w, -1) for p in drop.probs] if want_prob else [None] * M
+        return out, output, probs, [idx64[i].view(B, h, w) for i in range(M)]
     probs = [prob.view(B, h, w, M, K)[:, :, :, i, :] for i in range(M)] if (prob is not None and want_prob) else [None] * M
     return out, output, probs, [idx64[i].view(B, h, w) for i in range(M)]
 
@@ -205,6 +219,37 @@ def _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M: int, K: int):
     return zq.reshape(B, h, w, D).permute(0, 3, 1, 2).contiguous(), commit, cb_loss
 
 
+class _Dropped:
+    """What one ``pq_dropout`` assignment leaves behind: per-subspace soft assignments of different widths, the keep
+    masks, and the number of kept codes as an [M] tensor."""
+
+    def __init__(self, probs: List[torch.Tensor], keeps: List[torch.Tensor]):
+        self.probs, self.keeps = probs, keeps
+        self.kept = torch.stack([k.sum() for k in keeps]).float()
+
+    def soft_stats(self):
+        """jsd / entropy per subspace on the kept codes, then the wrapper's mean over subspaces (dino_new_vq.py:447-450)."""
+        jsd, ent = JSDLoss(), EntropyLoss()
+        halves = [torch.chunk(p, chunks=2, dim=0) for p in self.probs]
+        return (torch.stack([jsd(a, b) for a, b in halves]).mean(), torch.stack([ent(a, b) for a, b in halves]).mean())
+
+
+def _dropout_quantize(z, cbn, gather_src, mode, norm_a, norm_b, M: int, q0):
+    """The ``pq_dropout`` branch shared by Codebook and EMACodebook: draw + assign in host PyTorch, then the gather /
+    loss kernel on the drawn indices (which address the FULL ``gather_src``, as in the reference).  Returns
+    (idx int32 [M, n], z_q NCHW, mse_commit [M], mse_codebook [M], _Dropped)."""
+    B, D, h, w = z.shape
+    zr = core._normalize_rows(core._rows(z.float(), M), mode, norm_a, norm_b)         # (n, M, d), differentiable
+    idx_d, probs, keeps = hp.dropout_assign(zr, cbn, q0.pq_dropout, q0.jsd_ts)
+    idx, out, mse_commit, mse_cb, _ = core.pq_quantize(z, cbn, gather_src, mode, norm_a, norm_b, want_prob=False, idx=idx_d)
+    if q0.use_weighted_sum:                                                          # soft sum over the kept codes only
+        zq = torch.stack([p @ cbn[i][k] for i, (p, k) in enumerate(zip(probs, keeps))], dim=1)      # (n, M, d)
+        mse_commit = ((zr - zq.detach()) ** 2).mean(dim=(0, 2))
+        mse_cb = ((zq - zr.detach()) ** 2).mean(dim=(0, 2))
+        out = zq.reshape(B, h, w, D).permute(0, 3, 1, 2).contiguous()
+    return idx, out, mse_commit, mse_cb, _Dropped(probs, keeps)
+
+
 def _soft_stats(z, cbn, mode, norm_a, norm_b, jsd_ts, prob, M, K):
     """jsd / entropy of the soft assignment (dino_new_vq.py:447-450): from the materialised differentiable tensor
     when there is one, else by the fused kernel that never writes the N x K*M probabilities."""
@@ -221,8 +266,8 @@ class EMACodebook(nn.Module):
                  use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "none",
                  pq_dropout: float = 0.0, jsd_ts: float = 1.0, **_ignored):
         super().__init__()
-        _unsupported(pq_dropout=pq_dropout > 0.0,
-                     need_initialized=need_initialized not in ("none", "rand", "uni", "normal"))
+        _unsupported(need_initialized=need_initialized not in ("none", "rand", "uni", "normal"))
+        self.pq_dropout = pq_dropout
         self.use_weighted_sum = use_weighted_sum
         if use_weighted_sum:
             assert normalize == "none", "Weight_sum should be unnormalized"          # dino_new_vq.py:276-277
@@ -282,11 +327,16 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
         cbn = core.normalize_codebook(weight, mode, ema_style=True)
         src = weight.clone()                             # raw codebook gathered, as it is BEFORE this step's update (:403)
     grad_path = core._wants_grad(z, norm_a, norm_b)
-    idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b,
-                                                     want_prob=want_prob or grad_path or q0.use_weighted_sum,
-                                                     temperature=q0.jsd_ts)
-    if q0.use_weighted_sum:                                                          # dino_new_vq.py:400-401,438
-        out, mse_commit, _ = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
+    drop = None
+    if q0.pq_dropout > 0.0:                                                          # dino_new_vq.py:388-391, every call
+        idx, out, mse_commit, _, drop = _dropout_quantize(z, cbn, src, mode, norm_a, norm_b, M, q0)
+        prob = torch.cat(drop.probs, dim=-1)                                         # (n, sum of kept codes)
+    else:
+        idx, out, mse_commit, _, prob = core.pq_quantize(z, cbn, src, mode, norm_a, norm_b,
+                                                         want_prob=want_prob or grad_path or q0.use_weighted_sum,
+                                                         temperature=q0.jsd_ts)
+        if q0.use_weighted_sum:                                                      # dino_new_vq.py:400-401,438
+            out, mse_commit, _ = _weighted_sum(z, prob, cbn, mode, norm_a, norm_b, M, K)
     output: Dict[str, torch.Tensor] = {}
     if training:
         with torch.no_grad():
@@ -303,10 +353,12 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
                 rows = z.detach().float().permute(0, 2, 3, 1).reshape(B * h * w, M, d)
                 for i, q in enumerate(mods):
                     q.prepare_restart(packed[i, :, d], rows[:, i])
-            output["codebook-usage"] = ((K - unused.float()) / K).mean()            # :431-432
+            kept = drop.kept if drop is not None else K
+            output["codebook-usage"] = ((kept - unused.float()) / kept).mean()      # :431-432
     output["vq-loss"] = q0.beta * mse_commit.mean()                                 # :435-436
     output["codebook-sum"] = torch.sum(torch.abs(torch.stack([q.codebook.weight for q in mods]))) / M
-    output["jsd"], output["entropy"] = _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K)   # :447-450
+    output["jsd"], output["entropy"] = (drop.soft_stats() if drop is not None else
+                                        _soft_stats(z, cbn, mode, norm_a, norm_b, q0.jsd_ts, prob, M, K))   # :447-450
     return out, output, (prob if want_prob else None)
 
 
@@ -376,7 +428,7 @@ class NewVQProductQuantizerWrapper(_WrapperBase):
             return z_q, outputs, None
         B, D, h, w = z.shape
         K = qs[0].num_codebook_vectors
-        return z_q, outputs, torch.cat([p.reshape(B * h * w, K) for p in probs], dim=-1)
+        return z_q, outputs, torch.cat([p.reshape(B * h * w, -1) for p in probs], dim=-1)   # K columns each (fewer under pq_dropout)
 
 
 class PQGOClsProductQuantizerWrapper(PQGOProductQuantizerWrapper):

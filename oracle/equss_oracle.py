@@ -265,15 +265,22 @@ def jsd_loss(p: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
 def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch.Tensor, *, normalize: str,
                        beta: float = 0.25, jsd_ts: float = 1.0, training: bool = True,
                        z_mean: Optional[torch.Tensor] = None, z_log_var: Optional[torch.Tensor] = None,
-                       allreduce=None, use_weighted_sum: bool = False
+                       allreduce=None, use_weighted_sum: bool = False, dropout_keep: Optional[torch.Tensor] = None
                        ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
-    """dino_new_vq.EMACodebook.forward (model/dino_new_vq.py:327-459), top-1 path without pq_dropout / init:
+    """dino_new_vq.EMACodebook.forward (model/dino_new_vq.py:327-459), top-1 path without init:
     NCHW in, the quantised rows come from the RAW codebook as it was before this step's update (:403),
-    EMA sums of raw z (:411), softmax(-d / jsd_ts), JSD / entropy between the two batch halves (:447-450)."""
+    EMA sums of raw z (:411), softmax(-d / jsd_ts), JSD / entropy between the two batch halves (:447-450).
+    ``dropout_keep``: the boolean keep mask of pq_dropout (:388-391, drawn in training AND evaluation): distances,
+    argmin and soft assignment run over the kept codes only, while the indices -- positions in the KEPT list --
+    still address the full codebook in the gather (:403), the one-hot (:408) and the EMA update; the usage ratio
+    is taken over the kept codes (:431-432)."""
     b, d, h, w = z_nchw.shape
     K = state.weight.shape[0]
     z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)                  # :333-334
     z_norm, cb_norm = normalize_pair(z_flat, state.weight, normalize, z_mean, z_log_var)   # :366-387
+    if dropout_keep is not None:
+        cb_norm = cb_norm[dropout_keep]                                           # :390-391
+    kept = cb_norm.shape[0]
     dist = sq_distance(z_norm, cb_norm)
     idx = torch.argmin(dist, dim=1)
     prob = F.softmax(-dist / jsd_ts, dim=1)                                       # :398
@@ -289,7 +296,7 @@ def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch
             count, total = allreduce(count), allreduce(total)
         exact_count += count                                                      # :415
         state.update(count, total)                                                # :422
-        out["codebook-usage"] = (K - int((count == 0).sum())) / K                 # :431-432
+        out["codebook-usage"] = (kept - int((count == 0).sum())) / kept           # :431-432
     commitment = F.mse_loss(z_norm, q)
     out["vq-loss"] = beta * commitment                                            # :435-436
     out["codebook-sum"] = torch.sum(torch.abs(state.weight))                      # :445 (after the update)
@@ -303,16 +310,21 @@ def new_vq_ema_forward(z_nchw: torch.Tensor, state: EmaState, exact_count: torch
 def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_count: torch.Tensor, *,
                             variant: str, normalize: str, beta: float = 0.25, book: float = 1.0,
                             jsd_ts: float = 1.0, training: bool = True, z_mean: Optional[torch.Tensor] = None,
-                            z_log_var: Optional[torch.Tensor] = None, use_weighted_sum: bool = False
+                            z_log_var: Optional[torch.Tensor] = None, use_weighted_sum: bool = False,
+                            dropout_keep: Optional[torch.Tensor] = None
                             ) -> Tuple[torch.Tensor, Dict, torch.Tensor, torch.Tensor]:
     """The learned-codebook ``Codebook.forward`` of dino_new_vq.py:537-671 (variant "new_vq"), dino_pqgo.py:579-705
     ("pqgo") and dino_pqgo_cls.py:303-405 ("pqgo_cls"): raw embedding gathered, counts in training only,
     ``vq-loss`` = [book *] codebook + beta * commitment; new_vq adds jsd / entropy.  prob is returned flat (n, K);
-    the callers reshape it (pqgo / pqgo_cls: (b, h, w, K))."""
+    the callers reshape it (pqgo / pqgo_cls: (b, h, w, K)).  ``dropout_keep``: pq_dropout's keep mask
+    (dino_new_vq.py:600-603, dino_pqgo.py:641-644), semantics as in new_vq_ema_forward."""
     b, d, h, w = z_nchw.shape
     K = codebook.shape[0]
     z_flat = z_nchw.permute(0, 2, 3, 1).contiguous().view(-1, d)
     z_norm, cb_norm = normalize_pair(z_flat, codebook, normalize, z_mean, z_log_var)
+    if dropout_keep is not None:
+        cb_norm = cb_norm[dropout_keep]
+    kept = cb_norm.shape[0]
     dist = sq_distance(z_norm, cb_norm)
     idx = torch.argmin(dist, dim=1)
     prob = F.softmax(-dist / jsd_ts, dim=1)
@@ -321,7 +333,7 @@ def inline_codebook_forward(z_nchw: torch.Tensor, codebook: torch.Tensor, exact_
     if training:
         count = F.one_hot(idx, K).to(z_flat.dtype).sum(dim=0)
         exact_count += count
-        out["codebook-usage"] = (K - int((count == 0).sum())) / K
+        out["codebook-usage"] = (kept - int((count == 0).sum())) / kept
     cb_loss, commit = F.mse_loss(q, z_norm), F.mse_loss(z_norm, q)
     out["vq-loss"] = (book if variant == "pqgo" else 1.0) * cb_loss + beta * commit
     if variant == "new_vq":

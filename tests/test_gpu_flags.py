@@ -187,9 +187,9 @@ def test_inline_codebook_weighted_sum_matches_reference(golden_dir, variant):
 def test_unreproducible_flags_still_fail_loudly():
     from equss_b200.codebooks import Codebook, EMACodebook
     with pytest.raises(NotImplementedError):
-        EMACodebook(8, 4, pq_dropout=0.1)
+        Codebook(8, 4, pq_dropout=0.1, variant="pqgo_cls")           # dino_pqgo_cls.py has no pq_dropout
     with pytest.raises(NotImplementedError):
-        Codebook(8, 4, pq_dropout=0.1)
+        Codebook(8, 4, use_split=True)
     with pytest.raises(AssertionError):
         EMACodebook(8, 4, normalize="l2", use_weighted_sum=True)     # dino_new_vq.py:276-277
     with pytest.raises(AssertionError):

@@ -59,3 +59,210 @@ def test_weighted_sum_matches_reference_values_and_gradients(golden_dir):
         ((out * torch.from_numpy(g["go"])).sum() + loss).backward()
         np.testing.assert_allclose(z.grad.numpy(), g["grad_z"], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(w.grad.numpy(), g["grad_w"], rtol=1e-4, atol=1e-6)
+
+
+def _fixed_keep(draws, p):
+    calls = [0]
+
+    def fake(num_codes, prob, device):
+        u = draws[calls[0]]
+        calls[0] += 1
+        assert u.shape == (num_codes,) and prob == p
+        return u.to(device) > p
+    return fake, calls
+
+
+def test_pq_dropout_assignment_follows_the_reference(golden_dir, monkeypatch):
+    """``pq_dropout`` (dino_new_vq.EMACodebook, fixture of oracle/make_golden_dropout.py): with the reference's uniform
+    draws injected, the host assignment yields the reference's indices (positions in the kept list), its soft
+    assignment (one column per kept code), its jsd / entropy and its usage ratio; gathering the FULL raw codebook at
+    those indices gives the reference's quantised output."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _host_paths as hp
+    from equss_b200 import _pq_core as core
+    from equss_b200.codebooks import _Dropped
+    g = np.load(os.path.join(golden_dir, "pq_flag_newvq_ema_dropout.npz"))
+    M, K, p, ts = int(g["M"]), int(g["K"]), float(g["pq_dropout"]), float(g["jsd_ts"])
+    weight = torch.from_numpy(g["weight0"])
+    for s in range(3):
+        z = torch.from_numpy(g[f"z{s}"])
+        B, D, h, w = z.shape
+        d = D // M
+        fake, calls = _fixed_keep(list(torch.from_numpy(g[f"u{s}"])), p)
+        monkeypatch.setattr(hp, "dropout_keep_mask", fake)
+        zr = core._normalize_rows(core._rows(z, M), "l2", None, None)
+        idx, probs, keeps = hp.dropout_assign(zr, F.normalize(weight, dim=2), p, ts)
+        assert calls[0] == M and idx.dtype == torch.int32
+        assert np.array_equal(idx.numpy(), g[f"idx{s}"])
+        assert [int(k.sum()) for k in keeps] == [int(c) for c in (g[f"u{s}"] > p).sum(axis=1)]
+        np.testing.assert_allclose(torch.cat(probs, dim=-1).numpy(), g[f"prob{s}"], rtol=1e-5, atol=1e-7)
+        drop = _Dropped(probs, keeps)
+        jsd, ent = drop.soft_stats()
+        assert abs(float(jsd) - float(g[f"out{s}/jsd"])) <= 1e-5 * abs(float(g[f"out{s}/jsd"])) + 1e-8
+        assert abs(float(ent) - float(g[f"out{s}/entropy"])) <= 1e-5 * abs(float(g[f"out{s}/entropy"])) + 1e-8
+        q = torch.stack([weight[i][idx[i].long()] for i in range(M)], dim=1)          # full raw codebook, kept-list indices
+        out = (zr + (q - zr)).reshape(B, h, w, D).permute(0, 3, 1, 2)
+        np.testing.assert_allclose(out.numpy(), g[f"zq{s}"], rtol=1e-5, atol=1e-6)
+        commit = ((zr - q) ** 2).mean(dim=(0, 2)).mean()
+        assert abs(0.25 * float(commit) - float(g[f"out{s}/vq-loss"])) <= 1e-5 * float(g[f"out{s}/vq-loss"])
+        if s < 2:
+            count = torch.stack([torch.bincount(idx[i].long(), minlength=K) for i in range(M)])
+            usage = ((drop.kept - (count == 0).sum(dim=1).float()) / drop.kept).mean()
+            assert abs(float(usage) - float(g[f"out{s}/codebook-usage"])) <= 1e-6
+            weight = torch.from_numpy(g[f"weight_after{s}"])                          # the EMA update itself is the kernel's
+
+
+def test_pq_dropout_gradients_through_the_host_assignment(golden_dir, monkeypatch):
+    """Learned Codebook of dino_new_vq / dino_pqgo with pq_dropout (and with the weighted sum): the host assignment's
+    soft assignment carries the reference's gradients to z and to the codebook; the straight-through gather and the two
+    losses (the kernels' part on the device) are written out in torch here."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _host_paths as hp
+    from equss_b200 import _pq_core as core
+    from equss_b200.codebooks import _Dropped
+    for name in ("new_vq", "pqgo", "new_vq_weighted"):
+        g = np.load(os.path.join(golden_dir, f"pq_flag_inline_{name}_dropout.npz"))
+        K, p, ts, mode, variant = int(g["K"]), float(g["pq_dropout"]), float(g["jsd_ts"]), str(g["mode"]), str(g["variant"])
+        weighted = bool(g["weighted"])
+        z = torch.from_numpy(g["z"]).requires_grad_(True)
+        wt = torch.from_numpy(g["weight"]).clone().requires_grad_(True)
+        B, d, h, w = z.shape
+        fake, calls = _fixed_keep([torch.from_numpy(g["u"])], p)
+        monkeypatch.setattr(hp, "dropout_keep_mask", fake)
+        zr = core._normalize_rows(core._rows(z, 1), mode, None, None)
+        cbn = core.normalize_codebook(wt.unsqueeze(0), mode, ema_style=True)
+        idx, probs, keeps = hp.dropout_assign(zr, cbn, p, ts)
+        assert calls[0] == 1 and np.array_equal(idx[0].numpy(), g["idx"])
+        np.testing.assert_allclose(probs[0].detach().numpy(), g["prob"].reshape(B * h * w, -1), rtol=1e-5, atol=1e-7)
+        zn = zr[:, 0]
+        q = probs[0] @ cbn[0][keeps[0]] if weighted else wt[idx[0].long()]
+        cb_loss, commit = ((q - zn.detach()) ** 2).mean(), ((zn - q.detach()) ** 2).mean()
+        out = q if weighted else zn + (q - zn).detach()
+        out = out.reshape(B, h, w, d).permute(0, 3, 1, 2)
+        np.testing.assert_allclose(out.detach().numpy(), g["zq"], rtol=1e-5, atol=1e-6)
+        vq_loss = cb_loss + 0.25 * commit
+        assert abs(float(vq_loss) - float(g["out/vq-loss"])) <= 1e-5 * abs(float(g["out/vq-loss"]))
+        total = (out * torch.from_numpy(g["go"])).sum() + vq_loss + (probs[0] * torch.from_numpy(g["gp"])).sum()
+        if variant == "new_vq":
+            jsd, ent = _Dropped(probs, keeps).soft_stats()
+            assert abs(float(jsd) - float(g["out/jsd"])) <= 1e-5 * abs(float(g["out/jsd"])) + 1e-8
+            total = total + 0.3 * jsd + 0.2 * ent
+        total.backward()
+        np.testing.assert_allclose(z.grad.numpy(), g["grad_z"], rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(wt.grad.numpy(), g["grad_w"], rtol=2e-4, atol=2e-6)
+
+
+def _emulate_kernels(monkeypatch):
+    """Torch stand-ins for the four kernel entry points the pq_dropout branch reaches (gather + losses with the
+    straight-through estimator, scatter-add, EMA update), so that the MODULE plumbing around the host assignment can
+    run without a device.  The kernels themselves are pinned by the GPU tests."""
+    from equss_b200 import _pq_core as core
+    from equss_b200 import ops
+
+    def pq_quantize(z, codebook_norm, gather_src, normalize, norm_a=None, norm_b=None, *, want_prob=True,
+                    temperature=1.0, algo=0, cnorm2=None, idx=None):
+        assert idx is not None and not want_prob          # the dropout branch always brings its own indices
+        M = gather_src.shape[0]
+        zr = core._normalize_rows(core._rows(z.float(), M), normalize, norm_a, norm_b)
+        q = torch.stack([gather_src[i][idx[i].long()] for i in range(M)], dim=1)
+        commit = ((zr - q.detach()) ** 2).mean(dim=(0, 2))
+        cb = ((q - zr.detach()) ** 2).mean(dim=(0, 2))
+        out = zr + (q - zr).detach()
+        B, D, h, w = z.shape
+        return idx, out.reshape(B, h, w, D).permute(0, 3, 1, 2).contiguous(), commit, cb, None
+
+    def pq_accumulate(z, idx, K, **kw):
+        M = idx.shape[0]
+        zr = core._rows(z, M)
+        packed = torch.zeros(M, K, zr.shape[2] + 1)
+        for i in range(M):
+            packed[i, :, :-1].index_add_(0, idx[i].long(), zr[:, i])
+            packed[i, :, -1] = torch.bincount(idx[i].long(), minlength=K).float()
+        return packed
+
+    def ema_update(packed, decay, eps, vqc, wavg, wnew, exact):
+        count, total = packed[:, :, -1], packed[:, :, :-1]
+        K = count.shape[1]
+        exact += count
+        vqc.mul_(decay).add_(count, alpha=1 - decay)
+        wavg.mul_(decay).add_(total, alpha=1 - decay)
+        n = vqc.sum(dim=1, keepdim=True)
+        wnew.copy_(wavg / ((vqc + eps) / (n + K * eps) * n).unsqueeze(-1))
+        return (count == 0).sum(dim=1)
+
+    monkeypatch.setattr(core, "pq_quantize", pq_quantize)
+    monkeypatch.setattr(ops, "pq_accumulate", pq_accumulate)
+    monkeypatch.setattr(ops, "ema_update", ema_update)
+
+
+def test_pq_dropout_module_plumbing_with_emulated_kernels(golden_dir, monkeypatch):
+    """NewVQProductQuantizerWrapper(EMACodebook, pq_dropout) and the learned Codebook variants end to end on CPU with
+    the kernels replaced by torch stand-ins: return tuples, ragged soft-assignment widths, usage over the kept codes,
+    jsd / entropy, the EMA trajectory and the gradients equal the unmodified reference's."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _host_paths as hp
+    from equss_b200.codebooks import (Codebook, EMACodebook, NewVQProductQuantizerWrapper, PQGOProductQuantizerWrapper)
+    _emulate_kernels(monkeypatch)
+    g = np.load(os.path.join(golden_dir, "pq_flag_newvq_ema_dropout.npz"))
+    M, K, p, ts = int(g["M"]), int(g["K"]), float(g["pq_dropout"]), float(g["jsd_ts"])
+    D = g["z0"].shape[1]
+    pq = NewVQProductQuantizerWrapper(M, K, D, beta=0.25, normalize="l2", jsd_ts=ts, pq_dropout=p, quantizer_cls=EMACodebook)
+    with torch.no_grad():
+        for i, q in enumerate(pq.quantizers):
+            q.codebook.weight.copy_(torch.from_numpy(g["weight0"][i])); q.codebook.weight_avg.copy_(q.codebook.weight)
+    pq.train()
+    for s in range(3):
+        if s == 2:
+            pq.eval()
+        fake, calls = _fixed_keep(list(torch.from_numpy(g[f"u{s}"])), p)
+        monkeypatch.setattr(hp, "dropout_keep_mask", fake)
+        with torch.no_grad():
+            zq, out, prob = pq(torch.from_numpy(g[f"z{s}"]), s)
+        assert calls[0] == M                                   # drawn in evaluation too, like the reference
+        np.testing.assert_allclose(zq.numpy(), g[f"zq{s}"], rtol=1e-5, atol=1e-6)
+        assert prob.shape == g[f"prob{s}"].shape
+        np.testing.assert_allclose(prob.numpy(), g[f"prob{s}"], rtol=1e-5, atol=1e-7)
+        keys = {k.split("/", 1)[1] for k in g.files if k.startswith(f"out{s}/")}
+        assert set(out.keys()) == keys
+        for k in keys:
+            assert abs(float(out[k]) - float(g[f"out{s}/{k}"])) <= 1e-5 * abs(float(g[f"out{s}/{k}"])) + 1e-7, (s, k)
+        for name, get in (("weight", lambda q: q.codebook.weight), ("weight_avg", lambda q: q.codebook.weight_avg),
+                          ("vq_count", lambda q: q.codebook.vq_count), ("exact", lambda q: q.vq_count)):
+            got = torch.stack([get(q) for q in pq.quantizers]).numpy()
+            np.testing.assert_allclose(got, g[f"{name}_after{s}"], rtol=1e-5, atol=1e-6)
+
+    for name in ("new_vq", "pqgo", "new_vq_weighted"):
+        g = np.load(os.path.join(golden_dir, f"pq_flag_inline_{name}_dropout.npz"))
+        K, p, ts, mode, variant = int(g["K"]), float(g["pq_dropout"]), float(g["jsd_ts"]), str(g["mode"]), str(g["variant"])
+        z = torch.from_numpy(g["z"]).requires_grad_(True)
+        B, d, h, w = z.shape
+        cb = Codebook(K, d, beta=0.25, normalize=mode, jsd_ts=ts, pq_dropout=p, use_weighted_sum=bool(g["weighted"]), variant=variant)
+        with torch.no_grad():
+            cb.embedding.weight.copy_(torch.from_numpy(g["weight"]))
+        cb.train()
+        fake, calls = _fixed_keep([torch.from_numpy(g["u"])], p)
+        monkeypatch.setattr(hp, "dropout_keep_mask", fake)
+        res = cb(z, 0, 0) if variant == "new_vq" else cb(z, torch.zeros_like(z))
+        zq, out, prob = res[0], res[1], res[2]
+        assert tuple(prob.shape) == tuple(g["prob"].shape)     # (n, kept) for new_vq, (b, h, w, kept) for pqgo
+        np.testing.assert_allclose(zq.detach().numpy(), g["zq"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(prob.detach().numpy(), g["prob"], rtol=1e-5, atol=1e-7)
+        if variant == "pqgo":
+            assert np.array_equal(res[3].numpy(), g["ridx"])
+        for k in {k.split("/", 1)[1] for k in g.files if k.startswith("out/")}:
+            assert abs(float(out[k]) - float(g[f"out/{k}"])) <= 1e-5 * abs(float(g[f"out/{k}"])) + 1e-7, (name, k)
+        np.testing.assert_allclose(cb.vq_count.numpy(), g["exact_after"])
+        total = (zq * torch.from_numpy(g["go"])).sum() + out["vq-loss"] + (prob.reshape(B * h * w, -1) * torch.from_numpy(g["gp"])).sum()
+        if variant == "new_vq":
+            total = total + 0.3 * out["jsd"] + 0.2 * out["entropy"]
+        total.backward()
+        np.testing.assert_allclose(z.grad.numpy(), g["grad_z"], rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(cb.embedding.weight.grad.numpy(), g["grad_w"], rtol=2e-4, atol=2e-6)
+
+    # the wrapper of dino_pqgo concatenates the ragged per-subspace soft assignments on the last axis
+    fake, calls = _fixed_keep([torch.rand(8) for _ in range(2)], 0.25)
+    monkeypatch.setattr(hp, "dropout_keep_mask", fake)
+    wrap = PQGOProductQuantizerWrapper(2, 8, 8, normalize="l2", pq_dropout=0.25)
+    zq, (z_split, zqs, idxs), out, prob = wrap(torch.randn(2, 8, 3, 3), torch.zeros(2, 8, 3, 3))
+    assert calls[0] == 2 and zq.shape == (2, 8, 3, 3) and prob.shape[:3] == (2, 3, 3) and prob.shape[3] <= 16
+    assert idxs[0].shape == (2, 3, 3) and "codebook-usage" in out

@@ -350,3 +350,40 @@ def test_research_flags_inline(golden_dir):
                                                  training=True, use_weighted_sum=True)
         np.testing.assert_allclose(q.numpy(), g["zq"], rtol=1e-6, atol=1e-8)
         assert float(out["vq-loss"]) == pytest.approx(float(g["out/vq-loss"]), rel=1e-5)
+
+
+def test_research_flag_pq_dropout(golden_dir):
+    """pq_dropout of dino_new_vq / dino_pqgo (fixtures: oracle/make_golden_dropout.py, the unmodified reference with
+    ``torch.cuda.FloatTensor`` replaced by the stored uniform draws)."""
+    g = _load(golden_dir, "pq_flag_newvq_ema_dropout.npz")
+    M, K, ts, p = int(g["M"]), int(g["K"]), float(g["jsd_ts"]), float(g["pq_dropout"])
+    w0 = torch.from_numpy(g["weight0"])
+    states = [O.EmaState(w0[i]) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    for s in range(3):
+        z = torch.from_numpy(g[f"z{s}"])
+        keep = torch.from_numpy(g[f"u{s}"]) > p
+        d = z.shape[1] // M
+        res = [O.new_vq_ema_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize="l2", beta=0.25, jsd_ts=ts,
+                                    training=s < 2, dropout_keep=keep[i]) for i in range(M)]
+        assert np.array_equal(torch.stack([r[3] for r in res]).numpy().astype(np.int32), g[f"idx{s}"])
+        assert all(int(r[3].max()) < int(keep[i].sum()) for i, r in enumerate(res))       # positions in the kept list
+        np.testing.assert_allclose(torch.cat([r[0] for r in res], dim=1).numpy(), g[f"zq{s}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(torch.cat([r[2] for r in res], dim=-1).numpy(), g[f"prob{s}"], rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(torch.stack([st.weight for st in states]).numpy(), g[f"weight_after{s}"], rtol=1e-5, atol=1e-7)
+        for k in ("vq-loss", "jsd", "entropy") + (("codebook-usage",) if s < 2 else ()):
+            got = sum(float(r[1][k]) for r in res) / M
+            assert got == pytest.approx(float(g[f"out{s}/{k}"]), rel=1e-5, abs=1e-8), (s, k)
+    for name in ("new_vq", "pqgo", "new_vq_weighted"):
+        g = _load(golden_dir, f"pq_flag_inline_{name}_dropout.npz")
+        K = int(g["K"])
+        keep = torch.from_numpy(g["u"]) > float(g["pq_dropout"])
+        q, out, prob, idx = O.inline_codebook_forward(torch.from_numpy(g["z"]), torch.from_numpy(g["weight"]), torch.zeros(K),
+                                                      variant=str(g["variant"]), normalize=str(g["mode"]), beta=0.25,
+                                                      jsd_ts=float(g["jsd_ts"]), training=True,
+                                                      use_weighted_sum=bool(g["weighted"]), dropout_keep=keep)
+        assert np.array_equal(idx.numpy().astype(np.int32), g["idx"]) and prob.shape[1] == int(keep.sum())
+        np.testing.assert_allclose(q.numpy(), g["zq"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(prob.numpy(), g["prob"].reshape(prob.shape), rtol=1e-6, atol=1e-8)
+        assert float(out["vq-loss"]) == pytest.approx(float(g["out/vq-loss"]), rel=1e-6)
+        assert float(out["codebook-usage"]) == pytest.approx(float(g["out/codebook-usage"]), rel=1e-6)
