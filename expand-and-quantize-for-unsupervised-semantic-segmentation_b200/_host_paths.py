@@ -14,7 +14,7 @@ from typing import List, Optional, Tuple, Union
 import torch
 import torch.nn.functional as F
 
-__all__ = ["draw_restart", "split_codes", "gumbel_indices", "dropout_keep_mask", "dropout_assign"]
+__all__ = ["draw_restart", "split_codes", "gumbel_indices", "dropout_keep_mask", "dropout_assign", "kmeans_centroids"]
 
 
 @torch.no_grad()
@@ -114,3 +114,14 @@ def dropout_assign(z_norm: torch.Tensor, codebook_norm: torch.Tensor, p: float, 
         probs.append(F.softmax(-distance / temperature, dim=1))
         keeps.append(keep)
     return idx, probs, keeps
+
+
+@torch.no_grad()
+def kmeans_centroids(rows: torch.Tensor, num_codes: int) -> torch.Tensor:
+    """``need_initialized == "kmeans"`` (model/dino_pqgo.py:595-601, dino_new_vq.py:345-352, dino_pqgo_cls.py:317-323,
+    quantizer.py:405-412): scikit-learn k-means++ / Lloyd with ``random_state=0`` on the first training batch's rows,
+    on the host, once.  Returns the (num_codes, d) centroids as fp32 on the rows' device."""
+    from sklearn.cluster import KMeans
+    clustering = KMeans(init="k-means++", n_clusters=num_codes, random_state=0)
+    clustering.fit(rows.detach().cpu().numpy())
+    return torch.from_numpy(clustering.cluster_centers_).float().to(rows.device)

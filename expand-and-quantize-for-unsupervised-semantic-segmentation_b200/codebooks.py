@@ -14,7 +14,7 @@ return tuples.  One ``Codebook`` class serves the three files; ``variant`` selec
 new_vq; the reference masks the codebook with ``torch.cuda.FloatTensor`` noise on every call and then indexes the FULL
 codebook with indices into the masked one) draws and assigns in host PyTorch (``_host_paths.dropout_assign``: the soft
 assignment has a different width per subspace) and feeds the drawn indices to the gather / scatter-add / EMA kernels.
-The k-means init is not offered; the inline classes' ``use_gumbel`` is only admitted next to the weighted sum,
+The inline classes' ``use_gumbel`` is only admitted next to the weighted sum,
 whose branch takes precedence (dino_pqgo.py:502-503,658-663), exactly as in the reference.
 """
 from __future__ import annotations
@@ -78,7 +78,7 @@ class Codebook(nn.Module):
                  num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
         _unsupported(pq_dropout=pq_dropout > 0.0 and variant == "pqgo_cls",       # dino_pqgo_cls.py has no such flag
-                     use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand"))
+                     use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand", "kmeans"))
         self.pq_dropout = pq_dropout
         self.use_weighted_sum = use_weighted_sum
         if use_weighted_sum:
@@ -129,16 +129,18 @@ class Codebook(nn.Module):
 
 
 def _init_codebooks(mods: List[Codebook], z: torch.Tensor, d: int) -> None:
-    """First-training-call initialisation (dino_pqgo.py:589-609): "rand" draws K rows of z, "uni" / "normal" re-draw
-    the embedding with Xavier; k-means init is not offered (sklearn on the host)."""
+    """First-training-call initialisation (dino_pqgo.py:589-609): "rand" draws K rows of z, "kmeans" runs scikit-learn
+    k-means on the rows (host, once), "uni" / "normal" re-draw the embedding with Xavier."""
     zf = None
     for i, q in enumerate(mods):
+        if q.need_initialized in ("rand", "kmeans") and zf is None:
+            zf = z.detach().permute(0, 2, 3, 1).reshape(-1, z.shape[1])
         if q.need_initialized == "rand":
-            if zf is None:
-                zf = z.detach().permute(0, 2, 3, 1).reshape(-1, z.shape[1])
             q.vq_count = q.vq_count.to(z.device)
             q.prepare_restart(torch.zeros(q.num_codebook_vectors, dtype=torch.long, device=z.device), zf[:, i * d:(i + 1) * d])
             q.restart()
+        elif q.need_initialized == "kmeans":
+            q.embedding.weight.data.copy_(hp.kmeans_centroids(zf[:, i * d:(i + 1) * d], q.num_codebook_vectors))
         elif q.need_initialized == "uni":
             nn.init.xavier_uniform_(q.embedding.weight)
         elif q.need_initialized == "normal":
@@ -266,7 +268,7 @@ class EMACodebook(nn.Module):
                  use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "none",
                  pq_dropout: float = 0.0, jsd_ts: float = 1.0, **_ignored):
         super().__init__()
-        _unsupported(need_initialized=need_initialized not in ("none", "rand", "uni", "normal"))
+        _unsupported(need_initialized=need_initialized not in ("none", "rand", "uni", "normal", "kmeans"))
         self.pq_dropout = pq_dropout
         self.use_weighted_sum = use_weighted_sum
         if use_weighted_sum:
@@ -314,6 +316,9 @@ def _ema_codebook_group_forward(mods: List[EMACodebook], z: torch.Tensor, want_p
             if q.need_initialized == "rand":
                 q.prepare_restart(torch.zeros(K, dtype=torch.long, device=z.device), zf[:, i * d:(i + 1) * d])
                 q.restart()
+            elif q.need_initialized == "kmeans":                                    # :345-352
+                centroids = hp.kmeans_centroids(zf[:, i * d:(i + 1) * d], K)
+                q.codebook.weight.data.copy_(centroids); q.codebook.weight_avg.data.copy_(centroids)
             elif q.need_initialized in ("uni", "normal"):
                 init = nn.init.xavier_uniform_ if q.need_initialized == "uni" else nn.init.xavier_normal_
                 init(q.codebook.weight); init(q.codebook.weight_avg)

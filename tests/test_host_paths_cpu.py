@@ -141,7 +141,7 @@ def test_pq_dropout_gradients_through_the_host_assignment(golden_dir, monkeypatc
         out = out.reshape(B, h, w, d).permute(0, 3, 1, 2)
         np.testing.assert_allclose(out.detach().numpy(), g["zq"], rtol=1e-5, atol=1e-6)
         vq_loss = cb_loss + 0.25 * commit
-        assert abs(float(vq_loss) - float(g["out/vq-loss"])) <= 1e-5 * abs(float(g["out/vq-loss"]))
+        assert abs(float(vq_loss.detach()) - float(g["out/vq-loss"])) <= 1e-5 * abs(float(g["out/vq-loss"]))
         total = (out * torch.from_numpy(g["go"])).sum() + vq_loss + (probs[0] * torch.from_numpy(g["gp"])).sum()
         if variant == "new_vq":
             jsd, ent = _Dropped(probs, keeps).soft_stats()
@@ -266,3 +266,46 @@ def test_pq_dropout_module_plumbing_with_emulated_kernels(golden_dir, monkeypatc
     zq, (z_split, zqs, idxs), out, prob = wrap(torch.randn(2, 8, 3, 3), torch.zeros(2, 8, 3, 3))
     assert calls[0] == 2 and zq.shape == (2, 8, 3, 3) and prob.shape[:3] == (2, 3, 3) and prob.shape[3] <= 16
     assert idxs[0].shape == (2, 3, 3) and "codebook-usage" in out
+
+
+def test_kmeans_initialisation_matches_the_reference(golden_dir, monkeypatch):
+    """need_initialized="kmeans" of the inline classes (fixture: oracle/make_golden_dropout.py::kmeans_init_case): the
+    first training call replaces the codebook by scikit-learn's centroids of the batch rows (random_state=0), then the
+    step runs on them; the flag is cleared."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _host_paths as hp
+    from equss_b200.codebooks import Codebook, EMACodebook, _init_codebooks
+    g = np.load(os.path.join(golden_dir, "pq_init_kmeans.npz"))
+    K, z = int(g["K"]), torch.from_numpy(g["z"])
+    d = z.shape[1]
+    rows = z.permute(0, 2, 3, 1).reshape(-1, d)
+    np.testing.assert_allclose(hp.kmeans_centroids(rows, K).numpy(), g["centroids"], rtol=1e-5, atol=1e-6)
+    cb = Codebook(K, d, beta=0.25, normalize="l2", need_initialized="kmeans", variant="pqgo").train()
+    _init_codebooks([cb], z, d)
+    assert cb.need_initialized == "none"
+    np.testing.assert_allclose(cb.embedding.weight.detach().numpy(), g["centroids"], rtol=1e-5, atol=1e-6)
+    # in evaluation mode nothing is initialised (dino_pqgo.py:589)
+    cb2 = Codebook(K, d, normalize="l2", need_initialized="kmeans", variant="pqgo").eval()
+    assert cb2.need_initialized == "kmeans"
+    # EMACodebook: centroids into weight and weight_avg, then the step's EMA update (kernels emulated in torch)
+    _emulate_kernels(monkeypatch)
+    from equss_b200 import _pq_core as core
+    real_q = core.pq_quantize                                 # the emulation insists on external indices; give it the argmin
+
+    def quantize_top1(zz, cbn, src, mode, na=None, nb=None, *, want_prob=True, temperature=1.0, **kw):
+        zr = core._normalize_rows(core._rows(zz.float(), cbn.shape[0]), mode, na, nb)
+        dist = ((zr.unsqueeze(2) - cbn.unsqueeze(0)) ** 2).sum(-1)                    # (n, M, K)
+        idx = dist.argmin(dim=2).t().to(torch.int32).contiguous()
+        res = real_q(zz, cbn, src, mode, na, nb, want_prob=False, idx=idx)
+        prob = F.softmax(-dist / temperature, dim=2).reshape(zr.shape[0], -1) if want_prob else None
+        return res[0], res[1], res[2], res[3], prob
+    monkeypatch.setattr(core, "pq_quantize", quantize_top1)
+    ema = EMACodebook(K, d, beta=0.25, normalize="l2", need_initialized="kmeans").train()
+    with torch.no_grad():
+        zq, out, prob = ema(z, 0, 0)
+    assert ema.need_initialized == "none"
+    np.testing.assert_allclose(zq.numpy(), g["ema_zq"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ema.codebook.weight.numpy(), g["ema_weight_after"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ema.codebook.weight_avg.numpy(), g["ema_weight_avg_after"], rtol=1e-5, atol=1e-6)
+    for k in ("vq-loss", "codebook-usage", "jsd", "entropy", "codebook-sum"):
+        assert abs(float(out[k]) - float(g[f"ema_out/{k}"])) <= 1e-5 * abs(float(g[f"ema_out/{k}"])) + 1e-7, k
