@@ -78,7 +78,8 @@ class Codebook(nn.Module):
                  num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
         _unsupported(pq_dropout=pq_dropout > 0.0 and variant == "pqgo_cls",       # dino_pqgo_cls.py has no such flag
-                     use_split=use_split, need_initialized=need_initialized not in ("none", "uni", "normal", "rand", "kmeans"))
+                     need_initialized=need_initialized not in ("none", "uni", "normal", "rand", "kmeans"))
+        self.use_split = use_split       # stored and never read, as in the reference (dino_pqgo.py:510; dino_new_vq.py:640 is a comment)
         self.pq_dropout = pq_dropout
         self.use_weighted_sum = use_weighted_sum
         if use_weighted_sum:

@@ -189,7 +189,8 @@ def test_unreproducible_flags_still_fail_loudly():
     with pytest.raises(NotImplementedError):
         Codebook(8, 4, pq_dropout=0.1, variant="pqgo_cls")           # dino_pqgo_cls.py has no pq_dropout
     with pytest.raises(NotImplementedError):
-        Codebook(8, 4, use_split=True)
+        Codebook(8, 4, need_initialized="faiss")
+    assert Codebook(8, 4, use_split=True).use_split                 # accepted and unused, as in the reference
     with pytest.raises(AssertionError):
         EMACodebook(8, 4, normalize="l2", use_weighted_sum=True)     # dino_new_vq.py:276-277
     with pytest.raises(AssertionError):
