@@ -3,7 +3,8 @@
 The kernels themselves need a B200; what is covered here is the plumbing around them: pixel sharding,
 the clone-and-return contract of all_reduce_tensor, and that ONE all-reduce of the packed [M, K, d+1]
 statistics buffer reproduces the single-process statistics (counts exactly, sums up to fp32 add order),
-so every rank applies an identical EMA update."""
+so every rank applies an identical EMA update; the query sharding + all_gather of the kNN table
+(ragged shards) and the single int64 all-reduce inside UnSegMetrics.compute."""
 import os
 import socket
 import sys
@@ -71,6 +72,43 @@ def _worker(rank, world, port, ret):
         gathered = [torch.empty_like(st.weight) for _ in range(world)]
         dist.all_gather(gathered, st.weight)
         assert torch.equal(gathered[0], gathered[1])
+        # kNN: queries sharded over the ranks (ragged: 203 rows over 2 ranks), database replicated, table all-gathered
+        # (data/precompute_knns.py:305-319).  The shard kernel is replaced by its torch definition; what runs here is
+        # the sharding, the -1 padding of the last shard and the all_gather.
+        from equss_b200 import knn as KN
+        from equss_b200 import ops
+        seen = []
+
+        def knn_stub(q, db, k):
+            seen.append(tuple(q.shape))
+            return torch.topk(q @ db.t(), k, dim=1).indices
+
+        real_knn, ops.knn_topk = ops.knn_topk, knn_stub
+        try:
+            feats = torch.nn.functional.normalize(torch.randn(n, 24), dim=1)
+            table = KN.precompute_knns(feats, k=5)
+            assert seen == [(hi - lo, 24)]
+            assert table.shape == (n, 5) and table.dtype == torch.int64
+            assert torch.equal(table, O.knn(feats, k=5)[0]) and torch.equal(table[:, 0], torch.arange(n))
+            assert KN.precompute_knns(feats, k=5, sharded=False).shape == (n, 5) and seen[-1] == (n, 24)
+        finally:
+            ops.knn_topk = real_knn
+        # UnSegMetrics.compute: ONE int64 all-reduce of the confusion matrix (model/metric.py:63), every rank then
+        # runs the Hungarian match on the same matrix
+        import tempfile
+        from equss_b200.metric import UnSegMetrics
+        os.chdir(tempfile.mkdtemp())                   # compute() writes ./class_matrix/*.csv like the reference
+        C = 5
+        lab = torch.randint(-1, C, (n,))
+        pred = (lab.clamp_min(0) + (torch.arange(n) % 7 == 0).long()) % C
+        met = UnSegMetrics(C, 0, True, torch.device("cpu"))
+        met.confusion_matrix += O.confusion_update(torch.zeros(C, C, dtype=torch.long), pred[lo:hi], lab[lo:hi], C)
+        res = met.compute("gloo")
+        full = O.confusion_update(torch.zeros(C, C, dtype=torch.long), pred, lab, C)
+        assert torch.equal(met.confusion_matrix.cpu(), full)
+        want = O.metrics_compute(full, True)
+        for k, v in want.items():
+            assert abs(float(res[k]) - float(v)) < 1e-6, (k, float(res[k]), float(v))
         ret[rank] = "ok"
     except BaseException as e:   # noqa
         ret[rank] = f"{type(e).__name__}: {e}"
