@@ -54,3 +54,39 @@ def test_argument_errors_mirror_reference():
     from equss_b200 import _native as N
     with pytest.raises(ValueError, match="divisible"):
         N.zdesc_for(torch.zeros(4, 10), 3)
+
+
+def test_host_side_shape_planning():
+    """The `*_supported` predicates and the workspace planners are host code (no device call): they answer on a box
+    without a GPU, follow the support matrix include/equss_b200.h documents, and size the workspaces the kernels need --
+    in particular no N x N (or shard x N) similarity matrix for the kNN path."""
+    import torch
+    import equss_b200
+    from equss_b200 import _native as N
+    L = N.load()
+    # fused assign + gather: l2 rows, d in {16, 32}, K <= 256, flat and NCHW (equss_b200.h: equss_pq_assign_gather)
+    flat, _, _ = N.zdesc_for(torch.zeros(64, 1024), 64)
+    nchw, _, _ = N.zdesc_for(torch.zeros(2, 1024, 4, 8), 64)
+    sup = lambda zd, M, K, d, mode: L.equss_pq_assign_gather_supported(ctypes.byref(zd), M, K, d, mode)
+    assert sup(flat, 64, 256, 16, 1) == 1 and sup(nchw, 64, 256, 16, 1) == 1 and sup(flat, 32, 256, 32, 1) == 1
+    assert sup(flat, 16, 512, 64, 1) == 0                      # C4 shape: two passes (assign, then gather)
+    assert sup(flat, 64, 256, 16, 2) == 0 and sup(flat, 64, 256, 16, 0) == 0      # z_norm / none rows: not fused
+    # assign workspace: the exact SIMT scan needs none; the tensor-core kernels need operand images + the re-score list
+    ws = [L.equss_pq_assign_workspace_bytes(51200, 64, 256, 16, a) for a in (0, 1, 2, 3)]
+    assert ws[1] == 0 and ws[0] > 0 and ws[2] > 0 and ws[3] > 0
+    assert ws[2] < 4 * 51200 * 64 * 256 // 16                  # far below a distance matrix (3.4 GB at this shape)
+    # probe logits on the tensor cores: D % 32 == 0, C_pad <= 64, h * w % 32 == 0
+    tc = L.equss_probe_logits_tc_supported
+    assert tc(1024, 40, 40, 56) == 1 and tc(1000, 40, 40, 56) == 0 and tc(1024, 40, 40, 68) == 0 and tc(1024, 5, 5, 56) == 0
+    assert L.equss_probe_image_bytes(1024, 56) == 2 * 4 * 1024 * 64       # hi + lo tf32 pieces of [D][64] (512 KB)
+    # kNN: workspace = fp16 copies + per-split survivor lists, O(rows) -- against 1.25 GB for a 6250 x 50000 fp32 shard
+    kws = L.equss_knn_workspace_bytes(6250, 50000, 768, 8)
+    assert 2 * (6250 + 50000) * 768 <= kws < 6250 * 50000 * 4 // 4
+    assert L.equss_knn_workspace_bytes(100, 100, 100, 8) > 0
+    # soft-assignment statistics kernel, EMA tail scratch, expansion-head GEMM
+    soft = L.equss_pq_soft_stats_supported
+    assert soft(256, 16) == 1 and soft(37, 16) == 1 and soft(2048, 16) == 0
+    assert L.equss_pq_train_tail_scratch_floats(64) >= 10 * 64
+    hg = L.equss_head_gemm_supported
+    assert hg(384, 0, 1600, 1) == 1 and hg(384, 384, 1600, 1) == 1 and hg(768, 768, 784, 1) == 1 and hg(100, 0, 1600, 1) == 0
+    assert L.equss_last_error_string() == b"ok" or isinstance(L.equss_last_error_string(), bytes)
