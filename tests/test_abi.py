@@ -90,3 +90,18 @@ def test_host_side_shape_planning():
     hg = L.equss_head_gemm_supported
     assert hg(384, 0, 1600, 1) == 1 and hg(384, 384, 1600, 1) == 1 and hg(768, 768, 784, 1) == 1 and hg(100, 0, 1600, 1) == 0
     assert L.equss_last_error_string() == b"ok" or isinstance(L.equss_last_error_string(), bytes)
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is the checker: only tests/, smoke() and bench.py's CPU legs may import it.  The package (host mirrors
+    and CUDA sources) must not mention it, and it must fail loudly -- not fall back -- without the native library."""
+    pkg = os.path.join(ROOT, "expand-and-quantize-for-unsupervised-semantic-segmentation_b200")
+    for base, _, files in os.walk(pkg):
+        if "_obj" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "equss_oracle" not in text and "oracle/" not in text and "import oracle" not in text, f
+    import equss_b200
+    assert issubclass(equss_b200._native.EqussNativeError, RuntimeError)
