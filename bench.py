@@ -558,6 +558,13 @@ def run_equss(args):
         cpu_base = {"value": px * len(ts) / sum(ts), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                     "sample": f"{n_img} of {B} images ({px} pixels) x {len(ts)} timed runs of the oracle port "
                               f"(PQ loop + evaluator + 2 confusion updates), {sum(ts):.1f} s of CPU work"}
+        # the same port on ONE host thread, on a smaller sample so that it stays within ~10 s
+        torch.set_num_threads(1)
+        cstep1, px1 = cpu_pipeline_factory(1)
+        ts1 = time_cpu(cstep1, 1, 2)
+        cpu_base["one_thread"] = {"value": px1 * len(ts1) / sum(ts1), "unit": UNIT, "cores": 1,
+                                  "sample": f"1 of {B} images ({px1} pixels) x {len(ts1)} timed runs, {sum(ts1):.1f} s of CPU work"}
+        torch.set_num_threads(os.cpu_count() or 1)
 
     # The same oracle code with its tensors on the GPU (library kernels, the reference's op sequence): what a user gets
     # from `.cuda()` on the reference today.  Reported next to cpu_baseline, one rank only, after every measurement of
