@@ -70,11 +70,13 @@ def _unsupported(**flags) -> None:
 
 
 class Codebook(nn.Module):
-    """Learned codebook, model/dino_pqgo.py:460-705, dino_new_vq.py:462-671, dino_pqgo_cls.py:191-405."""
+    """Learned codebook, model/dino_pqgo.py:460-705, dino_new_vq.py:462-671, dino_pqgo_cls.py:191-405.  Defaults are the
+    reference's (``need_initialized="kmeans"``: a directly constructed codebook re-initialises itself from the first
+    training batch; the wrappers pass their own default, "none")."""
 
     def __init__(self, num_codebook_vectors: int, latent_dim: int, beta=0.25, book=1.0, normalize: str = "none",
                  use_restart: bool = False, use_split: bool = False, use_weighted_sum: bool = False,
-                 use_gumbel: bool = False, need_initialized: str = "none", pq_dropout: float = 0.0, jsd_ts: float = 1.0,
+                 use_gumbel: bool = False, need_initialized: str = "kmeans", pq_dropout: float = 0.0, jsd_ts: float = 1.0,
                  num_query: int = 3, num_pos: int = 10, variant: str = "pqgo"):
         super().__init__()
         _unsupported(pq_dropout=pq_dropout > 0.0 and variant == "pqgo_cls",       # dino_pqgo_cls.py has no such flag
@@ -266,7 +268,7 @@ class EMACodebook(nn.Module):
     0.99 / 1e-5 in the reference (:267-268)."""
 
     def __init__(self, num_codebook_vectors: int, latent_dim: int, beta=0.25, normalize: str = "none",
-                 use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "none",
+                 use_restart: bool = False, use_weighted_sum: bool = False, need_initialized: str = "kmeans",
                  pq_dropout: float = 0.0, jsd_ts: float = 1.0, **_ignored):
         super().__init__()
         _unsupported(need_initialized=need_initialized not in ("none", "rand", "uni", "normal", "kmeans"))

@@ -76,7 +76,7 @@ def test_learned_codebook_variants_match_reference(golden_dir):
     np.testing.assert_allclose(prob.detach().cpu().numpy(), g["v1_prob"], rtol=2e-5, atol=1e-7)
     assert float(out["loss"]) == pytest.approx(float(g["v1_loss"]), rel=1e-5)
     assert float(out["codebook_loss"]) == pytest.approx(float(g["v1_codebook_loss"]), rel=1e-5)
-    cb = Codebook(K, d, beta=0.25, book=1.0, normalize="none").to(DEV).eval()
+    cb = Codebook(K, d, beta=0.25, book=1.0, normalize="none", need_initialized="none").to(DEV).eval()
     with torch.no_grad():
         cb.embedding.weight.copy_(torch.from_numpy(g["v5_codebook"]))
     q5, out5, prob5, idx5 = cb(z, torch.zeros_like(z))

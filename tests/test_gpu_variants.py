@@ -227,7 +227,7 @@ def test_restart_paths(golden_dir):
     assert float(out["loss"]) == pytest.approx(float(g["a_loss"]), rel=1e-5)
     zb = torch.from_numpy(g["b_z"]).to(DEV)
     for variant, key in (("pqgo", "b"), ("new_vq", "c")):
-        cb = Codebook(K, d, beta=0.25, book=1.0, normalize="l2", use_restart=True, variant=variant)
+        cb = Codebook(K, d, beta=0.25, book=1.0, normalize="l2", use_restart=True, need_initialized="none", variant=variant)
         with torch.no_grad():
             cb.embedding.weight.copy_(torch.from_numpy(g["b_weight0"]))
         cb = cb.to(DEV).train()

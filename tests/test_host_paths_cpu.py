@@ -236,7 +236,8 @@ def test_pq_dropout_module_plumbing_with_emulated_kernels(golden_dir, monkeypatc
         K, p, ts, mode, variant = int(g["K"]), float(g["pq_dropout"]), float(g["jsd_ts"]), str(g["mode"]), str(g["variant"])
         z = torch.from_numpy(g["z"]).requires_grad_(True)
         B, d, h, w = z.shape
-        cb = Codebook(K, d, beta=0.25, normalize=mode, jsd_ts=ts, pq_dropout=p, use_weighted_sum=bool(g["weighted"]), variant=variant)
+        cb = Codebook(K, d, beta=0.25, normalize=mode, need_initialized="none", jsd_ts=ts, pq_dropout=p,
+                      use_weighted_sum=bool(g["weighted"]), variant=variant)
         with torch.no_grad():
             cb.embedding.weight.copy_(torch.from_numpy(g["weight"]))
         cb.train()
