@@ -74,3 +74,59 @@ def test_quantizer_state_dicts_and_signatures_match(swapped):
     # (the reference's wrapper cannot build the learned-codebook flavour itself: it passes decay= to a ctor without it)
     assert sorted(VectorQuantizer(8, 16, normalize="l2").state_dict().keys()) == \
         sorted(ref_quant.VectorQuantizer(8, 16, normalize="l2").state_dict().keys())
+
+
+def test_every_mirrored_class_keeps_the_reference_constructor_and_forward(swapped):
+    """Drop-in surface, class by class: every constructor parameter of the reference exists in the mirror in
+    the same order with the same default (``quantizer_cls`` defaults to the mirror's own class), ``forward`` takes the
+    reference's arguments, and state dicts of the inline wrappers load with strict=True in both directions."""
+    import inspect
+    _, _, eq = swapped
+    pairs = []
+
+    def add(ref_mod, mir_mod, names):
+        r, m = importlib.import_module(ref_mod), importlib.import_module(mir_mod)
+        assert os.path.abspath(r.__file__).startswith(REF) and not os.path.abspath(m.__file__).startswith(REF)
+        for n in names:
+            rn, mn = n if isinstance(n, tuple) else (n, n)
+            pairs.append((f"{ref_mod}.{rn}", getattr(r, rn), getattr(m, mn)))
+
+    for k in ("model.quantizer", "model.evaluator", "model.metric"):       # compare against the REAL reference modules
+        sys.modules.pop(k, None)
+    add("model.quantizer", "equss_b200.quantizer", ["VectorQuantizer", "EMAVectorQuantizer", "EmbeddingEMA", "ProductQuantizerWrapper"])
+    add("model.quantizer_v2", "equss_b200.quantizer_v2", ["EMAVectorQuantizer", "ProductQuantizerWrapper"])
+    add("model.evaluator", "equss_b200.evaluator", ["UnSegEvaluator", "ClusterLookup"])
+    add("model.metric", "equss_b200.metric", ["UnSegMetrics"])
+    add("model.blocks.module", "equss_b200.head", ["SegmentationHead"])
+    add("model.loss", "equss_b200.losses", ["STEGOLoss"])
+    add("model.loss", "equss_b200.codebooks", ["JSDLoss", "EntropyLoss"])
+    add("model.dino_pqgo", "equss_b200.codebooks", ["Codebook", ("ProductQuantizerWrapper", "PQGOProductQuantizerWrapper")])
+    add("model.dino_new_vq", "equss_b200.codebooks", ["Codebook", "EMACodebook", ("ProductQuantizerWrapper", "NewVQProductQuantizerWrapper")])
+    add("model.dino_pqgo_cls", "equss_b200.codebooks", ["Codebook", ("ProductQuantizerWrapper", "PQGOClsProductQuantizerWrapper")])
+    assert len(pairs) == 20
+    for name, r, m in pairs:
+        rs, ms = inspect.signature(r.__init__).parameters, inspect.signature(m.__init__).parameters
+        assert [p for p in rs if p not in ms] == [], name
+        assert [p for p in ms if p in rs] == list(rs), name                               # same order
+        for k in rs:
+            if k != "quantizer_cls" and rs[k].default is not inspect.Parameter.empty:
+                assert rs[k].default == ms[k].default, (name, k, rs[k].default, ms[k].default)
+        if "Codebook" in name and "Wrapper" not in name:
+            continue                          # one mirror class serves three files: forward(z, *args), arity per variant
+        rf, mf = list(inspect.signature(r.forward).parameters), list(inspect.signature(m.forward).parameters)
+        assert mf[:len(rf)] == rf, (name, rf, mf)
+    import model.dino_new_vq as nv
+    import model.dino_pqgo as pqgo
+    import model.dino_pqgo_cls as pcls
+    cbm = eq.codebooks
+    for R, Mi, kw_r, kw_m in ((pqgo.ProductQuantizerWrapper, cbm.PQGOProductQuantizerWrapper, {}, {}),
+                              (pcls.ProductQuantizerWrapper, cbm.PQGOClsProductQuantizerWrapper, {}, {}),
+                              (nv.ProductQuantizerWrapper, cbm.NewVQProductQuantizerWrapper, {"quantizer_cls": nv.EMACodebook}, {"quantizer_cls": cbm.EMACodebook}),
+                              (nv.ProductQuantizerWrapper, cbm.NewVQProductQuantizerWrapper, {"quantizer_cls": nv.Codebook}, {})):
+        ref = R(4, 16, 32, normalize="z_trainable", need_initialized="none", **kw_r)
+        mir = Mi(4, 16, 32, normalize="z_trainable", need_initialized="none", **kw_m)
+        assert sorted(ref.state_dict().keys()) == sorted(mir.state_dict().keys())
+        mir.load_state_dict(ref.state_dict(), strict=True)
+        ref.load_state_dict(mir.state_dict(), strict=True)
+        for k, v in ref.state_dict().items():
+            assert torch.equal(mir.state_dict()[k], v)
