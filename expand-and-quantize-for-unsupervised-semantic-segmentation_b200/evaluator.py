@@ -23,7 +23,9 @@ __all__ = ["UnSegEvaluator", "ClusterLookup"]
 
 
 class ClusterLookup(nn.Module):
-    """model/evaluator.py:85-111 (kept for the CRF / soft-assignment branches and API parity)."""
+    """Cosine cluster probe, model/evaluator.py:85-111.  ``UnSegEvaluator`` runs the ``alpha=None`` case through the
+    probe kernels at token resolution; this module-level forward is the plain-torch definition kept for the callers
+    that use the class on its own (CRF branch, soft assignment with a temperature) -- same parameter, same returns."""
 
     def __init__(self, dim: int, n_classes: int):
         super().__init__()
@@ -32,18 +34,19 @@ class ClusterLookup(nn.Module):
         self.clusters = torch.nn.Parameter(torch.randn(n_classes, dim))
 
     def forward(self, x: torch.Tensor, alpha: Optional[float] = 2.0, log_probs: bool = False):
-        normed_clusters = F.normalize(self.clusters, dim=1)
-        normed_features = F.normalize(x, dim=1)
-        inner_products = torch.einsum("bchw,nc->bnhw", normed_features, normed_clusters)
+        """x: (b, dim, h, w).  Returns (loss, assignment (b, n_classes, h, w)): the assignment is the one-hot of the
+        most similar centre when ``alpha`` is None, else softmax(alpha * cosine); the loss is minus the mean
+        assignment-weighted cosine (:106); ``log_probs`` swaps the assignment for log_softmax(alpha * cosine) (:108-109)."""
+        centres = F.normalize(self.clusters, dim=1)
+        cosine = torch.einsum("bchw,nc->bnhw", F.normalize(x, dim=1), centres)
         if alpha is None:
-            cluster_probs = F.one_hot(torch.argmax(inner_products, dim=1), self.n_classes)
-            cluster_probs = cluster_probs.permute(0, 3, 1, 2).contiguous().to(torch.float32)
+            assignment = torch.zeros_like(cosine).scatter_(1, cosine.argmax(dim=1, keepdim=True), 1.0)
         else:
-            cluster_probs = F.softmax(inner_products * alpha, dim=1)
-        cluster_loss = -torch.sum(cluster_probs * inner_products, dim=1).mean()
+            assignment = torch.softmax(cosine * alpha, dim=1)
+        loss = -(assignment * cosine).sum(dim=1).mean()
         if log_probs:
-            return cluster_loss, F.log_softmax(inner_products * alpha, dim=1)
-        return cluster_loss, cluster_probs
+            return loss, torch.log_softmax(cosine * alpha, dim=1)
+        return loss, assignment
 
 
 def _taps(out_size: int, in_size: int, device):

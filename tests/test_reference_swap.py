@@ -130,3 +130,24 @@ def test_every_mirrored_class_keeps_the_reference_constructor_and_forward(swappe
         ref.load_state_dict(mir.state_dict(), strict=True)
         for k, v in ref.state_dict().items():
             assert torch.equal(mir.state_dict()[k], v)
+
+
+def test_cluster_lookup_forward_equals_the_reference(swapped):
+    """The stand-alone ClusterLookup.forward (hard assignment, temperature softmax, log-probabilities) against the
+    unmodified reference class on the same parameter and input -- plain torch on both sides, bit for bit."""
+    ref_eval, _, eq = swapped
+    torch.manual_seed(0)
+    ref = ref_eval.ClusterLookup(12, 7)
+    mir = eq.evaluator.ClusterLookup(12, 7)
+    mir.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(2, 12, 5, 4)
+    x[0, :, 0, 0] = 0.0                                              # a zero feature vector: all cosines tie at 0
+    for alpha, log_probs in ((None, False), (2.0, False), (0.5, False), (3.0, True)):
+        (rl, rp), (ml, mp) = ref(x, alpha=alpha, log_probs=log_probs), mir(x, alpha=alpha, log_probs=log_probs)
+        assert torch.equal(rl, ml) and torch.equal(rp, mp) and rp.dtype == mp.dtype, (alpha, log_probs)
+    xg = x.clone().requires_grad_(True)
+    mir(xg, alpha=2.0)[0].backward()
+    xr = x.clone().requires_grad_(True)
+    ref(xr, alpha=2.0)[0].backward()
+    assert torch.allclose(xg.grad, xr.grad, rtol=1e-6, atol=1e-8)
+    assert torch.allclose(mir.clusters.grad, ref.clusters.grad, rtol=1e-6, atol=1e-8)
