@@ -151,3 +151,30 @@ def test_cluster_lookup_forward_equals_the_reference(swapped):
     ref(xr, alpha=2.0)[0].backward()
     assert torch.allclose(xg.grad, xr.grad, rtol=1e-6, atol=1e-8)
     assert torch.allclose(mir.clusters.grad, ref.clusters.grad, rtol=1e-6, atol=1e-8)
+
+
+def test_embedding_ema_helper_calls_equal_the_reference(swapped):
+    """EmbeddingEMA's three public update pieces (vq_count_ema_update / weight_avg_ema_update / weight_update,
+    model/quantizer.py:241-254) and reset() are plain torch in the mirror too (update() itself is the kernel): same
+    buffers after the same calls, bit for bit."""
+    _, ref_quant, eq = swapped
+    torch.manual_seed(1)
+    ref = ref_quant.EmbeddingEMA(9, 6, decay=0.9, eps=1e-4)
+    mir = eq.quantizer.EmbeddingEMA(9, 6, decay=0.9, eps=1e-4)
+    mir.load_state_dict(ref.state_dict(), strict=True)
+    for step in range(3):
+        count = torch.randint(0, 5, (9,)).float()
+        total = torch.randn(9, 6)
+        for e in (ref, mir):
+            e.vq_count_ema_update(count)
+            e.weight_avg_ema_update(total)
+            e.weight_update()
+        for k, v in ref.state_dict().items():
+            assert torch.equal(mir.state_dict()[k], v), (step, k)
+    idx = torch.tensor([[0, 3], [8, 8]])
+    assert torch.equal(ref(idx), mir(idx))
+    ref.reset(); mir.reset()
+    for k, v in ref.state_dict().items():
+        assert torch.equal(mir.state_dict()[k], v), k
+    with pytest.raises(eq._native.EqussNativeError):
+        mir.update(torch.ones(9), torch.randn(9, 6))               # the fused update is the kernel: no CPU fallback
