@@ -178,3 +178,54 @@ def test_embedding_ema_helper_calls_equal_the_reference(swapped):
         assert torch.equal(mir.state_dict()[k], v), k
     with pytest.raises(eq._native.EqussNativeError):
         mir.update(torch.ones(9), torch.randn(9, 6))               # the fused update is the kernel: no CPU fallback
+
+
+def test_restart_and_split_draw_like_the_reference(swapped):
+    """prepare_restart / restart / split (model/quantizer.py:298-381) are host code on both sides: with the same seeds
+    of Python's ``random`` and of torch's CPU generator the mirror replaces the same codes by the same rows and splits
+    the same codes with the same noise -- compared with the live reference object, buffer by buffer."""
+    import random
+    _, ref_quant, eq = swapped
+    K, d = 12, 5
+    torch.manual_seed(4)
+    w0 = torch.randn(K, d)
+
+    def pair():
+        r = ref_quant.EMAVectorQuantizer(K, d, normalize="l2", use_restart=True, use_split=True)
+        m = eq.quantizer.EMAVectorQuantizer(K, d, normalize="l2", use_restart=True, use_split=True)
+        for q in (r, m):
+            q.codebook.weight.copy_(w0); q.codebook.weight_avg.copy_(w0 * 0.5)
+            q.codebook.vq_count.copy_(torch.arange(K, dtype=torch.float32).flip(0) + 1.0)
+            q.vq_count.fill_(3.0)
+        return r, m
+
+    def same_state(r, m, what):
+        for k, v in r.state_dict().items():
+            assert torch.equal(m.state_dict()[k], v), (what, k)
+        assert torch.equal(r.vq_count, m.vq_count), what
+
+    # (a) fewer dead codes than rows, (b) more dead codes than rows (the served codes are drawn too), (c) none dead
+    for name, count, n_rows in (("few_dead", torch.tensor([3, 0, 1, 0, 0, 2, 5, 0, 1, 1, 0, 4.0]), 40),
+                                ("more_dead_than_rows", torch.tensor([1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]), 4),
+                                ("none_dead", torch.ones(K), 10)):
+        r, m = pair()
+        rows = torch.randn(n_rows, d)
+        for q in (r, m):
+            random.seed(7)
+            q.prepare_restart(count, rows)
+        ri = r.update_indices.tolist() if torch.is_tensor(r.update_indices) else list(r.update_indices)
+        mi = m.update_indices.tolist() if torch.is_tensor(m.update_indices) else list(m.update_indices)
+        assert ri == mi and torch.equal(r.update_candidates, m.update_candidates), name
+        r.restart(); m.restart()
+        assert r.update_indices is None and m.update_indices is None
+        same_state(r, m, name)
+    # split: dead codes paired with the busiest codes, +- N(0, 0.02^2) noise, halved counts and running sums
+    for name, count in (("some_dead", torch.tensor([3, 0, 1, 0, 0, 2, 5, 0, 1, 1, 0, 4.0])), ("none_dead", torch.ones(K)),
+                        ("all_dead", torch.zeros(K))):
+        r, m = pair()
+        torch.manual_seed(11)
+        nr = r.split(count)
+        torch.manual_seed(11)
+        nm = m.split(count)
+        assert nr == nm == int((count == 0).sum()), name
+        same_state(r, m, "split/" + name)
