@@ -60,10 +60,11 @@ def _taps(out_size: int, in_size: int, device):
     return i0, i1, 1.0 - l1, l1
 
 
-@torch.no_grad()
 def _upsampled_feature_norm(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """|| bilinear_upsample(x)[b, :, Y, X] ||_2 for every label pixel, shape (B, H, W), from the 2x2 Gram
-    terms of the token grid: |sum_t w_t x_t|^2 = sum_{t,t'} w_t w_t' <x_t, x_t'>."""
+    terms of the token grid: |sum_t w_t x_t|^2 = sum_{t,t'} w_t w_t' <x_t, x_t'>.  Differentiable w.r.t. x (the
+    reference's F.normalize of the upsampled features is, model/evaluator.py:96); the squared norm is floored at
+    (1e-12)^2, F.normalize's own floor, so a zero feature vector has a finite (zero) gradient."""
     B, D, h, w = x.shape
     y0, y1, wy0, wy1 = _taps(H, h, x.device)
     x0, x1, wx0, wx1 = _taps(W, w, x.device)
@@ -88,7 +89,7 @@ def _upsampled_feature_norm(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     aa = torch.where(sx & sy, at(g_a, Y0, X1), torch.where(sx, h0, torch.where(sy, v1, s01)))   # <(y0,x1),(y1,x0)>
     n2 = (a * a * s00 + b_ * b_ * s01 + c * c * s10 + e * e * s11 +
           2 * (a * b_ * h0 + c * e * h1 + a * c * v0 + b_ * e * v1 + a * e * dd + b_ * c * aa))
-    return n2.clamp_min(0).sqrt()
+    return n2.clamp_min(1e-24).sqrt()
 
 
 class _ProbeLosses(torch.autograd.Function):

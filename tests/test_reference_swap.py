@@ -229,3 +229,42 @@ def test_restart_and_split_draw_like_the_reference(swapped):
         nm = m.split(count)
         assert nr == nm == int((count == 0).sum()), name
         same_state(r, m, "split/" + name)
+
+
+def test_evaluator_torch_losses_equal_the_reference(swapped):
+    """The differentiable PyTorch formulation of the evaluator losses (``UnSegEvaluator._losses_torch``: probes at token
+    resolution, interpolated logits, the norm of the upsampled feature from 2x2 Gram terms) against the unmodified
+    reference's forward at label resolution (model/evaluator.py:46-82,95-106): losses to 1e-5, gradients of the probe
+    parameters and of the features through the reference's own graph."""
+    import torch.nn.functional as F
+    ref_eval, _, eq = swapped
+    from equss_b200.evaluator import _upsampled_feature_norm
+    torch.manual_seed(2)
+    for (h, w, H, W) in ((10, 10, 40, 40), (7, 5, 20, 18), (6, 6, 6, 6)):
+        x = torch.randn(2, 16, h, w)
+        direct = F.interpolate(x, (H, W), mode="bilinear", align_corners=False).norm(dim=1) if (h, w) != (H, W) else x.norm(dim=1)
+        with torch.no_grad():
+            assert torch.allclose(_upsampled_feature_norm(x, H, W), direct, rtol=1e-5, atol=1e-6), (h, w, H, W)
+    D, C = 24, 27
+    ref = ref_eval.UnSegEvaluator(D, C, 0)
+    mir = eq.evaluator.UnSegEvaluator(D, C, 0)
+    mir.load_state_dict(ref.state_dict(), strict=True)
+    out = torch.randn(2, D, 10, 10)
+    label = torch.randint(-1, C, (2, 40, 40))
+    xr = out.clone().requires_grad_(True)
+    rl, rlp, rc, rcp = ref(xr, None, label)
+    xm = out.clone().requires_grad_(True)
+    ml, mc = mir._losses_torch(xm, label, rcp)
+    assert float(ml.detach()) == pytest.approx(float(rl.detach()), rel=1e-5) and float(mc.detach()) == pytest.approx(float(rc.detach()), rel=1e-5)
+    (rl + rc).backward()
+    (ml + mc).backward()
+    assert torch.allclose(mir.linear_probe.weight.grad, ref.linear_probe.weight.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(mir.linear_probe.bias.grad, ref.linear_probe.bias.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(mir.cluster_probe.clusters.grad, ref.cluster_probe.clusters.grad, rtol=1e-4, atol=1e-7)
+    # features that carry a gradient themselves: also through the norm of the upsampled feature vector
+    assert torch.allclose(xm.grad, xr.grad, rtol=1e-3, atol=1e-6 * float(xr.grad.abs().max()) + 1e-9)
+    xz = out.clone()
+    xz[0, :, 0, 0] = 0.0                                       # zero feature vector: finite gradients
+    xz.requires_grad_(True)
+    sum(mir._losses_torch(xz, label, rcp)).backward()
+    assert torch.isfinite(xz.grad).all()
