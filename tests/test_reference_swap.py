@@ -268,3 +268,38 @@ def test_evaluator_torch_losses_equal_the_reference(swapped):
     xz.requires_grad_(True)
     sum(mir._losses_torch(xz, label, rcp)).backward()
     assert torch.isfinite(xz.grad).all()
+
+
+def test_jsd_entropy_and_soft_assignment_stats_equal_the_reference(swapped):
+    """codebooks.JSDLoss / EntropyLoss and _pq_core.soft_assignment_stats (the per-subspace mean of both, what the V4
+    wrapper reports) against model/loss.py:490-525 on random soft assignments, values and gradients; out-of-range
+    inputs raise like the reference."""
+    _, _, eq = swapped
+    import model.loss as ref_loss
+    from equss_b200 import _pq_core as core
+    torch.manual_seed(6)
+    n, M, K = 64, 3, 11
+    logits = torch.randn(n, M, K) * 3
+    pr = torch.softmax(logits, dim=2).reshape(n, M * K).requires_grad_(True)
+    pm = pr.detach().clone().requires_grad_(True)
+    rj, re = ref_loss.JSDLoss(), ref_loss.EntropyLoss()
+    want_j = torch.stack([rj(*torch.chunk(pr.view(n, M, K)[:, i], 2, dim=0)) for i in range(M)]).mean()
+    want_e = torch.stack([re(*torch.chunk(pr.view(n, M, K)[:, i], 2, dim=0)) for i in range(M)]).mean()
+    got_j, got_e = core.soft_assignment_stats(pm, M, K)
+    assert float(got_j.detach()) == pytest.approx(float(want_j.detach()), rel=1e-5)
+    assert float(got_e.detach()) == pytest.approx(float(want_e.detach()), rel=1e-5)
+    (want_j + 0.5 * want_e).backward()
+    (got_j + 0.5 * got_e).backward()
+    assert torch.allclose(pm.grad, pr.grad, rtol=1e-4, atol=1e-8)
+    a, b = torch.chunk(pr.detach().view(n, M, K)[:, 0], 2, dim=0)
+    mj, me = eq.codebooks.JSDLoss(), eq.codebooks.EntropyLoss()
+    assert float(mj(a, b)) == pytest.approx(float(rj(a, b)), rel=1e-5)
+    assert float(me(a, b)) == pytest.approx(float(re(a, b)), rel=1e-6)
+    assert float(mj(a, a)) == pytest.approx(float(rj(a, a)), rel=1e-4, abs=1e-9)     # not 0: the 1e-6 smoothing is asymmetric
+    for bad in (a - 0.5, a + 0.9):
+        with pytest.raises(ValueError):
+            rj(bad, b)
+        with pytest.raises(ValueError):
+            mj(bad, b)
+    with pytest.raises(ValueError):
+        core.soft_assignment_stats(pm.detach()[:-1], M, K)          # odd number of rows: no two halves
