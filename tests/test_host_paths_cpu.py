@@ -4,6 +4,7 @@ need no device; the kernels around them are covered by tests/test_gpu_flags.py."
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -310,3 +311,65 @@ def test_kmeans_initialisation_matches_the_reference(golden_dir, monkeypatch):
     np.testing.assert_allclose(ema.codebook.weight_avg.numpy(), g["ema_weight_avg_after"], rtol=1e-5, atol=1e-6)
     for k in ("vq-loss", "codebook-usage", "jsd", "entropy", "codebook-sum"):
         assert abs(float(out[k]) - float(g[f"ema_out/{k}"])) <= 1e-5 * abs(float(g[f"ema_out/{k}"])) + 1e-7, k
+
+
+@pytest.mark.parametrize("mode", ["l2", "z_norm", "none", "z_trainable"])
+@pytest.mark.parametrize("nchw", [False, True])
+def test_distance_prob_backward_matches_autograd(monkeypatch, mode, nchw):
+    """_pq_core.DistanceProb: forward is the kernel, backward is hand-derived (softmax and distance Jacobians as batched
+    contractions, routed through the row normalisation).  With the kernel's forward replaced by its torch definition,
+    the gradients w.r.t. the activations, the (normalised) codebook and the z_trainable vectors must equal autograd's on
+    the plain formula  softmax(-(|z_n|^2 + |c|^2 - 2 z_n.c) / T)  (model/quantizer.py:457-468), for flat and NCHW input."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _pq_core as core
+    from equss_b200 import ops
+    torch.manual_seed(8)
+    M, K, d, T = 3, 7, 4, 0.7
+    D = M * d
+
+    def formula(z, cbn, a, b):
+        zr = core._normalize_rows(core._rows(z.float(), M), mode, a, b)                 # (n, M, d)
+        dist = (zr ** 2).sum(-1, keepdim=True) + (cbn ** 2).sum(-1).unsqueeze(0) - 2 * torch.einsum("nmd,mkd->nmk", zr, cbn)
+        return torch.softmax(-dist / T, dim=2).reshape(zr.shape[0], M * K)
+
+    def kernel_stub(z, cbn, cn2, normalize, norm_a=None, norm_b=None, temperature=1.0):
+        with torch.no_grad():
+            return formula(z, cbn, norm_a, norm_b)
+    monkeypatch.setattr(ops, "pq_distance_prob", kernel_stub)
+
+    z0 = torch.randn(2, D, 3, 5) if nchw else torch.randn(30, D)
+    c0 = torch.randn(M, K, d) * 0.7
+    a0 = torch.randn(D) * 0.1 if mode == "z_trainable" else None
+    b0 = torch.rand(D) + 0.5 if mode == "z_trainable" else None
+    g = torch.randn(z0.numel() // D, M * K)
+    grads = []
+    for fn in ("custom", "autograd"):
+        z, c = z0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+        a = a0.clone().requires_grad_(True) if a0 is not None else None
+        b = b0.clone().requires_grad_(True) if b0 is not None else None
+        if fn == "custom":
+            prob = core.DistanceProb.apply(z, c, (c.detach() ** 2).sum(-1), mode, a, b, T)
+        else:
+            prob = formula(z, c, a, b)
+        (prob * g).sum().backward()
+        grads.append([t.grad for t in (z, c, a, b) if t is not None])
+    for name, got, want in zip(("z", "codebook", "norm_a", "norm_b"), *grads):
+        assert got is not None and got.shape == want.shape, name
+        assert torch.allclose(got, want, rtol=2e-4, atol=1e-6 * float(want.abs().max()) + 1e-9), (mode, nchw, name)
+
+
+def test_affine_parameter_gradients_from_the_activation_gradient():
+    """z_trainable: z_norm = (z - a) / b per channel.  The backward kernel returns grad_z = g_znorm / b; the gradients
+    of the two vectors follow from it on the host (_pq_core._affine_param_grads) -- checked against autograd."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import _pq_core as core
+    torch.manual_seed(9)
+    M, d = 3, 4
+    for z in (torch.randn(20, M * d), torch.randn(2, M * d, 3, 2)):
+        z = z.clone().requires_grad_(True)
+        a = (torch.randn(M * d) * 0.2).requires_grad_(True)
+        b = (torch.rand(M * d) + 0.5).requires_grad_(True)
+        zn = core._normalize_rows(core._rows(z, M), "z_trainable", a, b)
+        (zn * torch.randn_like(zn)).sum().backward()
+        ga, gb = core._affine_param_grads(z.grad, z.detach(), M, a.detach(), b.detach(), True, True)
+        assert torch.allclose(ga, a.grad, rtol=1e-5, atol=1e-6) and torch.allclose(gb, b.grad, rtol=1e-5, atol=1e-6)
