@@ -139,3 +139,68 @@ def test_without_the_standins_a_cpu_tensor_is_refused():
     pq = ProductQuantizerWrapper(2, 8, 8, normalize="l2").eval()
     with pytest.raises(equss_b200._native.EqussNativeError):
         pq(torch.randn(4, 8))
+
+
+def _run_against_oracle(pq, O, M, K, d, mode, zs, *, update_norm=True, z_stats=None):
+    """Replays `zs` (training steps, the last one in evaluation mode) through the wrapper and through the oracle's
+    per-subspace restatement of EMAVectorQuantizer.forward; every output and every buffer must agree."""
+    w0 = torch.stack([q.codebook.weight.clone() for q in pq.quantizers])
+    states = [O.EmaState(w0[i]) for i in range(M)]
+    exact = [torch.zeros(K) for _ in range(M)]
+    pq.train()
+    for s, z in enumerate(zs):
+        training = s < len(zs) - 1
+        if not training:
+            pq.eval()
+        with torch.no_grad():
+            zq, out, prob = pq(z)
+        qs, oout = [], {}
+        for i in range(M):
+            kw = {}
+            if z_stats is not None:
+                kw = {"z_mean": z_stats[0][i], "z_log_var": z_stats[1][i]}
+            q, o, p, ix = O.ema_vq_forward(z[:, i * d:(i + 1) * d], states[i], exact[i], normalize=mode, beta=0.25,
+                                           training=training, update_norm=update_norm, **kw)
+            qs.append(q)
+            for k, v in o.items():
+                oout[k] = v if i == 0 else oout[k] + v
+        oout = {k: v / M for k, v in oout.items()}
+        np.testing.assert_allclose(zq.numpy(), torch.cat(qs, dim=1).numpy(), rtol=1e-5, atol=1e-6)
+        assert set(out.keys()) == set(oout.keys()), (s, sorted(out), sorted(oout))
+        for k, v in oout.items():
+            assert float(out[k]) == pytest.approx(float(v), rel=1e-5, abs=1e-7), (s, k)
+        for i, q in enumerate(pq.quantizers):
+            np.testing.assert_allclose(q.codebook.weight.numpy(), states[i].weight.numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(q.codebook.weight_avg.numpy(), states[i].weight_avg.numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(q.codebook.vq_count.numpy(), states[i].vq_count.numpy(), rtol=1e-5, atol=1e-7)
+            assert torch.equal(q.vq_count, exact[i])
+
+
+def test_rare_branches_of_the_ema_wrapper_on_cpu(monkeypatch):
+    """Branches the fixtures do not reach, against the oracle (itself pinned to the reference bit for bit): more than
+    1024 codes (no fused tail: EMA update + percentile calls), ``update_norm=False`` (raw codebook gathered from a
+    snapshot taken before the in-place update), and the z_trainable running statistics (model/quantizer.py:428-450)."""
+    import equss_oracle as O
+    import equss_b200  # noqa: F401
+    from equss_b200.quantizer import EMAVectorQuantizer, ProductQuantizerWrapper
+    kernel_standins.install(monkeypatch)
+    torch.manual_seed(12)
+
+    def make(M, K, D, mode, **kw):
+        pq = ProductQuantizerWrapper(M, K, D, beta=0.25, normalize=mode, quantizer_cls=EMAVectorQuantizer, **kw)
+        with torch.no_grad():
+            for q in pq.quantizers:
+                q.codebook.weight.copy_(torch.randn(K, D // M)); q.codebook.weight_avg.copy_(q.codebook.weight)
+        return pq
+
+    M, K, d = 2, 1030, 4
+    _run_against_oracle(make(M, K, M * d, "l2"), O, M, K, d, "l2", [torch.randn(96, M * d) for _ in range(3)])
+    M, K, d = 3, 16, 8
+    _run_against_oracle(make(M, K, M * d, "none", update_norm=False), O, M, K, d, "none",
+                        [torch.randn(80, M * d) for _ in range(3)], update_norm=False)
+    pq = make(M, K, M * d, "z_trainable")
+    stats = ([q.z_mean.clone() for q in pq.quantizers], [q.z_log_var.clone() for q in pq.quantizers])
+    _run_against_oracle(pq, O, M, K, d, "z_trainable", [torch.randn(80, M * d) * 1.5 + 0.3 for _ in range(3)], z_stats=stats)
+    for i, q in enumerate(pq.quantizers):
+        np.testing.assert_allclose(q.z_mean.numpy(), stats[0][i].numpy(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(q.z_log_var.numpy(), stats[1][i].numpy(), rtol=1e-5, atol=1e-7)
