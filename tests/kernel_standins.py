@@ -7,7 +7,6 @@ entry points the PQ modules call by the plain torch expression each kernel is sp
 in the docstrings of ``ops.py`` / ``include/equss_b200.h``), so that the reference's fixtures can be replayed through the
 mirrors without a device.  The kernels themselves are held to the same fixtures by the ``-m gpu`` tests.
 """
-from typing import Optional
 
 import torch
 
@@ -47,6 +46,30 @@ def install(monkeypatch):
         out = zr + (q - zr)                                                                  # model/quantizer.py:536
         sqerr = ((zr - q).double() ** 2).sum(dim=(0, 2))
         return like_z(out, z), sqerr, (like_z(zr, z) if want_znorm else None)
+
+    def pq_gather_loss_bwd(z, gather_src, idx, normalize, grad_out, coef, norm_a=None, norm_b=None, want_grad_z=True,
+                           cb_coef=None):
+        """include/equss_b200.h: g_znorm = grad_out + coef[m] (z_norm - q), grad_z = J_norm(z)^T g_znorm;
+        grad_gather_src += cb_coef[m] (q - z_norm) scattered by idx."""
+        src = gather_src.detach().float()
+        M, K, d = src.shape
+        n = idx.shape[1]
+        with torch.enable_grad():
+            zl = z.detach().float().requires_grad_(True)
+            zr = core._normalize_rows(core._rows(zl, M), normalize, norm_a, norm_b)
+        q = torch.gather(src, 1, idx.long().unsqueeze(-1).expand(M, n, d)).permute(1, 0, 2)
+        gz = gcb = None
+        if want_grad_z:
+            g_zn = torch.zeros_like(zr) if grad_out is None else core._rows(grad_out.detach().float(), M).clone()
+            if coef is not None:
+                g_zn = g_zn + coef.detach().float().reshape(1, M, 1) * (zr.detach() - q)
+            (gz,) = torch.autograd.grad(zr, zl, g_zn)
+        if cb_coef is not None:
+            gcb = torch.zeros_like(src)
+            contrib = cb_coef.detach().float().reshape(1, M, 1) * (q - zr.detach())
+            for m in range(M):
+                gcb[m].index_add_(0, idx[m].long(), contrib[:, m])
+        return gz, gcb
 
     def pq_assign_gather(z, codebook_norm, gather_src=None, cnorm2=None, normalize="l2", norm_a=None, norm_b=None, fused=None):
         idx = pq_assign(z, codebook_norm, cnorm2, normalize, norm_a, norm_b)

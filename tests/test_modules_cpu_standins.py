@@ -204,3 +204,68 @@ def test_rare_branches_of_the_ema_wrapper_on_cpu(monkeypatch):
     for i, q in enumerate(pq.quantizers):
         np.testing.assert_allclose(q.z_mean.numpy(), stats[0][i].numpy(), rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(q.z_log_var.numpy(), stats[1][i].numpy(), rtol=1e-5, atol=1e-7)
+
+
+def _close_grad(got, want, what):
+    want = torch.from_numpy(want)
+    assert got is not None and got.shape == want.shape, what
+    assert torch.allclose(got, want, rtol=1e-3, atol=2e-5 * float(want.abs().max()) + 1e-9), \
+        (what, float((got - want).abs().max()), float(want.abs().max()))
+
+
+@pytest.mark.parametrize("variant,mode", [("new_vq", "l2"), ("new_vq", "z_norm"), ("pqgo_cls", "l2"),
+                                          ("pqgo_cls", "z_trainable"), ("pqgo", "z_norm")])
+def test_inline_learned_codebooks_with_gradients_on_cpu(golden_dir, monkeypatch, variant, mode):
+    """V4 / V5 / V6 learned codebooks through their wrappers (training + evaluation call): return tuples, counts, losses,
+    and the gradients of the reference's own graph w.r.t. z, the embedding and the z_trainable parameters -- i.e. the
+    autograd plumbing of PQGatherLoss / DistanceProb around the (here: stand-in) forward and backward kernels."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import codebooks as CB
+    kernel_standins.install(monkeypatch)
+    g = np.load(os.path.join(golden_dir, f"pq_inline_{variant}_{mode}.npz"))
+    M, K, ts = int(g["M"]), int(g["K"]), float(g["jsd_ts"])
+    D = g["z0"].shape[1]
+    if variant == "new_vq":
+        pq = CB.NewVQProductQuantizerWrapper(M, K, D, beta=0.25, normalize=mode, need_initialized="none", jsd_ts=ts)
+    elif variant == "pqgo_cls":
+        pq = CB.PQGOClsProductQuantizerWrapper(M, K, D, beta=0.25, normalize=mode, need_initialized="none", jsd_ts=ts)
+    else:
+        pq = CB.PQGOProductQuantizerWrapper(M, K, D, beta=0.25, book=0.6, normalize=mode, need_initialized="none", jsd_ts=ts)
+    with torch.no_grad():
+        for i, q in enumerate(pq.quantizers):
+            q.embedding.weight.copy_(torch.from_numpy(g["codebook"][i]))
+            if mode == "z_trainable":
+                q.z_mean.copy_(torch.from_numpy(g["z_mean"][i])); q.z_log_var.copy_(torch.from_numpy(g["z_log_var"][i]))
+    for s, training in ((0, True), (1, False)):
+        pq.train(training)
+        pq.zero_grad()
+        z = torch.from_numpy(g[f"z{s}"]).requires_grad_(True)
+        B, _, h, w = z.shape
+        if variant == "new_vq":
+            zq, out, prob = pq(z, s)
+            idxs = None
+        elif variant == "pqgo_cls":
+            zq, out, prob, idxs = pq(z)
+            assert all(i.shape == (B * h * w,) for i in idxs)
+        else:
+            zq, (zs, zqs, idxs), out, prob = pq(z, torch.zeros_like(z))
+            assert all(i.shape == (B, h, w) for i in idxs) and len(zs) == M and len(zqs) == M
+        assert tuple(prob.shape) == tuple(g[f"prob{s}"].shape)
+        if idxs is not None:
+            assert np.array_equal(torch.stack([i.reshape(-1) for i in idxs]).numpy().astype(np.int32), g[f"idx{s}"])
+        np.testing.assert_allclose(zq.detach().numpy(), g[f"zq{s}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(prob.detach().numpy(), g[f"prob{s}"], rtol=1e-5, atol=1e-7)
+        keys = {k[len(f"out{s}/"):] for k in g.files if k.startswith(f"out{s}/")}
+        assert set(out.keys()) == keys
+        for k in keys:
+            assert float(out[k].detach() if torch.is_tensor(out[k]) else out[k]) == pytest.approx(float(g[f"out{s}/{k}"]), rel=1e-5, abs=1e-7), (s, k)
+        assert np.array_equal(torch.stack([q.vq_count for q in pq.quantizers]).numpy(), g[f"exact_after{s}"])
+        total = (zq * torch.from_numpy(g[f"go{s}"])).sum() + out["vq-loss"] + (prob * torch.from_numpy(g[f"gp{s}"])).sum()
+        if variant == "new_vq":
+            total = total + 0.3 * out["jsd"] + 0.2 * out["entropy"]
+        total.backward()
+        _close_grad(z.grad, g[f"grad_z{s}"], f"{variant}/{mode} dz step {s}")
+        _close_grad(torch.stack([q.embedding.weight.grad for q in pq.quantizers]), g[f"grad_cb{s}"], f"{variant}/{mode} dcodebook")
+        if mode == "z_trainable":
+            _close_grad(torch.stack([q.z_mean.grad for q in pq.quantizers]), g[f"grad_zmean{s}"], "dz_mean")
+            _close_grad(torch.stack([q.z_log_var.grad for q in pq.quantizers]), g[f"grad_zlogvar{s}"], "dz_log_var")
