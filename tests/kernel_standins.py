@@ -141,6 +141,108 @@ def install(monkeypatch):
         prob = pq_distance_prob(z, cbn, None, normalize, norm_a, norm_b, temperature)
         return core.soft_assignment_stats(prob, cbn.shape[0], cbn.shape[1])
 
+    # ---- evaluation: probes at token resolution, interpolation + argmax + histogram at label resolution ------------
+    import torch.nn.functional as F
+    from equss_b200 import _native as N
+
+    def probe_pack(wmat):
+        wmat = wmat.detach().float()
+        Ct, D = wmat.shape
+        cpad = int(N.lib().equss_probe_cpad(Ct))                     # host helper of the library: channel padding rule
+        wmat_t = torch.zeros(D, cpad)
+        wmat_t[:, :Ct] = wmat.t()
+        return wmat_t, Ct, None
+
+    def probe_logits(feat, wmat, bias=None, algo=0):
+        wmat_t, Ct, _ = wmat if isinstance(wmat, tuple) else probe_pack(wmat)
+        B, D, h, w = feat.shape
+        logits = feat.detach().float().permute(0, 2, 3, 1).reshape(-1, D) @ wmat_t
+        if bias is not None:
+            logits[:, :bias.numel()] += bias.detach().float().reshape(-1)
+        return logits
+
+    def upsampled(logits, B, h, w, H, W):
+        maps = logits.reshape(B, h, w, -1).permute(0, 3, 1, 2)
+        return maps if (h, w) == (H, W) else F.interpolate(maps, (H, W), mode="bilinear", align_corners=False)
+
+    def confusion_update(preds, label, num_classes, confusion):
+        p, l = preds.reshape(-1).long(), label.reshape(-1).long()
+        keep = (l >= 0) & (l < num_classes) & (p >= 0) & (p < num_classes)               # model/metric.py:49
+        confusion += torch.bincount(p[keep] * num_classes + l[keep], minlength=confusion.shape[0] * num_classes
+                                    ).reshape(confusion.shape[0], num_classes)
+
+    def probe_argmax_confusion(logits, B, h, w, c_total, label, num_classes, heads, want_preds=True, confusions=None):
+        H, W = label.shape[1:]
+        up = upsampled(logits, B, h, w, H, W)
+        preds = []
+        for i, (off, cnt) in enumerate(heads):
+            p = up[:, off:off + cnt].argmax(dim=1)
+            if confusions is not None and confusions[i] is not None:
+                confusion_update(p, label, num_classes, confusions[i])
+            preds.append(p if want_preds else None)
+        return preds
+
+    def token_gram(feat):
+        x = feat.detach().float()
+        B, D, h, w = x.shape
+        g = torch.zeros(B, h, w, 5)
+        g[..., 0] = (x * x).sum(1)
+        g[:, :, :-1, 1] = (x[..., :, :-1] * x[..., :, 1:]).sum(1)                         # <x, right>
+        g[:, :-1, :, 2] = (x[..., :-1, :] * x[..., 1:, :]).sum(1)                         # <x, down>
+        g[:, :-1, :-1, 3] = (x[..., :-1, :-1] * x[..., 1:, 1:]).sum(1)                    # <x, down-right>
+        g[:, :-1, 1:, 4] = (x[..., :-1, 1:] * x[..., 1:, :-1]).sum(1)                     # <x, down-left>
+        return g.reshape(B * h * w, 5)
+
+    def taps(out_size, in_size):
+        src = ((torch.arange(out_size, dtype=torch.float32) + 0.5) * (float(in_size) / float(out_size)) - 0.5).clamp_min(0.0)
+        i0 = src.floor().long().clamp_(max=in_size - 1)
+        i1 = (i0 + 1).clamp(max=in_size - 1)
+        return i0, i1, src - i0.float()
+
+    def norm_from_gram(gram, B, h, w, H, W):
+        """|sum_t w_t x_t| over the (up to) four taps of every label pixel, from the pairwise inner products."""
+        g = gram.reshape(B, h, w, 5)
+        y0, y1, ly = taps(H, h)
+        x0, x1, lx = taps(W, w)
+        Y0, Y1, X0, X1 = y0[:, None], y1[:, None], x0[None, :], x1[None, :]
+        wts = {(0, 0): (1 - ly)[:, None] * (1 - lx)[None, :], (0, 1): (1 - ly)[:, None] * lx[None, :],
+               (1, 0): ly[:, None] * (1 - lx)[None, :], (1, 1): ly[:, None] * lx[None, :]}
+        pos = {(0, 0): (Y0, X0), (0, 1): (Y0, X1), (1, 0): (Y1, X0), (1, 1): (Y1, X1)}
+
+        def inner(a, b):                                             # <x[pos a], x[pos b]> for every label pixel
+            (ya, xa), (yb, xb) = pos[a], pos[b]
+            ya, xa, yb, xb = (t.expand(H, W) for t in (ya, xa, yb, xb))
+            dy, dx = yb - ya, xb - xa                                # in {0, 1} x {-1, 0, 1} after ordering by row
+            swap = (dy < 0) | ((dy == 0) & (dx < 0))
+            ya2, xa2 = torch.where(swap, yb, ya), torch.where(swap, xb, xa)
+            dy, dx = torch.where(swap, -dy, dy), torch.where(swap, -dx, dx)
+            term = torch.where(dy == 0, torch.where(dx == 0, 0, 1), torch.where(dx == 0, 2, torch.where(dx > 0, 3, 4)))
+            return g[:, ya2, xa2, :].gather(-1, term.expand(B, H, W).unsqueeze(-1)).squeeze(-1)
+
+        n2 = torch.zeros(B, H, W)
+        keys = list(wts)
+        for a in keys:
+            for b in keys:
+                n2 = n2 + wts[a] * wts[b] * inner(a, b)
+        return n2.clamp_min(0).sqrt()
+
+    def probe_losses(logits, gram, B, h, w, c_total, label, num_classes, cluster_head, linear_head, want_grad=False):
+        """include/equss_b200.h K8b: sums[0] = sum over labelled pixels of logsumexp(v_lin) - v_lin[label],
+        sums[1] = sum over all pixels of max_c v_clu / |upsampled feature|; grad_logits = d sums / d token logits."""
+        H, W = label.shape[1:]
+        (oc, cc), (ol, cl) = cluster_head, linear_head
+        with torch.enable_grad():
+            lg = logits.detach().clone().requires_grad_(True)
+            up = upsampled(lg, B, h, w, H, W)
+            lin = up[:, ol:ol + cl].permute(0, 2, 3, 1).reshape(-1, cl)
+            lab = label.reshape(-1)
+            valid = (lab >= 0) & (lab < num_classes)
+            s_lin = (torch.logsumexp(lin[valid], dim=1) - lin[valid].gather(1, lab[valid].unsqueeze(1)).squeeze(1)).double().sum()
+            norm = norm_from_gram(gram, B, h, w, H, W).clamp_min(1e-12)
+            s_clu = (up[:, oc:oc + cc].max(dim=1).values / norm).double().sum()
+            g = torch.autograd.grad(s_lin + s_clu, lg)[0] if want_grad else None
+        return torch.stack([s_lin.detach(), s_clu.detach()]), valid.sum().reshape(1), g
+
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name):
             monkeypatch.setattr(ops, name, fn)

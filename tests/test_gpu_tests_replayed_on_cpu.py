@@ -9,10 +9,9 @@ import pytest
 
 import kernel_standins
 
-_SOURCES = ("test_gpu_modules", "test_gpu_variants", "test_gpu_flags", "test_gpu_flags_dropout")
+_SOURCES = ("test_gpu_modules", "test_gpu_variants", "test_gpu_flags", "test_gpu_flags_dropout")   # module-level tests
 _mods = {name: importlib.import_module(name) for name in _SOURCES}
 _GPU_ONLY = {
-    "test_gpu_modules.test_evaluator_and_metrics_modules",      # probe / confusion kernels called through the evaluator
     "test_gpu_modules.test_knn_module_and_npz_contract",        # kNN kernel
     "test_gpu_variants.test_stego_loss_matches_reference",      # feature-correlation kernel
     "test_gpu_variants.test_channel_moments_and_soft_stats_kernels",   # compares kernels with torch: nothing left to check
