@@ -243,6 +243,22 @@ def install(monkeypatch):
             g = torch.autograd.grad(s_lin + s_clu, lg)[0] if want_grad else None
         return torch.stack([s_lin.detach(), s_clu.detach()]), valid.sum().reshape(1), g
 
+    def head_gemm(a1, w, bias=None, a2=None, relu=False, out=None):
+        """out[r, o] = act(sum_k [a1 | a2][r, k] w[o, k] + bias[o]); a1 NCHW (B, C1, h, w) or flat rows."""
+        a = a1.detach().float()
+        if a.dim() == 4:
+            a = a.permute(0, 2, 3, 1).reshape(-1, a.shape[1])
+        if a2 is not None:
+            a = torch.cat([a, a2.detach().float()], dim=1)
+        y = a @ w.detach().float().reshape(w.shape[0], -1).t()
+        if bias is not None:
+            y = y + bias.detach().float().reshape(1, -1)
+        y = torch.relu(y) if relu else y
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name):
             monkeypatch.setattr(ops, name, fn)

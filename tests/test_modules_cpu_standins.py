@@ -136,3 +136,82 @@ def test_rare_branches_of_the_ema_wrapper_on_cpu(monkeypatch):
     for i, q in enumerate(pq.quantizers):
         np.testing.assert_allclose(q.z_mean.numpy(), stats[0][i].numpy(), rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(q.z_log_var.numpy(), stats[1][i].numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_evaluator_probe_weight_cache_on_cpu(monkeypatch):
+    """UnSegEvaluator packs both probes into one operand.  In eval() mode the packed operand is cached on the
+    parameters' storage + version counters: an in-place update (optimizer step, ``copy_`` under no_grad) is seen, a write
+    through ``.data`` is not until ``invalidate_cache()``; in train() mode the operand is rebuilt on every call."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import ops
+    from equss_b200.evaluator import UnSegEvaluator
+    kernel_standins.install(monkeypatch)
+    packs = []
+    real_pack = ops.probe_pack
+    monkeypatch.setattr(ops, "probe_pack", lambda w: (packs.append(1), real_pack(w))[1])
+    torch.manual_seed(13)
+    D, C = 16, 5
+    ev = UnSegEvaluator(D, C).eval()
+    feat, label = torch.randn(2, D, 6, 6), torch.randint(-1, C, (2, 24, 24))
+
+    def fresh_preds():
+        other = UnSegEvaluator(D, C).eval()
+        other.load_state_dict(ev.state_dict())
+        return other.predict(feat, label)
+
+    lp0, cp0 = ev.predict(feat, label)
+    ev.predict(feat, label)
+    assert len(packs) == 1                                            # second call served from the cache
+    with torch.no_grad():
+        ev.cluster_probe.clusters.copy_(torch.randn(C, D))            # in-place: version counter moves
+    lp1, cp1 = ev.predict(feat, label)
+    assert len(packs) == 2 and not torch.equal(cp1, cp0) and torch.equal(lp1, lp0)
+    want = fresh_preds()
+    assert torch.equal(cp1, want[1]) and torch.equal(lp1, want[0])
+    ev.linear_probe.weight.data = torch.randn(C, D, 1, 1)             # new storage: seen through data_ptr
+    lp2, _ = ev.predict(feat, label)
+    assert not torch.equal(lp2, lp1) and torch.equal(lp2, fresh_preds()[0])
+    n = len(packs)
+    ev.linear_probe.bias.data.add_(torch.tensor([50.0, 0, 0, 0, 0]))   # .data write: no version bump, same storage
+    stale, _ = ev.predict(feat, label)
+    assert len(packs) == n and torch.equal(stale, lp2)                # documented: stale until invalidated
+    ev.invalidate_cache()
+    lp3, _ = ev.predict(feat, label)
+    assert len(packs) == n + 1 and (lp3 == 0).float().mean() > (lp2 == 0).float().mean() and torch.equal(lp3, fresh_preds()[0])
+    ev.train()
+    n = len(packs)
+    ev.predict(feat, label); ev.predict(feat, label)
+    assert len(packs) == n + 2                                        # training: rebuilt every call
+
+
+def test_expansion_head_kernel_path_on_cpu(golden_dir, monkeypatch):
+    """SegmentationHead without gradients: hidden = relu(W2 x + b2), code = [W1 | W3] [x ; hidden] + (b1 + b3) -- two GEMM
+    calls, result a (B, D, h, w) view of NHWC memory -- against the reference module's output (fixture of
+    oracle/make_golden_head.py); the packed operand follows parameter updates in eval() mode like the probe cache."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import ops
+    from equss_b200.head import SegmentationHead
+    kernel_standins.install(monkeypatch)
+    calls = []
+    real = ops.head_gemm
+    monkeypatch.setattr(ops, "head_gemm", lambda *a, **k: (calls.append((tuple(a[1].shape), k.get("relu", False))), real(*a, **k))[1])
+    g = np.load(os.path.join(golden_dir, "expansion_head.npz"))
+    head = SegmentationHead(64, 96).eval()
+    head.load_state_dict({k.replace("_", ".", 2) if k.startswith("cluster") else k: torch.from_numpy(v)
+                          for k, v in g.items() if k.startswith("cluster")}, strict=True)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        code = head(x)
+    assert calls == [((64, 64, 1, 1), True), ((96, 128), False)]                 # hidden layer, then both branches at once
+    assert code.shape == (2, 96, 8, 8) and code.permute(0, 2, 3, 1).is_contiguous()      # NHWC memory: flat rows for the PQ ops
+    np.testing.assert_allclose(code.numpy(), g["out"], rtol=1e-5, atol=1e-6)
+    with torch.no_grad():
+        head.cluster1[0].bias.add_(1.0)                                           # in-place update: seen by the cache
+        np.testing.assert_allclose(head(x).numpy(), g["out"] + 1.0, rtol=1e-5, atol=1e-5)
+        head.cluster2[2].bias.data.sub_(1.0)                                      # .data write: needs invalidate_cache()
+        np.testing.assert_allclose(head(x).numpy(), g["out"] + 1.0, rtol=1e-5, atol=1e-5)
+        head.invalidate_cache()
+        np.testing.assert_allclose(head(x).numpy(), g["out"], rtol=1e-5, atol=1e-5)
+    # with gradients the reference's convolutions run (autograd), same values
+    xg = x.clone().requires_grad_(True)
+    np.testing.assert_allclose(head(xg).detach().numpy(), g["out"], rtol=1e-5, atol=1e-5)
