@@ -4,7 +4,8 @@ The kernels themselves need a B200; what is covered here is the plumbing around 
 the clone-and-return contract of all_reduce_tensor, and that ONE all-reduce of the packed [M, K, d+1]
 statistics buffer reproduces the single-process statistics (counts exactly, sums up to fp32 add order),
 so every rank applies an identical EMA update; the query sharding + all_gather of the kNN table
-(ragged shards) and the single int64 all-reduce inside UnSegMetrics.compute."""
+(ragged shards), the single int64 all-reduce inside UnSegMetrics.compute, and ProductQuantizerWrapper.train() itself on two
+ranks (kernel entry points replaced by their torch definitions): replicas bit-identical, equal to the oracle on the whole batch."""
 import os
 import socket
 import sys
@@ -109,6 +110,48 @@ def _worker(rank, world, port, ret):
         want = O.metrics_compute(full, True)
         for k, v in want.items():
             assert abs(float(res[k]) - float(v)) < 1e-6, (k, float(res[k]), float(v))
+        # The MODULE on two ranks: ProductQuantizerWrapper.train() on each rank's shard (kernel entry points replaced by
+        # their torch definitions, tests/kernel_standins.py), packed statistics all-reduced by the module itself
+        # (one call for all subspaces), z_trainable moments by one [2, D] all-reduce.  Replicas must stay bit-identical
+        # and equal the single-process oracle on the whole batch.
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import kernel_standins
+
+        class _Patch:
+            def setattr(self, obj, name, value):
+                setattr(obj, name, value)
+        kernel_standins.install(_Patch())
+        from equss_b200.quantizer import EMAVectorQuantizer, ProductQuantizerWrapper
+        for mode in ("l2", "z_trainable"):
+            torch.manual_seed(5)
+            Mq, Kq, dq, nq = 2, 8, 4, 60
+            pq = ProductQuantizerWrapper(Mq, Kq, Mq * dq, beta=0.25, normalize=mode, quantizer_cls=EMAVectorQuantizer)
+            wq = torch.randn(Mq, Kq, dq)
+            with torch.no_grad():
+                for i, q in enumerate(pq.quantizers):
+                    q.codebook.weight.copy_(wq[i]); q.codebook.weight_avg.copy_(wq[i])
+            states = [O.EmaState(wq[i]) for i in range(Mq)]
+            exact = [torch.zeros(Kq) for _ in range(Mq)]
+            zstat = ([torch.zeros(dq) for _ in range(Mq)], [torch.zeros(dq) for _ in range(Mq)])
+            pq.train()
+            for step in range(3):
+                zfull = torch.randn(nq, Mq * dq) + 0.2 * step
+                a, b = DU.shard_range(nq)
+                with torch.no_grad():
+                    zq, out, _ = pq(zfull[a:b])
+                ref_rows = []
+                for i in range(Mq):
+                    kw = {"z_mean": zstat[0][i], "z_log_var": zstat[1][i]} if mode == "z_trainable" else {}
+                    qi, oi, _, _ = O.ema_vq_forward(zfull[:, i * dq:(i + 1) * dq], states[i], exact[i], normalize=mode,
+                                                    beta=0.25, training=True, **kw)
+                    ref_rows.append(qi)
+                torch.testing.assert_close(zq, torch.cat(ref_rows, dim=1)[a:b], rtol=1e-5, atol=1e-6)
+                for i, q in enumerate(pq.quantizers):
+                    torch.testing.assert_close(q.codebook.weight, states[i].weight, rtol=1e-5, atol=1e-6)
+                    assert torch.equal(q.vq_count, exact[i])                     # exact counts of the WHOLE batch
+                    both = [torch.empty_like(q.codebook.weight) for _ in range(world)]
+                    dist.all_gather(both, q.codebook.weight.contiguous())
+                    assert torch.equal(both[0], both[1])                         # replicas bit-identical
         ret[rank] = "ok"
     except BaseException as e:   # noqa
         ret[rank] = f"{type(e).__name__}: {e}"
