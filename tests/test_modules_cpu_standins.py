@@ -215,3 +215,38 @@ def test_expansion_head_kernel_path_on_cpu(golden_dir, monkeypatch):
     # with gradients the reference's convolutions run (autograd), same values
     xg = x.clone().requires_grad_(True)
     np.testing.assert_allclose(head(xg).detach().numpy(), g["out"], rtol=1e-5, atol=1e-5)
+
+
+def test_new_vq_soft_statistics_paths_agree_on_cpu(golden_dir, monkeypatch):
+    """dino_new_vq learned codebooks report jsd / entropy of the soft assignment.  Three routes must give the same
+    numbers: the materialised differentiable tensor (materialize_prob=True), the differentiable tensor built only for
+    the statistics (materialize_prob=False with gradients: nothing returned, but jsd / entropy carry a graph), and the
+    fused statistics entry point (materialize_prob=False without gradients: no N x K*M tensor at all)."""
+    import equss_b200  # noqa: F401
+    from equss_b200 import codebooks as CB
+    from equss_b200 import ops
+    kernel_standins.install(monkeypatch)
+    fused_calls = []
+    real = ops.pq_soft_stats
+    monkeypatch.setattr(ops, "pq_soft_stats", lambda *a, **k: (fused_calls.append(1), real(*a, **k))[1])
+    g = np.load(os.path.join(golden_dir, "pq_inline_new_vq_l2.npz"))
+    M, K, ts = int(g["M"]), int(g["K"]), float(g["jsd_ts"])
+    D = g["z0"].shape[1]
+    pq = CB.NewVQProductQuantizerWrapper(M, K, D, beta=0.25, normalize="l2", need_initialized="none", jsd_ts=ts).eval()
+    with torch.no_grad():
+        for i, q in enumerate(pq.quantizers):
+            q.embedding.weight.copy_(torch.from_numpy(g["codebook"][i]))
+    z = torch.from_numpy(g["z1"])
+    zq_a, out_a, prob_a = pq(z.clone().requires_grad_(True), 1)
+    assert prob_a is not None and prob_a.requires_grad and not fused_calls
+    pq.materialize_prob = False
+    zq_b, out_b, prob_b = pq(z.clone().requires_grad_(True), 1)
+    assert prob_b is None and out_b["jsd"].requires_grad and out_b["entropy"].requires_grad and not fused_calls
+    with torch.no_grad():
+        zq_c, out_c, prob_c = pq(z, 1)
+    assert prob_c is None and len(fused_calls) == 1
+    for k in ("jsd", "entropy", "vq-loss"):
+        ref = float(g[f"out1/{k}"])
+        for out in (out_a, out_b, out_c):
+            assert float(out[k].detach()) == pytest.approx(ref, rel=1e-5, abs=1e-8), k
+    assert torch.equal(zq_a.detach(), zq_b.detach()) and torch.equal(zq_a.detach(), zq_c)
