@@ -103,5 +103,6 @@ def test_product_path_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "equss_oracle" not in text and "oracle/" not in text and "import oracle" not in text, f
+                assert "kernel_standins" not in text, f          # the CPU suite's torch stand-ins live in tests/ only
     import equss_b200
     assert issubclass(equss_b200._native.EqussNativeError, RuntimeError)
