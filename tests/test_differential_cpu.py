@@ -1,0 +1,211 @@
+"""Differential test of the module mirrors' host logic against the LIVE reference modules on CPU, over configurations the
+fixtures do not enumerate (normalisation x update_norm x weighted sum x restart / split x layouts x sizes).
+
+Both sides get the same state dict, the same inputs and the same seeds of ``random`` / torch; the mirror runs with the
+kernel entry points replaced by their torch definitions (tests/kernel_standins.py), so every difference found here is a
+difference in the Python around the kernels.  Needs /root/reference (build container only)."""
+import itertools
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import kernel_standins
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+
+
+@pytest.fixture()
+def ref(monkeypatch):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from make_golden import import_reference
+    import_reference()
+    import model.dino_new_vq as nv
+    import model.dino_pqgo as pqgo
+    import model.dino_pqgo_cls as pcls
+    import model.quantizer as q1
+    import equss_b200  # noqa: F401
+    kernel_standins.install(monkeypatch)
+    return {"q1": q1, "nv": nv, "pqgo": pqgo, "pcls": pcls}
+
+
+def _f(v):
+    if v is None:
+        return float("nan")
+    return float(v.detach()) if torch.is_tensor(v) else float(v)
+
+
+def _same_outputs(ro, mo, what):
+    assert set(ro.keys()) == set(mo.keys()), (what, sorted(ro), sorted(mo))
+    for k in ro:
+        a, b = _f(ro[k]), _f(mo[k])
+        assert (np.isnan(a) and np.isnan(b)) or b == pytest.approx(a, rel=2e-5, abs=1e-7), (what, k, a, b)
+
+
+def _same_state(r, m, what):
+    rs, ms = r.state_dict(), m.state_dict()
+    assert sorted(rs) == sorted(ms), what
+    for k in rs:
+        assert torch.allclose(ms[k], rs[k], rtol=2e-5, atol=1e-6), (what, k, float((ms[k] - rs[k]).abs().max()))
+
+
+@pytest.mark.parametrize("mode,update_norm,weighted,restart,split", [
+    ("l2", True, False, False, False), ("l2", False, False, True, False), ("z_norm", True, False, False, True),
+    ("none", False, True, False, False), ("none", True, True, False, False), ("z_trainable", True, False, True, True),
+    ("z_norm", False, False, True, True), ("l2", True, True, False, False)])
+def test_ema_wrapper_against_the_live_reference(ref, mode, update_norm, weighted, restart, split):
+    """model/quantizer.py ProductQuantizerWrapper(EMAVectorQuantizer): 3 training steps + 1 evaluation step."""
+    from equss_b200.quantizer import EMAVectorQuantizer, ProductQuantizerWrapper
+    q1 = ref["q1"]
+    torch.manual_seed(21)
+    M, K, d, n = 3, 12, 6, 90
+    kw = dict(beta=0.3, normalize=mode, decay=0.95, eps=1e-4, use_restart=restart, use_split=split,
+              use_weighted_sum=weighted, update_norm=update_norm)
+    r = q1.ProductQuantizerWrapper(M, K, M * d, quantizer_cls=q1.EMAVectorQuantizer, **kw)
+    m = ProductQuantizerWrapper(M, K, M * d, quantizer_cls=EMAVectorQuantizer, **kw)
+    with torch.no_grad():
+        for q in r.quantizers:
+            q.codebook.weight.copy_(torch.randn(K, d) * (0.05 if mode == "none" else 1.0)); q.codebook.weight_avg.copy_(q.codebook.weight)
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+    for step in range(4):
+        if step == 3:
+            r.eval(); m.eval()
+        z = torch.randn(n, M * d) * (0.05 if mode == "none" else 1.0) + 0.01 * step
+        outs = []
+        for mod in (r, m):
+            random.seed(100 + step); torch.manual_seed(200 + step)
+            with torch.no_grad():
+                outs.append(mod(z))
+        (rq, ro, rp), (mq, mo, mp) = outs
+        assert torch.allclose(mq, rq, rtol=2e-5, atol=2e-6), (step, float((mq - rq).abs().max()))
+        assert torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"step {step}")
+        _same_state(r, m, f"step {step}")
+        for qr, qm in zip(r.quantizers, m.quantizers):
+            if weighted:                                     # soft counts: fp32 sums in a different order
+                assert torch.allclose(qm.vq_count, qr.vq_count, rtol=1e-5), step
+            else:
+                assert torch.equal(qm.vq_count, qr.vq_count), step
+            if restart and step < 3:                         # drawn by the forward, applied by the trainer (restart())
+                random.seed(300 + step)
+                qr.restart(); qm.restart()
+        _same_state(r, m, f"step {step} after restart")
+
+
+@pytest.mark.parametrize("variant,cls,mode,restart,weighted", [
+    ("nv", "EMACodebook", "l2", True, False), ("nv", "EMACodebook", "z_norm", False, False), ("nv", "EMACodebook", "none", False, True),
+    ("nv", "Codebook", "z_norm", True, False), ("nv", "Codebook", "none", False, True),
+    ("pqgo", "Codebook", "l2", True, False), ("pqgo", "Codebook", "none", False, True), ("pcls", "Codebook", "z_trainable", False, False),
+    # (dino_pqgo.Codebook with z_trainable cannot run in the reference: z_pos_norm is never assigned, dino_pqgo.py:650)
+    ("pcls", "Codebook", "z_norm", True, False), ("pcls", "Codebook", "l2", False, False)])
+def test_inline_wrappers_against_the_live_reference(ref, variant, cls, mode, restart, weighted):
+    """The inline ProductQuantizerWrapper copies of dino_new_vq / dino_pqgo / dino_pqgo_cls: 2 training calls + 1
+    evaluation call, every element of the variant's return tuple."""
+    from equss_b200 import codebooks as CB
+    R = ref[variant]
+    Mir = {"nv": CB.NewVQProductQuantizerWrapper, "pqgo": CB.PQGOProductQuantizerWrapper, "pcls": CB.PQGOClsProductQuantizerWrapper}[variant]
+    torch.manual_seed(23)
+    M, K, d, B, h, w = 2, 10, 6, 2, 5, 4
+    kw = dict(beta=0.3, normalize=mode, use_restart=restart, use_weighted_sum=weighted, need_initialized="none", jsd_ts=0.6)
+    if variant == "pqgo":
+        kw["book"] = 0.7
+    r = R.ProductQuantizerWrapper(M, K, M * d, quantizer_cls=getattr(R, cls), **kw)
+    m = Mir(M, K, M * d, quantizer_cls=getattr(CB, cls), **kw)
+    scale = 0.3 if mode == "none" else 1.0
+    with torch.no_grad():
+        for q in r.quantizers:
+            if cls == "EMACodebook":
+                q.codebook.weight.copy_(torch.randn(K, d) * scale); q.codebook.weight_avg.copy_(q.codebook.weight)
+            else:
+                q.embedding.weight.copy_(torch.randn(K, d) * scale)
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+    for step in range(3):
+        if step == 2:
+            r.eval(); m.eval()
+        z = torch.randn(B, M * d, h, w) * scale
+        res = []
+        for mod in (r, m):
+            random.seed(400 + step); torch.manual_seed(500 + step)
+            with torch.no_grad():
+                res.append(mod(z, step) if variant != "pqgo" else mod(z, torch.zeros_like(z), step))
+        rr, mr = res
+        assert len(rr) == len(mr)
+        assert torch.allclose(mr[0], rr[0], rtol=2e-5, atol=2e-6), step
+        if variant == "nv":
+            (_, ro, rp), (_, mo, mp) = rr, mr
+        elif variant == "pcls":
+            (_, ro, rp, ri), (_, mo, mp, mi) = rr, mr
+            assert all(torch.equal(a, b) for a, b in zip(ri, mi))
+        else:
+            (_, (rs, rqs, ri), ro, rp), (_, (ms, mqs, mi), mo, mp) = rr, mr
+            assert all(torch.equal(a, b) for a, b in zip(ri, mi)) and all(torch.equal(a, b) for a, b in zip(rs, ms))
+            assert all(torch.allclose(a, b, rtol=2e-5, atol=2e-6) for a, b in zip(rqs, mqs))
+        assert mp.shape == rp.shape and torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"{variant}/{cls} step {step}")
+        _same_state(r, m, f"{variant}/{cls} step {step}")
+        for qr, qm in zip(r.quantizers, m.quantizers):
+            assert torch.equal(qm.vq_count.cpu(), qr.vq_count.cpu()), step
+            if restart and cls == "EMACodebook" and step < 2:
+                qr.restart(); qm.restart()
+        _same_state(r, m, f"{variant}/{cls} step {step} after restart")
+
+
+@pytest.mark.parametrize("variant,cls,mode,weighted", [("nv", "EMACodebook", "z_norm", False), ("nv", "Codebook", "l2", False),
+                                                       ("pqgo", "Codebook", "none", True), ("nv", "EMACodebook", "none", True)])
+def test_pq_dropout_wrappers_against_the_live_reference(ref, monkeypatch, variant, cls, mode, weighted):
+    """pq_dropout through the wrappers: the reference's ``torch.cuda.FloatTensor(K).uniform_()`` and the mirror's own draw
+    are fed the same uniform numbers (one (K,) vector per subspace per call, evaluation calls included)."""
+    from equss_b200 import _host_paths as hp
+    from equss_b200 import codebooks as CB
+    R = ref[variant]
+    Mir = {"nv": CB.NewVQProductQuantizerWrapper, "pqgo": CB.PQGOProductQuantizerWrapper}[variant]
+    torch.manual_seed(29)
+    M, K, d, B, h, w, p = 3, 14, 6, 2, 5, 4, 0.3
+    kw = dict(beta=0.3, normalize=mode, use_weighted_sum=weighted, need_initialized="none", jsd_ts=0.6, pq_dropout=p)
+    r = R.ProductQuantizerWrapper(M, K, M * d, quantizer_cls=getattr(R, cls), **kw)
+    m = Mir(M, K, M * d, quantizer_cls=getattr(CB, cls), **kw)
+    scale = 0.3 if mode == "none" else 1.0
+    with torch.no_grad():
+        for q in r.quantizers:
+            if cls == "EMACodebook":
+                q.codebook.weight.copy_(torch.randn(K, d) * scale); q.codebook.weight_avg.copy_(q.codebook.weight)
+            else:
+                q.embedding.weight.copy_(torch.randn(K, d) * scale)
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+
+    class _Pending:
+        def __init__(self, u):
+            self.u = u
+
+        def uniform_(self):
+            return self.u
+
+    for step in range(3):
+        if step == 2:
+            r.eval(); m.eval()
+        z = torch.randn(B, M * d, h, w) * scale
+        draws = list(torch.rand(M, K))
+        it_r, it_m = iter(draws), iter(draws)
+        monkeypatch.setattr(torch.cuda, "FloatTensor", lambda n: _Pending(next(it_r)), raising=False)
+        monkeypatch.setattr(hp, "dropout_keep_mask", lambda n, prob, device: next(it_m).to(device) > prob)
+        with torch.no_grad():
+            rr = r(z, step) if variant != "pqgo" else r(z, torch.zeros_like(z), step)
+            mr = m(z, step) if variant != "pqgo" else m(z, torch.zeros_like(z), step)
+        assert next(it_r, None) is None and next(it_m, None) is None          # M draws each, evaluation included
+        assert torch.allclose(mr[0], rr[0], rtol=2e-5, atol=2e-6), step
+        ro, mo = (rr[1], mr[1]) if variant == "nv" else (rr[2], mr[2])
+        rp, mp = (rr[2], mr[2]) if variant == "nv" else (rr[3], mr[3])
+        assert mp.shape == rp.shape and torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step      # ragged widths concatenated
+        if variant == "pqgo":
+            assert all(torch.equal(a, b) for a, b in zip(rr[1][2], mr[1][2]))
+        _same_outputs(ro, mo, f"dropout {variant}/{cls} step {step}")
+        _same_state(r, m, f"dropout {variant}/{cls} step {step}")
+        for qr, qm in zip(r.quantizers, m.quantizers):
+            assert torch.equal(qm.vq_count.cpu(), qr.vq_count.cpu()), step
