@@ -209,3 +209,36 @@ def test_pq_dropout_wrappers_against_the_live_reference(ref, monkeypatch, varian
         _same_state(r, m, f"dropout {variant}/{cls} step {step}")
         for qr, qm in zip(r.quantizers, m.quantizers):
             assert torch.equal(qm.vq_count.cpu(), qr.vq_count.cpu()), step
+
+
+@pytest.mark.parametrize("B,D,h,w,H,W,extra", [(2, 24, 7, 5, 23, 31, 0), (1, 16, 6, 6, 6, 6, 0), (2, 32, 5, 8, 40, 64, 3)])
+def test_evaluator_and_metrics_against_the_live_reference(ref, monkeypatch, tmp_path, B, D, h, w, H, W, extra):
+    """UnSegEvaluator.forward + UnSegMetrics.update / compute (Hungarian matching, extra cluster rows) next to the
+    reference at label resolution: non-integer scale factors, equal sizes, extra classes."""
+    import model.evaluator as ref_eval
+    import model.metric as ref_metric
+    from equss_b200.evaluator import UnSegEvaluator
+    from equss_b200.metric import UnSegMetrics
+    monkeypatch.chdir(tmp_path)                                # compute() writes ./class_matrix/...
+    torch.manual_seed(31)
+    C = 9
+    r = ref_eval.UnSegEvaluator(D, C, extra).eval()
+    m = UnSegEvaluator(D, C, extra).eval()
+    m.load_state_dict(r.state_dict(), strict=True)
+    out = torch.randn(B, D, h, w)
+    label = torch.randint(-1, C, (B, H, W))
+    with torch.no_grad():
+        rl, rlp, rc, rcp = r(out, None, label)
+        ml, mlp, mc, mcp = m(out, None, label)
+    assert float((mlp != rlp).float().mean()) < 2e-3 and float((mcp != rcp).float().mean()) < 2e-3     # fp32 near-ties only
+    assert float(ml) == pytest.approx(float(rl), rel=2e-5) and float(mc) == pytest.approx(float(rc), rel=2e-4)
+    for hung, preds_r, preds_m, ex in ((True, rcp, rcp, extra), (False, rlp, rlp, 0)):
+        rm = ref_metric.UnSegMetrics(C, ex, hung, torch.device("cpu"))
+        mm = UnSegMetrics(C, ex, hung, torch.device("cpu"))
+        rm.update(preds_r, label); mm.update(preds_m, label)
+        assert torch.equal(mm.confusion_matrix, rm.confusion_matrix)
+        rr, mr = rm.compute("t"), mm.compute("t")
+        for k in rr:
+            assert float(mr[k]) == pytest.approx(float(rr[k]), rel=1e-6), k
+        if hung:
+            assert torch.equal(mm.map_clusters(preds_m), rm.map_clusters(preds_r))
