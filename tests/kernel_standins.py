@@ -259,6 +259,16 @@ def install(monkeypatch):
             return out
         return y
 
+    def stego_feature_corr(f1, f2, pointwise=True):
+        """model/loss.py:679-687: cosine correlation of the sampled positions, rows centred, global mean restored."""
+        a, b = F.normalize(f1.detach().float(), dim=1, eps=1e-10), F.normalize(f2.detach().float(), dim=1, eps=1e-10)
+        fd = torch.einsum("nchw,ncij->nhwij", a, b)
+        if pointwise:
+            old_mean = fd.mean()
+            fd = fd - fd.mean(dim=[3, 4], keepdim=True)
+            fd = fd - fd.mean() + old_mean
+        return fd
+
     for name, fn in list(locals().items()):
         if callable(fn) and hasattr(ops, name):
             monkeypatch.setattr(ops, name, fn)

@@ -242,3 +242,91 @@ def test_evaluator_and_metrics_against_the_live_reference(ref, monkeypatch, tmp_
             assert float(mr[k]) == pytest.approx(float(rr[k]), rel=1e-6), k
         if hung:
             assert torch.equal(mm.map_clusters(preds_m), rm.map_clusters(preds_r))
+
+
+@pytest.mark.parametrize("mode,restart,gumbel", [("l2", False, False), ("z_norm", True, False), ("z_trainable", False, False),
+                                                 ("none", False, False), ("l2", False, True)])
+def test_learned_vector_quantizer_against_the_live_reference(ref, mode, restart, gumbel):
+    """model/quantizer.py VectorQuantizer (NCHW, learned codebook): training call with the gradients of the reference's
+    graph (straight-through output, both losses), exact counters, evaluation call."""
+    from equss_b200.quantizer import VectorQuantizer
+    q1 = ref["q1"]
+    torch.manual_seed(37)
+    K, d, B, h, w = 11, 8, 2, 5, 4
+    r = q1.VectorQuantizer(K, d, beta=0.3, normalize=mode, use_restart=restart, use_gumbel=gumbel)
+    m = VectorQuantizer(K, d, beta=0.3, normalize=mode, use_restart=restart, use_gumbel=gumbel)
+    m.load_state_dict(r.state_dict(), strict=True)
+    go = torch.randn(B, d, h, w)
+    for step, training in enumerate((True, False)):
+        r.train(training); m.train(training)
+        z = torch.randn(B, d, h, w) * (0.3 if mode == "none" else 1.0)
+        res = []
+        for mod in (r, m):
+            mod.zero_grad()
+            zi = z.clone().requires_grad_(True)
+            random.seed(600 + step); torch.manual_seed(700 + step)
+            q, out, prob = mod(zi)
+            (out["loss"] + (q * go).sum() + (prob * prob).sum()).backward()
+            res.append((q, out, prob, zi.grad))
+        (rq, ro, rp, rg), (mq, mo, mp, mg) = res
+        assert torch.allclose(mq, rq, rtol=2e-5, atol=2e-6) and torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"V1 {mode} step {step}")
+        assert torch.allclose(mg, rg, rtol=1e-3, atol=1e-6 * float(rg.abs().max()) + 1e-9), (step, float((mg - rg).abs().max()))
+        for (kn, pr), (_, pm) in zip(r.named_parameters(), m.named_parameters()):
+            assert (pr.grad is None) == (pm.grad is None), kn
+            if pr.grad is not None:
+                assert torch.allclose(pm.grad, pr.grad, rtol=1e-3, atol=1e-6 * float(pr.grad.abs().max()) + 1e-9), (step, kn)
+        assert torch.equal(m.vq_count, r.vq_count)
+        if restart and training:
+            r.restart(); m.restart()
+        _same_state(r, m, f"V1 {mode} step {step}")
+
+
+def test_quantizer_v2_against_the_live_reference(ref):
+    """model/quantizer_v2.py (V3): EMA quantiser that gathers rows of z_norm (a quirk kept for parity), 3 training steps +
+    evaluation through its wrapper."""
+    import model.quantizer_v2 as q2
+    from equss_b200 import quantizer_v2 as m2
+    torch.manual_seed(41)
+    M, K, d, B, h, w = 2, 9, 6, 2, 5, 4
+    r = q2.ProductQuantizerWrapper(M, K, M * d, beta=0.3, normalize="l2", decay=0.9, eps=1e-4)
+    m = m2.ProductQuantizerWrapper(M, K, M * d, beta=0.3, normalize="l2", decay=0.9, eps=1e-4)
+    with torch.no_grad():
+        for q in r.quantizers:
+            q.embeddings.copy_(torch.randn(K, d)); q.z_avg.copy_(q.embeddings)
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+    for step in range(4):
+        if step == 3:
+            r.eval(); m.eval()
+        z = torch.randn(B, M * d, h, w)
+        with torch.no_grad():
+            (rq, ro, rp), (mq, mo, mp) = r(z), m(z)
+        assert torch.allclose(mq, rq, rtol=2e-5, atol=2e-6) and torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"V3 step {step}")
+        _same_state(r, m, f"V3 step {step}")
+
+
+@pytest.mark.parametrize("pointwise,zero_clamp,stabilize", [(True, True, False), (False, False, True)])
+def test_stego_loss_against_the_live_reference(ref, pointwise, zero_clamp, stabilize):
+    """model/loss.py STEGOLoss: same sampled coordinates and negative permutations (torch seeds), loss value and the
+    gradient that reaches the code maps."""
+    import model.loss as ref_loss
+    from equss_b200.losses import STEGOLoss
+    cfg = {"pointwise": pointwise, "zero_clamp": zero_clamp, "stabilize": stabilize, "feature_samples": 7, "neg_samples": 2,
+           "pos_intra_shift": 0.18, "pos_inter_shift": 0.12, "neg_inter_shift": 0.46,
+           "pos_intra_weight": 0.67, "pos_inter_weight": 0.25, "neg_inter_weight": 0.63}
+    torch.manual_seed(43)
+    n, C, Cc, h, w = 4, 12, 10, 9, 9
+    feats, feats_pos = torch.randn(n, C, h, w), torch.randn(n, C, h, w)
+    code, code_pos = torch.randn(n, Cc, h, w), torch.randn(n, Cc, h, w)
+    res = []
+    for L in (ref_loss.STEGOLoss(cfg), STEGOLoss(cfg)):
+        c1, c2 = code.clone().requires_grad_(True), code_pos.clone().requires_grad_(True)
+        torch.manual_seed(800)
+        loss = L(feats, feats_pos, c1, c2)
+        loss.backward()
+        res.append((loss.detach(), c1.grad, c2.grad))
+    (rl, rg1, rg2), (ml, mg1, mg2) = res
+    assert float(ml) == pytest.approx(float(rl), rel=2e-5)
+    assert torch.allclose(mg1, rg1, rtol=1e-3, atol=1e-8) and torch.allclose(mg2, rg2, rtol=1e-3, atol=1e-8)
