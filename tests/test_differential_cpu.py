@@ -330,3 +330,29 @@ def test_stego_loss_against_the_live_reference(ref, pointwise, zero_clamp, stabi
     (rl, rg1, rg2), (ml, mg1, mg2) = res
     assert float(ml) == pytest.approx(float(rl), rel=2e-5)
     assert torch.allclose(mg1, rg1, rtol=1e-3, atol=1e-8) and torch.allclose(mg2, rg2, rtol=1e-3, atol=1e-8)
+
+
+def test_user_supplied_quantizer_class_takes_the_reference_loop(ref):
+    """``quantizer_cls`` may be any module with the quantiser signature (model/quantizer.py:577-611): the mirror then runs
+    the reference's per-subspace loop -- chunk, call, concatenate, mean of the output dictionaries."""
+    from equss_b200.quantizer import ProductQuantizerWrapper
+    q1 = ref["q1"]
+
+    class Halver(torch.nn.Module):
+        def __init__(self, num_codebook, embed_dim, **kw):
+            super().__init__()
+            self.scale = torch.nn.Parameter(torch.full((embed_dim,), 0.5))
+            self.kw = kw
+
+        def forward(self, z):
+            return z * self.scale, {"loss": (z ** 2).mean(), "n": float(z.shape[1])}, torch.softmax(z[:, :3], dim=1)
+
+    torch.manual_seed(47)
+    r = q1.ProductQuantizerWrapper(3, 8, 12, normalize="l2", quantizer_cls=Halver)
+    m = ProductQuantizerWrapper(3, 8, 12, normalize="l2", quantizer_cls=Halver)
+    m.load_state_dict(r.state_dict(), strict=True)
+    z = torch.randn(10, 12)
+    (rq, ro, rp), (mq, mo, mp) = r(z), m(z)
+    assert torch.equal(mq, rq) and torch.equal(mp, rp) and mp.shape == (10, 9)
+    _same_outputs(ro, mo, "custom class")
+    assert m.quantizers[0].kw.keys() == r.quantizers[0].kw.keys()            # same keyword arguments handed down
