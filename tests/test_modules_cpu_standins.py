@@ -250,3 +250,28 @@ def test_new_vq_soft_statistics_paths_agree_on_cpu(golden_dir, monkeypatch):
         for out in (out_a, out_b, out_c):
             assert float(out[k].detach()) == pytest.approx(ref, rel=1e-5, abs=1e-8), k
     assert torch.equal(zq_a.detach(), zq_b.detach()) and torch.equal(zq_a.detach(), zq_c)
+
+
+@pytest.mark.parametrize("b1,b2,b3", [(True, True, True), (False, True, False), (True, False, False), (False, False, True)])
+def test_expansion_head_bias_combinations_on_cpu(monkeypatch, b1, b2, b3):
+    """expansion_head on user-built 1x1-convolution stacks with any subset of biases: the packed [W1 | W3] operand and
+    b1 + b3 equal the convolutions' sum (model/dino_pqgo.py:127-128); other stacks are refused with the reference layout."""
+    import torch.nn as nn
+    import equss_b200  # noqa: F401
+    from equss_b200.head import expansion_head
+    kernel_standins.install(monkeypatch)
+    torch.manual_seed(53)
+    C, D = 12, 20
+    c1 = nn.Sequential(nn.Conv2d(C, D, (1, 1), bias=b1)).eval()
+    c2 = nn.Sequential(nn.Conv2d(C, C, (1, 1), bias=b2), nn.ReLU(), nn.Conv2d(C, D, (1, 1), bias=b3)).eval()
+    x = torch.randn(2, C, 5, 6)
+    with torch.no_grad():
+        want = c1(x) + c2(x)
+        got = expansion_head(x, c1, c2)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        expansion_head(x, c2, c1)
+    with pytest.raises(ValueError):
+        expansion_head(x, nn.Sequential(nn.Conv2d(C, D, (3, 3), padding=1)), c2)
+    with pytest.raises(ValueError):
+        expansion_head(x[0], c1, c2)
