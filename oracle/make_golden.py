@@ -224,7 +224,8 @@ def main():
 
     # ------------------------------------------------------------------ kNN
     # data/precompute_knns.py needs hydra / pytorch_lightning (absent) to import, so its three kNN lines
-    # (:313-315) are the oracle's restatement; the fixture pins the einsum+topk result on this torch build.
+    # (:313-315) are the oracle's restatement here; the fixture pins the einsum+topk result on this torch build.
+    # oracle/make_golden_knn.py executes the reference's own statements (taken from its AST) and pins the oracle to them.
     torch.manual_seed(26)   # first seed whose top-9 similarity gaps all exceed 1e-5 (no fp32 near-ties)
     feats = torch.nn.functional.normalize(torch.randn(300, 48), dim=1)
     idx, vals = O.knn(feats, k=8)

@@ -1,0 +1,113 @@
+"""Generate tests/golden/knn_ref_loop.npz from the UNMODIFIED kNN statements of the reference
+(/root/reference/data/precompute_knns.py:307-317).
+
+Run in the build container only:   PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden_knn.py
+
+``data/precompute_knns.py`` cannot be imported here (hydra / pytorch_lightning are absent) and its kNN arithmetic sits
+inside ``my_app``, between dataset and model construction.  So this script does not import it: it parses the file,
+finds the ``all_nns = []`` ... ``nearest_neighbors = torch.cat(all_nns, dim=0)`` statements inside ``my_app`` by their
+structure (the assignment to ``all_nns``, the ``step`` assignment, the ``for`` loop over ``tqdm(range(...))`` that calls
+``torch.einsum`` and ``torch.topk``, the concatenation), compiles exactly those AST nodes and executes them on seeded
+features with ``tqdm`` replaced by the identity.  Nothing of the reference is copied into the repository -- the
+statements are read from /root/reference every time the script runs.  The oracle restatement
+(oracle/equss_oracle.py::knn, k = 30 as the reference hard-codes) must reproduce the result bit for bit, for the
+reference's own ``n_batches = 1`` (:271) and for a chunked run (``n_batches = 4`` on 301 rows: four chunks of 75 and a
+ragged one of 1), which yields the same table.  The seed is the first whose 30th / 31st similarities differ by more
+than 1e-5 in every row (no fp32 near-tie decides membership) and whose in-row gaps exceed 1e-6 (3e-7 at F = 768, where
+the similarities lie closer together; fp32 evaluation orders differ by a few 1e-8) so that no near-tie decides the order."""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("EQUSS_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.dont_write_bytecode = True
+
+
+def _calls(node, dotted):
+    """True when `node` contains a call of `dotted` (e.g. "torch.topk")."""
+    for n in ast.walk(node):
+        if isinstance(n, ast.Call) and ast.unparse(n.func) == dotted:
+            return True
+    return False
+
+
+def reference_knn_statements():
+    """The AST nodes of precompute_knns.py that turn ``normed_feats`` + ``n_batches`` into ``nearest_neighbors``, and the
+    reference's own ``n_batches`` constant."""
+    path = os.path.join(REF, "data", "precompute_knns.py")
+    tree = ast.parse(open(path).read(), path)
+    picked, n_batches = [], None
+    for fn in ast.walk(tree):
+        if not (isinstance(fn, ast.FunctionDef) and fn.name == "my_app"):
+            continue
+        for n in ast.walk(fn):
+            if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name):
+                name = n.targets[0].id
+                if name == "n_batches" and isinstance(n.value, ast.Constant):
+                    n_batches = n.value.value
+                if name == "all_nns" or name == "nearest_neighbors" or (name == "step" and "normed_feats" in ast.unparse(n.value)):
+                    picked.append(n)
+            if isinstance(n, ast.For) and _calls(n.iter, "tqdm") and _calls(n, "torch.einsum") and _calls(n, "torch.topk"):
+                picked.append(n)
+    picked.sort(key=lambda n: n.lineno)
+    kinds = [type(n).__name__ for n in picked]
+    assert kinds == ["Assign", "Assign", "For", "Assign"] and n_batches is not None, (kinds, n_batches)
+    return picked, n_batches, path
+
+
+def run_reference(picked, path, normed_feats, n_batches):
+    mod = ast.Module(body=picked, type_ignores=[])
+    env = {"torch": torch, "tqdm": lambda it: it, "normed_feats": normed_feats, "n_batches": n_batches}
+    exec(compile(mod, path, "exec"), env)                       # torch.cuda.empty_cache() is a no-op without CUDA
+    return env["nearest_neighbors"]
+
+
+def seeded_features(seed, n, Fd):
+    """Unit-norm rows from torch's CPU generator (what the tests regenerate for the F = 768 case)."""
+    torch.manual_seed(int(seed))
+    return torch.nn.functional.normalize(torch.randn(n, Fd), dim=1)
+
+
+def main():
+    torch.set_num_threads(1)
+    sys.path.insert(0, HERE)
+    import equss_oracle as O
+    picked, ref_batches, path = reference_knn_statements()
+    print("reference statements: lines", [(n.lineno, n.end_lineno) for n in picked], "n_batches =", ref_batches)
+    k, fix = 30, {"n_batches": np.int64(ref_batches)}
+    # two cases: F = 48 (features stored) and F = 768, the reference's ViT-B width and the kernel's tensor-core screening
+    # path (features regenerated from the stored seed by the tests; their float64 sum is stored to detect generator drift)
+    for tag, n, Fd, store, order_gap in (("f48", 301, 48, True, 1e-6), ("f768", 301, 768, False, 3e-7)):
+        for seed in range(5000):
+            feats = seeded_features(seed, n, Fd)
+            top = torch.topk(feats.double() @ feats.double().t(), k + 1)[0]
+            if float((top[:, :-1] - top[:, 1:]).min()) > order_gap and float((top[:, k - 1] - top[:, k]).min()) > 1e-5:
+                break
+        else:
+            raise SystemExit("no seed without near-ties")
+        with torch.no_grad():
+            whole = run_reference(picked, path, feats, ref_batches)
+            chunked = run_reference(picked, path, feats, 4)
+        assert whole.dtype == torch.int64 and tuple(whole.shape) == (n, k)
+        assert torch.equal(whole, chunked), "the chunked reference loop disagrees with the one-batch run"
+        idx, vals = O.knn(feats, k=k)
+        assert torch.equal(idx, whole), "oracle != reference statements"
+        assert torch.equal(whole[:, 0], torch.arange(n))        # column 0 is the query itself (dataset_aug.py:520)
+        fix.update({f"{tag}_nns": whole.numpy(), f"{tag}_vals": vals.numpy(), f"{tag}_seed": np.int64(seed),
+                    f"{tag}_shape": np.array([n, Fd], dtype=np.int64), f"{tag}_sum": np.float64(feats.double().sum())})
+        if store:
+            fix[f"{tag}_feats"] = feats.numpy()
+        print(f"{tag}: seed {seed}, nns {tuple(whole.shape)} ok")
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "knn_ref_loop.npz"), **fix)
+    print("knn_ref_loop.npz written")
+
+
+if __name__ == "__main__":
+    main()

@@ -373,3 +373,18 @@ def test_affine_parameter_gradients_from_the_activation_gradient():
         (zn * torch.randn_like(zn)).sum().backward()
         ga, gb = core._affine_param_grads(z.grad, z.detach(), M, a.detach(), b.detach(), True, True)
         assert torch.allclose(ga, a.grad, rtol=1e-5, atol=1e-6) and torch.allclose(gb, b.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["f48", "f768"])
+def test_knn_reference_table_test_body_on_cpu(golden_dir, tmp_path, monkeypatch, tag):
+    """tests/test_gpu_knn_ref.py re-run on CPU tensors with ``ops.knn_topk`` replaced by its torch definition: the test
+    body, the fixture handling and the ``precompute_knns`` / ``save_nns`` / ``load_nns`` plumbing (not the kernels)."""
+    import test_gpu_knn_ref as T
+    from equss_b200 import ops
+
+    def knn_topk(queries, db, k, return_sims=False):
+        sims, idx = torch.topk(torch.einsum("nf,mf->nm", queries, db), k)
+        return (idx, sims) if return_sims else idx
+    monkeypatch.setattr(ops, "knn_topk", knn_topk)
+    monkeypatch.setattr(T, "DEV", "cpu")
+    T.test_knn_equals_reference_statements(golden_dir, tmp_path, tag)

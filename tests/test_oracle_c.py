@@ -145,6 +145,23 @@ def test_knn_matches_the_fixture(lib, golden_dir):
     assert np.array_equal(idx, g["idx"]) and np.array_equal(idx[:, 0], np.arange(n))
 
 
+@pytest.mark.parametrize("tag", ["f48", "f768"])
+def test_knn_matches_the_reference_statements(lib, golden_dir, tag):
+    """k = 30 table produced by the reference's own statements (oracle/make_golden_knn.py), whole and in query chunks."""
+    from test_oracle_golden import knn_ref_case
+    g = np.load(os.path.join(golden_dir, "knn_ref_loop.npz"))
+    feats, nns, _ = knn_ref_case(g, tag)
+    feats = np.ascontiguousarray(feats.numpy())
+    n, F = feats.shape
+    idx = np.empty((n, 30), np.int64)
+    assert lib.eqo_knn_topk(_p(feats), C.c_int64(n), _p(feats), C.c_int64(n), F, 30, _p(idx)) == 0
+    assert np.array_equal(idx, nns)
+    part = np.empty((75, 30), np.int64)
+    q = np.ascontiguousarray(feats[150:225])
+    assert lib.eqo_knn_topk(_p(q), C.c_int64(75), _p(feats), C.c_int64(n), F, 30, _p(part)) == 0
+    assert np.array_equal(part, nns[150:225])
+
+
 def test_c_and_torch_restatements_agree_on_random_inputs(lib):
     """Seeded random inputs beyond the fixtures: ragged sizes, d not a multiple of 4, K = 1, duplicate codes (the first
     of equal distances wins), percentiles that are never reached."""

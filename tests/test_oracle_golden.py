@@ -97,6 +97,56 @@ def test_knn(golden_dir):
     assert np.array_equal(idx[:, 0].numpy(), np.arange(idx.shape[0]))   # column 0 is the query itself
 
 
+def knn_ref_case(g, tag):
+    """Features + the neighbour table the reference's own statements produced (oracle/make_golden_knn.py).  F = 48:
+    features stored; F = 768: regenerated from the stored seed, checked against their stored float64 sum."""
+    n, Fd = (int(v) for v in g[f"{tag}_shape"])
+    if f"{tag}_feats" in g.files:
+        feats = torch.from_numpy(g[f"{tag}_feats"])
+    else:
+        torch.manual_seed(int(g[f"{tag}_seed"]))
+        feats = torch.nn.functional.normalize(torch.randn(n, Fd), dim=1)
+        if float(feats.double().sum()) != float(g[f"{tag}_sum"]):
+            pytest.skip("torch's CPU generator on this host does not reproduce the fixture's features")
+    return feats, g[f"{tag}_nns"], g[f"{tag}_vals"]
+
+
+@pytest.mark.parametrize("tag", ["f48", "f768"])
+def test_knn_reference_statements(golden_dir, tag):
+    """The table computed by the reference's OWN kNN statements (data/precompute_knns.py:307-317, executed from the
+    reference file by oracle/make_golden_knn.py; top-30 as hard-coded there) == the oracle's, bit for bit; computing
+    it in query chunks (the reference's n_batches loop) changes nothing."""
+    g = _load(golden_dir, "knn_ref_loop.npz")
+    feats, nns, vals = knn_ref_case(g, tag)
+    idx, v = O.knn(feats, k=30)
+    assert np.array_equal(idx.numpy(), nns) and idx.dtype == torch.int64
+    np.testing.assert_allclose(v.numpy(), vals, rtol=0, atol=1e-6)
+    parts = [O.knn(feats, k=30, queries=feats[a:a + 75])[0] for a in range(0, feats.shape[0], 75)]
+    assert np.array_equal(torch.cat(parts).numpy(), nns)
+    assert np.array_equal(nns[:, 0], np.arange(nns.shape[0]))            # column 0 is the query itself
+
+
+def test_knn_reference_statements_live(golden_dir):
+    """On the build box (reference present): re-extract the statements from the reference file and re-run them -- the
+    stored table is what they produce today."""
+    ref = os.environ.get("EQUSS_REFERENCE", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "data", "precompute_knns.py")):
+        pytest.skip("reference tree not present (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_make_golden_knn", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "make_golden_knn.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    picked, n_batches, path = mk.reference_knn_statements()
+    g = _load(golden_dir, "knn_ref_loop.npz")
+    assert n_batches == int(g["n_batches"])
+    for tag in ("f48", "f768"):
+        feats, nns, _ = knn_ref_case(g, tag)
+        with torch.no_grad():
+            for nb in (n_batches, 4):
+                assert np.array_equal(mk.run_reference(picked, path, feats, nb).numpy(), nns)
+
+
 def test_histogram_percentiles_none_when_unreached():
     out = O.histogram_percentiles(torch.zeros(8), "x")
     assert out == {"x-p10": None, "x-p50": None, "x-p90": None}
