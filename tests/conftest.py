@@ -9,7 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-_FIRST_HARDWARE_RUN = {"test_gpu_flags_dropout.py", "test_gpu_knn_ref.py"}
+_FIRST_HARDWARE_RUN = {"test_gpu_flags_dropout.py", "test_gpu_knn_ref.py", "test_gpu_yaml_shapes.py"}
 
 
 def pytest_configure(config):

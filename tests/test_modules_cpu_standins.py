@@ -127,6 +127,8 @@ def test_rare_branches_of_the_ema_wrapper_on_cpu(monkeypatch):
 
     M, K, d = 2, 1030, 4
     _run_against_oracle(make(M, K, M * d, "l2"), O, M, K, d, "l2", [torch.randn(96, M * d) for _ in range(3)])
+    M, K, d = 2, 1024, 256                     # config/pq_baseline.yaml:32-33,41 (embed_dims 512, num_pq 2, 1024 codes)
+    _run_against_oracle(make(M, K, M * d, "l2"), O, M, K, d, "l2", [torch.randn(120, M * d) for _ in range(3)])
     M, K, d = 3, 16, 8
     _run_against_oracle(make(M, K, M * d, "none", update_norm=False), O, M, K, d, "none",
                         [torch.randn(80, M * d) for _ in range(3)], update_norm=False)
