@@ -14,6 +14,8 @@ this oracle is pinned against outputs of the reference ITSELF: ``oracle/make_gol
 reference modules from /root/reference (with stubs for the off-path torchmetrics / pydensecrf imports),
 runs them on seeded inputs, asserts this oracle reproduces them bit for bit, and writes the vectors to
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` re-checks the oracle against those files.
+``data/precompute_knns.py`` cannot be imported (hydra / pytorch_lightning are absent): ``oracle/make_golden_knn.py``
+executes its kNN statements (:307-317) straight out of the reference file's AST and pins ``knn`` below to their result.
 """
 from __future__ import annotations
 
