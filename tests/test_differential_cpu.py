@@ -356,3 +356,104 @@ def test_user_supplied_quantizer_class_takes_the_reference_loop(ref):
     assert torch.equal(mq, rq) and torch.equal(mp, rp) and mp.shape == (10, 9)
     _same_outputs(ro, mo, "custom class")
     assert m.quantizers[0].kw.keys() == r.quantizers[0].kw.keys()            # same keyword arguments handed down
+
+
+@pytest.mark.parametrize("yaml_file,variant,cls", [
+    ("config/pqgo_baseline.yaml", "pqgo", "Codebook"), ("config/cityscapes/pqgo_baseline.yaml", "pqgo", "Codebook"),
+    ("config/new_vq_baseline.yaml", "nv", "Codebook"), ("config/new_vq_baseline.yaml", "nv", "EMACodebook"),
+    ("config/pqgo_cls.yaml", "pcls", "Codebook")])
+def test_yaml_literal_inline_configuration_against_the_live_reference(ref, yaml_file, variant, cls):
+    """The trainer paths exactly as the reference's YAML files configure them: the ``vq`` section is read with
+    ``yaml.safe_load`` and turned into the wrapper's arguments the way the model constructors do it (``train.py``:
+    model/dino_pqgo.py:38-76 -- cocostuff27 64 subspaces x 256 codes on 1024 channels, cityscapes 32 x 32; ``train_vq.py``:
+    model/dino_new_vq.py:56-98 -- 32 x 512, with the learned codebook the file selects and the EMA one its comment offers;
+    model/dino_pqgo_cls.py:41-68 -- 64 x 256), including ``need_initialized: "uni"`` (the first training call re-draws the
+    codebook), a zero ``pq_dropout`` and the jsd temperature of the loss section.  2 training calls + 1 evaluation call on a
+    small token grid; every element of the return tuple, the output dictionary and the state agree."""
+    import yaml
+    from equss_b200 import codebooks as CB
+    cfg_all = yaml.safe_load(open(os.path.join(os.environ.get("EQUSS_REFERENCE", "/root/reference"), yaml_file)))
+    vq, jsd = cfg_all["model"]["vq"], cfg_all["loss"]["jsd"]
+    assert vq["vq_type"] == "param"
+    kw = dict(beta=vq["beta"], normalize=vq.get("normalize", "none"), use_restart=vq.get("use_restart", False),
+              use_weighted_sum=vq.get("use_weighted_sum", False), need_initialized=vq.get("need_initialized", False),
+              pq_dropout=vq.get("pq_dropout", 0.0), jsd_ts=jsd.get("temperature", 1.0))
+    if variant in ("pqgo", "pcls"):
+        kw.update(use_split=vq.get("use_split", False), num_query=jsd.get("num_query", 3), num_pos=jsd.get("num_pos", 10))
+    if variant == "pqgo":
+        kw["book"] = vq.get("book", 1.0)
+    M, K, D = vq["num_pq"][0], vq["num_codebooks"][0], vq["embed_dims"][0]
+    R = ref[variant]
+    Mir = {"nv": CB.NewVQProductQuantizerWrapper, "pqgo": CB.PQGOProductQuantizerWrapper, "pcls": CB.PQGOClsProductQuantizerWrapper}[variant]
+    torch.manual_seed(31)
+    r = R.ProductQuantizerWrapper(M, K, D, **kw, quantizer_cls=getattr(R, cls))
+    m = Mir(M, K, D, **kw, quantizer_cls=getattr(CB, cls))
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+    B, h, w = 2, 5, 4                                                     # even row count: jsd splits the batch in halves
+    for step in range(3):
+        if step == 2:
+            r.eval(); m.eval()
+        z = torch.randn(B, D, h, w)
+        res = []
+        for mod in (r, m):
+            random.seed(600 + step); torch.manual_seed(700 + step)
+            with torch.no_grad():
+                res.append(mod(z, step) if variant != "pqgo" else mod(z, torch.zeros_like(z), step))
+        rr, mr = res
+        assert len(rr) == len(mr) and torch.allclose(mr[0], rr[0], rtol=2e-5, atol=2e-6), step
+        if variant == "nv":
+            (_, ro, rp), (_, mo, mp) = rr, mr
+        elif variant == "pcls":
+            (_, ro, rp, ri), (_, mo, mp, mi) = rr, mr
+            assert len(ri) == len(mi) and all(torch.equal(a, b) for a, b in zip(ri, mi))
+        else:
+            (_, (rs, rqs, ri), ro, rp), (_, (ms, mqs, mi), mo, mp) = rr, mr
+            assert len(ri) == len(mi) == M and all(torch.equal(a, b) for a, b in zip(ri, mi))
+            assert all(torch.equal(a, b) for a, b in zip(rs, ms))
+            assert all(torch.allclose(a, b, rtol=2e-5, atol=2e-6) for a, b in zip(rqs, mqs))
+        assert mp.shape == rp.shape and torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"{yaml_file} {cls} step {step}")
+        _same_state(r, m, f"{yaml_file} {cls} step {step}")
+        assert all(torch.equal(qm.vq_count.cpu(), qr.vq_count.cpu()) for qr, qm in zip(r.quantizers, m.quantizers)), step
+
+
+@pytest.mark.parametrize("yaml_file,block", [("config/pq_baseline.yaml", 0), ("config/pq_baseline.yaml", 1),
+                                             ("config/pq_vae.yaml", 0), ("config/pq_vae.yaml", 1)])
+def test_yaml_literal_ema_configuration_against_the_live_reference(ref, yaml_file, block):
+    """model/quantizer.py's EMA wrapper exactly as the reference's YAML files configure it (``vq`` section read with
+    ``yaml.safe_load``, arguments assembled like ``DINOContra.__init__`` / ``DINOVae.__init__`` do, model/dino_contra.py:41-70):
+    1024 codes on 512 channels, 2 / 16 subspaces (d = 256 / 32), ``use_split`` as the file says, ``need_initialized``
+    left at the constructor's ``False`` when the file has no such key.  3 training steps + 1 evaluation step."""
+    import yaml
+    from equss_b200.quantizer import EMAVectorQuantizer, ProductQuantizerWrapper
+    vq = yaml.safe_load(open(os.path.join(os.environ.get("EQUSS_REFERENCE", "/root/reference"), yaml_file)))["model"]["vq"]
+    assert vq["vq_type"] == "ema"
+    kw = dict(beta=vq["beta"], normalize=vq["normalize"], use_restart=vq.get("use_restart", False),
+              use_gumbel=vq.get("use_gumbel", False), use_split=vq.get("use_split", False),
+              use_weighted_sum=vq.get("use_weighted_sum", False), need_initialized=vq.get("need_initialized", False),
+              decay=vq["decay"], eps=vq["eps"])
+    if kw["need_initialized"] == "kmeans":
+        pytest.skip("k-means initialisation of 1024 codes: pinned separately (tests/golden/pq_init_kmeans.npz)")
+    M, K, D = vq["num_pq"][block], vq["num_codebooks"][block], vq["embed_dims"][block]
+    q1 = ref["q1"]
+    torch.manual_seed(41 + block)
+    r = q1.ProductQuantizerWrapper(M, K, D, **kw, quantizer_cls=q1.EMAVectorQuantizer)
+    m = ProductQuantizerWrapper(M, K, D, **kw, quantizer_cls=EMAVectorQuantizer)
+    m.load_state_dict(r.state_dict(), strict=True)
+    r.train(); m.train()
+    for step in range(4):
+        if step == 3:
+            r.eval(); m.eval()
+        z = torch.randn(150, D) + 0.01 * step
+        outs = []
+        for mod in (r, m):
+            random.seed(800 + step); torch.manual_seed(900 + step)
+            with torch.no_grad():
+                outs.append(mod(z))
+        (rq, ro, rp), (mq, mo, mp) = outs
+        assert torch.allclose(mq, rq, rtol=2e-5, atol=2e-6), (step, float((mq - rq).abs().max()))
+        assert torch.allclose(mp, rp, rtol=2e-5, atol=1e-7), step
+        _same_outputs(ro, mo, f"{yaml_file}[{block}] step {step}")
+        _same_state(r, m, f"{yaml_file}[{block}] step {step}")
+        assert all(torch.equal(qm.vq_count, qr.vq_count) for qr, qm in zip(r.quantizers, m.quantizers)), step
