@@ -11,7 +11,8 @@ structure (the assignment to ``all_nns``, the ``step`` assignment, the ``for`` l
 features with ``tqdm`` replaced by the identity.  Nothing of the reference is copied into the repository -- the
 statements are read from /root/reference every time the script runs.  The oracle restatement
 (oracle/equss_oracle.py::knn, k = 30 as the reference hard-codes) must reproduce the result bit for bit, for the
-reference's own ``n_batches = 1`` (:271) and for a chunked run (``n_batches = 4`` on 301 rows: four chunks of 75 and a
+reference's own ``n_batches = 1`` (:271), for the duplicate of the same statements in ``cal_knn.py`` (:78-87, ``n_batches = 16``)
+and for a chunked run (``n_batches = 4`` on 301 rows: four chunks of 75 and a
 ragged one of 1), which yields the same table.  The seed is the first whose 30th / 31st similarities differ by more
 than 1e-5 in every row (no fp32 near-tie decides membership) and whose in-row gaps exceed 1e-6 (3e-7 at F = 768, where
 the similarities lie closer together; fp32 evaluation orders differ by a few 1e-8) so that no near-tie decides the order."""
@@ -37,14 +38,14 @@ def _calls(node, dotted):
     return False
 
 
-def reference_knn_statements():
-    """The AST nodes of precompute_knns.py that turn ``normed_feats`` + ``n_batches`` into ``nearest_neighbors``, and the
-    reference's own ``n_batches`` constant."""
-    path = os.path.join(REF, "data", "precompute_knns.py")
+def reference_knn_statements(rel_path=os.path.join("data", "precompute_knns.py"), function="my_app"):
+    """The AST nodes of precompute_knns.py (or of its duplicate, cal_knn.py::main) that turn ``normed_feats`` +
+    ``n_batches`` into ``nearest_neighbors``, and the file's own ``n_batches`` constant."""
+    path = os.path.join(REF, rel_path)
     tree = ast.parse(open(path).read(), path)
     picked, n_batches = [], None
     for fn in ast.walk(tree):
-        if not (isinstance(fn, ast.FunctionDef) and fn.name == "my_app"):
+        if not (isinstance(fn, ast.FunctionDef) and fn.name == function):
             continue
         for n in ast.walk(fn):
             if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name):
@@ -80,6 +81,8 @@ def main():
     import equss_oracle as O
     picked, ref_batches, path = reference_knn_statements()
     print("reference statements: lines", [(n.lineno, n.end_lineno) for n in picked], "n_batches =", ref_batches)
+    dup, dup_batches, dup_path = reference_knn_statements("cal_knn.py", "main")          # the duplicate script (:78-87, n_batches = 16)
+    print("cal_knn.py statements: lines", [(n.lineno, n.end_lineno) for n in dup], "n_batches =", dup_batches)
     k, fix = 30, {"n_batches": np.int64(ref_batches)}
     # two cases: F = 48 (features stored) and F = 768, the reference's ViT-B width and the kernel's tensor-core screening
     # path (features regenerated from the stored seed by the tests; their float64 sum is stored to detect generator drift)
@@ -96,6 +99,8 @@ def main():
             chunked = run_reference(picked, path, feats, 4)
         assert whole.dtype == torch.int64 and tuple(whole.shape) == (n, k)
         assert torch.equal(whole, chunked), "the chunked reference loop disagrees with the one-batch run"
+        with torch.no_grad():
+            assert torch.equal(run_reference(dup, dup_path, feats, dup_batches), whole), "cal_knn.py disagrees with precompute_knns.py"
         idx, vals = O.knn(feats, k=k)
         assert torch.equal(idx, whole), "oracle != reference statements"
         assert torch.equal(whole[:, 0], torch.arange(n))        # column 0 is the query itself (dataset_aug.py:520)
